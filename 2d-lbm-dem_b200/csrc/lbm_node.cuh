@@ -1,0 +1,310 @@
+/*
+ * lbm_node.cuh -- node-level arithmetic of the coupled D2Q9 MRT step, written once for host
+ * and device.
+ *
+ * The reference (cb-geo/2d-lbm-dem, src/main.c) does one LBM step as five in-place sweeps over
+ * f[x][y][q]: re-initialise solid nodes (:966-986), MRT-collide fluid nodes (:1077-1119),
+ * wall-ring copies (:1123-1145), interpolated bounce-back on active solid nodes (:1154-1222)
+ * and two swap passes that stream (:1224-1242).  This header states the SAME map
+ *      f_old  ->  f_new
+ * as a pure function of f_old, so that every lattice node can be produced independently:
+ *
+ *      f_new[q](p) = G[q](p - e_q)        if p - e_q lies inside the array,
+ *                  = G[opp q](p)          otherwise                      (swap passes, :1224-1242)
+ *
+ * where G(s) is the content of node s after the first four sweeps.  G is evaluated on demand
+ * from f_old, the old/new obstacle maps and the grain records (functions A, ring_value and
+ * G_value below).  Operand order and int/float/double promotions follow the reference source
+ * expression by expression (they decide the last bit, and in the -DSINGLE_PRECISION build the
+ * `1.`/`4.5`/`fabs`/`sqrt` promotions to double are part of the result).
+ *
+ * Two users:
+ *   - lbm_kernels.cu: the tiled TMA kernel uses the arithmetic helpers on shared-memory tiles
+ *     and falls back to G_value() (global memory) for the rare nodes next to the wall ring;
+ *     the "generic" kernel calls pull_value() for every node and is the device-side
+ *     cross-check of the tiled kernel.
+ *   - tests/hostcheck: the same header compiled by g++ to pin the formulation against the
+ *     oracle on the CPU, bit for bit (test infrastructure only; not a product path).
+ */
+#pragma once
+#include <math.h>
+#include <stddef.h>
+
+#if defined(__CUDACC__)
+#define LBM_HD __host__ __device__ __forceinline__
+#else
+#define LBM_HD inline
+#endif
+
+namespace lbm {
+
+constexpr int NQ = 9;
+constexpr int CELL_FLUID = -1;          /* obst == -1 (src/main.c:999) */
+constexpr int CELL_ACT = 1 << 30;       /* act[x][y] == 1 of a solid node, folded into the map */
+constexpr int CELL_IDX = CELL_ACT - 1;
+
+/* src/main.c:70-71 */
+LBM_HD int ex_of(int q) { return (q >= 1 && q <= 3) ? -1 : ((q >= 5 && q <= 7) ? 1 : 0); }
+LBM_HD int ey_of(int q) { return (q == 1 || q == 7 || q == 8) ? 1 : ((q >= 3 && q <= 5) ? -1 : 0); }
+LBM_HD int opp_of(int q) { return q == 0 ? 0 : (q <= 4 ? q + 4 : q - 4); }
+
+LBM_HD bool cell_is_fluid(int c) { return c < 0; }
+LBM_HD int cell_obst(int c) { return c < 0 ? -1 : (c & CELL_IDX); }
+LBM_HD bool cell_is_act(int c) { return c >= 0 && (c & CELL_ACT) != 0; }
+
+/* what the LBM kernels need to know about one grain (filled by the rasteriser, K2) */
+template <typename real>
+struct GrainRec {
+  real xc, yc, r2;        /* (x1-Mgx)/dx, (x2-Mby)/dx, rLB^2   src/main.c:1009-1011 */
+  real x1, x2, v1, v2, v3;
+};
+
+template <typename real>
+struct Lattice {
+  int lx, ly;             /* global lattice size */
+  int x0;                 /* global x of local row 0 (strip decomposition; 0 on one GPU) */
+  int nxl;                /* rows held locally, ghost rows included */
+  int pitch;              /* elements per row (>= ly) */
+  size_t plane;           /* elements per population plane = nxl * pitch */
+  int ngrains;
+  real dx, c, Mgx, Mby, lid6;
+  real s2, s3, s5, s7, s8, s9;
+  real w[NQ];
+  const real *f;          /* f_old, [q][x-x0][y] */
+  const int *cell_new;    /* obstacle map of this step (act bit folded in), [x-x0][y] */
+  const int *cell_old;    /* obstacle map of the previous step */
+  const GrainRec<real> *grains;
+};
+
+template <typename real>
+LBM_HD size_t node_index(const Lattice<real> &L, int x, int y) {
+  return (size_t)(x - L.x0) * L.pitch + y;
+}
+template <typename real>
+LBM_HD bool in_array(const Lattice<real> &L, int x, int y) {
+  return x >= 0 && y >= 0 && x < L.lx && y < L.ly;
+}
+template <typename real>
+LBM_HD bool is_ring(const Lattice<real> &L, int x, int y) {
+  return x == 0 || y == 0 || x == L.lx - 1 || y == L.ly - 1;
+}
+
+/* rigid-body velocity of a grain at lattice node (x,y): the sub-expressions of :974-980 */
+template <typename real>
+LBM_HD real wall_ux(const Lattice<real> &L, const GrainRec<real> &g, int y) {
+  return g.v1 - (y * L.dx + L.Mby - g.x2) * g.v3;
+}
+template <typename real>
+LBM_HD real wall_uy(const Lattice<real> &L, const GrainRec<real> &g, int x) {
+  return g.v2 + (x * L.dx + L.Mgx - g.x1) * g.v3;
+}
+
+/* src/main.c:974-981 */
+template <typename real>
+LBM_HD void equilibrium(const Lattice<real> &L, const GrainRec<real> &g, int x, int y, real *out) {
+  const real ux = wall_ux(L, g, y), uy = wall_uy(L, g, x);
+  const real u_squ = (ux * ux + uy * uy) / (L.c * L.c);
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const real eu = (ex_of(q) * ux + ey_of(q) * uy) / L.c;
+    out[q] = L.w[q] * (1. + 3 * eu + 4.5 * eu * eu - 1.5 * u_squ);
+  }
+}
+
+/* src/main.c:1082-1116 */
+template <typename real>
+LBM_HD void mrt_collide(const Lattice<real> &L, real *p) {
+  const real a = 1. / 36;
+  real rho = p[0] + p[1] + p[2] + p[3] + p[4] + p[5] + p[6] + p[7] + p[8];
+  real e = -4 * p[0] + 2 * p[1] - p[2] + 2 * p[3] - p[4] + 2 * p[5] - p[6] + 2 * p[7] - p[8];
+  real eps = 4 * p[0] + p[1] - 2 * p[2] + p[3] - 2 * p[4] + p[5] - 2 * p[6] + p[7] - 2 * p[8];
+  real j_x = p[5] + p[6] + p[7] - p[1] - p[2] - p[3];
+  real q_x = -p[1] + 2 * p[2] - p[3] + p[5] - 2 * p[6] + p[7];
+  real j_y = p[1] + p[8] + p[7] - p[3] - p[4] - p[5];
+  real q_y = p[1] - p[3] + 2 * p[4] - p[5] + p[7] - 2 * p[8];
+  real p_xx = p[2] - p[4] + p[6] - p[8];
+  real p_xy = -p[1] + p[3] - p[5] + p[7];
+  real j_x2 = j_x * j_x, j_y2 = j_y * j_y;
+  real eO = e - L.s2 * (e + 2 * rho - 3 * (j_x2 + j_y2) / rho);
+  real epsO = eps - L.s3 * (eps - rho + 3 * (j_x2 + j_y2) / rho);
+  real q_xO = q_x - L.s5 * (q_x + j_x);
+  real q_yO = q_y - L.s7 * (q_y + j_y);
+  real p_xxO = p_xx - L.s8 * (p_xx - (j_x2 - j_y2) / rho);
+  real p_xyO = p_xy - L.s9 * (p_xy - j_x * j_y / rho);
+  p[0] = a * (4 * rho - 4 * eO + 4 * epsO);
+  p[2] = a * (4 * rho - eO - 2 * epsO - 6 * j_x + 6 * q_xO + 9 * p_xxO);
+  p[4] = a * (4 * rho - eO - 2 * epsO - 6 * j_y + 6 * q_yO - 9 * p_xxO);
+  p[6] = a * (4 * rho - eO - 2 * epsO + 6 * j_x - 6 * q_xO + 9 * p_xxO);
+  p[8] = a * (4 * rho - eO - 2 * epsO + 6 * j_y - 6 * q_yO - 9 * p_xxO);
+  p[1] = a * (4 * rho + 2 * eO + epsO - 6 * j_x - 3 * q_xO + 6 * j_y + 3 * q_yO - 9 * p_xyO);
+  p[3] = a * (4 * rho + 2 * eO + epsO - 6 * j_x - 3 * q_xO - 6 * j_y - 3 * q_yO + 9 * p_xyO);
+  p[5] = a * (4 * rho + 2 * eO + epsO + 6 * j_x + 3 * q_xO - 6 * j_y - 3 * q_yO - 9 * p_xyO);
+  p[7] = a * (4 * rho + 2 * eO + epsO + 6 * j_x + 3 * q_xO + 6 * j_y + 3 * q_yO + 9 * p_xyO);
+}
+
+/* src/main.c:1053-1058: link fraction for the link from solid node (x,y) along q to its fluid
+ * neighbour, measured from the fluid node.  C semantics: fabs/sqrt are the double functions. */
+template <typename real>
+LBM_HD real link_delta(const GrainRec<real> &g, int x, int y, int q) {
+  const int ex = ex_of(q), ey = ey_of(q);
+  const real aa = fabs((double)ex) + fabs((double)ey);
+  const real bb = (x + ex - g.xc) * ex + (y + ey - g.yc) * ey;
+  const real cc = (x + ex - g.xc) * (x + ex - g.xc) + (y + ey - g.yc) * (y + ey - g.yc) - g.r2;
+  return (bb - sqrt(fabs((double)(bb * bb - aa * cc)))) / aa;
+}
+
+/* src/main.c:1166-1185 (and :1198-1217): the two interpolated bounce-back formulas.
+ * Fn_oq = F[n][opp q], Fn_q = F[n][q], Xnn_oq = f[nn][opp q] as seen by the reference's sweep,
+ * eu = ex*u_wall_x + ey*u_wall_y at the SOLID node.  `keep` is returned when delta <= 0. */
+template <typename real>
+LBM_HD real bounce_value(const Lattice<real> &L, int q, real d, real Fn_oq, real Fn_q, real Xnn_oq, real eu,
+                         real keep) {
+  real v = keep;
+  if (d >= 0.5) v = Fn_oq / (2 * d) + (2 * d - 1) * Fn_q / (2 * d) + 3 * (L.w[q] / L.c) * eu / d;
+  if (d > 0. && d < 0.5) v = 2 * d * Fn_oq + (1 - 2 * d) * Xnn_oq + 6 * (L.w[q] / L.c) * eu;
+  return v;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * On-demand evaluation from global memory (exact, slow): used for every node by the generic
+ * kernel / the host check, and for nodes on or next to the wall ring by the tiled kernel.
+ * ---------------------------------------------------------------------------------------- */
+
+/* f after reinit_obst_density (:966-986): equilibrium where the OLD map is solid. */
+template <typename real>
+LBM_HD void fprime(const Lattice<real> &L, int x, int y, real *out) {
+  const size_t k = node_index(L, x, y);
+  if (!is_ring(L, x, y)) {
+    const int co = L.cell_old[k];
+    if (!cell_is_fluid(co)) {
+      equilibrium(L, L.grains[cell_obst(co)], x, y, out);
+      return;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) out[q] = L.f[q * L.plane + k];
+}
+
+/* node content after sweeps 1-2 (re-init, collide) -- ring nodes are not touched by either */
+template <typename real>
+LBM_HD void A_node(const Lattice<real> &L, int x, int y, real *out) {
+  fprime(L, x, y, out);
+  if (!is_ring(L, x, y) && cell_is_fluid(L.cell_new[node_index(L, x, y)])) mrt_collide(L, out);
+}
+template <typename real>
+LBM_HD real A_value(const Lattice<real> &L, int x, int y, int q) {
+  if (is_ring(L, x, y)) return L.f[q * L.plane + node_index(L, x, y)];
+  real t[NQ];
+  A_node(L, x, y, t);
+  real v = t[0];
+#pragma unroll
+  for (int k = 1; k < NQ; ++k)
+    if (k == q) v = t[k];
+  return v;
+}
+
+/* ring node content after the wall-ring sweep (:1123-1145).  Order of the reference: rows
+ * y=0 / y=ly-1 for x=1..lx-2 reading the pre-sweep state, then columns x=0 / x=lx-1 for
+ * y=1..ly-2 reading what the row loop left, then the corners.  The only column reads that hit
+ * a row-loop result are the four spelled out below. */
+template <typename real>
+LBM_HD real ring_value(const Lattice<real> &L, int x, int y, int q) {
+  const int lx = L.lx, ly = L.ly;
+  const bool xin = x >= 1 && x <= lx - 2, yin = y >= 1 && y <= ly - 2;
+  if (y == 0 && xin) {
+    if (q == 8) return A_value(L, x, 1, 4);
+    if (q == 7) return A_value(L, x + 1, 1, 3);
+    if (q == 1) return A_value(L, x - 1, 1, 5);
+  } else if (y == ly - 1 && xin) {
+    if (q == 4) return A_value(L, x, ly - 2, 8);
+    if (q == 3) return A_value(L, x - 1, ly - 2, 7) - L.lid6;
+    if (q == 5) return A_value(L, x + 1, ly - 2, 1) + L.lid6;
+  } else if (x == 0 && yin) {
+    if (q == 6) return A_value(L, 1, y, 2);
+    if (q == 7) return (y + 1 == ly - 1) ? (real)(A_value(L, 0, ly - 2, 7) - L.lid6) : A_value(L, 1, y + 1, 3);
+    if (q == 5) return (y - 1 == 0) ? A_value(L, 0, 1, 5) : A_value(L, 1, y - 1, 1);
+  } else if (x == lx - 1 && yin) {
+    if (q == 2) return A_value(L, lx - 2, y, 6);
+    if (q == 3) return (y - 1 == 0) ? A_value(L, lx - 1, 1, 3) : A_value(L, lx - 2, y - 1, 7);
+    if (q == 1) return (y + 1 == ly - 1) ? (real)(A_value(L, lx - 1, ly - 2, 1) + L.lid6) : A_value(L, lx - 2, y + 1, 5);
+  } else if (x == 0 && y == 0) {
+    if (q == 7) return A_value(L, 1, 1, 3);
+  } else if (x == lx - 1 && y == 0) {
+    if (q == 1) return A_value(L, lx - 2, 1, 5);
+  } else if (x == 0 && y == ly - 1) {
+    if (q == 5) return A_value(L, 1, ly - 2, 1);
+  } else if (x == lx - 1 && y == ly - 1) {
+    if (q == 3) return A_value(L, lx - 2, ly - 2, 7);
+  }
+  return L.f[q * L.plane + node_index(L, x, y)];
+}
+
+/* content of node (x,y), population q, after sweeps 1-3 (what the swap passes then move) */
+template <typename real>
+LBM_HD real state3(const Lattice<real> &L, int x, int y, int q) {
+  return is_ring(L, x, y) ? ring_value(L, x, y, q) : A_value(L, x, y, q);
+}
+
+/* content of node (x,y), population q, after the grain bounce-back sweep (:1154-1222).
+ * NESTED marks the one level of look-back the serial sweep allows: when the second fluid-
+ * side node nn of a short link (delta < 1/2) is itself an active solid node that the x-outer,
+ * y-inner sweep visited earlier, the reference reads its already-updated value. */
+template <typename real, bool NESTED = false>
+LBM_HD real G_value(const Lattice<real> &L, int x, int y, int q) {
+  if (is_ring(L, x, y)) return ring_value(L, x, y, q);
+  const int cn = L.cell_new[node_index(L, x, y)];
+  if (cell_is_fluid(cn) || !cell_is_act(cn) || q == 0) return A_value(L, x, y, q);
+  const int ex = ex_of(q), ey = ey_of(q), oq = opp_of(q);
+  const int nx = x + ex, ny = y + ey;
+  if (!cell_is_fluid(L.cell_new[node_index(L, nx, ny)])) return L.w[q];
+  const GrainRec<real> g = L.grains[cell_obst(cn)];
+  const real d = link_delta(g, x, y, q);
+  const real eu = ex * wall_ux(L, g, y) + ey * wall_uy(L, g, x);
+  real Fn[NQ];
+  A_node(L, nx, ny, Fn);
+  real Fn_q = Fn[0], Fn_oq = Fn[0];
+#pragma unroll
+  for (int k = 1; k < NQ; ++k) {
+    if (k == q) Fn_q = Fn[k];
+    if (k == oq) Fn_oq = Fn[k];
+  }
+  real X = 0;
+  if (d > 0. && d < 0.5) {
+    const int nnx = nx + ex, nny = ny + ey;
+    bool look_back = false;
+    if (!NESTED && !is_ring(L, nnx, nny)) {
+      const int cnn = L.cell_new[node_index(L, nnx, nny)];
+      look_back = cell_is_act(cnn) && (nnx < x || (nnx == x && nny < y));
+    }
+    if constexpr (!NESTED) {
+      X = look_back ? G_value<real, true>(L, nnx, nny, oq) : state3(L, nnx, nny, oq);
+    } else {
+      X = state3(L, nnx, nny, oq);
+    }
+  }
+  return bounce_value(L, q, d, Fn_oq, Fn_q, X, eu, (d > 0.) ? (real)0 : A_value(L, x, y, q));
+}
+
+/* the streamed value: what the two swap passes leave in f[x][y][q] (:1224-1242) */
+template <typename real>
+LBM_HD real pull_value(const Lattice<real> &L, int x, int y, int q) {
+  if (q == 0) return G_value(L, x, y, 0);
+  const int sx = x - ex_of(q), sy = y - ey_of(q);
+  if (!in_array(L, sx, sy)) return G_value(L, x, y, opp_of(q));
+  return G_value(L, sx, sy, q);
+}
+
+/* One boundary link of forces_fluid (src/main.c:1313-1320).  fs_oq = f_new[s][opp q] and
+ * fn_q = f_new[n][q] (both POST-stream), s = (x,y) a node owned by the grain, n = s + e_q a
+ * node NOT owned by it.  Accumulates in the reference's expression order. */
+template <typename real>
+LBM_HD void force_link(int q, real fs_oq, real fn_q, int x, int y, real xc, real yc, real *fh1, real *fh2, real *fh3) {
+  const int oq = opp_of(q);
+  const real fnx = (fs_oq + fn_q) * ex_of(oq);
+  const real fny = (fs_oq + fn_q) * ey_of(oq);
+  *fh1 = *fh1 + fnx;
+  *fh2 = *fh2 + fny;
+  *fh3 = *fh3 - fnx * (y - yc) + fny * (x - xc);
+}
+
+}  // namespace lbm

@@ -1,0 +1,214 @@
+/*
+ * tests/hostcheck/hostcheck.cpp -- TEST INFRASTRUCTURE, never linked into the product.
+ *
+ * Compiles the product's host+device node headers (csrc/lbm_node.cuh, raster_node.cuh,
+ * dem_node.cuh) with g++ and drives them with plain serial loops, so that the *formulation*
+ * the CUDA kernels implement -- the pull / on-demand restatement of the LBM step, the
+ * atomicMax-style rasteriser with the act rule, the gather-form DEM step over a sorted full
+ * neighbour list -- can be pinned against the oracle on a machine without a GPU
+ * (tests/test_hostcheck.py).  It is not a CPU fallback: nothing under 2d-lbm-dem_b200/ loads it.
+ *
+ * Build: g++ -O2 -ffp-contract=off -shared -fPIC (tests/hostcheck/build.py).
+ */
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "dem_node.cuh"
+#include "lbm_node.cuh"
+#include "raster_node.cuh"
+
+using namespace lbm;
+
+namespace {
+
+template <typename real>
+struct Scalars {
+  real dx, c, Mgx, Mby, lid;
+};
+
+/* K2 on the host: owner = highest-index covering grain, then the act rule. */
+template <typename real>
+void raster_host(int lx, int ly, int n, const RasterParams<real> &P, const real *x1, const real *x2, const real *r,
+                 const real *rLB, const real *v1, const real *v2, const real *v3, std::vector<int> &cell,
+                 std::vector<GrainRec<real>> &rec) {
+  cell.assign((size_t)lx * ly, -1);
+  for (int x = 0; x < lx; ++x) cell[(size_t)x * ly] = cell[(size_t)x * ly + ly - 1] = n;
+  for (int y = 0; y < ly; ++y) cell[y] = cell[(size_t)(lx - 1) * ly + y] = n;
+  rec.resize(n);
+  std::vector<GrainBox> box(n);
+  std::vector<real> R2(n);
+  for (int i = 0; i < n; ++i) {
+    GrainRec<real> &g = rec[i];
+    grain_geometry(P, x1[i], x2[i], r[i], rLB[i], &g.xc, &g.yc, &g.r2, &R2[i], &box[i]);
+    g.x1 = x1[i]; g.x2 = x2[i]; g.v1 = v1[i]; g.v2 = v2[i]; g.v3 = v3[i];
+    for (int x = box[i].xi; x <= box[i].xf; ++x)
+      for (int y = box[i].yi; y <= box[i].yf; ++y)
+        if (disc_covers(g.xc, g.yc, g.r2, R2[i], x, y)) cell[(size_t)x * ly + y] = std::max(cell[(size_t)x * ly + y], i);
+  }
+  for (int i = 0; i < n; ++i) {
+    const GrainRec<real> &g = rec[i];
+    for (int x = box[i].xi; x <= box[i].xf; ++x)
+      for (int y = box[i].yi; y <= box[i].yf; ++y) {
+        if (cell_obst(cell[(size_t)x * ly + y]) != i) continue;
+        bool act = false;
+        for (int q = 1; q < NQ; ++q) {
+          const int nx = x + ex_of(q), ny = y + ey_of(q);
+          if (fluid_when_grain_ran(cell[(size_t)nx * ly + ny], i, n, g.xc, g.yc, g.r2, R2[i], box[i], nx, ny)) act = true;
+        }
+        if (act) cell[(size_t)x * ly + y] = i | CELL_ACT;
+      }
+  }
+}
+
+template <typename real>
+int lbm_step_host(int lx, int ly, int n, const double *scal, const double *grains /* [n][7]: x1 x2 v1 v2 v3 r rLB */,
+                  const double *f_in /* [x][y][q] */, const int *obst_old, double *f_out, int *obst_new, int *act_new,
+                  double *fhf /* [n][3], unscaled */) {
+  std::vector<real> x1(n), x2(n), v1(n), v2(n), v3(n), r(n), rLB(n);
+  for (int i = 0; i < n; ++i) {
+    const double *g = grains + 7 * (size_t)i;
+    x1[i] = (real)g[0]; x2[i] = (real)g[1]; v1[i] = (real)g[2]; v2[i] = (real)g[3]; v3[i] = (real)g[4];
+    r[i] = (real)g[5]; rLB[i] = (real)g[6];
+  }
+  RasterParams<real> RP;
+  RP.lx = lx; RP.ly = ly; RP.dx = (real)scal[0]; RP.Mgx = (real)scal[2]; RP.Mby = (real)scal[3];
+  std::vector<int> cell_new;
+  std::vector<GrainRec<real>> rec;
+  raster_host(lx, ly, n, RP, x1.data(), x2.data(), r.data(), rLB.data(), v1.data(), v2.data(), v3.data(), cell_new, rec);
+
+  const size_t nn = (size_t)lx * ly;
+  std::vector<real> fs(nn * NQ), fn(nn * NQ);
+  for (size_t k = 0; k < nn; ++k)
+    for (int q = 0; q < NQ; ++q) fs[q * nn + k] = (real)f_in[k * NQ + q];
+  std::vector<int> cell_old(obst_old, obst_old + nn);
+
+  Lattice<real> L;
+  L.lx = lx; L.ly = ly; L.x0 = 0; L.nxl = lx; L.pitch = ly; L.plane = nn; L.ngrains = n;
+  L.dx = (real)scal[0]; L.c = (real)scal[1]; L.Mgx = (real)scal[2]; L.Mby = (real)scal[3];
+  const real lid = (real)scal[4];
+  L.lid6 = lid / 6;
+  L.s2 = 1.5; L.s3 = 1.4; L.s5 = 1.5; L.s7 = 1.5; L.s8 = 1.9841; L.s9 = 1.9841;
+  const real w0[NQ] = {4. / 9, 1. / 36, 1. / 9, 1. / 36, 1. / 9, 1. / 36, 1. / 9, 1. / 36, 1. / 9};
+  for (int q = 0; q < NQ; ++q) L.w[q] = w0[q];
+  L.f = fs.data(); L.cell_new = cell_new.data(); L.cell_old = cell_old.data(); L.grains = rec.data();
+
+  for (int x = 0; x < lx; ++x)
+    for (int y = 0; y < ly; ++y)
+      for (int q = 0; q < NQ; ++q) fn[q * nn + (size_t)x * ly + y] = pull_value(L, x, y, q);
+
+  for (size_t k = 0; k < nn; ++k) {
+    for (int q = 0; q < NQ; ++q) f_out[k * NQ + q] = fn[q * nn + k];
+    obst_new[k] = cell_obst(cell_new[k]);
+    act_new[k] = cell_is_act(cell_new[k]) ? 1 : 0;
+  }
+  /* forces_fluid on the streamed field, reference order (src/main.c:1295-1325) */
+  for (int i = 0; i < n; ++i) {
+    real R2;
+    GrainBox b;
+    real xc, yc, r2;
+    grain_geometry(RP, x1[i], x2[i], r[i], rLB[i], &xc, &yc, &r2, &R2, &b);
+    real h1 = 0, h2 = 0, h3 = 0;
+    for (int x = b.xi; x <= b.xf; ++x)
+      for (int y = b.yi; y <= b.yf; ++y) {
+        if (cell_obst(cell_new[(size_t)x * ly + y]) != i) continue;
+        for (int q = 1; q < NQ; ++q) {
+          const int ax = x + ex_of(q), ay = y + ey_of(q);
+          if (cell_obst(cell_new[(size_t)ax * ly + ay]) == i) continue;
+          force_link<real>(q, fn[opp_of(q) * nn + (size_t)x * ly + y], fn[q * nn + (size_t)ax * ly + ay], x, y, xc, yc,
+                           &h1, &h2, &h3);
+        }
+      }
+    fhf[3 * (size_t)i] = h1; fhf[3 * (size_t)i + 1] = h2; fhf[3 * (size_t)i + 2] = h3;
+  }
+  return 0;
+}
+
+/* gather-form DEM step over a sorted FULL neighbour list (what K4 does), serial on the host */
+template <typename real>
+int dem_step_host(int n, const double *par /* see below */, int film, double *state /* [n][9] x1 x2 x3 v1 v2 v3 a1 a2 a3 */,
+                  const double *props /* [n][3] r m It */, const double *fhf /* [n][3] */, int rebuild, int *nbr_count,
+                  int *nbr /* [n][cap] */, int cap, int *wflags) {
+  dem::Params<real> P;
+  P.kg = (real)par[0]; P.kt = (real)par[1]; P.km = (real)par[2]; P.ktm = (real)par[3]; P.nug = (real)par[4];
+  P.num = (real)par[5]; P.numb = (real)par[6]; P.nugt = (real)par[7]; P.mu = (real)par[8]; P.mum = (real)par[9];
+  P.mumb = (real)par[10]; P.murf = (real)par[11]; P.freq = (real)par[12]; P.amp = (real)par[13]; P.t = (real)par[14];
+  P.distVerlet = (real)par[15]; P.dt = (real)par[16]; P.dt2 = (real)par[17]; P.xG = (real)par[18]; P.yG = (real)par[19];
+  P.Mgx = (real)par[20]; P.Mdx = (real)par[21]; P.Mby = (real)par[22]; P.Mhy = (real)par[23];
+  std::vector<real> s(9 * (size_t)n), pr(3 * (size_t)n), fh(3 * (size_t)n);
+  for (size_t k = 0; k < 9 * (size_t)n; ++k) s[k] = (real)state[k];
+  for (size_t k = 0; k < 3 * (size_t)n; ++k) { pr[k] = (real)props[k]; fh[k] = (real)fhf[k]; }
+  if (rebuild) {
+    for (int i = 0; i < n; ++i) {
+      int cnt = 0;
+      for (int j = 0; j < n; ++j) {
+        if (j == i) continue;
+        const int a = std::min(i, j), b = std::max(i, j);
+        if (dem::verlet_pair(P, s[9 * a], s[9 * a + 1], pr[3 * a], s[9 * b], s[9 * b + 1], pr[3 * b])) {
+          if (cnt >= cap) return -1;
+          nbr[(size_t)i * cap + cnt++] = j; /* ascending j */
+        }
+      }
+      nbr_count[i] = cnt;
+      wflags[i] = dem::wall_flags(P, s[9 * i], s[9 * i + 1], pr[3 * i]);
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    real *g = &s[9 * (size_t)i];
+    dem::kick_drift(P, &g[0], &g[3], g[6]);
+    dem::kick_drift(P, &g[1], &g[4], g[7]);
+    dem::kick_drift(P, &g[2], &g[5], g[8]);
+  }
+  std::vector<real> acc(3 * (size_t)n);
+  for (int i = 0; i < n; ++i) {
+    const real *gi = &s[9 * (size_t)i];
+    real a1 = fh[3 * i], a2 = fh[3 * i + 1], a3 = fh[3 * i + 2];
+    for (int k = 0; k < nbr_count[i]; ++k) {
+      const int j = nbr[(size_t)i * cap + k];
+      const int a = std::min(i, j), b = std::max(i, j);
+      const real *ga = &s[9 * (size_t)a], *gb = &s[9 * (size_t)b];
+      dem::Force<real> F;
+      if (!dem::pair_force(P, film != 0, ga[0], ga[1], ga[3], ga[4], ga[5], pr[3 * a], gb[0], gb[1], gb[3], gb[4], gb[5],
+                           pr[3 * b], &F))
+        continue;
+      if (i == a) { a1 = a1 + F.f1; a2 = a2 + F.f2; a3 = a3 + F.f3; }
+      else        { a1 = a1 - F.f1; a2 = a2 - F.f2; a3 = a3 + F.f3; }
+    }
+    dem::add_wall_forces(P, wflags[i], gi[0], gi[1], gi[3], gi[4], gi[5], pr[3 * i], &a1, &a2, &a3);
+    dem::finish_acceleration(P, pr[3 * i + 1], pr[3 * i + 2], &a1, &a2, &a3);
+    acc[3 * i] = a1; acc[3 * i + 1] = a2; acc[3 * i + 2] = a3;
+  }
+  for (int i = 0; i < n; ++i) {
+    real *g = &s[9 * (size_t)i];
+    g[6] = acc[3 * i]; g[7] = acc[3 * i + 1]; g[8] = acc[3 * i + 2];
+    dem::kick(P, &g[3], g[6]);
+    dem::kick(P, &g[4], g[7]);
+    dem::kick(P, &g[5], g[8]);
+  }
+  for (size_t k = 0; k < 9 * (size_t)n; ++k) state[k] = s[k];
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+#define EXPORT __attribute__((visibility("default")))
+/* scal: dx c Mgx Mby lid */
+EXPORT int hc_lbm_step_f64(int lx, int ly, int n, const double *scal, const double *grains, const double *f_in,
+                           const int *obst_old, double *f_out, int *obst_new, int *act_new, double *fhf) {
+  return lbm_step_host<double>(lx, ly, n, scal, grains, f_in, obst_old, f_out, obst_new, act_new, fhf);
+}
+EXPORT int hc_lbm_step_f32(int lx, int ly, int n, const double *scal, const double *grains, const double *f_in,
+                           const int *obst_old, double *f_out, int *obst_new, int *act_new, double *fhf) {
+  return lbm_step_host<float>(lx, ly, n, scal, grains, f_in, obst_old, f_out, obst_new, act_new, fhf);
+}
+EXPORT int hc_dem_step_f64(int n, const double *par, int film, double *state, const double *props, const double *fhf,
+                           int rebuild, int *nbr_count, int *nbr, int cap, int *wflags) {
+  return dem_step_host<double>(n, par, film, state, props, fhf, rebuild, nbr_count, nbr, cap, wflags);
+}
+EXPORT int hc_dem_step_f32(int n, const double *par, int film, double *state, const double *props, const double *fhf,
+                           int rebuild, int *nbr_count, int *nbr, int cap, int *wflags) {
+  return dem_step_host<float>(n, par, film, state, props, fhf, rebuild, nbr_count, nbr, cap, wflags);
+}
+}

@@ -1,0 +1,125 @@
+"""CPU pin of the FORMULATION the CUDA kernels implement (no GPU needed).
+
+The product's node headers (csrc/lbm_node.cuh, raster_node.cuh, dem_node.cuh) are compiled by
+g++ (tests/hostcheck) and driven serially; results must be BIT-IDENTICAL to the oracle
+(oracle/lbmdem_oracle.c, itself pinned bit-identical to the compiled reference):
+  - the pull / on-demand restatement of reinit + collide + ring + grain bounce-back + swap
+    streaming incl. ring nodes, solid nodes, moving grains;
+  - the max-owner rasteriser with the act rule (src/main.c:991-1065);
+  - forces_fluid from post-stream values (src/main.c:1285-1333);
+  - the gather-form DEM step over a sorted full neighbour list (src/main.c:1336-1516, :1733-1763).
+"""
+import numpy as np
+import pytest
+
+from oracle.oraclewrap import Oracle
+from util import DEM_CONST, scale_fhf, load_hostcheck, perturbed_f, random_kinematics, small_packing
+
+
+def _grain_table(g):
+    # oracle grains(): x1 x2 x3 v1 v2 v3 a1 a2 a3 r m It rLB -> hostcheck: x1 x2 v1 v2 v3 r rLB
+    return np.ascontiguousarray(g[:, [0, 1, 3, 4, 5, 9, 12]])
+
+
+def _lbm_case(prec, lx, ly, scale, seed, lid=0.0, steps=4, n_target=None):
+    hc = load_hostcheck()
+    fn = getattr(hc, f"hc_lbm_step_{prec}")
+    real = np.float64 if prec == "f64" else np.float32
+    o = Oracle(lx, ly, scale, prec)
+    r, x, y = small_packing(lx, ly, scale, seed, n_target=n_target)
+    n = o.init_arrays(r, x, y)
+    if lid:
+        o.set_lid(lid)
+    o.set_f(perturbed_f(lx, ly, seed + 1))
+    v, w, a = random_kinematics(n, seed + 2)
+    rng = np.random.default_rng(seed + 3)
+    sc = o.scalars()
+    for step in range(steps):
+        g = o.grains()
+        st = g[:, :9].copy()
+        # move the grains by a fraction of a lattice spacing so that nodes change state
+        st[:, 0:2] += rng.uniform(-0.6, 0.6, size=(n, 2)) * sc["dx"]
+        st[:, 3:5] = v * (1 + 0.1 * step)
+        st[:, 5:6] = w
+        o.set_grain_state(st)
+        g = o.grains()
+        f_in, obst_old = o.f(), o.obst()
+        o.lbm_step()
+        f_ref, obst_ref, act_ref, fhf_ref = o.f(), o.obst(), o.act(), o.fhf()
+        scal = np.array([sc["dx"], sc["c"], sc["Mgx"], sc["Mby"], lid], dtype=np.float64)
+        f_out = np.empty_like(f_in)
+        obst_new = np.empty_like(obst_old)
+        act_new = np.empty_like(obst_old)
+        fhf = np.empty((n, 3))
+        assert fn(lx, ly, n, scal, _grain_table(g), f_in, obst_old, f_out, obst_new, act_new, fhf) == 0
+        assert np.array_equal(obst_new, obst_ref), f"obst differs at step {step}"
+        solid = (obst_ref >= 0) & (obst_ref < n)
+        assert solid.sum() > 0
+        assert np.array_equal(act_new[solid], act_ref[solid]), f"act differs at step {step}"
+        bad = np.argwhere(f_out != f_ref)
+        assert bad.size == 0, f"step {step}: {len(bad)} populations differ, first {bad[:5]}"
+        fh = scale_fhf(fhf, sc["dx"], prec)
+        assert np.array_equal(fh, fhf_ref), f"fhf differs at step {step}"
+    # the case must actually have exercised the boundary machinery
+    return dict(n=n, solid=int(solid.sum()), changed=int((obst_old != obst_ref).sum()))
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_lbm_step_formulation_bit_exact_small(prec):
+    info = _lbm_case(prec, 64, 48, 1.0, seed=10)
+    assert info["n"] >= 6 and info["changed"] > 0
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_lbm_step_formulation_with_lid(prec):
+    _lbm_case(prec, 40, 56, 1.0, seed=20, lid=0.05, steps=3)
+
+
+def test_lbm_step_formulation_dense_scaled():
+    # many small grains: one-node gaps between reduced discs, short links reading ring / solid nodes
+    info = _lbm_case("f64", 96, 80, 1.0, seed=30, steps=3, n_target=120)
+    assert info["n"] >= 60
+
+
+def _dem_params(sc):
+    keys = ["kg", "kt", "km", "ktm", "nug", "num", "numb", "nugt", "mu", "mum", "mumb", "murf", "freq", "amp", "t",
+            "distVerlet"]
+    p = [DEM_CONST[k] for k in keys]
+    p += [sc["dt"], sc["dt2"], sc["xG"], sc["yG"], sc["Mgx"], sc["Mdx"], sc["Mby"], sc["Mhy"]]
+    return np.array(p, dtype=np.float64)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_dem_step_gather_form_bit_exact(prec):
+    hc = load_hostcheck()
+    fn = getattr(hc, f"hc_dem_step_{prec}")
+    lx, ly = 64, 48
+    o = Oracle(lx, ly, 1.0, prec)
+    r, x, y = small_packing(lx, ly, 1.0, seed=5, overlap=0.03)
+    n = o.init_arrays(r, x, y)
+    v, w, a = random_kinematics(n, 6, vmax=0.02, wmax=5.0, amax=5.0)
+    st = o.grains()[:, :9].copy()
+    st[:, 3:5], st[:, 5:6], st[:, 6:9] = v, w, a
+    o.set_grain_state(st)
+    cap = 32
+    cnt = np.zeros(n, dtype=np.int32)
+    nbr = np.zeros((n, cap), dtype=np.int32)
+    wfl = np.zeros(n, dtype=np.int32)
+    touched = 0
+    for step in range(230):
+        nb = o.scalars()["nbsteps"]
+        g = o.grains()
+        state = np.ascontiguousarray(g[:, :9])
+        props = np.ascontiguousarray(g[:, [9, 10, 11]])
+        o.step(1)
+        sc = o.scalars()          # Mdx/Mhy as left by VerletWall of this step
+        fhf = o.fhf()             # as left by the LBM step of this step (if any)
+        rc = fn(n, _dem_params(sc), int(nb % 8000 == 0), state, props, np.ascontiguousarray(fhf), int(nb % 100 == 0),
+                cnt, nbr, cap, wfl)
+        assert rc == 0
+        ref = o.grains()[:, :9]
+        assert np.array_equal(state, ref), f"DEM step {nb}: max diff {np.abs(state - ref).max()}"
+        touched = max(touched, int(cnt.sum()))
+    cum, half = o.verlet()
+    assert touched == 2 * len(half) and touched > 0
+    assert any(len(l) for l in o.wall_lists())
