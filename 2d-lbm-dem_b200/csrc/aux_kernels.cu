@@ -1,0 +1,511 @@
+/*
+ * aux_kernels.cu -- K2 (rasteriser), K3 (Verlet lists), K4 (DEM sub-step), K5 (density),
+ * K6 (output fields), force post-processing and layout conversion for sm_100a.
+ *
+ * Compiled with -fmad=false: the obstacle map must be bit-exact with the reference
+ * (src/main.c:1026-1029) and the DEM step reproduces the reference bit for bit when its inputs
+ * do (gather form over a sorted full neighbour list == the reference's scatter order, see
+ * dem_forces_kernel).
+ */
+#include "kernels.h"
+
+namespace lbmdem {
+
+using namespace lbm;
+
+/* ------------------------------------------------------------------------------------------
+ * K2: obst_construction (src/main.c:991-1065) without the delta[] array and without act[]
+ * ---------------------------------------------------------------------------------------- */
+template <typename real>
+__global__ void grain_prepare_kernel(RasterParams<real> P, int n, GrainArrays<real> g, GrainRec<real> *rec, real *R2,
+                                     GrainBox *boxes) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  GrainRec<real> r;
+  GrainBox b;
+  real R2i;
+  grain_geometry(P, g.x1[i], g.x2[i], g.r[i], g.rLB[i], &r.xc, &r.yc, &r.r2, &R2i, &b);
+  r.x1 = g.x1[i]; r.x2 = g.x2[i]; r.v1 = g.v1[i]; r.v2 = g.v2[i]; r.v3 = g.v3[i];
+  rec[i] = r;
+  R2[i] = R2i;
+  boxes[i] = b;
+}
+
+/* one warp per grain; the owner of a node is the highest-index grain covering it (:1028 run
+ * in index order), hence atomicMax over the fluid value -1 */
+template <typename real>
+__global__ void raster_kernel(int n, const GrainRec<real> *rec, const real *R2, const GrainBox *boxes, int *cell, int x0,
+                              int nxl, int pitch) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const GrainBox b = boxes[i];
+  const real xc = rec[i].xc, yc = rec[i].yc, r2 = rec[i].r2, RR = R2[i];
+  const int xa = max(b.xi, x0), xb = min(b.xf, x0 + nxl - 1);
+  for (int x = xa; x <= xb; ++x)
+    for (int y = b.yi + lane; y <= b.yf; y += 32)
+      if (disc_covers(xc, yc, r2, RR, x, y)) atomicMax(&cell[(size_t)(x - x0) * pitch + y], i);
+}
+
+/* init_obst's frame (:674-687): ring = nbgrains, interior = -1 */
+__global__ void cell_frame_kernel(int *cell, int lx, int ly, int x0, int nxl, int pitch, int ring_value) {
+  const int y = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = blockIdx.y;
+  if (y >= pitch || row >= nxl) return;
+  const int x = x0 + row;
+  int v = -1;
+  if (x <= 0 || x >= lx - 1 || y <= 0 || y >= ly - 1) v = ring_value;
+  cell[(size_t)row * pitch + y] = v;
+}
+
+template <typename real>
+cudaError_t launch_raster(const RasterParams<real> &P, int n, const GrainArrays<real> &g, GrainRec<real> *rec, real *R2,
+                          GrainBox *boxes, int *cell, int x0, int nxl, int pitch, cudaStream_t s) {
+  grain_prepare_kernel<real><<<(n + 127) / 128, 128, 0, s>>>(P, n, g, rec, R2, boxes);
+  /* clear the interior: rows with global x in [1, lx-2], columns [1, ly-2] (:997-1005) */
+  const int ra = max(1 - x0, 0), rb = min(P.lx - 2 - x0, nxl - 1);
+  if (rb >= ra) {
+    cudaError_t e = cudaMemset2DAsync(cell + (size_t)ra * pitch + 1, sizeof(int) * pitch, 0xFF, sizeof(int) * (P.ly - 2),
+                                      rb - ra + 1, s);
+    if (e != cudaSuccess) return e;
+  }
+  raster_kernel<real><<<(n * 32 + 255) / 256, 256, 0, s>>>(n, rec, R2, boxes, cell, x0, nxl, pitch);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cell_frame(int *cell, int lx, int ly, int x0, int nxl, int pitch, int ring_value, cudaStream_t s) {
+  dim3 grid((pitch + 255) / 256, nxl);
+  cell_frame_kernel<<<grid, 256, 0, s>>>(cell, lx, ly, x0, nxl, pitch, ring_value);
+  return cudaGetLastError();
+}
+
+template <typename real>
+__global__ void act_map_kernel(Lattice<real> L, int xlo, int xhi, int *act_out) {
+  const int y = blockIdx.x * blockDim.x + threadIdx.x;
+  const int x = xlo + blockIdx.y;
+  if (y >= L.ly || x >= xhi) return;
+  int a = 0;
+  if (!is_ring(L, x, y)) {
+    const int c = L.cell_new[node_index(L, x, y)];
+    a = cell_is_fluid(c) ? 1 : (node_act(L, x, y, c) ? 1 : 0); /* the reference clears act to 1 on fluid nodes */
+  }
+  act_out[(size_t)(x - xlo) * L.ly + y] = a;
+}
+template <typename real>
+cudaError_t launch_act_map(const Lattice<real> &L, int xlo, int xhi, int *act_out, cudaStream_t s) {
+  dim3 grid((L.ly + 255) / 256, xhi - xlo);
+  act_map_kernel<real><<<grid, 256, 0, s>>>(L, xlo, xhi, act_out);
+  return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------------------------------
+ * hydrodynamic force post-processing (src/main.c:1327-1332)
+ * ---------------------------------------------------------------------------------------- */
+template <typename real>
+__global__ void force_finish_kernel(long long *facc, int n, double k12, double k3, real *fhf1, real *fhf2, real *fhf3) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const real h1 = (real)((double)facc[i] / FORCE_FIX);
+  const real h2 = (real)((double)facc[n + i] / FORCE_FIX);
+  const real h3 = (real)((double)facc[2 * n + i] / TORQUE_FIX);
+  fhf1[i] = (real)((double)h1 * k12);
+  fhf2[i] = (real)((double)h2 * k12);
+  fhf3[i] = (real)((double)h3 * k3);
+  facc[i] = 0; facc[n + i] = 0; facc[2 * n + i] = 0;
+}
+template <typename real>
+cudaError_t launch_force_finish(long long *facc, int n, double k12, double k3, real *fhf1, real *fhf2, real *fhf3,
+                                cudaStream_t s) {
+  force_finish_kernel<real><<<(n + 127) / 128, 128, 0, s>>>(facc, n, k12, k3, fhf1, fhf2, fhf3);
+  return cudaGetLastError();
+}
+
+/* forces_fluid exactly as written (:1295-1325): one thread per grain, x outer, y inner, q inner */
+template <typename real>
+__global__ void force_serial_kernel(Lattice<real> L, const real *f_new, int xlo, int xhi, double *partial) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = L.ngrains;
+  if (i >= n) return;
+  const GrainBox b = L.boxes[i];
+  const real xc = L.grains[i].xc, yc = L.grains[i].yc;
+  real h1 = 0, h2 = 0, h3 = 0;
+  for (int x = max(b.xi, xlo); x <= min(b.xf, xhi - 1); ++x)
+    for (int y = b.yi; y <= b.yf; ++y) {
+      const size_t k = node_index(L, x, y);
+      if (cell_obst(L.cell_new[k]) != i) continue;
+      for (int q = 1; q < NQ; ++q) {
+        const size_t kn = node_index(L, x + ex_of(q), y + ey_of(q));
+        if (cell_obst(L.cell_new[kn]) == i) continue;
+        force_link<real>(q, f_new[opp_of(q) * L.plane + k], f_new[q * L.plane + kn], x, y, xc, yc, &h1, &h2, &h3);
+      }
+    }
+  partial[i] = h1; partial[n + i] = h2; partial[2 * n + i] = h3;
+}
+template <typename real>
+cudaError_t launch_force_serial(const Lattice<real> &L, const real *f_new, int xlo, int xhi, double *partial,
+                                cudaStream_t s) {
+  force_serial_kernel<real><<<(L.ngrains + 63) / 64, 64, 0, s>>>(L, f_new, xlo, xhi, partial);
+  return cudaGetLastError();
+}
+template <typename real>
+__global__ void force_scale_kernel(const double *partial, int n, double k12, double k3, real *fhf1, real *fhf2, real *fhf3) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  fhf1[i] = (real)((double)(real)partial[i] * k12);
+  fhf2[i] = (real)((double)(real)partial[n + i] * k12);
+  fhf3[i] = (real)((double)(real)partial[2 * n + i] * k3);
+}
+template <typename real>
+cudaError_t launch_force_scale(const double *partial, int n, double k12, double k3, real *fhf1, real *fhf2, real *fhf3,
+                               cudaStream_t s) {
+  force_scale_kernel<real><<<(n + 127) / 128, 128, 0, s>>>(partial, n, k12, k3, fhf1, fhf2, fhf3);
+  return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------------------------------
+ * K3: Verlet lists from a hashed uniform cell list.  The reference builds a half list with an
+ * O(N^2) double loop (initVerlet, :1519-1543); here every grain gets its FULL list (both
+ * directions), sorted by neighbour index, which is the order in which the reference's scatter
+ * loop adds contributions to that grain.
+ * ---------------------------------------------------------------------------------------- */
+__device__ __forceinline__ unsigned cell_hash(int cx, int cy) {
+  return ((unsigned)cx * 73856093u) ^ ((unsigned)cy * 19349663u);
+}
+
+template <typename real>
+__global__ void verlet_cells_kernel(int n, const real *x1, const real *x2, real cell_size, VerletBuffers vb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int cx = (int)floor((double)x1[i] / (double)cell_size), cy = (int)floor((double)x2[i] / (double)cell_size);
+  vb.gcx[i] = cx;
+  vb.gcy[i] = cy;
+  atomicAdd(&vb.bucket_count[cell_hash(cx, cy) & (vb.nbuckets - 1)], 1);
+}
+
+/* exclusive scan of bucket_count[0..nbuckets] in place, one CTA */
+__global__ void verlet_scan_kernel(VerletBuffers vb) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  const int total = vb.nbuckets + 1;
+  for (int base = 0; base < total; base += blockDim.x) {
+    const int idx = base + tid;
+    const int v = (idx < vb.nbuckets) ? vb.bucket_count[idx] : 0;
+    int incl = v;
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      int ws = (lane < (int)(blockDim.x >> 5)) ? warp_sums[lane] : 0;
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, ws, d);
+        if (lane >= d) ws += t;
+      }
+      warp_sums[lane] = ws; /* inclusive over warps */
+    }
+    __syncthreads();
+    const int before = carry + (wid ? warp_sums[wid - 1] : 0) + incl - v;
+    if (idx < total) vb.bucket_count[idx] = before;
+    __syncthreads();
+    if (tid == 0) carry += warp_sums[(blockDim.x >> 5) - 1];
+    __syncthreads();
+  }
+}
+
+__global__ void verlet_fill_kernel(int n, VerletBuffers vb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned b = cell_hash(vb.gcx[i], vb.gcy[i]) & (vb.nbuckets - 1);
+  vb.sorted[vb.bucket_count[b] + atomicAdd(&vb.bucket_cursor[b], 1)] = i;
+}
+
+template <typename real>
+__global__ void verlet_lists_kernel(dem::Params<real> P, int n, const real *x1, const real *x2, const real *r,
+                                    VerletBuffers vb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int cx = vb.gcx[i], cy = vb.gcy[i];
+  const real xi1 = x1[i], xi2 = x2[i], ri = r[i];
+  int *lst = vb.nbr + (size_t)i * vb.cap;
+  int cnt = 0;
+  bool overflow = false;
+  for (int dx = -1; dx <= 1; ++dx)
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int tx = cx + dx, ty = cy + dy;
+      const unsigned b = cell_hash(tx, ty) & (vb.nbuckets - 1);
+      for (int k = vb.bucket_count[b]; k < vb.bucket_count[b + 1]; ++k) {
+        const int j = vb.sorted[k];
+        if (j == i || vb.gcx[j] != tx || vb.gcy[j] != ty) continue;
+        /* the reference evaluates the criterion with the lower index first (:1525-1532) */
+        const bool in = (i < j) ? dem::verlet_pair(P, xi1, xi2, ri, x1[j], x2[j], r[j])
+                                : dem::verlet_pair(P, x1[j], x2[j], r[j], xi1, xi2, ri);
+        if (!in) continue;
+        if (cnt >= vb.cap) { overflow = true; continue; }
+        int p = cnt++; /* insertion sort, ascending */
+        while (p > 0 && lst[p - 1] > j) { lst[p] = lst[p - 1]; --p; }
+        lst[p] = j;
+      }
+    }
+  vb.nbr_count[i] = cnt;
+  vb.wflags[i] = dem::wall_flags(P, xi1, xi2, ri);
+  if (overflow) atomicExch(vb.error, 1);
+}
+
+template <typename real>
+cudaError_t launch_verlet(const dem::Params<real> &P, int n, const GrainArrays<real> &g, real cell_size,
+                          const VerletBuffers &vb, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(vb.bucket_count, 0, sizeof(int) * (vb.nbuckets + 1), s);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(vb.bucket_cursor, 0, sizeof(int) * vb.nbuckets, s);
+  if (e != cudaSuccess) return e;
+  const int nb = (n + 127) / 128;
+  verlet_cells_kernel<real><<<nb, 128, 0, s>>>(n, g.x1, g.x2, cell_size, vb);
+  verlet_scan_kernel<<<1, 1024, 0, s>>>(vb);
+  verlet_fill_kernel<<<nb, 128, 0, s>>>(n, vb);
+  verlet_lists_kernel<real><<<nb, 128, 0, s>>>(P, n, g.x1, g.x2, g.r, vb);
+  return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------------------------------
+ * K4: one DEM step = kick-drift (:1748-1753), forces (:1336-1516), kick (:1758-1763)
+ * ---------------------------------------------------------------------------------------- */
+template <typename real>
+__global__ void dem_kick_drift_kernel(dem::Params<real> P, int n, GrainArrays<real> g) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  real x, v;
+  x = g.x1[i]; v = g.v1[i]; dem::kick_drift(P, &x, &v, g.a1[i]); g.x1[i] = x; g.v1[i] = v;
+  x = g.x2[i]; v = g.v2[i]; dem::kick_drift(P, &x, &v, g.a2[i]); g.x2[i] = x; g.v2[i] = v;
+  x = g.x3[i]; v = g.v3[i]; dem::kick_drift(P, &x, &v, g.a3[i]); g.x3[i] = x; g.v3[i] = v;
+}
+
+/* One warp per grain.  Lane k evaluates the contact with the k-th neighbour (the expensive
+ * part: sqrt, divisions); the contributions are then added in neighbour order by every lane
+ * redundantly, which is exactly the order in which the reference's half-list loop touches
+ * this grain: lower-index partners first (their outer-loop turn comes earlier), then its own
+ * list, both ascending (:1434-1450).  Walls follow in the order B, T, L, R (:1455-1508). */
+template <typename real>
+__global__ void dem_forces_kernel(dem::Params<real> P, int n, bool film, GrainArrays<real> g, VerletBuffers vb) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const real xi1 = g.x1[i], xi2 = g.x2[i], vi1 = g.v1[i], vi2 = g.v2[i], vi3 = g.v3[i], ri = g.r[i];
+  real a1 = g.fhf1[i], a2 = g.fhf2[i], a3 = g.fhf3[i];
+  const int cnt = vb.nbr_count[i];
+  for (int base = 0; base < cnt; base += 32) {
+    const int k = base + lane;
+    real c1 = 0, c2 = 0, c3 = 0;
+    bool touch = false;
+    if (k < cnt) {
+      const int j = vb.nbr[(size_t)i * vb.cap + k];
+      const real xj1 = g.x1[j], xj2 = g.x2[j], vj1 = g.v1[j], vj2 = g.v2[j], vj3 = g.v3[j], rj = g.r[j];
+      dem::Force<real> F;
+      if (i < j) {
+        touch = dem::pair_force(P, film, xi1, xi2, vi1, vi2, vi3, ri, xj1, xj2, vj1, vj2, vj3, rj, &F);
+        if (touch) { c1 = F.f1; c2 = F.f2; c3 = F.f3; }
+      } else {
+        touch = dem::pair_force(P, film, xj1, xj2, vj1, vj2, vj3, rj, xi1, xi2, vi1, vi2, vi3, ri, &F);
+        if (touch) { c1 = -F.f1; c2 = -F.f2; c3 = F.f3; }
+      }
+    }
+    unsigned m = __ballot_sync(0xffffffffu, touch);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      a1 = a1 + __shfl_sync(0xffffffffu, c1, src);
+      a2 = a2 + __shfl_sync(0xffffffffu, c2, src);
+      a3 = a3 + __shfl_sync(0xffffffffu, c3, src);
+    }
+  }
+  if (lane != 0) return;
+  dem::add_wall_forces(P, vb.wflags[i], xi1, xi2, vi1, vi2, vi3, ri, &a1, &a2, &a3);
+  dem::finish_acceleration(P, g.m[i], g.It[i], &a1, &a2, &a3);
+  g.a1[i] = a1; g.a2[i] = a2; g.a3[i] = a3;
+}
+
+template <typename real>
+__global__ void dem_kick_kernel(dem::Params<real> P, int n, GrainArrays<real> g) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  real v;
+  v = g.v1[i]; dem::kick(P, &v, g.a1[i]); g.v1[i] = v;
+  v = g.v2[i]; dem::kick(P, &v, g.a2[i]); g.v2[i] = v;
+  v = g.v3[i]; dem::kick(P, &v, g.a3[i]); g.v3[i] = v;
+}
+
+template <typename real>
+cudaError_t launch_dem_step(const dem::Params<real> &P, int n, bool film, const GrainArrays<real> &g,
+                            const VerletBuffers &vb, cudaStream_t s) {
+  const int nb = (n + 127) / 128;
+  dem_kick_drift_kernel<real><<<nb, 128, 0, s>>>(P, n, g);
+  dem_forces_kernel<real><<<(n * 32 + 127) / 128, 128, 0, s>>>(P, n, film, g, vb);
+  dem_kick_kernel<real><<<nb, 128, 0, s>>>(P, n, g);
+  return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------------------------------
+ * K5: check_density / final_density (src/main.c:1249-1273), fixed-shape two-stage sum in fp64
+ * ---------------------------------------------------------------------------------------- */
+template <typename real>
+__global__ void density_partial_kernel(const real *f, int ly, int x0, int xlo, int xhi, int pitch, size_t plane,
+                                       double *partials) {
+  __shared__ double sh[256];
+  const size_t per_plane = (size_t)(xhi - xlo) * ly;
+  const size_t total = per_plane * NQ;
+  double acc = 0;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int q = (int)(t / per_plane);
+    const size_t rem = t - (size_t)q * per_plane;
+    const int row = (int)(rem / ly), y = (int)(rem - (size_t)row * ly);
+    acc += (double)f[q * plane + (size_t)(xlo - x0 + row) * pitch + y];
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int d = 128; d > 0; d >>= 1) {
+    if ((int)threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partials[blockIdx.x] = sh[0];
+}
+__global__ void density_final_kernel(const double *partials, int np, double *out) {
+  double acc = 0;
+  for (int k = 0; k < np; ++k) acc += partials[k];
+  *out = acc;
+}
+template <typename real>
+cudaError_t launch_density(const real *f, int ly, int x0, int xlo, int xhi, int pitch, size_t plane, double *partials,
+                           int npartials, double *out, cudaStream_t s) {
+  density_partial_kernel<real><<<npartials, 256, 0, s>>>(f, ly, x0, xlo, xhi, pitch, plane, partials);
+  density_final_kernel<<<1, 1, 0, s>>>(partials, npartials, out);
+  return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------------------------------
+ * K6: write_vtk's five point fields (src/main.c:284-323) for the owned rows, [y][x] order
+ * ---------------------------------------------------------------------------------------- */
+template <typename real>
+__global__ void fields_kernel(const real *f, const int *cell, GrainArrays<real> g, const real *gp, int n, int ly, int x0,
+                              int xlo, int xhi, int pitch, size_t plane, real rho_moy, float *grain_p, float *grain_v,
+                              float *grain_a, float *fluid_p, float *fluid_v) {
+  const int y = blockIdx.x * blockDim.x + threadIdx.x;
+  const int x = xlo + blockIdx.y;
+  if (y >= ly || x >= xhi) return;
+  const size_t k = (size_t)(x - x0) * pitch + y;
+  const size_t o = (size_t)y * (xhi - xlo) + (x - xlo);
+  const int i = cell_obst(cell[k]);
+  if (i >= 0 && i < n) {
+    grain_p[o] = gp ? (float)gp[i] : 0.f;
+    grain_v[3 * o] = (float)g.v1[i]; grain_v[3 * o + 1] = (float)g.v2[i]; grain_v[3 * o + 2] = 0.f;
+    grain_a[3 * o] = (float)g.a1[i]; grain_a[3 * o + 1] = (float)g.a2[i]; grain_a[3 * o + 2] = 0.f;
+    fluid_p[o] = 0.f;
+    fluid_v[3 * o] = 0.f; fluid_v[3 * o + 1] = 0.f; fluid_v[3 * o + 2] = 0.f;
+  } else {
+    real p[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) p[q] = f[q * plane + k];
+    /* :308-313: the reference accumulates into float fields, one population at a time */
+    float fp = 0.f, ux = 0.f, uy = 0.f;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      fp = (float)(fp + p[q]);
+      ux = (float)(ux + p[q] * ex_of(q));
+      uy = (float)(uy + p[q] * ey_of(q));
+    }
+    grain_p[o] = -1.f;
+    grain_v[3 * o] = 0.f; grain_v[3 * o + 1] = 0.f; grain_v[3 * o + 2] = 0.f;
+    grain_a[3 * o] = 0.f; grain_a[3 * o + 1] = 0.f; grain_a[3 * o + 2] = 0.f;
+    fluid_p[o] = (float)((1. / 3.) * rho_moy * (fp - 1.));
+    fluid_v[3 * o] = ux; fluid_v[3 * o + 1] = uy; fluid_v[3 * o + 2] = 0.f;
+  }
+}
+template <typename real>
+cudaError_t launch_fields(const real *f, const int *cell, const GrainArrays<real> &g, const real *gp, int n, int ly,
+                          int x0, int xlo, int xhi, int pitch, size_t plane, real rho_moy, float *grain_p, float *grain_v,
+                          float *grain_a, float *fluid_p, float *fluid_v, cudaStream_t s) {
+  dim3 grid((ly + 127) / 128, xhi - xlo);
+  fields_kernel<real><<<grid, 128, 0, s>>>(f, cell, g, gp, n, ly, x0, xlo, xhi, pitch, plane, rho_moy, grain_p, grain_v,
+                                           grain_a, fluid_p, fluid_v);
+  return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------------------------------
+ * layout conversion: reference f[x][y][q] (as double) <-> device f[q][x][y] (real)
+ * ---------------------------------------------------------------------------------------- */
+template <typename real>
+__global__ void f_to_host_kernel(const real *f, int ly, int pitch, size_t plane, int row0, int nrows, double *out) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)nrows * ly * NQ;
+  if (t >= total) return;
+  const int q = (int)(t % NQ);
+  const size_t node = t / NQ;
+  const int row = (int)(node / ly), y = (int)(node - (size_t)row * ly);
+  out[t] = (double)f[q * plane + (size_t)(row0 + row) * pitch + y];
+}
+template <typename real>
+__global__ void f_from_host_kernel(real *f, int ly, int pitch, size_t plane, int row0, int nrows, const double *in) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)nrows * ly * NQ;
+  if (t >= total) return;
+  const int q = (int)(t % NQ);
+  const size_t node = t / NQ;
+  const int row = (int)(node / ly), y = (int)(node - (size_t)row * ly);
+  f[q * plane + (size_t)(row0 + row) * pitch + y] = (real)in[t];
+}
+template <typename real>
+cudaError_t launch_f_to_host_layout(const real *f, int ly, int pitch, size_t plane, int row0, int nrows, double *out,
+                                    cudaStream_t s) {
+  const size_t total = (size_t)nrows * ly * NQ;
+  f_to_host_kernel<real><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(f, ly, pitch, plane, row0, nrows, out);
+  return cudaGetLastError();
+}
+template <typename real>
+cudaError_t launch_f_from_host_layout(real *f, int ly, int pitch, size_t plane, int row0, int nrows, const double *in,
+                                      cudaStream_t s) {
+  const size_t total = (size_t)nrows * ly * NQ;
+  f_from_host_kernel<real><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(f, ly, pitch, plane, row0, nrows, in);
+  return cudaGetLastError();
+}
+
+/* init_density (src/main.c:716-724): f = w everywhere */
+template <typename real>
+__global__ void fill_rest_kernel(real *f, size_t plane, Lattice<real> Lw) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= plane) return;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) f[q * plane + t] = Lw.w[q];
+}
+template <typename real>
+cudaError_t launch_fill_rest(real *f, size_t plane, const Lattice<real> &Lw, cudaStream_t s) {
+  fill_rest_kernel<real><<<(unsigned)((plane + 255) / 256), 256, 0, s>>>(f, plane, Lw);
+  return cudaGetLastError();
+}
+
+#define INSTANTIATE(real)                                                                                               \
+  template cudaError_t launch_raster<real>(const RasterParams<real> &, int, const GrainArrays<real> &, GrainRec<real> *,  \
+                                           real *, GrainBox *, int *, int, int, int, cudaStream_t);                      \
+  template cudaError_t launch_act_map<real>(const Lattice<real> &, int, int, int *, cudaStream_t);                        \
+  template cudaError_t launch_force_finish<real>(long long *, int, double, double, real *, real *, real *, cudaStream_t); \
+  template cudaError_t launch_force_serial<real>(const Lattice<real> &, const real *, int, int, double *, cudaStream_t);  \
+  template cudaError_t launch_force_scale<real>(const double *, int, double, double, real *, real *, real *,              \
+                                                cudaStream_t);                                                            \
+  template cudaError_t launch_verlet<real>(const dem::Params<real> &, int, const GrainArrays<real> &, real,               \
+                                           const VerletBuffers &, cudaStream_t);                                         \
+  template cudaError_t launch_dem_step<real>(const dem::Params<real> &, int, bool, const GrainArrays<real> &,             \
+                                             const VerletBuffers &, cudaStream_t);                                       \
+  template cudaError_t launch_density<real>(const real *, int, int, int, int, int, size_t, double *, int, double *,       \
+                                            cudaStream_t);                                                                \
+  template cudaError_t launch_fields<real>(const real *, const int *, const GrainArrays<real> &, const real *, int, int,  \
+                                           int, int, int, int, size_t, real, float *, float *, float *, float *, float *, \
+                                           cudaStream_t);                                                                 \
+  template cudaError_t launch_f_to_host_layout<real>(const real *, int, int, size_t, int, int, double *, cudaStream_t);   \
+  template cudaError_t launch_f_from_host_layout<real>(real *, int, int, size_t, int, int, const double *, cudaStream_t); \
+  template cudaError_t launch_fill_rest<real>(real *, size_t, const Lattice<real> &, cudaStream_t);
+INSTANTIATE(float)
+INSTANTIATE(double)
+
+}  // namespace lbmdem

@@ -32,8 +32,10 @@
 
 #if defined(__CUDACC__)
 #define LBM_HD __host__ __device__ __forceinline__
+#define LBM_HD_SLOW __host__ __device__ __noinline__ /* on-demand path: one copy, called */
 #else
 #define LBM_HD inline
+#define LBM_HD_SLOW inline
 #endif
 
 namespace lbm {
@@ -59,6 +61,34 @@ struct GrainRec {
   real x1, x2, v1, v2, v3;
 };
 
+/* clamped bounding box of a grain, src/main.c:1016-1023 (empty when xi > xf or yi > yf) */
+struct GrainBox {
+  int xi, xf, yi, yf;
+};
+LBM_HD bool box_has(const GrainBox &b, int x, int y) { return x >= b.xi && x <= b.xf && y >= b.yi && y <= b.yf; }
+
+/* src/main.c:1026-1029 */
+template <typename real>
+LBM_HD bool disc_covers(real xc, real yc, real r2, real R2, int x, int y) {
+  const real dist2 = (x - xc) * (x - xc) + (y - yc) * (y - yc);
+  return dist2 <= R2 && dist2 <= r2;
+}
+
+/* Was node n "fluid" when the reference's grain loop reached grain i (:1047)?  At that moment
+ * the map holds grains 0..i only.  n is fluid then iff no grain j <= i covers it: final map
+ * -1, or final owner k > i while grain i itself does not cover n.  (A node covered by k > i
+ * AND by some j < i but not by i -- three mutually overlapping reduced discs -- would be
+ * misjudged; reduced discs are 0.85 r, so even a pair only overlaps at > 15 % interpenetration.)
+ */
+template <typename real>
+LBM_HD bool fluid_when_grain_ran(int cell_n, int i, int ngrains, real xc, real yc, real r2, real R2,
+                                 const GrainBox &b, int nx, int ny) {
+  if (cell_is_fluid(cell_n)) return true;
+  const int k = cell_obst(cell_n);
+  if (k >= ngrains || k <= i) return false;
+  return !(box_has(b, nx, ny) && disc_covers(xc, yc, r2, R2, nx, ny));
+}
+
 template <typename real>
 struct Lattice {
   int lx, ly;             /* global lattice size */
@@ -74,6 +104,9 @@ struct Lattice {
   const int *cell_new;    /* obstacle map of this step (act bit folded in), [x-x0][y] */
   const int *cell_old;    /* obstacle map of the previous step */
   const GrainRec<real> *grains;
+  const GrainBox *boxes;  /* per grain, with R2 = (r/dx)^2: only the act rule needs them */
+  const real *R2;
+  int act_folded;         /* 1: cell_new already carries CELL_ACT; 0: derive act on demand */
 };
 
 template <typename real>
@@ -87,6 +120,24 @@ LBM_HD bool in_array(const Lattice<real> &L, int x, int y) {
 template <typename real>
 LBM_HD bool is_ring(const Lattice<real> &L, int x, int y) {
   return x == 0 || y == 0 || x == L.lx - 1 || y == L.ly - 1;
+}
+
+/* act[x][y] of an interior solid node (src/main.c:1038-1052): some neighbour was fluid when the
+ * owner grain was rasterised.  Either read from the folded bit or derived from the map. */
+template <typename real>
+LBM_HD_SLOW bool node_act(const Lattice<real> &L, int x, int y, int c) {
+  if (c < 0) return false;
+  if (c & CELL_ACT) return true;
+  if (L.act_folded) return false;
+  const int i = cell_obst(c);
+  if (i >= L.ngrains) return false;
+  const GrainRec<real> &g = L.grains[i];
+  for (int q = 1; q < NQ; ++q) {
+    const int nx = x + ex_of(q), ny = y + ey_of(q);
+    if (fluid_when_grain_ran(L.cell_new[node_index(L, nx, ny)], i, L.ngrains, g.xc, g.yc, g.r2, L.R2[i], L.boxes[i], nx, ny))
+      return true;
+  }
+  return false;
 }
 
 /* rigid-body velocity of a grain at lattice node (x,y): the sub-expressions of :974-980 */
@@ -187,7 +238,7 @@ LBM_HD void fprime(const Lattice<real> &L, int x, int y, real *out) {
 
 /* node content after sweeps 1-2 (re-init, collide) -- ring nodes are not touched by either */
 template <typename real>
-LBM_HD void A_node(const Lattice<real> &L, int x, int y, real *out) {
+LBM_HD_SLOW void A_node(const Lattice<real> &L, int x, int y, real *out) {
   fprime(L, x, y, out);
   if (!is_ring(L, x, y) && cell_is_fluid(L.cell_new[node_index(L, x, y)])) mrt_collide(L, out);
 }
@@ -208,7 +259,7 @@ LBM_HD real A_value(const Lattice<real> &L, int x, int y, int q) {
  * y=1..ly-2 reading what the row loop left, then the corners.  The only column reads that hit
  * a row-loop result are the four spelled out below. */
 template <typename real>
-LBM_HD real ring_value(const Lattice<real> &L, int x, int y, int q) {
+LBM_HD_SLOW real ring_value(const Lattice<real> &L, int x, int y, int q) {
   const int lx = L.lx, ly = L.ly;
   const bool xin = x >= 1 && x <= lx - 2, yin = y >= 1 && y <= ly - 2;
   if (y == 0 && xin) {
@@ -250,10 +301,10 @@ LBM_HD real state3(const Lattice<real> &L, int x, int y, int q) {
  * side node nn of a short link (delta < 1/2) is itself an active solid node that the x-outer,
  * y-inner sweep visited earlier, the reference reads its already-updated value. */
 template <typename real, bool NESTED = false>
-LBM_HD real G_value(const Lattice<real> &L, int x, int y, int q) {
+LBM_HD_SLOW real G_value(const Lattice<real> &L, int x, int y, int q) {
   if (is_ring(L, x, y)) return ring_value(L, x, y, q);
   const int cn = L.cell_new[node_index(L, x, y)];
-  if (cell_is_fluid(cn) || !cell_is_act(cn) || q == 0) return A_value(L, x, y, q);
+  if (cell_is_fluid(cn) || q == 0 || !node_act(L, x, y, cn)) return A_value(L, x, y, q);
   const int ex = ex_of(q), ey = ey_of(q), oq = opp_of(q);
   const int nx = x + ex, ny = y + ey;
   if (!cell_is_fluid(L.cell_new[node_index(L, nx, ny)])) return L.w[q];
@@ -274,7 +325,7 @@ LBM_HD real G_value(const Lattice<real> &L, int x, int y, int q) {
     bool look_back = false;
     if (!NESTED && !is_ring(L, nnx, nny)) {
       const int cnn = L.cell_new[node_index(L, nnx, nny)];
-      look_back = cell_is_act(cnn) && (nnx < x || (nnx == x && nny < y));
+      look_back = (nnx < x || (nnx == x && nny < y)) && node_act(L, nnx, nny, cnn);
     }
     if constexpr (!NESTED) {
       X = look_back ? G_value<real, true>(L, nnx, nny, oq) : state3(L, nnx, nny, oq);

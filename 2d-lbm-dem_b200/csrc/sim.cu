@@ -1,0 +1,897 @@
+/*
+ * sim.cu -- host side of liblbmdem_gpu.so: the simulation object that owns the device state
+ * and sequences the kernels the way renderScene() sequences the reference's loops
+ * (src/main.c:1697-1777), plus the C ABI of include/lbmdem_gpu.h.
+ *
+ * Device layout (DESIGN.md "data layout"):
+ *   f[2]     double-buffered populations, structure of arrays [q][x - x0][y], y contiguous, rows
+ *            padded to a multiple of 32 elements (128-byte aligned rows, TMA-legal strides)
+ *   cell[2]  obstacle map [x - x0][y] (int32: -1 fluid, grain index, nbgrains = wall ring);
+ *            the buffer written by this step's rasteriser is "new", the other one is the "old"
+ *            map reinit_obst_density reads (src/main.c:970)
+ *   grains   structure of arrays of `real`, replicated on every rank
+ * Strip decomposition: rank k of P owns the global rows [xlo, xhi); with P > 1 the local arrays
+ * carry two extra rows on each side (x0 = xlo - 2): f needs one ghost row (exchanged before
+ * every LBM step), the obstacle map two (recomputed locally, grains are replicated).
+ */
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/lbmdem_gpu.h"
+#include "kernels.h"
+
+namespace lbmdem {
+
+using namespace lbm;
+
+static thread_local std::string g_create_error;
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) return fail(LBMDEM_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+/* ---- NCCL, bound at run time so that single-GPU use has no NCCL dependency ---- */
+struct NcclApi {
+  struct UniqueId { char internal[128]; };
+  typedef int (*GetUniqueId_t)(UniqueId *);
+  typedef int (*CommInitRank_t)(void **, int, UniqueId, int);
+  typedef int (*CommDestroy_t)(void *);
+  typedef int (*Send_t)(const void *, size_t, int, int, void *, cudaStream_t);
+  typedef int (*Recv_t)(void *, size_t, int, int, void *, cudaStream_t);
+  typedef int (*Group_t)(void);
+  typedef int (*AllReduce_t)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+  typedef const char *(*ErrStr_t)(int);
+  void *handle = nullptr;
+  GetUniqueId_t GetUniqueId = nullptr;
+  CommInitRank_t CommInitRank = nullptr;
+  CommDestroy_t CommDestroy = nullptr;
+  Send_t Send = nullptr;
+  Recv_t Recv = nullptr;
+  Group_t GroupStart = nullptr, GroupEnd = nullptr;
+  AllReduce_t AllReduce = nullptr;
+  ErrStr_t GetErrorString = nullptr;
+  enum { Int64 = 4, Float32 = 7, Float64 = 8, Sum = 0 };
+  bool load(std::string *why) {
+    if (handle) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+      handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (handle) break;
+    }
+    if (!handle) { *why = std::string("dlopen libnccl.so.2: ") + dlerror(); return false; }
+#define SYM(field, name)                                  \
+  field = (decltype(field))dlsym(handle, name);           \
+  if (!field) { *why = std::string("dlsym ") + name; return false; }
+    SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
+    SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd")
+    SYM(AllReduce, "ncclAllReduce") SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    return true;
+  }
+};
+static NcclApi g_nccl;
+
+typedef CUresult (*EncodeTiled_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct SimBase {
+  lbmdem_params P;
+  std::string err;
+  int last_code = 0;
+  virtual ~SimBase() {}
+  int fail(int code, const std::string &msg) {
+    err = msg;
+    last_code = code;
+    return code;
+  }
+  virtual int init_device() = 0;
+  virtual int load_sample(const char *path) = 0;
+  virtual int set_grains(int n, const double *r, const double *x1, const double *x2) = 0;
+  virtual int step(long n) = 0;
+  virtual int lbm_step() = 0;
+  virtual int lbm_steps(long n) = 0;
+  virtual int build_verlet() = 0;
+  virtual int get_scalars(double *d, long *l) = 0;
+  virtual int set_nbsteps(long n) = 0;
+  virtual int get_strip(int *xlo, int *xhi) = 0;
+  virtual int total_density(double *sum) = 0;
+  virtual int get_f(double *out) = 0;
+  virtual int set_f(const double *in) = 0;
+  virtual int get_obst(int *out) = 0;
+  virtual int set_obst(const int *in) = 0;
+  virtual int get_act(int *out) = 0;
+  virtual int get_grains(double *out) = 0;
+  virtual int set_grain_state(const double *in) = 0;
+  virtual int get_fhf(double *out) = 0;
+  virtual int set_fhf(const double *in) = 0;
+  virtual int get_verlet(int *count, int *nbr, int capacity, int *wall_flags) = 0;
+  virtual int get_fields(const double *gp, float *a, float *b, float *c, float *d, float *e) = 0;
+  virtual int step_host(const double *state_in, long n, double *state_out, double *fhf_out, double *dens) = 0;
+  virtual int attach_nccl(const void *id) = 0;
+  virtual int get_kernel_timer(double *ms, long *k1, long *all) = 0;
+  virtual int reset_kernel_timer(int enable) = 0;
+  virtual void *stream_ptr() = 0;
+};
+
+template <typename real>
+struct Sim : SimBase {
+  /* geometry */
+  int lx = 0, ly = 0, xlo = 0, xhi = 0, x0 = 0, nxl = 0, pitch = 0;
+  size_t plane = 0;
+  int n = 0; /* nbgrains */
+  bool ready = false;
+  /* reference globals, kept in `real` like the reference keeps them (src/main.c:52-165) */
+  real dx = 0, dtLB = 0, c = 0, dt = 0, dt2 = 0, Mgx = 0, Mdx = 0, Mby = 0, Mhy = 0, xG = 0, yG = 0, rmax = 0;
+  int npDEM = 1;
+  long nbsteps = 0, nFile = 0;
+  double k12 = 0, k3 = 0; /* fhf scale factors (:1329-1331) */
+  /* device */
+  cudaStream_t stream = nullptr;
+  real *f[2] = {nullptr, nullptr};
+  int *cell[2] = {nullptr, nullptr};
+  int cur = 0, cur_cell = 0;
+  CUtensorMap tmap[2];
+  std::vector<real *> grain_bufs;
+  GrainArrays<real> g{};
+  GrainRec<real> *rec = nullptr;
+  real *R2 = nullptr;
+  GrainBox *boxes = nullptr;
+  long long *facc = nullptr;
+  double *fpartial = nullptr;
+  VerletBuffers vb{};
+  double *dens_partials = nullptr, *dens_out = nullptr;
+  double *stage = nullptr; /* device staging for layout conversion */
+  size_t stage_elems = 0;
+  double *hstage = nullptr; /* pinned host staging for grain I/O */
+  size_t hstage_elems = 0;
+  /* NCCL */
+  void *comm = nullptr;
+  /* instrumentation */
+  bool events_on = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+  size_t ev_used = 0;
+  double k1_ms_acc = 0;
+  long k1_launches = 0, all_launches = 0;
+
+  ~Sim() override {
+    if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+    for (auto &e : ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    for (int k = 0; k < 2; ++k) { cudaFree(f[k]); cudaFree(cell[k]); }
+    for (real *p : grain_bufs) cudaFree(p);
+    cudaFree(rec); cudaFree(R2); cudaFree(boxes); cudaFree(facc); cudaFree(fpartial);
+    cudaFree(vb.bucket_count); cudaFree(vb.bucket_cursor); cudaFree(vb.sorted); cudaFree(vb.gcx); cudaFree(vb.gcy);
+    cudaFree(vb.nbr_count); cudaFree(vb.nbr); cudaFree(vb.wflags); cudaFree(vb.error);
+    cudaFree(dens_partials); cudaFree(dens_out); cudaFree(stage);
+    if (hstage) cudaFreeHost(hstage);
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  static constexpr int DENS_BLOCKS = 1184; /* 8 x 148 SMs */
+
+  int init_device() override {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+      return fail(LBMDEM_ECUDA, "no CUDA device visible: liblbmdem_gpu has no CPU path");
+    if (P.device < 0 || P.device >= ndev) return fail(LBMDEM_EINVAL, "device ordinal out of range");
+    CK(cudaSetDevice(P.device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, P.device));
+    if (prop.major < 10)
+      return fail(LBMDEM_ECUDA, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                    "; the kernels are built for sm_100a only");
+    lx = P.lx; ly = P.ly;
+    if (lx < 8 || ly < 8) return fail(LBMDEM_EINVAL, "lattice must be at least 8 x 8");
+    if (P.nranks < 1 || P.rank < 0 || P.rank >= P.nranks) return fail(LBMDEM_EINVAL, "bad rank / nranks");
+    const int base = lx / P.nranks, rem = lx % P.nranks;
+    xlo = P.rank * base + std::min(P.rank, rem);
+    xhi = xlo + base + (P.rank < rem ? 1 : 0);
+    if (P.nranks > 1 && xhi - xlo < 4) return fail(LBMDEM_EINVAL, "strips must be at least 4 rows wide");
+    if (P.nranks > 1) { x0 = xlo - 2; nxl = xhi - xlo + 4; } else { x0 = 0; nxl = lx; }
+    pitch = (ly + 31) / 32 * 32;
+    plane = (size_t)nxl * pitch;
+    CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+      CK(cudaMalloc(&f[k], sizeof(real) * plane * NQ));
+      CK(cudaMemsetAsync(f[k], 0, sizeof(real) * plane * NQ, stream));
+      CK(cudaMalloc(&cell[k], sizeof(int) * plane));
+    }
+    CK(cudaMalloc(&dens_partials, sizeof(double) * DENS_BLOCKS));
+    CK(cudaMalloc(&dens_out, sizeof(double)));
+    /* TMA descriptors: 3-D (y, x, q) view of each population buffer */
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(LBMDEM_ECUDA, "cuTensorMapEncodeTiled not available");
+    EncodeTiled_t encode = (EncodeTiled_t)fn;
+    for (int k = 0; k < 2; ++k) {
+      const cuuint64_t dims[3] = {(cuuint64_t)ly, (cuuint64_t)nxl, (cuuint64_t)NQ};
+      const cuuint64_t strides[2] = {(cuuint64_t)pitch * sizeof(real), (cuuint64_t)plane * sizeof(real)};
+      const cuuint32_t box[3] = {(cuuint32_t)TileBox<real>::BY, (cuuint32_t)TileBox<real>::BX, (cuuint32_t)NQ};
+      const cuuint32_t estr[3] = {1, 1, 1};
+      const CUresult r = encode(&tmap[k], sizeof(real) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                                3, f[k], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(LBMDEM_ECUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    }
+    CK(cudaStreamSynchronize(stream));
+    return 0;
+  }
+
+  /* ---- grains ---- */
+  int alloc_grains(int n_) {
+    if (n_ <= 0) return fail(LBMDEM_EINVAL, "need at least one grain (the reference reads g[0], src/main.c:220)");
+    for (real *p : grain_bufs) cudaFree(p);
+    grain_bufs.clear();
+    n = n_;
+    real **slots[] = {&g.x1, &g.x2, &g.x3, &g.v1, &g.v2, &g.v3, &g.a1, &g.a2, &g.a3, &g.r, &g.m, &g.It, &g.rLB,
+                      &g.fhf1, &g.fhf2, &g.fhf3};
+    for (real **s : slots) {
+      CK(cudaMalloc(s, sizeof(real) * n));
+      CK(cudaMemsetAsync(*s, 0, sizeof(real) * n, stream));
+      grain_bufs.push_back(*s);
+    }
+    cudaFree(rec); cudaFree(R2); cudaFree(boxes); cudaFree(facc); cudaFree(fpartial);
+    CK(cudaMalloc(&rec, sizeof(GrainRec<real>) * n));
+    CK(cudaMalloc(&R2, sizeof(real) * n));
+    CK(cudaMalloc(&boxes, sizeof(GrainBox) * n));
+    CK(cudaMalloc(&facc, sizeof(long long) * 3 * n));
+    CK(cudaMemsetAsync(facc, 0, sizeof(long long) * 3 * n, stream));
+    CK(cudaMalloc(&fpartial, sizeof(double) * 3 * n));
+    cudaFree(vb.bucket_count); cudaFree(vb.bucket_cursor); cudaFree(vb.sorted); cudaFree(vb.gcx); cudaFree(vb.gcy);
+    cudaFree(vb.nbr_count); cudaFree(vb.nbr); cudaFree(vb.wflags); cudaFree(vb.error);
+    int nb = 1024;
+    while (nb < 2 * n) nb <<= 1;
+    vb.nbuckets = nb;
+    vb.cap = P.neighbour_capacity > 0 ? P.neighbour_capacity : 32;
+    CK(cudaMalloc(&vb.bucket_count, sizeof(int) * (nb + 1)));
+    CK(cudaMalloc(&vb.bucket_cursor, sizeof(int) * nb));
+    CK(cudaMalloc(&vb.sorted, sizeof(int) * n));
+    CK(cudaMalloc(&vb.gcx, sizeof(int) * n));
+    CK(cudaMalloc(&vb.gcy, sizeof(int) * n));
+    CK(cudaMalloc(&vb.nbr_count, sizeof(int) * n));
+    CK(cudaMemsetAsync(vb.nbr_count, 0, sizeof(int) * n, stream));
+    CK(cudaMalloc(&vb.nbr, sizeof(int) * (size_t)n * vb.cap));
+    CK(cudaMalloc(&vb.wflags, sizeof(int) * n));
+    CK(cudaMemsetAsync(vb.wflags, 0, sizeof(int) * n, stream));
+    CK(cudaMalloc(&vb.error, sizeof(int)));
+    CK(cudaMemsetAsync(vb.error, 0, sizeof(int), stream));
+    if (hstage) cudaFreeHost(hstage);
+    hstage_elems = (size_t)n * 16;
+    CK(cudaMallocHost(&hstage, sizeof(double) * hstage_elems));
+    return 0;
+  }
+
+  int upload(real *dst, const std::vector<real> &src) {
+    CK(cudaMemcpyAsync(dst, src.data(), sizeof(real) * src.size(), cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+    return 0;
+  }
+
+  /* main():1834-1861 once r, x1, x2 (metres, `real`) are known */
+  int finish_setup(const std::vector<real> &r, const std::vector<real> &x1, const std::vector<real> &x2) {
+    int rc = alloc_grains((int)r.size());
+    if (rc) return rc;
+    const double pi = 3.14159265358979; /* src/main.c:42 */
+    const real tau = (real)P.tau, nu = (real)P.nu, rho_moy = (real)P.rho_moy, reductionR = (real)P.reductionR;
+    const real G = (real)P.G, angleG = (real)P.angleG, kg = (real)P.kg, iterDEM = (real)P.iterDEM;
+    std::vector<real> m(n), It(n), rLB(n);
+    for (int i = 0; i < n; ++i) { /* :624-626 */
+      m[i] = P.rhoS * pi * r[i] * r[i];
+      It[i] = m[i] * r[i] * r[i] / 2;
+    }
+    Mgx = 0.;
+    Mdx = 1.e-3 * lx / 10;
+    Mhy = 1.e-3 * ly / 10;
+    Mby = 0.;
+    xG = -G * sin((double)angleG);
+    yG = -G * cos((double)angleG);
+    dx = (1. / P.scale) * (Mdx - Mgx) / (lx - 1);
+    real rMin = r[0];
+    rmax = r[0];
+    for (int i = 1; i < n; ++i) { rMin = fmin((double)rMin, (double)r[i]); rmax = std::max(rmax, r[i]); }
+    const real dtmax = (1 / iterDEM) * pi * rMin * sqrt(pi * P.rhoS / kg);
+    dtLB = dx * dx * (tau - 0.5) / (3 * nu);
+    npDEM = (int)(dtLB / dtmax + 1);
+    c = dx / dtLB;
+    dt = dtLB / npDEM;
+    dt2 = dt * dt;
+    for (int i = 0; i < n; ++i) rLB[i] = reductionR * r[i] / dx;
+    /* :1329-1331 with the reference's promotions ((tau - 0.5) is double) */
+    k12 = (double)(real)(rho_moy * 9 * nu * nu) / ((double)dx * ((double)tau - 0.5) * ((double)tau - 0.5));
+    k3 = (double)(real)(dx * rho_moy * 9 * nu * nu) / ((double)dx * ((double)tau - 0.5) * ((double)tau - 0.5));
+    if ((rc = upload(g.r, r)) || (rc = upload(g.x1, x1)) || (rc = upload(g.x2, x2)) || (rc = upload(g.m, m)) ||
+        (rc = upload(g.It, It)) || (rc = upload(g.rLB, rLB)))
+      return rc;
+    /* init_density (:716-724) and init_obst (:663-711) */
+    const Lattice<real> L = lattice(0);
+    CK(launch_fill_rest<real>(f[0], plane, L, stream));
+    CK(launch_fill_rest<real>(f[1], plane, L, stream));
+    for (int k = 0; k < 2; ++k) CK(launch_cell_frame(cell[k], lx, ly, x0, nxl, pitch, n, stream));
+    cur = 0;
+    cur_cell = 0;
+    CK(launch_raster<real>(raster_params(), n, g, rec, R2, boxes, cell[cur_cell], x0, nxl, pitch, stream));
+    CK(cudaStreamSynchronize(stream));
+    nbsteps = 0;
+    nFile = 0;
+    ready = true;
+    return n;
+  }
+
+  int load_sample(const char *path) override {
+    FILE *fp = fopen(path, "r");
+    if (!fp) return fail(LBMDEM_EIO, std::string("cannot open ") + path);
+    char com[256];
+    int cnt = 0;
+    if (!fgets(com, sizeof com, fp) || fscanf(fp, "%d\n", &cnt) != 1 || cnt <= 0) {
+      fclose(fp);
+      return fail(LBMDEM_EIO, std::string("bad header in ") + path);
+    }
+    std::vector<real> r(cnt), x1(cnt), x2(cnt);
+    const real rs = (real)P.rscale;
+    for (int i = 0; i < cnt; ++i) {
+      double a, b, cc; /* %le into double then rounded == %e into float for the values that occur? no: parse in `real` */
+      if (sizeof(real) == 8) {
+        if (fscanf(fp, "%le %le %le;\n", &a, &b, &cc) != 3) { fclose(fp); return fail(LBMDEM_EIO, "short sample file"); }
+        r[i] = (real)a; x1[i] = (real)b; x2[i] = (real)cc;
+      } else {
+        float fa, fb, fc;
+        if (fscanf(fp, "%e %e %e;\n", &fa, &fb, &fc) != 3) { fclose(fp); return fail(LBMDEM_EIO, "short sample file"); }
+        r[i] = (real)fa; x1[i] = (real)fb; x2[i] = (real)fc;
+      }
+      r[i] = r[i] * rs; /* :623-628 */
+      x1[i] = x1[i] * rs;
+      x2[i] = x2[i] * rs;
+    }
+    fclose(fp);
+    return finish_setup(r, x1, x2);
+  }
+
+  int set_grains(int n_, const double *r_, const double *x1_, const double *x2_) override {
+    if (n_ <= 0 || !r_ || !x1_ || !x2_) return fail(LBMDEM_EINVAL, "set_grains: bad arguments");
+    std::vector<real> r(n_), x1(n_), x2(n_);
+    for (int i = 0; i < n_; ++i) { r[i] = (real)r_[i]; x1[i] = (real)x1_[i]; x2[i] = (real)x2_[i]; }
+    return finish_setup(r, x1, x2);
+  }
+
+  /* ---- parameter blocks ---- */
+  RasterParams<real> raster_params() const {
+    RasterParams<real> R;
+    R.lx = lx; R.ly = ly; R.dx = dx; R.Mgx = Mgx; R.Mby = Mby;
+    return R;
+  }
+  Lattice<real> lattice(int fbuf) const {
+    Lattice<real> L;
+    L.lx = lx; L.ly = ly; L.x0 = x0; L.nxl = nxl; L.pitch = pitch; L.plane = plane; L.ngrains = n;
+    L.dx = dx; L.c = c; L.Mgx = Mgx; L.Mby = Mby;
+    const real lid = (real)P.lid_u;
+    L.lid6 = lid / 6;
+    L.s2 = (real)P.s2; L.s3 = (real)P.s3; L.s5 = (real)P.s5; L.s7 = (real)P.s7; L.s8 = (real)P.s8; L.s9 = (real)P.s9;
+    const real w0[NQ] = {4. / 9, 1. / 36, 1. / 9, 1. / 36, 1. / 9, 1. / 36, 1. / 9, 1. / 36, 1. / 9}; /* :53-54 */
+    for (int q = 0; q < NQ; ++q) L.w[q] = w0[q];
+    L.f = f[fbuf];
+    L.cell_new = cell[cur_cell];
+    L.cell_old = cell[1 - cur_cell];
+    L.grains = rec; L.boxes = boxes; L.R2 = R2; L.act_folded = 0;
+    return L;
+  }
+  dem::Params<real> dem_params() const {
+    dem::Params<real> D;
+    D.kg = (real)P.kg; D.kt = (real)P.kt; D.km = (real)P.km; D.ktm = (real)P.ktm; D.nug = (real)P.nug;
+    D.num = (real)P.num; D.numb = (real)P.numb; D.nugt = (real)P.nugt; D.mu = (real)P.mu; D.mum = (real)P.mum;
+    D.mumb = (real)P.mumb; D.murf = (real)P.murf; D.freq = (real)P.freq; D.amp = (real)P.amp; D.t = 0;
+    D.distVerlet = (real)P.distVerlet; D.dt = dt; D.dt2 = dt2; D.xG = xG; D.yG = yG;
+    D.Mgx = Mgx; D.Mdx = Mdx; D.Mby = Mby; D.Mhy = Mhy;
+    return D;
+  }
+
+  int nccl_fail(int r, const char *what) {
+    return fail(LBMDEM_ENCCL, std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+  }
+
+  /* one ghost row of pre-collision populations per side */
+  int halo_exchange() {
+    if (P.nranks == 1) return 0;
+    if (!comm) return fail(LBMDEM_ESTATE, "nranks > 1 but no communicator attached (lbmdem_attach_nccl)");
+    const int dtype = sizeof(real) == 8 ? NcclApi::Float64 : NcclApi::Float32;
+    int r = g_nccl.GroupStart();
+    if (r) return nccl_fail(r, "ncclGroupStart");
+    real *F = f[cur];
+    for (int q = 0; q < NQ && !r; ++q) {
+      real *pl = F + (size_t)q * plane;
+      if (P.rank > 0) { /* left neighbour: send first owned row (local 2), receive into ghost row (local 1) */
+        r = g_nccl.Send(pl + (size_t)2 * pitch, ly, dtype, P.rank - 1, comm, stream);
+        if (!r) r = g_nccl.Recv(pl + (size_t)1 * pitch, ly, dtype, P.rank - 1, comm, stream);
+      }
+      if (!r && P.rank < P.nranks - 1) {
+        const int last = xhi - xlo + 1; /* local row of the last owned row */
+        r = g_nccl.Send(pl + (size_t)last * pitch, ly, dtype, P.rank + 1, comm, stream);
+        if (!r) r = g_nccl.Recv(pl + (size_t)(last + 1) * pitch, ly, dtype, P.rank + 1, comm, stream);
+      }
+    }
+    const int r2 = g_nccl.GroupEnd();
+    if (r) return nccl_fail(r, "ncclSend/Recv");
+    if (r2) return nccl_fail(r2, "ncclGroupEnd");
+    return 0;
+  }
+
+  int record_k1_begin(std::pair<cudaEvent_t, cudaEvent_t> **slot) {
+    *slot = nullptr;
+    if (!events_on) return 0;
+    if (ev_used == ev_pool.size()) {
+      if (ev_pool.size() >= 8192) { /* fold what we have so far */
+        int rc = fold_events();
+        if (rc) return rc;
+      } else {
+        std::pair<cudaEvent_t, cudaEvent_t> p;
+        CK(cudaEventCreate(&p.first));
+        CK(cudaEventCreate(&p.second));
+        ev_pool.push_back(p);
+      }
+    }
+    *slot = &ev_pool[ev_used++];
+    CK(cudaEventRecord((*slot)->first, stream));
+    return 0;
+  }
+  int fold_events() {
+    CK(cudaStreamSynchronize(stream));
+    for (size_t k = 0; k < ev_used; ++k) {
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, ev_pool[k].first, ev_pool[k].second));
+      k1_ms_acc += ms;
+    }
+    ev_used = 0;
+    return 0;
+  }
+
+  /* the LBM part of renderScene (:1711-1717), asynchronous on `stream` */
+  int lbm_step_async() {
+    if (!ready) return fail(LBMDEM_ESTATE, "no grains loaded");
+    int rc = halo_exchange();
+    if (rc) return rc;
+    cur_cell ^= 1; /* the rasteriser writes the other map; the previous one becomes "old" */
+    CK(launch_raster<real>(raster_params(), n, g, rec, R2, boxes, cell[cur_cell], x0, nxl, pitch, stream));
+    StepArgs<real> a;
+    a.L = lattice(cur);
+    a.f_new = f[1 - cur];
+    a.facc = P.strict_fp ? nullptr : facc;
+    a.xlo = xlo; a.xhi = xhi;
+    std::pair<cudaEvent_t, cudaEvent_t> *ev;
+    if ((rc = record_k1_begin(&ev))) return rc;
+    if (P.kernel == 1) {
+      CK(P.strict_fp ? k1_strict::launch_lbm_generic<real>(a, stream) : k1_fast::launch_lbm_generic<real>(a, stream));
+    } else {
+      CK(P.strict_fp ? k1_strict::launch_lbm_tiled<real>(tmap[cur], a, stream)
+                     : k1_fast::launch_lbm_tiled<real>(tmap[cur], a, stream));
+    }
+    if (ev) CK(cudaEventRecord(ev->second, stream));
+    ++k1_launches;
+    all_launches += 4; /* grain_prepare, raster, K1, force post-processing (memsets not counted) */
+    if (P.strict_fp) {
+      CK(launch_force_serial<real>(a.L, a.f_new, xlo, xhi, fpartial, stream));
+      ++all_launches;
+      if (P.nranks > 1) {
+        const int r = g_nccl.AllReduce(fpartial, fpartial, (size_t)3 * n, NcclApi::Float64, NcclApi::Sum, comm, stream);
+        if (r) return nccl_fail(r, "ncclAllReduce");
+      }
+      CK(launch_force_scale<real>(fpartial, n, k12, k3, g.fhf1, g.fhf2, g.fhf3, stream));
+    } else {
+      if (P.nranks > 1) { /* integer sum: exact, identical on every rank, independent of the decomposition */
+        const int r = g_nccl.AllReduce(facc, facc, (size_t)3 * n, NcclApi::Int64, NcclApi::Sum, comm, stream);
+        if (r) return nccl_fail(r, "ncclAllReduce");
+      }
+      CK(launch_force_finish<real>(facc, n, k12, k3, g.fhf1, g.fhf2, g.fhf3, stream));
+    }
+    cur ^= 1;
+    return 0;
+  }
+
+  int verlet_async() {
+    if (!ready) return fail(LBMDEM_ESTATE, "no grains loaded");
+    /* VerletWall (:1555-1561): the confining walls move out once nbsteps*dt >= dtt */
+    if (nbsteps * dt < (real)P.dtt) {
+      Mdx = 1.e-3 * lx / 10;
+      Mhy = (1.e-3 * ly / 10);
+    } else {
+      Mdx = 1.e-3 * lx;
+      Mhy = 1.e-3 * ly;
+    }
+    const real cell_size = 2 * rmax + (real)P.distVerlet;
+    CK(launch_verlet<real>(dem_params(), n, g, cell_size, vb, stream));
+    all_launches += 4;
+    return 0;
+  }
+
+  int check_verlet_overflow() {
+    int flag = 0;
+    CK(cudaMemcpyAsync(&flag, vb.error, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (flag) return fail(LBMDEM_ECAP, "a grain has more Verlet neighbours than neighbour_capacity");
+    return 0;
+  }
+
+  int step_async(long nsteps, bool *built) {
+    for (long k = 0; k < nsteps; ++k) {
+      int rc;
+      if (nbsteps % npDEM == 0 && (rc = lbm_step_async())) return rc;
+      if (nbsteps % P.UpdateVerlet == 0) {
+        if ((rc = verlet_async())) return rc;
+        *built = true;
+      }
+      const bool film = (nbsteps % P.stepFilm == 0);
+      CK(launch_dem_step<real>(dem_params(), n, film, g, vb, stream));
+      all_launches += 3;
+      ++nbsteps;
+      if (nbsteps % P.stepFilm == 0) ++nFile;
+    }
+    return 0;
+  }
+
+  int step(long nsteps) override {
+    if (!ready) return fail(LBMDEM_ESTATE, "no grains loaded");
+    bool built = false;
+    int rc = step_async(nsteps, &built);
+    if (rc) return rc;
+    if (built) return check_verlet_overflow();
+    CK(cudaStreamSynchronize(stream));
+    return 0;
+  }
+  int lbm_step() override {
+    int rc = lbm_step_async();
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(stream));
+    return 0;
+  }
+  int lbm_steps(long k) override {
+    for (long i = 0; i < k; ++i) {
+      int rc = lbm_step_async();
+      if (rc) return rc;
+    }
+    CK(cudaStreamSynchronize(stream));
+    return 0;
+  }
+  int build_verlet() override {
+    int rc = verlet_async();
+    if (rc) return rc;
+    return check_verlet_overflow();
+  }
+
+  int get_scalars(double *d, long *l) override {
+    d[0] = dx; d[1] = dtLB; d[2] = dt; d[3] = dt2; d[4] = c; d[5] = Mgx; d[6] = Mdx; d[7] = Mby; d[8] = Mhy;
+    d[9] = xG; d[10] = yG;
+    l[0] = npDEM; l[1] = nbsteps; l[2] = nFile; l[3] = n;
+    return 0;
+  }
+  int set_nbsteps(long v) override { nbsteps = v; return 0; }
+  int get_strip(int *a, int *b) override { *a = xlo; *b = xhi; return 0; }
+
+  int total_density(double *sum) override {
+    CK(launch_density<real>(f[cur], ly, x0, xlo, xhi, pitch, plane, dens_partials, DENS_BLOCKS, dens_out, stream));
+    CK(cudaMemcpyAsync(sum, dens_out, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    return 0;
+  }
+
+  int ensure_stage(size_t elems) {
+    if (elems <= stage_elems) return 0;
+    cudaFree(stage);
+    stage = nullptr;
+    stage_elems = 0;
+    CK(cudaMalloc(&stage, sizeof(double) * elems));
+    stage_elems = elems;
+    return 0;
+  }
+  int get_f(double *out) override {
+    const int chunk = 64;
+    int rc = ensure_stage((size_t)chunk * ly * NQ);
+    if (rc) return rc;
+    for (int r0 = xlo; r0 < xhi; r0 += chunk) {
+      const int nr = std::min(chunk, xhi - r0);
+      CK(launch_f_to_host_layout<real>(f[cur], ly, pitch, plane, r0 - x0, nr, stage, stream));
+      CK(cudaMemcpyAsync(out + (size_t)(r0 - xlo) * ly * NQ, stage, sizeof(double) * (size_t)nr * ly * NQ,
+                         cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+    }
+    return 0;
+  }
+  int set_f(const double *in) override {
+    const int chunk = 64;
+    int rc = ensure_stage((size_t)chunk * ly * NQ);
+    if (rc) return rc;
+    for (int r0 = xlo; r0 < xhi; r0 += chunk) {
+      const int nr = std::min(chunk, xhi - r0);
+      CK(cudaMemcpyAsync(stage, in + (size_t)(r0 - xlo) * ly * NQ, sizeof(double) * (size_t)nr * ly * NQ,
+                         cudaMemcpyHostToDevice, stream));
+      CK(launch_f_from_host_layout<real>(f[cur], ly, pitch, plane, r0 - x0, nr, stage, stream));
+      CK(cudaStreamSynchronize(stream));
+    }
+    return 0;
+  }
+  int get_obst(int *out) override {
+    CK(cudaMemcpy2DAsync(out, sizeof(int) * ly, cell[cur_cell] + (size_t)(xlo - x0) * pitch, sizeof(int) * pitch,
+                         sizeof(int) * ly, xhi - xlo, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    return 0;
+  }
+  int set_obst(const int *in) override {
+    CK(cudaMemcpy2DAsync(cell[cur_cell] + (size_t)(xlo - x0) * pitch, sizeof(int) * pitch, in, sizeof(int) * ly,
+                         sizeof(int) * ly, xhi - xlo, cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+    return 0;
+  }
+  int get_act(int *out) override {
+    if (!ready) return fail(LBMDEM_ESTATE, "no grains loaded");
+    int *d = nullptr;
+    CK(cudaMalloc(&d, sizeof(int) * (size_t)(xhi - xlo) * ly));
+    const Lattice<real> L = lattice(cur);
+    cudaError_t e = launch_act_map<real>(L, xlo, xhi, d, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d, sizeof(int) * (size_t)(xhi - xlo) * ly, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(d);
+    CK(e);
+    return 0;
+  }
+
+  /* grains: gather the structure of arrays into rows of doubles through one pinned buffer */
+  int download_cols(real *const *cols, int ncols, double *out, int out_stride, int out_col0) {
+    std::vector<real> tmp((size_t)n * ncols);
+    for (int k = 0; k < ncols; ++k)
+      CK(cudaMemcpyAsync(tmp.data() + (size_t)k * n, cols[k], sizeof(real) * n, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    for (int k = 0; k < ncols; ++k)
+      for (int i = 0; i < n; ++i) out[(size_t)i * out_stride + out_col0 + k] = tmp[(size_t)k * n + i];
+    return 0;
+  }
+  int upload_cols(real *const *cols, int ncols, const double *in, int in_stride, int in_col0) {
+    std::vector<real> tmp((size_t)n * ncols);
+    for (int k = 0; k < ncols; ++k)
+      for (int i = 0; i < n; ++i) tmp[(size_t)k * n + i] = (real)in[(size_t)i * in_stride + in_col0 + k];
+    for (int k = 0; k < ncols; ++k)
+      CK(cudaMemcpyAsync(cols[k], tmp.data() + (size_t)k * n, sizeof(real) * n, cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+    return 0;
+  }
+  int get_grains(double *out) override {
+    if (!ready) return fail(LBMDEM_ESTATE, "no grains loaded");
+    real *cols[13] = {g.x1, g.x2, g.x3, g.v1, g.v2, g.v3, g.a1, g.a2, g.a3, g.r, g.m, g.It, g.rLB};
+    return download_cols(cols, 13, out, 13, 0);
+  }
+  int set_grain_state(const double *in) override {
+    if (!ready) return fail(LBMDEM_ESTATE, "no grains loaded");
+    real *cols[9] = {g.x1, g.x2, g.x3, g.v1, g.v2, g.v3, g.a1, g.a2, g.a3};
+    return upload_cols(cols, 9, in, 9, 0);
+  }
+  int get_fhf(double *out) override {
+    if (!ready) return fail(LBMDEM_ESTATE, "no grains loaded");
+    real *cols[3] = {g.fhf1, g.fhf2, g.fhf3};
+    return download_cols(cols, 3, out, 3, 0);
+  }
+  int set_fhf(const double *in) override {
+    if (!ready) return fail(LBMDEM_ESTATE, "no grains loaded");
+    real *cols[3] = {g.fhf1, g.fhf2, g.fhf3};
+    return upload_cols(cols, 3, in, 3, 0);
+  }
+  int get_verlet(int *count, int *nbr, int capacity, int *wall_flags) override {
+    if (!ready) return fail(LBMDEM_ESTATE, "no grains loaded");
+    if (capacity < vb.cap) return fail(LBMDEM_EINVAL, "get_verlet: capacity smaller than the context's");
+    std::vector<int> tmp((size_t)n * vb.cap);
+    CK(cudaMemcpyAsync(count, vb.nbr_count, sizeof(int) * n, cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(tmp.data(), vb.nbr, sizeof(int) * (size_t)n * vb.cap, cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(wall_flags, vb.wflags, sizeof(int) * n, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    for (int i = 0; i < n; ++i)
+      for (int k = 0; k < capacity; ++k) nbr[(size_t)i * capacity + k] = (k < count[i] && k < vb.cap) ? tmp[(size_t)i * vb.cap + k] : -1;
+    return 0;
+  }
+
+  int get_fields(const double *gp_in, float *gpress, float *gvel, float *gacc, float *fpress, float *fvel) override {
+    if (!ready) return fail(LBMDEM_ESTATE, "no grains loaded");
+    const size_t nn = (size_t)(xhi - xlo) * ly;
+    float *d = nullptr;
+    real *gp = nullptr;
+    CK(cudaMalloc(&d, sizeof(float) * nn * 11));
+    cudaError_t e = cudaSuccess;
+    if (gp_in) {
+      std::vector<real> tmp(n);
+      for (int i = 0; i < n; ++i) tmp[i] = (real)gp_in[i];
+      e = cudaMalloc(&gp, sizeof(real) * n);
+      if (e == cudaSuccess) e = cudaMemcpy(gp, tmp.data(), sizeof(real) * n, cudaMemcpyHostToDevice);
+    }
+    float *p0 = d, *p1 = d + nn, *p2 = d + 4 * nn, *p3 = d + 7 * nn, *p4 = d + 8 * nn;
+    if (e == cudaSuccess)
+      e = launch_fields<real>(f[cur], cell[cur_cell], g, gp, n, ly, x0, xlo, xhi, pitch, plane, (real)P.rho_moy, p0, p1, p2,
+                              p3, p4, stream);
+    if (e == cudaSuccess && gpress) e = cudaMemcpyAsync(gpress, p0, sizeof(float) * nn, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess && gvel) e = cudaMemcpyAsync(gvel, p1, sizeof(float) * nn * 3, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess && gacc) e = cudaMemcpyAsync(gacc, p2, sizeof(float) * nn * 3, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess && fpress) e = cudaMemcpyAsync(fpress, p3, sizeof(float) * nn, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess && fvel) e = cudaMemcpyAsync(fvel, p4, sizeof(float) * nn * 3, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(d);
+    cudaFree(gp);
+    CK(e);
+    return 0;
+  }
+
+  /* end-to-end step with host buffers: pinned staging, async copies on the work stream */
+  int step_host(const double *state_in, long nsteps, double *state_out, double *fhf_out, double *dens) override {
+    if (!ready) return fail(LBMDEM_ESTATE, "no grains loaded");
+    real *st[9] = {g.x1, g.x2, g.x3, g.v1, g.v2, g.v3, g.a1, g.a2, g.a3};
+    real *fh[3] = {g.fhf1, g.fhf2, g.fhf3};
+    real *hs = reinterpret_cast<real *>(hstage); /* 16 n doubles >= 12 n reals */
+    if (state_in) {
+      for (int k = 0; k < 9; ++k)
+        for (int i = 0; i < n; ++i) hs[(size_t)k * n + i] = (real)state_in[(size_t)i * 9 + k];
+      for (int k = 0; k < 9; ++k)
+        CK(cudaMemcpyAsync(st[k], hs + (size_t)k * n, sizeof(real) * n, cudaMemcpyHostToDevice, stream));
+    }
+    bool built = false;
+    int rc = step_async(nsteps, &built);
+    if (rc) return rc;
+    if (state_out)
+      for (int k = 0; k < 9; ++k)
+        CK(cudaMemcpyAsync(hs + (size_t)k * n, st[k], sizeof(real) * n, cudaMemcpyDeviceToHost, stream));
+    if (fhf_out)
+      for (int k = 0; k < 3; ++k)
+        CK(cudaMemcpyAsync(hs + (size_t)(9 + k) * n, fh[k], sizeof(real) * n, cudaMemcpyDeviceToHost, stream));
+    if (dens) {
+      CK(launch_density<real>(f[cur], ly, x0, xlo, xhi, pitch, plane, dens_partials, DENS_BLOCKS, dens_out, stream));
+      CK(cudaMemcpyAsync(dens, dens_out, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    }
+    if (built) {
+      if ((rc = check_verlet_overflow())) return rc;
+    } else {
+      CK(cudaStreamSynchronize(stream));
+    }
+    if (state_out)
+      for (int k = 0; k < 9; ++k)
+        for (int i = 0; i < n; ++i) state_out[(size_t)i * 9 + k] = hs[(size_t)k * n + i];
+    if (fhf_out)
+      for (int k = 0; k < 3; ++k)
+        for (int i = 0; i < n; ++i) fhf_out[(size_t)i * 3 + k] = hs[(size_t)(9 + k) * n + i];
+    return 0;
+  }
+
+  int attach_nccl(const void *id) override {
+    std::string why;
+    if (!g_nccl.load(&why)) return fail(LBMDEM_ENCCL, why);
+    NcclApi::UniqueId uid;
+    memcpy(&uid, id, sizeof uid);
+    CK(cudaSetDevice(P.device));
+    const int r = g_nccl.CommInitRank(&comm, P.nranks, uid, P.rank);
+    if (r) return nccl_fail(r, "ncclCommInitRank");
+    return 0;
+  }
+
+  int get_kernel_timer(double *ms, long *k1, long *all) override {
+    int rc = fold_events();
+    if (rc) return rc;
+    if (ms) *ms = k1_ms_acc;
+    if (k1) *k1 = k1_launches;
+    if (all) *all = all_launches;
+    return 0;
+  }
+  int reset_kernel_timer(int enable) override {
+    int rc = fold_events();
+    if (rc) return rc;
+    k1_ms_acc = 0;
+    k1_launches = 0;
+    all_launches = 0;
+    events_on = enable != 0;
+    return 0;
+  }
+  void *stream_ptr() override { return (void *)stream; }
+};
+
+}  // namespace lbmdem
+
+/* ================================ C ABI ================================ */
+using lbmdem::SimBase;
+struct lbmdem_ctx {
+  SimBase *sim;
+};
+
+extern "C" {
+
+#define API __attribute__((visibility("default")))
+
+API int lbmdem_default_params(lbmdem_params *p) {
+  if (!p) return LBMDEM_EINVAL;
+  memset(p, 0, sizeof *p);
+  p->lx = 7826; p->ly = 2325; p->scale = 1.; /* src/main.c:24-32 */
+  p->single_precision = 0; p->device = 0; p->rank = 0; p->nranks = 1;
+  p->tau = 0.504; p->nu = 1e-6; p->rho_moy = 1000; p->reductionR = 0.85; /* :74-94 */
+  p->s2 = 1.5; p->s3 = 1.4; p->s5 = 1.5; p->s7 = 1.5; p->s8 = 1.9841; p->s9 = 1.9841;
+  p->G = 9.81; p->angleG = 0.0; /* :97-118 */
+  p->kg = 1.6e+6; p->kt = 1.0e+6; p->km = 3e+6; p->ktm = 2e+6;
+  p->nug = 6.4e+1; p->num = 8.7e+1; p->numb = 8.7e+1; p->nugt = 5e-1;
+  p->mu = .5317; p->mum = .466; p->mumb = .466; p->murf = 0.01;
+  p->rscale = 1e-3; p->distVerlet = 5e-4; p->dtt = 0.; p->iterDEM = 100.;
+  p->freq = 5; p->amp = 4.e-4; p->rhoS = 2650;
+  p->UpdateVerlet = 100; p->stepFilm = 8000;
+  p->lid_u = 0; p->strict_fp = 0; p->kernel = 0; p->neighbour_capacity = 32;
+  return 0;
+}
+
+API int lbmdem_sizeof_params(void) { return (int)sizeof(lbmdem_params); }
+
+API int lbmdem_create(const lbmdem_params *p, lbmdem_ctx **out) {
+  if (!p || !out) return LBMDEM_EINVAL;
+  SimBase *s = p->single_precision ? (SimBase *)new lbmdem::Sim<float>() : (SimBase *)new lbmdem::Sim<double>();
+  s->P = *p;
+  const int rc = s->init_device();
+  if (rc) {
+    lbmdem::g_create_error = s->err;
+    delete s;
+    return rc;
+  }
+  *out = new lbmdem_ctx{s};
+  return 0;
+}
+API void lbmdem_destroy(lbmdem_ctx *ctx) {
+  if (!ctx) return;
+  delete ctx->sim;
+  delete ctx;
+}
+API const char *lbmdem_last_error(const lbmdem_ctx *ctx) {
+  return ctx ? ctx->sim->err.c_str() : lbmdem::g_create_error.c_str();
+}
+
+#define CTX_OR_FAIL if (!ctx || !ctx->sim) return LBMDEM_EINVAL
+API int lbmdem_load_sample(lbmdem_ctx *ctx, const char *path) { CTX_OR_FAIL; return ctx->sim->load_sample(path); }
+API int lbmdem_set_grains(lbmdem_ctx *ctx, int n, const double *r, const double *x1, const double *x2) {
+  CTX_OR_FAIL; return ctx->sim->set_grains(n, r, x1, x2);
+}
+API int lbmdem_step(lbmdem_ctx *ctx, long n) { CTX_OR_FAIL; return ctx->sim->step(n); }
+API int lbmdem_lbm_step(lbmdem_ctx *ctx) { CTX_OR_FAIL; return ctx->sim->lbm_step(); }
+API int lbmdem_lbm_steps(lbmdem_ctx *ctx, long n) { CTX_OR_FAIL; return ctx->sim->lbm_steps(n); }
+API int lbmdem_build_verlet(lbmdem_ctx *ctx) { CTX_OR_FAIL; return ctx->sim->build_verlet(); }
+API int lbmdem_get_scalars(lbmdem_ctx *ctx, double *d, long *l) { CTX_OR_FAIL; return ctx->sim->get_scalars(d, l); }
+API int lbmdem_set_nbsteps(lbmdem_ctx *ctx, long n) { CTX_OR_FAIL; return ctx->sim->set_nbsteps(n); }
+API int lbmdem_get_strip(lbmdem_ctx *ctx, int *a, int *b) { CTX_OR_FAIL; return ctx->sim->get_strip(a, b); }
+API int lbmdem_total_density(lbmdem_ctx *ctx, double *s) { CTX_OR_FAIL; return ctx->sim->total_density(s); }
+API int lbmdem_get_f(lbmdem_ctx *ctx, double *out) { CTX_OR_FAIL; return ctx->sim->get_f(out); }
+API int lbmdem_set_f(lbmdem_ctx *ctx, const double *in) { CTX_OR_FAIL; return ctx->sim->set_f(in); }
+API int lbmdem_get_obst(lbmdem_ctx *ctx, int *out) { CTX_OR_FAIL; return ctx->sim->get_obst(out); }
+API int lbmdem_set_obst(lbmdem_ctx *ctx, const int *in) { CTX_OR_FAIL; return ctx->sim->set_obst(in); }
+API int lbmdem_get_act(lbmdem_ctx *ctx, int *out) { CTX_OR_FAIL; return ctx->sim->get_act(out); }
+API int lbmdem_get_grains(lbmdem_ctx *ctx, double *out) { CTX_OR_FAIL; return ctx->sim->get_grains(out); }
+API int lbmdem_set_grain_state(lbmdem_ctx *ctx, const double *in) { CTX_OR_FAIL; return ctx->sim->set_grain_state(in); }
+API int lbmdem_get_fhf(lbmdem_ctx *ctx, double *out) { CTX_OR_FAIL; return ctx->sim->get_fhf(out); }
+API int lbmdem_set_fhf(lbmdem_ctx *ctx, const double *in) { CTX_OR_FAIL; return ctx->sim->set_fhf(in); }
+API int lbmdem_get_verlet(lbmdem_ctx *ctx, int *count, int *nbr, int capacity, int *wf) {
+  CTX_OR_FAIL; return ctx->sim->get_verlet(count, nbr, capacity, wf);
+}
+API int lbmdem_get_fields(lbmdem_ctx *ctx, const double *gp, float *a, float *b, float *c, float *d, float *e) {
+  CTX_OR_FAIL; return ctx->sim->get_fields(gp, a, b, c, d, e);
+}
+API int lbmdem_step_host(lbmdem_ctx *ctx, const double *in, long n, double *out, double *fhf, double *dens) {
+  CTX_OR_FAIL; return ctx->sim->step_host(in, n, out, fhf, dens);
+}
+API int lbmdem_nccl_unique_id(void *id128) {
+  std::string why;
+  if (!id128) return LBMDEM_EINVAL;
+  if (!lbmdem::g_nccl.load(&why)) { lbmdem::g_create_error = why; return LBMDEM_ENCCL; }
+  lbmdem::NcclApi::UniqueId uid;
+  const int r = lbmdem::g_nccl.GetUniqueId(&uid);
+  if (r) { lbmdem::g_create_error = lbmdem::g_nccl.GetErrorString(r); return LBMDEM_ENCCL; }
+  memcpy(id128, &uid, sizeof uid);
+  return 0;
+}
+API int lbmdem_attach_nccl(lbmdem_ctx *ctx, const void *id128) { CTX_OR_FAIL; return ctx->sim->attach_nccl(id128); }
+API int lbmdem_get_kernel_timer(lbmdem_ctx *ctx, double *ms, long *k1, long *all) {
+  CTX_OR_FAIL; return ctx->sim->get_kernel_timer(ms, k1, all);
+}
+API int lbmdem_reset_kernel_timer(lbmdem_ctx *ctx, int enable) { CTX_OR_FAIL; return ctx->sim->reset_kernel_timer(enable); }
+API void *lbmdem_stream(lbmdem_ctx *ctx) { return (ctx && ctx->sim) ? ctx->sim->stream_ptr() : nullptr; }
+
+}  // extern "C"

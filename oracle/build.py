@@ -50,6 +50,8 @@ PREBUILT = [
     (4096, 4096, "2.7", "f64", True, True),   # same lattice in fp64
     (4096, 4096, "2.7", "f32", False, True),  # serial variants of the timed baseline
     (4096, 4096, "2.7", "f64", False, True),
+    (2048, 2048, "1.", "f64", True, True),    # BASELINE cfg 3 / cfg 2 timed baselines (bench.py --workload)
+    (1024, 1024, "1.", "f64", True, True),
 ]
 
 

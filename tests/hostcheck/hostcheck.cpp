@@ -23,22 +23,19 @@ using namespace lbm;
 
 namespace {
 
-template <typename real>
-struct Scalars {
-  real dx, c, Mgx, Mby, lid;
-};
+int g_act_folded = 1; /* 0: hand the on-demand path a bare obstacle map (what the device kernels get) */
 
 /* K2 on the host: owner = highest-index covering grain, then the act rule. */
 template <typename real>
 void raster_host(int lx, int ly, int n, const RasterParams<real> &P, const real *x1, const real *x2, const real *r,
                  const real *rLB, const real *v1, const real *v2, const real *v3, std::vector<int> &cell,
-                 std::vector<GrainRec<real>> &rec) {
+                 std::vector<GrainRec<real>> &rec, std::vector<GrainBox> &box, std::vector<real> &R2) {
   cell.assign((size_t)lx * ly, -1);
   for (int x = 0; x < lx; ++x) cell[(size_t)x * ly] = cell[(size_t)x * ly + ly - 1] = n;
   for (int y = 0; y < ly; ++y) cell[y] = cell[(size_t)(lx - 1) * ly + y] = n;
   rec.resize(n);
-  std::vector<GrainBox> box(n);
-  std::vector<real> R2(n);
+  box.resize(n);
+  R2.resize(n);
   for (int i = 0; i < n; ++i) {
     GrainRec<real> &g = rec[i];
     grain_geometry(P, x1[i], x2[i], r[i], rLB[i], &g.xc, &g.yc, &g.r2, &R2[i], &box[i]);
@@ -76,7 +73,13 @@ int lbm_step_host(int lx, int ly, int n, const double *scal, const double *grain
   RP.lx = lx; RP.ly = ly; RP.dx = (real)scal[0]; RP.Mgx = (real)scal[2]; RP.Mby = (real)scal[3];
   std::vector<int> cell_new;
   std::vector<GrainRec<real>> rec;
-  raster_host(lx, ly, n, RP, x1.data(), x2.data(), r.data(), rLB.data(), v1.data(), v2.data(), v3.data(), cell_new, rec);
+  std::vector<GrainBox> box;
+  std::vector<real> R2v;
+  raster_host(lx, ly, n, RP, x1.data(), x2.data(), r.data(), rLB.data(), v1.data(), v2.data(), v3.data(), cell_new, rec,
+              box, R2v);
+  std::vector<int> cell_bare(cell_new);
+  for (auto &c : cell_bare)
+    if (c >= 0) c &= CELL_IDX;
 
   const size_t nn = (size_t)lx * ly;
   std::vector<real> fs(nn * NQ), fn(nn * NQ);
@@ -92,7 +95,9 @@ int lbm_step_host(int lx, int ly, int n, const double *scal, const double *grain
   L.s2 = 1.5; L.s3 = 1.4; L.s5 = 1.5; L.s7 = 1.5; L.s8 = 1.9841; L.s9 = 1.9841;
   const real w0[NQ] = {4. / 9, 1. / 36, 1. / 9, 1. / 36, 1. / 9, 1. / 36, 1. / 9, 1. / 36, 1. / 9};
   for (int q = 0; q < NQ; ++q) L.w[q] = w0[q];
-  L.f = fs.data(); L.cell_new = cell_new.data(); L.cell_old = cell_old.data(); L.grains = rec.data();
+  L.f = fs.data(); L.cell_old = cell_old.data(); L.grains = rec.data();
+  L.cell_new = g_act_folded ? cell_new.data() : cell_bare.data();
+  L.boxes = box.data(); L.R2 = R2v.data(); L.act_folded = g_act_folded;
 
   for (int x = 0; x < lx; ++x)
     for (int y = 0; y < ly; ++y)
@@ -194,6 +199,7 @@ int dem_step_host(int n, const double *par /* see below */, int film, double *st
 
 extern "C" {
 #define EXPORT __attribute__((visibility("default")))
+EXPORT void hc_set_act_folded(int v) { g_act_folded = v; }
 /* scal: dx c Mgx Mby lid */
 EXPORT int hc_lbm_step_f64(int lx, int ly, int n, const double *scal, const double *grains, const double *f_in,
                            const int *obst_old, double *f_out, int *obst_new, int *act_new, double *fhf) {

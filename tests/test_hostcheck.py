@@ -75,6 +75,17 @@ def test_lbm_step_formulation_with_lid(prec):
     _lbm_case(prec, 40, 56, 1.0, seed=20, lid=0.05, steps=3)
 
 
+def test_lbm_step_act_derived_on_demand():
+    # the device kernels get a bare obstacle map and derive act[][] themselves (node_act)
+    hc = load_hostcheck()
+    hc.hc_set_act_folded(0)
+    try:
+        _lbm_case("f64", 64, 48, 1.0, seed=11, steps=2)
+        _lbm_case("f64", 96, 80, 1.0, seed=31, steps=2, n_target=120)
+    finally:
+        hc.hc_set_act_folded(1)
+
+
 def test_lbm_step_formulation_dense_scaled():
     # many small grains: one-node gaps between reduced discs, short links reading ring / solid nodes
     info = _lbm_case("f64", 96, 80, 1.0, seed=30, steps=3, n_target=120)
