@@ -29,8 +29,11 @@ constexpr int TILE_X = 16;
 constexpr int TILE_Y = 64;
 template <typename real>
 struct TileBox {
-  /* inner (y) extent of the TMA box: TILE_Y + 2 rounded up so that the row is a 16-byte multiple */
-  static constexpr int BY = (sizeof(real) == 8) ? TILE_Y + 2 : TILE_Y + 4;
+  /* The TMA unit wants the byte offset of the box origin along the contiguous dimension to be a
+   * multiple of 16 (measured on B200: any other inner coordinate raises "illegal instruction",
+   * tools/tma_probe.cu), so the y halo is HY = 16 / sizeof(real) nodes wide instead of one. */
+  static constexpr int HY = 16 / (int)sizeof(real);
+  static constexpr int BY = TILE_Y + 2 * HY;
   static constexpr int BX = TILE_X + 2;
   static constexpr size_t bytes = (size_t)BY * BX * lbm::NQ * sizeof(real);
 };

@@ -144,8 +144,9 @@ __device__ __forceinline__ bool act_from_tile(const StepArgs<real> &a, const int
 template <typename real>
 __global__ void __launch_bounds__(NTHREADS, (sizeof(real) == 8) ? 2 : 4)
     lbm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs<real> a) {
-  constexpr int BY = TileBox<real>::BY, BX = TileBox<real>::BX;
+  constexpr int BY = TileBox<real>::BY, BX = TileBox<real>::BX, HY = TileBox<real>::HY;
   constexpr int CX = TILE_X + 4, CY = TILE_Y + 4;
+  /* node (gx0 + rx, gy0 + ry): population tile [rx + 1][ry + HY], map tile [rx + 2][ry + 2] */
   extern __shared__ __align__(128) unsigned char smem_raw[];
   real *sA = reinterpret_cast<real *>(smem_raw);                       /* [NQ][BX][BY] */
   int *sc = reinterpret_cast<int *>(smem_raw + TileBox<real>::bytes);   /* [CX][CY] */
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(real) == 8) ? 2 : 4)
     mbar_init(bar, 1);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_expect_tx(bar, (uint32_t)TileBox<real>::bytes);
-    tma_load_3d(sA, &tmap, bar, gy0 - 1, gx0 - 1 - L.x0, 0);
+    tma_load_3d(sA, &tmap, bar, gy0 - HY, gx0 - 1 - L.x0, 0);
   }
 
   /* obstacle map, tile + 2 halo */
@@ -187,11 +188,12 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(real) == 8) ? 2 : 4)
 
   /* sweeps 1-2 in place: re-init where the old map is solid, collide where the new one is fluid */
   for (int idx = tid; idx < BX * (TILE_Y + 2); idx += NTHREADS) {
-    const int bx = idx / (TILE_Y + 2), by = idx - bx * (TILE_Y + 2);
-    const int gx = gx0 - 1 + bx, gy = gy0 - 1 + by;
+    const int bx = idx / (TILE_Y + 2), hy = idx - bx * (TILE_Y + 2);
+    const int by = hy + HY - 1;
+    const int gx = gx0 - 1 + bx, gy = gy0 - 1 + hy;
     if (!in_array(L, gx, gy) || is_ring(L, gx, gy)) continue;
     if (gx < L.x0 || gx >= L.x0 + L.nxl) continue;
-    const int cn = sc[(bx + 1) * CY + by + 1];
+    const int cn = sc[(bx + 1) * CY + hy + 1];
     const int co = L.cell_old[node_index(L, gx, gy)];
     const bool reinit = !cell_is_fluid(co), coll = cell_is_fluid(cn);
     if (!reinit && !coll) continue;
@@ -217,16 +219,17 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(real) == 8) ? 2 : 4)
       node_on_demand(a, gx, gy);
       continue;
     }
-    const int bx = tx + 1, by = ty + 1; /* position in the population tile */
+    const int bx = tx + 1, by = ty + HY; /* position in the population tile */
+    const int cx = tx + 2, cy = ty + 2;  /* position in the map tile */
     const size_t k = node_index(L, gx, gy);
-    const int cp = sc[(bx + 1) * CY + by + 1];
+    const int cp = sc[cx * CY + cy];
     const bool p_fluid = cell_is_fluid(cp);
     a.f_new[k] = sA[(0 * BX + bx) * BY + by];
 #pragma unroll
     for (int q = 1; q < NQ; ++q) {
       const int ex = ex_of(q), ey = ey_of(q), oq = opp_of(q);
       const int sbx = bx - ex, sby = by - ey;
-      const int cs = sc[(sbx + 1) * CY + sby + 1];
+      const int cs = sc[(cx - ex) * CY + cy - ey];
       const real As_q = sA[(q * BX + sbx) * BY + sby];
       real v = As_q;
       if (!cell_is_fluid(cs)) {
@@ -241,7 +244,7 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(real) == 8) ? 2 : 4)
           const real Fn_oq = sA[(oq * BX + bx) * BY + by], Fn_q = sA[(q * BX + bx) * BY + by];
           real X = 0;
           if (d > 0. && d < 0.5) {
-            const int cnn = sc[(bx + ex + 1) * CY + by + ey + 1];
+            const int cnn = sc[(cx + ex) * CY + cy + ey];
             const int nnx = gx + ex, nny = gy + ey;
             if (cell_is_act(cnn) && (nnx < sx || (nnx == sx && nny < sy)))
               X = G_value<real, true>(L, nnx, nny, oq); /* serial-sweep look-back, ~1 link per step */
