@@ -272,3 +272,76 @@ def test_errors_are_reported():
     with pytest.raises(G.LbmdemError) as ei:
         t.step(1)
     assert ei.value.code == -6
+
+
+# ---- against the committed reference fixtures (tests/golden, written by the compiled reference) ----
+import hashlib
+import os
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_golden_a08d83_strict_build_is_bit_exact():
+    """bin/a08d83.data on a 512 x 512 fp64 lattice: the strict CUDA build must give
+    the reference's own bits after 15, 100 and 202 renderScene() calls."""
+    gold = np.load(os.path.join(GOLD, "a08d83_512_f64.npz"))
+    s = G.Solver(512, 512, 1.0, "f64", strict_fp=1)
+    n = s.init(os.path.join(GOLD, "a08d83.data"))
+    assert n == 726
+    sc = s.scalars()
+    for k in sc:
+        assert sc[k] == gold[f"scalar_{k}"], k
+    assert np.array_equal(s.grains(), gold["init_grains"])
+    assert _sha(s.obst()) == str(gold["init_obst_sha256"])
+    done = 0
+    for upto in (15, 100, 202):
+        s.step(upto - done)
+        done = upto
+        tag = f"s{upto}"
+        assert np.array_equal(s.grains()[:, :9], gold[f"{tag}_grains"]), tag
+        assert np.array_equal(s.fhf(), gold[f"{tag}_fhf"]), tag
+        assert _sha(s.obst()) == str(gold[f"{tag}_obst_sha256"]), tag
+        assert _sha(s.f()) == str(gold[f"{tag}_f_sha256"]), tag
+        assert abs(s.total_density() - float(gold[f"{tag}_density"])) < 1e-9 * 512 * 512
+
+
+def test_golden_a08d83_default_build_within_tolerance():
+    """Same run with the default (contracted, fixed-point force sums) build: node indices bit-exact,
+    trajectories and rho, u within 1e-6 relative at the 100-call horizon (north_star)."""
+    gold = np.load(os.path.join(GOLD, "a08d83_512_f64.npz"))
+    s = G.Solver(512, 512, 1.0, "f64")
+    s.init(os.path.join(GOLD, "a08d83.data"))
+    s.step(100)
+    go, gs = gold["s100_grains"], s.grains()[:, :9]
+    assert _sha(s.obst()) == str(gold["s100_obst_sha256"])
+    assert _relerr(gs[:, 0:3], go[:, 0:3]) < 1e-6 and _relerr(gs[:, 3:6], go[:, 3:6]) < 1e-6
+    assert _relerr(s.fhf(), gold["s100_fhf"]) < 1e-6
+    fs, fo = s.f()[5::16, 7::16], gold["s100_f_sample"]
+    assert _relerr(fs.sum(-1), fo.sum(-1)) < 1e-6
+    ex = np.array([0, -1, -1, -1, 0, 1, 1, 1, 0.0])
+    ey = np.array([0, 1, 0, -1, -1, -1, 0, 1, 1.0])
+    for e in (ex, ey):
+        jo, js = (fo * e).sum(-1), (fs * e).sum(-1)
+        assert np.abs(js - jo).max() < 1e-6 * max(np.abs(jo).max(), 1e-3)
+    assert abs(s.total_density() - float(gold["s100_density"])) < 1e-9 * 512 * 512
+
+
+@pytest.mark.parametrize("name,prec", [("pack_64x48", "f64"), ("pack_64x48", "f32"),
+                                       ("pack_256x256", "f64"), ("pack_256x256", "f32")])
+def test_golden_packings_strict_build_is_bit_exact(name, prec):
+    gold = np.load(os.path.join(GOLD, f"{name}_{prec}.npz"))
+    lx, ly = (int(v) for v in name.split("_")[1].split("x"))
+    s = G.Solver(lx, ly, 1.0, prec, strict_fp=1)
+    s.init(os.path.join(GOLD, f"{name}_{prec}.data"))
+    f0 = gold["start_f"] if "start_f" in gold else perturbed_f(lx, ly, int(gold["start_f_seed"]))
+    s.set_f(f0)
+    s.set_grain_state(gold["start_state"])
+    s.step(int(gold["steps"]))
+    assert np.array_equal(s.grains()[:, :9], gold["end_grains"])
+    assert np.array_equal(s.fhf(), gold["end_fhf"])
+    assert _sha(s.obst()) == str(gold["end_obst_sha256"])
+    assert _sha(s.f()) == str(gold["end_f_sha256"])

@@ -1,0 +1,153 @@
+"""tools/make_golden.py -- writes tests/golden/*.npz from the COMPILED REFERENCE.
+
+Runs only where /root/reference exists (the authoring container): every vector below is
+produced by the unmodified src/main.c of cb-geo/2d-lbm-dem, compiled in place by
+oracle/build.py (gcc -std=c99 -O2 -ffp-contract=off, serial) and driven through
+oracle/ref_shim.c.  The fixtures travel to the GPU box, the reference does not.
+
+    python tools/make_golden.py            # regenerates every fixture
+
+Cases
+  a08d83_512_f64   bin/a08d83.data (726 grains; copied to tests/golden/a08d83.data as the input
+                   fixture), 512 x 512, scale 1, fp64 -- SURVEY.md 4.4's known-answer configuration.
+                   State after 15, 100 and 202 renderScene() calls.
+  pack_64x48_<p>   seeded synthetic packing + perturbed populations + random grain kinematics on
+                   a 64 x 48 lattice, 30 renderScene() calls, p in f64 / f32; full state stored.
+  pack_256_<p>     same on 256 x 256 with ~200 grains, 100 (f64) / 30 (f32) calls; sampled state.
+Large arrays are stored as a SHA-256 of their bytes (bit-exact check for the oracle and the
+strict CUDA build) plus a strided sample (tolerance check for the default CUDA build).
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+from oracle.refwrap import Reference  # noqa: E402
+from util import perturbed_f, random_kinematics, small_packing  # noqa: E402
+import make_sample  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+SAMPLE_STRIDE = (16, 5, 7)   # nodes with x % 16 == 5 and y % 16 == 7
+
+
+def sha(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def sample_nodes(a):
+    s, ox, oy = SAMPLE_STRIDE
+    return np.ascontiguousarray(a[ox::s, oy::s])
+
+
+def snapshot(ref, tag, out, full=False):
+    f, obst = ref.f(), ref.obst()
+    out[f"{tag}_grains"] = ref.grains()[:, :9]
+    out[f"{tag}_fhf"] = ref.fhf()
+    out[f"{tag}_density"] = np.float64(ref.total_density())
+    out[f"{tag}_f_sha256"] = np.array(sha(f))
+    out[f"{tag}_obst_sha256"] = np.array(sha(obst))
+    out[f"{tag}_act_sha256"] = np.array(sha(ref.act()))
+    out[f"{tag}_solid_nodes"] = np.int64(((obst >= 0) & (obst < ref.n)).sum())
+    if full:
+        out[f"{tag}_f"] = f
+        out[f"{tag}_obst"] = obst
+        out[f"{tag}_act"] = ref.act()
+    else:
+        out[f"{tag}_f_sample"] = sample_nodes(f)
+        out[f"{tag}_obst_sample"] = sample_nodes(obst)
+
+
+def scalars_of(ref, out):
+    sc = ref.scalars()
+    for k, v in sc.items():
+        out[f"scalar_{k}"] = np.float64(v) if isinstance(v, float) else np.int64(v)
+
+
+def case_a08d83():
+    src = "/root/reference/bin/a08d83.data"
+    dst = os.path.join(GOLD, "a08d83.data")
+    if not os.path.exists(dst):
+        shutil.copyfile(src, dst)
+    ref = Reference(512, 512, "1.", "f64")
+    out = {}
+    cwd = os.getcwd()
+    os.chdir(tempfile.mkdtemp(prefix="golden_"))
+    try:
+        n = ref.init(dst)
+        assert n == 726
+        scalars_of(ref, out)
+        out["init_grains"] = ref.grains()
+        out["init_obst_sha256"] = np.array(sha(ref.obst()))
+        done = 0
+        for upto in (15, 100, 202):
+            ref.step(upto - done)
+            done = upto
+            snapshot(ref, f"s{upto}", out)
+        cum, half = ref.verlet()
+        out["verlet_cumul"], out["verlet_half"] = cum, half
+        for name, lst in zip("BTLR", ref.wall_lists()):
+            out[f"wall_{name}"] = lst
+    finally:
+        os.chdir(cwd)
+    np.savez_compressed(os.path.join(GOLD, "a08d83_512_f64.npz"), **out)
+    print("a08d83_512_f64: density after 15 / 202 steps", out["s15_density"], out["s202_density"])
+
+
+def case_packing(lx, ly, prec, seed, steps, n_target, full):
+    ref = Reference(lx, ly, "1.", prec)
+    r, x, y = small_packing(lx, ly, 1.0, seed, n_target=n_target)
+    tmp = tempfile.mkdtemp(prefix="golden_")
+    path = os.path.join(tmp, "pack.data")
+    # the reference only reads files: write the packing in its format (mm), read it back the
+    # same way the tests will (values in the file are the fixture, not the numpy arrays)
+    make_sample.write_sample(path, r * 1e3, x * 1e3, y * 1e3, comment=f"# small_packing seed={seed}")
+    name = f"pack_{lx}x{ly}_{prec}"
+    shutil.copyfile(path, os.path.join(GOLD, name + ".data"))
+    out = {}
+    cwd = os.getcwd()
+    os.chdir(tmp)
+    try:
+        n = ref.init(path)
+        scalars_of(ref, out)
+        f0 = perturbed_f(lx, ly, seed + 1)
+        v, w, a = random_kinematics(n, seed + 2, vmax=0.02)
+        st = ref.grains()[:, :9].copy()
+        st[:, 3:5], st[:, 5:6], st[:, 6:9] = v, w, a * 0.1
+        ref.set_f(f0)
+        ref.set_grain_state(st)
+        # what the reference actually holds after rounding to its `real`
+        out["start_state"] = ref.grains()[:, :9]
+        if full:
+            out["start_f"] = ref.f()
+        else:
+            out["start_f_seed"] = np.int64(seed + 1)
+        ref.step(steps)
+        out["steps"] = np.int64(steps)
+        snapshot(ref, "end", out, full=full)
+    finally:
+        os.chdir(cwd)
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(name, "n =", n, "density", out["end_density"])
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    case_a08d83()
+    case_packing(64, 48, "f64", 3, 30, None, True)
+    case_packing(64, 48, "f32", 3, 30, None, True)
+    case_packing(256, 256, "f64", 41, 100, 200, False)
+    case_packing(256, 256, "f32", 41, 30, 200, False)
+
+
+if __name__ == "__main__":
+    main()
