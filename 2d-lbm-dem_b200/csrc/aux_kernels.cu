@@ -14,7 +14,7 @@ namespace lbmdem {
 using namespace lbm;
 
 /* ------------------------------------------------------------------------------------------
- * K2: obst_construction (src/main.c:991-1065) without the delta[] array and without act[]
+ * K2: obst_construction (src/main.c:991-1065) without the delta[] array; act[] is a bit of the map
  * ---------------------------------------------------------------------------------------- */
 template <typename real>
 __global__ void grain_prepare_kernel(RasterParams<real> P, int n, GrainArrays<real> g, GrainRec<real> *rec, real *R2,
@@ -47,6 +47,34 @@ __global__ void raster_kernel(int n, const GrainRec<real> *rec, const real *R2, 
       if (disc_covers(xc, yc, r2, RR, x, y)) atomicMax(&cell[(size_t)(x - x0) * pitch + y], i);
 }
 
+/* act[x][y] (:1036-1052), one warp per grain, after ALL grains are rasterised: a node of grain i
+ * is active iff one of its eight neighbours was fluid when the reference's loop reached grain i
+ * (lbm_node.cuh, fluid_when_grain_ran).  The flag is folded into the map as CELL_ACT; readers
+ * of a neighbour mask it off, so concurrent folding of other nodes is harmless. */
+template <typename real>
+__global__ void act_fold_kernel(int n, const GrainRec<real> *rec, const real *R2, const GrainBox *boxes, int *cell, int x0,
+                                int nxl, int pitch) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const GrainBox b = boxes[i];
+  const real xc = rec[i].xc, yc = rec[i].yc, r2 = rec[i].r2, RR = R2[i];
+  /* rows whose neighbours are held locally */
+  const int xa = max(b.xi, x0 + 1), xb = min(b.xf, x0 + nxl - 2);
+  for (int x = xa; x <= xb; ++x)
+    for (int y = b.yi + lane; y <= b.yf; y += 32) {
+      const size_t k = (size_t)(x - x0) * pitch + y;
+      if (cell_obst(cell[k]) != i) continue;
+      bool act = false;
+#pragma unroll
+      for (int q = 1; q < NQ; ++q) {
+        const int nx = x + ex_of(q), ny = y + ey_of(q);
+        if (fluid_when_grain_ran(cell[(size_t)(nx - x0) * pitch + ny], i, n, xc, yc, r2, RR, b, nx, ny)) act = true;
+      }
+      if (act) atomicOr(&cell[k], CELL_ACT);
+    }
+}
+
 /* init_obst's frame (:674-687): ring = nbgrains, interior = -1 */
 __global__ void cell_frame_kernel(int *cell, int lx, int ly, int x0, int nxl, int pitch, int ring_value) {
   const int y = blockIdx.x * blockDim.x + threadIdx.x;
@@ -70,6 +98,7 @@ cudaError_t launch_raster(const RasterParams<real> &P, int n, const GrainArrays<
     if (e != cudaSuccess) return e;
   }
   raster_kernel<real><<<(n * 32 + 255) / 256, 256, 0, s>>>(n, rec, R2, boxes, cell, x0, nxl, pitch);
+  act_fold_kernel<real><<<(n * 32 + 255) / 256, 256, 0, s>>>(n, rec, R2, boxes, cell, x0, nxl, pitch);
   return cudaGetLastError();
 }
 
@@ -80,29 +109,81 @@ cudaError_t launch_cell_frame(int *cell, int lx, int ly, int x0, int nxl, int pi
 }
 
 template <typename real>
-__global__ void act_map_kernel(Lattice<real> L, int xlo, int xhi, int *act_out) {
+__global__ void act_map_kernel(Lattice<real> L, Stored<real> S, int xlo, int xhi, int *act_out) {
   const int y = blockIdx.x * blockDim.x + threadIdx.x;
   const int x = xlo + blockIdx.y;
   if (y >= L.ly || x >= xhi) return;
   int a = 0;
   if (!is_ring(L, x, y)) {
-    const int c = L.cell_new[node_index(L, x, y)];
-    a = cell_is_fluid(c) ? 1 : (node_act(L, x, y, c) ? 1 : 0); /* the reference clears act to 1 on fluid nodes */
+    const int c = S.cell[node_index(L, x, y)];
+    a = cell_is_fluid(c) ? 1 : (node_act(L, S, x, y, c) ? 1 : 0); /* the reference clears act to 1 on fluid nodes */
   }
   act_out[(size_t)(x - xlo) * L.ly + y] = a;
 }
 template <typename real>
-cudaError_t launch_act_map(const Lattice<real> &L, int xlo, int xhi, int *act_out, cudaStream_t s) {
+cudaError_t launch_act_map(const Lattice<real> &L, const Stored<real> &S, int xlo, int xhi, int *act_out, cudaStream_t s) {
   dim3 grid((L.ly + 255) / 256, xhi - xlo);
-  act_map_kernel<real><<<grid, 256, 0, s>>>(L, xlo, xhi, act_out);
+  act_map_kernel<real><<<grid, 256, 0, s>>>(L, S, xlo, xhi, act_out);
   return cudaGetLastError();
 }
 
 /* ------------------------------------------------------------------------------------------
- * hydrodynamic force post-processing (src/main.c:1327-1332)
+ * K1f: forces_fluid (src/main.c:1285-1333) from the stored state.  For a node s of grain i and a
+ * link q to a node n not owned by i the reference adds (f_new[s][opp q] + f_new[n][q]) e_{opp q}
+ * AFTER streaming; by the pull identity these are G[n][opp q] and G[s][q] before streaming.
  * ---------------------------------------------------------------------------------------- */
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+/* one warp per grain; every link is rounded to 64-bit fixed point before it is added, so the
+ * result is independent of the lane order and of the strip decomposition */
 template <typename real>
-__global__ void force_finish_kernel(long long *facc, int n, double k12, double k3, real *fhf1, real *fhf2, real *fhf3) {
+__global__ void force_warp_kernel(const __grid_constant__ Lattice<real> L, const __grid_constant__ Stored<real> S, int xlo,
+                                  int xhi, long long *facc) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n = L.ngrains;
+  if (i >= n) return;
+  const GrainBox b = S.boxes[i];
+  const real xc = S.grains[i].xc, yc = S.grains[i].yc;
+  const int xa = max(b.xi, xlo), xb = min(b.xf, xhi - 1);
+  const int ny = b.yf - b.yi + 1;
+  long long s1 = 0, s2 = 0, s3 = 0;
+  if (ny > 0 && xb >= xa) {
+    const int total = (xb - xa + 1) * ny;
+    for (int t = lane; t < total; t += 32) {
+      const int x = xa + t / ny, y = b.yi + t % ny;
+      if (cell_obst(S.cell[node_index(L, x, y)]) != i) continue;
+#pragma unroll 1
+      for (int q = 1; q < NQ; ++q) {
+        const int ax = x + ex_of(q), ay = y + ey_of(q);
+        if (cell_obst(S.cell[node_index(L, ax, ay)]) == i) continue;
+        real h1 = 0, h2 = 0, h3 = 0;
+        force_link<real>(q, G_value(L, S, ax, ay, opp_of(q)), G_value(L, S, x, y, q), x, y, xc, yc, &h1, &h2, &h3);
+        s1 += __double2ll_rn((double)h1 * FORCE_FIX);
+        s2 += __double2ll_rn((double)h2 * FORCE_FIX);
+        s3 += __double2ll_rn((double)h3 * TORQUE_FIX);
+      }
+    }
+  }
+  s1 = warp_sum_ll(s1);
+  s2 = warp_sum_ll(s2);
+  s3 = warp_sum_ll(s3);
+  if (lane == 0) { facc[i] = s1; facc[n + i] = s2; facc[2 * n + i] = s3; }
+}
+template <typename real>
+cudaError_t launch_force_warp(const Lattice<real> &L, const Stored<real> &S, int xlo, int xhi, long long *facc,
+                              cudaStream_t s) {
+  force_warp_kernel<real><<<(L.ngrains * 32 + 127) / 128, 128, 0, s>>>(L, S, xlo, xhi, facc);
+  return cudaGetLastError();
+}
+
+template <typename real>
+__global__ void force_finish_kernel(const long long *facc, int n, double k12, double k3, real *fhf1, real *fhf2,
+                                    real *fhf3) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const real h1 = (real)((double)facc[i] / FORCE_FIX);
@@ -111,10 +192,9 @@ __global__ void force_finish_kernel(long long *facc, int n, double k12, double k
   fhf1[i] = (real)((double)h1 * k12);
   fhf2[i] = (real)((double)h2 * k12);
   fhf3[i] = (real)((double)h3 * k3);
-  facc[i] = 0; facc[n + i] = 0; facc[2 * n + i] = 0;
 }
 template <typename real>
-cudaError_t launch_force_finish(long long *facc, int n, double k12, double k3, real *fhf1, real *fhf2, real *fhf3,
+cudaError_t launch_force_finish(const long long *facc, int n, double k12, double k3, real *fhf1, real *fhf2, real *fhf3,
                                 cudaStream_t s) {
   force_finish_kernel<real><<<(n + 127) / 128, 128, 0, s>>>(facc, n, k12, k3, fhf1, fhf2, fhf3);
   return cudaGetLastError();
@@ -122,29 +202,30 @@ cudaError_t launch_force_finish(long long *facc, int n, double k12, double k3, r
 
 /* forces_fluid exactly as written (:1295-1325): one thread per grain, x outer, y inner, q inner */
 template <typename real>
-__global__ void force_serial_kernel(Lattice<real> L, const real *f_new, int xlo, int xhi, double *partial) {
+__global__ void force_serial_kernel(const __grid_constant__ Lattice<real> L, const __grid_constant__ Stored<real> S,
+                                    int xlo, int xhi, double *partial) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = L.ngrains;
   if (i >= n) return;
-  const GrainBox b = L.boxes[i];
-  const real xc = L.grains[i].xc, yc = L.grains[i].yc;
+  const GrainBox b = S.boxes[i];
+  const real xc = S.grains[i].xc, yc = S.grains[i].yc;
   real h1 = 0, h2 = 0, h3 = 0;
   for (int x = max(b.xi, xlo); x <= min(b.xf, xhi - 1); ++x)
     for (int y = b.yi; y <= b.yf; ++y) {
-      const size_t k = node_index(L, x, y);
-      if (cell_obst(L.cell_new[k]) != i) continue;
+      if (cell_obst(S.cell[node_index(L, x, y)]) != i) continue;
+#pragma unroll 1
       for (int q = 1; q < NQ; ++q) {
-        const size_t kn = node_index(L, x + ex_of(q), y + ey_of(q));
-        if (cell_obst(L.cell_new[kn]) == i) continue;
-        force_link<real>(q, f_new[opp_of(q) * L.plane + k], f_new[q * L.plane + kn], x, y, xc, yc, &h1, &h2, &h3);
+        const int ax = x + ex_of(q), ay = y + ey_of(q);
+        if (cell_obst(S.cell[node_index(L, ax, ay)]) == i) continue;
+        force_link<real>(q, G_value(L, S, ax, ay, opp_of(q)), G_value(L, S, x, y, q), x, y, xc, yc, &h1, &h2, &h3);
       }
     }
   partial[i] = h1; partial[n + i] = h2; partial[2 * n + i] = h3;
 }
 template <typename real>
-cudaError_t launch_force_serial(const Lattice<real> &L, const real *f_new, int xlo, int xhi, double *partial,
+cudaError_t launch_force_serial(const Lattice<real> &L, const Stored<real> &S, int xlo, int xhi, double *partial,
                                 cudaStream_t s) {
-  force_serial_kernel<real><<<(L.ngrains + 63) / 64, 64, 0, s>>>(L, f_new, xlo, xhi, partial);
+  force_serial_kernel<real><<<(L.ngrains + 63) / 64, 64, 0, s>>>(L, S, xlo, xhi, partial);
   return cudaGetLastError();
 }
 template <typename real>
@@ -488,9 +569,13 @@ cudaError_t launch_fill_rest(real *f, size_t plane, const Lattice<real> &Lw, cud
 #define INSTANTIATE(real)                                                                                               \
   template cudaError_t launch_raster<real>(const RasterParams<real> &, int, const GrainArrays<real> &, GrainRec<real> *,  \
                                            real *, GrainBox *, int *, int, int, int, cudaStream_t);                      \
-  template cudaError_t launch_act_map<real>(const Lattice<real> &, int, int, int *, cudaStream_t);                        \
-  template cudaError_t launch_force_finish<real>(long long *, int, double, double, real *, real *, real *, cudaStream_t); \
-  template cudaError_t launch_force_serial<real>(const Lattice<real> &, const real *, int, int, double *, cudaStream_t);  \
+  template cudaError_t launch_act_map<real>(const Lattice<real> &, const Stored<real> &, int, int, int *, cudaStream_t);  \
+  template cudaError_t launch_force_warp<real>(const Lattice<real> &, const Stored<real> &, int, int, long long *,        \
+                                               cudaStream_t);                                                             \
+  template cudaError_t launch_force_finish<real>(const long long *, int, double, double, real *, real *, real *,          \
+                                                 cudaStream_t);                                                           \
+  template cudaError_t launch_force_serial<real>(const Lattice<real> &, const Stored<real> &, int, int, double *,         \
+                                                 cudaStream_t);                                                           \
   template cudaError_t launch_force_scale<real>(const double *, int, double, double, real *, real *, real *,              \
                                                 cudaStream_t);                                                            \
   template cudaError_t launch_verlet<real>(const dem::Params<real> &, int, const GrainArrays<real> &, real,               \

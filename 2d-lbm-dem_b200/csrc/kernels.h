@@ -4,9 +4,10 @@
  * include/lbmdem_gpu.h.
  *
  * Kernel legend:
- *   K1  lbm_step        fused re-init + MRT collide + wall ring + grain bounce-back + pull
- *                       stream + momentum exchange      (src/main.c:966-986, :1071-1243, :1285-1325)
- *   K2  raster          grain records + obstacle map    (src/main.c:991-1065)
+ *   K1  lbm_rows        fused wall ring + grain bounce-back + pull stream of the stored step, then
+ *                       re-init + MRT collide of this step  (src/main.c:966-986, :1071-1243)
+ *   K1f force           momentum exchange per grain     (src/main.c:1285-1333)
+ *   K2  raster          grain records + obstacle map + act bits (src/main.c:991-1065)
  *   K3  verlet          hash-grid cell list -> sorted full neighbour lists + wall flags
  *                                                       (src/main.c:1519-1594)
  *   K4  dem             kick-drift, contact forces, kick (src/main.c:1733-1763, :1336-1516)
@@ -24,32 +25,47 @@
 
 namespace lbmdem {
 
-/* tile of the fused LBM kernel (nodes); the TMA box adds a one-node halo on every side */
-constexpr int TILE_X = 16;
-constexpr int TILE_Y = 64;
+/* Row pipeline of the fused LBM kernel.  A CTA owns TY consecutive y-columns and marches along
+ * x; each TMA transaction brings ONE lattice row of the strip into a ring of NS shared-memory
+ * slots: the nine population planes (TY nodes plus a halo of HY nodes per side), the matching
+ * row of the stored step's obstacle map (halo HC) and of this step's map (no halo).
+ * The TMA unit wants the byte offset of the box origin along the contiguous dimension to be a
+ * multiple of 16 (measured on B200: any other inner coordinate raises "illegal instruction",
+ * tools/tma_probe.cu), so the y halo is 16 / sizeof(element) nodes wide instead of one. */
 template <typename real>
-struct TileBox {
-  /* The TMA unit wants the byte offset of the box origin along the contiguous dimension to be a
-   * multiple of 16 (measured on B200: any other inner coordinate raises "illegal instruction",
-   * tools/tma_probe.cu), so the y halo is HY = 16 / sizeof(real) nodes wide instead of one. */
+struct RowCfg {
+  static constexpr int TY = 128;            /* nodes (= threads) per CTA row; a TMA box is at most 256 wide */
   static constexpr int HY = 16 / (int)sizeof(real);
-  static constexpr int BY = TILE_Y + 2 * HY;
-  static constexpr int BX = TILE_X + 2;
-  static constexpr size_t bytes = (size_t)BY * BX * lbm::NQ * sizeof(real);
+  static constexpr int HC = 4;
+  static constexpr int NS = (sizeof(real) == 8) ? 6 : 8;   /* ring slots */
+  static constexpr int BY = TY + 2 * HY;
+  static constexpr int BC = TY + 2 * HC;
+  static constexpr int A_BYTES = lbm::NQ * BY * (int)sizeof(real);
+  static constexpr int CO_BYTES = BC * 4, CN_BYTES = TY * 4;
+  static constexpr int A_PAD = (A_BYTES + 127) / 128 * 128;
+  static constexpr int CO_PAD = (CO_BYTES + 127) / 128 * 128;
+  static constexpr int CN_PAD = (CN_BYTES + 127) / 128 * 128;
+  static constexpr int SLOT = A_PAD + CO_PAD + CN_PAD;
+  static constexpr int SMEM = NS * SLOT;
 };
 
-/* momentum-exchange accumulators are 64-bit fixed point: integer adds commute, so the sum
- * does not depend on the order in which tiles / GPUs contribute */
+/* hydrodynamic-force sums are 64-bit fixed point: integer adds commute, so the sum does not
+ * depend on the order in which lanes / GPUs contribute */
 constexpr double FORCE_FIX = 4503599627370496.0;   /* 2^52 : fhf1, fhf2 (|sum| < 2^11) */
 constexpr double TORQUE_FIX = 281474976710656.0;   /* 2^48 : fhf3       (|sum| < 2^15) */
 
+/* One fused launch: sweeps 3-5 of the stored step (ring, grain bounce-back, streaming), then
+ * sweeps 1-2 of this step (re-init, collide).  out may alias nothing in S. */
 template <typename real>
-struct StepArgs {
+struct FusedArgs {
   lbm::Lattice<real> L;
-  real *f_new;                  /* [q][x-x0][y] */
-  long long *facc;              /* [3][ngrains] fixed-point accumulators, or nullptr */
-  int xlo, xhi;                 /* owned global rows [xlo, xhi) */
+  lbm::Stored<real> S;                     /* step n-1 */
+  const int *cell_new;                     /* obstacle map of step n */
+  const lbm::GrainRec<real> *grains_new;   /* grain records of step n */
+  real *out;                               /* [q][x-x0][y] */
+  int xlo, xhi;                            /* owned global rows [xlo, xhi) */
 };
+enum SlowMode { SLOW_EDGE = 0, SLOW_ALL = 1, SLOW_STREAM_ONLY = 2 };
 
 template <typename real>
 struct GrainArrays {
@@ -58,32 +74,46 @@ struct GrainArrays {
 };
 
 /* ---- K1 (two builds of the same source: contraction on = fast, off = strict) ---- */
-#define LBMDEM_DECLARE_K1(NS)                                                                              \
-  namespace NS {                                                                                           \
-  template <typename real>                                                                                 \
-  cudaError_t launch_lbm_tiled(const CUtensorMap &tmap, const StepArgs<real> &a, cudaStream_t s);          \
-  template <typename real>                                                                                 \
-  cudaError_t launch_lbm_generic(const StepArgs<real> &a, cudaStream_t s);                                 \
+#define LBMDEM_DECLARE_K1(NS)                                                                                          \
+  namespace NS {                                                                                                       \
+  /* nodes at least two away from the array edge, TMA row pipeline; returns the grid it used */                        \
+  template <typename real>                                                                                             \
+  cudaError_t launch_lbm_rows(const CUtensorMap &tmA, const CUtensorMap &tmCo, const CUtensorMap &tmCn,                \
+                              const FusedArgs<real> &a, cudaStream_t s);                                               \
+  /* on-demand evaluation from global memory: edge nodes, or every node (cross-check / stream only) */                 \
+  template <typename real>                                                                                             \
+  cudaError_t launch_lbm_slow(const FusedArgs<real> &a, int mode, cudaStream_t s);                                     \
+  /* sweeps 1-2 alone, in place (first step, or after the populations were set from outside) */                        \
+  template <typename real>                                                                                             \
+  cudaError_t launch_lbm_h1(const lbm::Lattice<real> &L, real *f, const int *cell_prev, const int *cell_now,           \
+                            const lbm::GrainRec<real> *grains_new, int xlo, int xhi, cudaStream_t s);                  \
   }
 LBMDEM_DECLARE_K1(k1_fast)
 LBMDEM_DECLARE_K1(k1_strict)
 
 /* ---- everything below lives in the contraction-free translation unit (aux_kernels.cu) ---- */
+/* grain records + obstacle map + act bits of one step (K2) */
 template <typename real>
 cudaError_t launch_raster(const lbm::RasterParams<real> &P, int ngrains, const GrainArrays<real> &g,
                           lbm::GrainRec<real> *rec, real *R2, lbm::GrainBox *boxes, int *cell, int x0, int nxl, int pitch,
                           cudaStream_t s);
 cudaError_t launch_cell_frame(int *cell, int lx, int ly, int x0, int nxl, int pitch, int ring_value, cudaStream_t s);
-/* act[x][y] as the reference would hold it (tests / diagnostics); L.act_folded must be 0 */
+/* act[x][y] as the reference would hold it (tests / diagnostics) */
 template <typename real>
-cudaError_t launch_act_map(const lbm::Lattice<real> &L, int xlo, int xhi, int *act_out, cudaStream_t s);
-/* fixed-point accumulators -> fhf (scaled, src/main.c:1329-1331); zeroes the accumulators */
+cudaError_t launch_act_map(const lbm::Lattice<real> &L, const lbm::Stored<real> &S, int xlo, int xhi, int *act_out,
+                           cudaStream_t s);
+/* forces_fluid (src/main.c:1295-1325) from the stored state, one warp per grain, fixed-point sums
+ * over the links whose solid node lies in the owned rows; overwrites facc[3][n] */
 template <typename real>
-cudaError_t launch_force_finish(long long *facc, int ngrains, double k12, double k3, real *fhf1, real *fhf2, real *fhf3,
-                                cudaStream_t s);
+cudaError_t launch_force_warp(const lbm::Lattice<real> &L, const lbm::Stored<real> &S, int xlo, int xhi, long long *facc,
+                              cudaStream_t s);
+/* fixed-point sums -> fhf (scaled, src/main.c:1329-1331) */
+template <typename real>
+cudaError_t launch_force_finish(const long long *facc, int ngrains, double k12, double k3, real *fhf1, real *fhf2,
+                                real *fhf3, cudaStream_t s);
 /* forces_fluid in the reference's own summation order, one thread per grain (strict mode) */
 template <typename real>
-cudaError_t launch_force_serial(const lbm::Lattice<real> &L, const real *f_new, int xlo, int xhi,
+cudaError_t launch_force_serial(const lbm::Lattice<real> &L, const lbm::Stored<real> &S, int xlo, int xhi,
                                 double *partial /* [3][n] unscaled */, cudaStream_t s);
 template <typename real>
 cudaError_t launch_force_scale(const double *partial, int ngrains, double k12, double k3, real *fhf1, real *fhf2,

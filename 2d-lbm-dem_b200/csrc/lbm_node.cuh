@@ -3,26 +3,29 @@
  * and device.
  *
  * The reference (cb-geo/2d-lbm-dem, src/main.c) does one LBM step as five in-place sweeps over
- * f[x][y][q]: re-initialise solid nodes (:966-986), MRT-collide fluid nodes (:1077-1119),
- * wall-ring copies (:1123-1145), interpolated bounce-back on active solid nodes (:1154-1222)
- * and two swap passes that stream (:1224-1242).  This header states the SAME map
- *      f_old  ->  f_new
- * as a pure function of f_old, so that every lattice node can be produced independently:
+ * f[x][y][q]: (1) re-initialise solid nodes (:966-986), (2) MRT-collide fluid nodes
+ * (:1077-1119), (3) wall-ring copies (:1123-1145), (4) interpolated bounce-back on active solid
+ * nodes (:1154-1222) and (5) two swap passes that stream (:1224-1242).
  *
- *      f_new[q](p) = G[q](p - e_q)        if p - e_q lies inside the array,
- *                  = G[opp q](p)          otherwise                      (swap passes, :1224-1242)
+ * Sweeps 1-2 are node-local (reinit_collide below).  Sweeps 3-5 are restated as a pure
+ * function of the state "A" that sweeps 1-2 leave behind:
  *
- * where G(s) is the content of node s after the first four sweeps.  G is evaluated on demand
- * from f_old, the old/new obstacle maps and the grain records (functions A, ring_value and
- * G_value below).  Operand order and int/float/double promotions follow the reference source
- * expression by expression (they decide the last bit, and in the -DSINGLE_PRECISION build the
- * `1.`/`4.5`/`fabs`/`sqrt` promotions to double are part of the result).
+ *      f_next[q](p) = G[q](p - e_q)        if p - e_q lies inside the array,
+ *                   = G[opp q](p)          otherwise                      (swap passes, :1224-1242)
+ *
+ * where G(s) is the content of node s after sweeps 3-4, evaluated on demand from A, the
+ * obstacle map and the grain records of that step (ring_value, G_value, pull_value).  The
+ * device therefore stores A between steps and one fused kernel does "sweeps 3-5 of step n-1,
+ * then sweeps 1-2 of step n" per node (lbm_kernels.cu); the hydrodynamic force of step n
+ * (forces_fluid, :1285-1333) is a function of G as well (force_link).  Operand order and
+ * int/float/double promotions follow the reference source expression by expression (they
+ * decide the last bit, and in the -DSINGLE_PRECISION build the `1.`/`4.5`/`fabs`/`sqrt`
+ * promotions to double are part of the result).
  *
  * Two users:
- *   - lbm_kernels.cu: the tiled TMA kernel uses the arithmetic helpers on shared-memory tiles
- *     and falls back to G_value() (global memory) for the rare nodes next to the wall ring;
- *     the "generic" kernel calls pull_value() for every node and is the device-side
- *     cross-check of the tiled kernel.
+ *   - lbm_kernels.cu / aux_kernels.cu: the tiled TMA kernel uses the arithmetic helpers on
+ *     shared-memory rows and calls G_value() (global memory) only for the rare look-back links;
+ *     the edge / generic / stream kernels and the force kernels call pull_value() / G_value().
  *   - tests/hostcheck: the same header compiled by g++ to pin the formulation against the
  *     oracle on the CPU, bit for bit (test infrastructure only; not a product path).
  */
@@ -89,6 +92,7 @@ LBM_HD bool fluid_when_grain_ran(int cell_n, int i, int ngrains, real xc, real y
   return !(box_has(b, nx, ny) && disc_covers(xc, yc, r2, R2, nx, ny));
 }
 
+/* geometry and constants of the lattice (strip-local storage: rows x0 .. x0+nxl-1) */
 template <typename real>
 struct Lattice {
   int lx, ly;             /* global lattice size */
@@ -100,13 +104,20 @@ struct Lattice {
   real dx, c, Mgx, Mby, lid6;
   real s2, s3, s5, s7, s8, s9;
   real w[NQ];
-  const real *f;          /* f_old, [q][x-x0][y] */
-  const int *cell_new;    /* obstacle map of this step (act bit folded in), [x-x0][y] */
-  const int *cell_old;    /* obstacle map of the previous step */
+};
+
+/* The lattice state the device keeps between LBM steps: the populations of step n AFTER the
+ * re-init and collide sweeps ("A"), together with the obstacle map and the grain records of
+ * that same step.  Everything the remaining sweeps of step n produce (wall ring, grain
+ * bounce-back, streaming, hydrodynamic forces) is a pure function of this. */
+template <typename real>
+struct Stored {
+  const real *A;          /* [q][x-x0][y] */
+  const int *cell;        /* obstacle map of the step (act bit folded in when act_folded) */
   const GrainRec<real> *grains;
   const GrainBox *boxes;  /* per grain, with R2 = (r/dx)^2: only the act rule needs them */
   const real *R2;
-  int act_folded;         /* 1: cell_new already carries CELL_ACT; 0: derive act on demand */
+  int act_folded;         /* 1: cell carries CELL_ACT; 0: derive act on demand */
 };
 
 template <typename real>
@@ -125,16 +136,16 @@ LBM_HD bool is_ring(const Lattice<real> &L, int x, int y) {
 /* act[x][y] of an interior solid node (src/main.c:1038-1052): some neighbour was fluid when the
  * owner grain was rasterised.  Either read from the folded bit or derived from the map. */
 template <typename real>
-LBM_HD_SLOW bool node_act(const Lattice<real> &L, int x, int y, int c) {
+LBM_HD_SLOW bool node_act(const Lattice<real> &L, const Stored<real> &S, int x, int y, int c) {
   if (c < 0) return false;
   if (c & CELL_ACT) return true;
-  if (L.act_folded) return false;
+  if (S.act_folded) return false;
   const int i = cell_obst(c);
   if (i >= L.ngrains) return false;
-  const GrainRec<real> &g = L.grains[i];
+  const GrainRec<real> &g = S.grains[i];
   for (int q = 1; q < NQ; ++q) {
     const int nx = x + ex_of(q), ny = y + ey_of(q);
-    if (fluid_when_grain_ran(L.cell_new[node_index(L, nx, ny)], i, L.ngrains, g.xc, g.yc, g.r2, L.R2[i], L.boxes[i], nx, ny))
+    if (fluid_when_grain_ran(S.cell[node_index(L, nx, ny)], i, L.ngrains, g.xc, g.yc, g.r2, S.R2[i], S.boxes[i], nx, ny))
       return true;
   }
   return false;
@@ -216,42 +227,24 @@ LBM_HD real bounce_value(const Lattice<real> &L, int q, real d, real Fn_oq, real
   return v;
 }
 
+/* Sweeps 1-2 of one LBM step at one node, in registers: reinit_obst_density (:966-986) where the
+ * PREVIOUS step's map is solid, then the MRT collision (:1077-1119) where THIS step's map is
+ * fluid.  Ring nodes are touched by neither sweep.  `grains` are this step's records. */
+template <typename real>
+LBM_HD void reinit_collide(const Lattice<real> &L, const GrainRec<real> *grains, int cell_prev, int cell_now, int x, int y,
+                           real *p) {
+  if (!cell_is_fluid(cell_prev)) equilibrium(L, grains[cell_obst(cell_prev)], x, y, p);
+  if (cell_is_fluid(cell_now)) mrt_collide(L, p);
+}
+
 /* ------------------------------------------------------------------------------------------
- * On-demand evaluation from global memory (exact, slow): used for every node by the generic
- * kernel / the host check, and for nodes on or next to the wall ring by the tiled kernel.
+ * Sweeps 3-5 evaluated on demand from the stored state (exact, slow): used for every node by
+ * the generic kernel / the host check, for nodes on or next to the wall ring by the edge kernel,
+ * for the rare look-back links by the tiled kernel, and by the force kernels.
  * ---------------------------------------------------------------------------------------- */
-
-/* f after reinit_obst_density (:966-986): equilibrium where the OLD map is solid. */
 template <typename real>
-LBM_HD void fprime(const Lattice<real> &L, int x, int y, real *out) {
-  const size_t k = node_index(L, x, y);
-  if (!is_ring(L, x, y)) {
-    const int co = L.cell_old[k];
-    if (!cell_is_fluid(co)) {
-      equilibrium(L, L.grains[cell_obst(co)], x, y, out);
-      return;
-    }
-  }
-#pragma unroll
-  for (int q = 0; q < NQ; ++q) out[q] = L.f[q * L.plane + k];
-}
-
-/* node content after sweeps 1-2 (re-init, collide) -- ring nodes are not touched by either */
-template <typename real>
-LBM_HD_SLOW void A_node(const Lattice<real> &L, int x, int y, real *out) {
-  fprime(L, x, y, out);
-  if (!is_ring(L, x, y) && cell_is_fluid(L.cell_new[node_index(L, x, y)])) mrt_collide(L, out);
-}
-template <typename real>
-LBM_HD real A_value(const Lattice<real> &L, int x, int y, int q) {
-  if (is_ring(L, x, y)) return L.f[q * L.plane + node_index(L, x, y)];
-  real t[NQ];
-  A_node(L, x, y, t);
-  real v = t[0];
-#pragma unroll
-  for (int k = 1; k < NQ; ++k)
-    if (k == q) v = t[k];
-  return v;
+LBM_HD real A_value(const Lattice<real> &L, const Stored<real> &S, int x, int y, int q) {
+  return S.A[q * L.plane + node_index(L, x, y)];
 }
 
 /* ring node content after the wall-ring sweep (:1123-1145).  Order of the reference: rows
@@ -259,41 +252,42 @@ LBM_HD real A_value(const Lattice<real> &L, int x, int y, int q) {
  * y=1..ly-2 reading what the row loop left, then the corners.  The only column reads that hit
  * a row-loop result are the four spelled out below. */
 template <typename real>
-LBM_HD_SLOW real ring_value(const Lattice<real> &L, int x, int y, int q) {
+LBM_HD_SLOW real ring_value(const Lattice<real> &L, const Stored<real> &S, int x, int y, int q) {
   const int lx = L.lx, ly = L.ly;
   const bool xin = x >= 1 && x <= lx - 2, yin = y >= 1 && y <= ly - 2;
   if (y == 0 && xin) {
-    if (q == 8) return A_value(L, x, 1, 4);
-    if (q == 7) return A_value(L, x + 1, 1, 3);
-    if (q == 1) return A_value(L, x - 1, 1, 5);
+    if (q == 8) return A_value(L, S, x, 1, 4);
+    if (q == 7) return A_value(L, S, x + 1, 1, 3);
+    if (q == 1) return A_value(L, S, x - 1, 1, 5);
   } else if (y == ly - 1 && xin) {
-    if (q == 4) return A_value(L, x, ly - 2, 8);
-    if (q == 3) return A_value(L, x - 1, ly - 2, 7) - L.lid6;
-    if (q == 5) return A_value(L, x + 1, ly - 2, 1) + L.lid6;
+    if (q == 4) return A_value(L, S, x, ly - 2, 8);
+    if (q == 3) return A_value(L, S, x - 1, ly - 2, 7) - L.lid6;
+    if (q == 5) return A_value(L, S, x + 1, ly - 2, 1) + L.lid6;
   } else if (x == 0 && yin) {
-    if (q == 6) return A_value(L, 1, y, 2);
-    if (q == 7) return (y + 1 == ly - 1) ? (real)(A_value(L, 0, ly - 2, 7) - L.lid6) : A_value(L, 1, y + 1, 3);
-    if (q == 5) return (y - 1 == 0) ? A_value(L, 0, 1, 5) : A_value(L, 1, y - 1, 1);
+    if (q == 6) return A_value(L, S, 1, y, 2);
+    if (q == 7) return (y + 1 == ly - 1) ? (real)(A_value(L, S, 0, ly - 2, 7) - L.lid6) : A_value(L, S, 1, y + 1, 3);
+    if (q == 5) return (y - 1 == 0) ? A_value(L, S, 0, 1, 5) : A_value(L, S, 1, y - 1, 1);
   } else if (x == lx - 1 && yin) {
-    if (q == 2) return A_value(L, lx - 2, y, 6);
-    if (q == 3) return (y - 1 == 0) ? A_value(L, lx - 1, 1, 3) : A_value(L, lx - 2, y - 1, 7);
-    if (q == 1) return (y + 1 == ly - 1) ? (real)(A_value(L, lx - 1, ly - 2, 1) + L.lid6) : A_value(L, lx - 2, y + 1, 5);
+    if (q == 2) return A_value(L, S, lx - 2, y, 6);
+    if (q == 3) return (y - 1 == 0) ? A_value(L, S, lx - 1, 1, 3) : A_value(L, S, lx - 2, y - 1, 7);
+    if (q == 1)
+      return (y + 1 == ly - 1) ? (real)(A_value(L, S, lx - 1, ly - 2, 1) + L.lid6) : A_value(L, S, lx - 2, y + 1, 5);
   } else if (x == 0 && y == 0) {
-    if (q == 7) return A_value(L, 1, 1, 3);
+    if (q == 7) return A_value(L, S, 1, 1, 3);
   } else if (x == lx - 1 && y == 0) {
-    if (q == 1) return A_value(L, lx - 2, 1, 5);
+    if (q == 1) return A_value(L, S, lx - 2, 1, 5);
   } else if (x == 0 && y == ly - 1) {
-    if (q == 5) return A_value(L, 1, ly - 2, 1);
+    if (q == 5) return A_value(L, S, 1, ly - 2, 1);
   } else if (x == lx - 1 && y == ly - 1) {
-    if (q == 3) return A_value(L, lx - 2, ly - 2, 7);
+    if (q == 3) return A_value(L, S, lx - 2, ly - 2, 7);
   }
-  return L.f[q * L.plane + node_index(L, x, y)];
+  return A_value(L, S, x, y, q);
 }
 
-/* content of node (x,y), population q, after sweeps 1-3 (what the swap passes then move) */
+/* content of node (x,y), population q, after sweeps 1-3 (what the grain sweep reads) */
 template <typename real>
-LBM_HD real state3(const Lattice<real> &L, int x, int y, int q) {
-  return is_ring(L, x, y) ? ring_value(L, x, y, q) : A_value(L, x, y, q);
+LBM_HD real state3(const Lattice<real> &L, const Stored<real> &S, int x, int y, int q) {
+  return is_ring(L, x, y) ? ring_value(L, S, x, y, q) : A_value(L, S, x, y, q);
 }
 
 /* content of node (x,y), population q, after the grain bounce-back sweep (:1154-1222).
@@ -301,48 +295,41 @@ LBM_HD real state3(const Lattice<real> &L, int x, int y, int q) {
  * side node nn of a short link (delta < 1/2) is itself an active solid node that the x-outer,
  * y-inner sweep visited earlier, the reference reads its already-updated value. */
 template <typename real, bool NESTED = false>
-LBM_HD_SLOW real G_value(const Lattice<real> &L, int x, int y, int q) {
-  if (is_ring(L, x, y)) return ring_value(L, x, y, q);
-  const int cn = L.cell_new[node_index(L, x, y)];
-  if (cell_is_fluid(cn) || q == 0 || !node_act(L, x, y, cn)) return A_value(L, x, y, q);
+LBM_HD_SLOW real G_value(const Lattice<real> &L, const Stored<real> &S, int x, int y, int q) {
+  if (is_ring(L, x, y)) return ring_value(L, S, x, y, q);
+  const int cn = S.cell[node_index(L, x, y)];
+  if (cell_is_fluid(cn) || q == 0 || !node_act(L, S, x, y, cn)) return A_value(L, S, x, y, q);
   const int ex = ex_of(q), ey = ey_of(q), oq = opp_of(q);
   const int nx = x + ex, ny = y + ey;
-  if (!cell_is_fluid(L.cell_new[node_index(L, nx, ny)])) return L.w[q];
-  const GrainRec<real> g = L.grains[cell_obst(cn)];
+  if (!cell_is_fluid(S.cell[node_index(L, nx, ny)])) return L.w[q];
+  const GrainRec<real> g = S.grains[cell_obst(cn)];
   const real d = link_delta(g, x, y, q);
   const real eu = ex * wall_ux(L, g, y) + ey * wall_uy(L, g, x);
-  real Fn[NQ];
-  A_node(L, nx, ny, Fn);
-  real Fn_q = Fn[0], Fn_oq = Fn[0];
-#pragma unroll
-  for (int k = 1; k < NQ; ++k) {
-    if (k == q) Fn_q = Fn[k];
-    if (k == oq) Fn_oq = Fn[k];
-  }
+  const real Fn_q = A_value(L, S, nx, ny, q), Fn_oq = A_value(L, S, nx, ny, oq);
   real X = 0;
   if (d > 0. && d < 0.5) {
     const int nnx = nx + ex, nny = ny + ey;
     bool look_back = false;
     if (!NESTED && !is_ring(L, nnx, nny)) {
-      const int cnn = L.cell_new[node_index(L, nnx, nny)];
-      look_back = (nnx < x || (nnx == x && nny < y)) && node_act(L, nnx, nny, cnn);
+      const int cnn = S.cell[node_index(L, nnx, nny)];
+      look_back = (nnx < x || (nnx == x && nny < y)) && node_act(L, S, nnx, nny, cnn);
     }
     if constexpr (!NESTED) {
-      X = look_back ? G_value<real, true>(L, nnx, nny, oq) : state3(L, nnx, nny, oq);
+      X = look_back ? G_value<real, true>(L, S, nnx, nny, oq) : state3(L, S, nnx, nny, oq);
     } else {
-      X = state3(L, nnx, nny, oq);
+      X = state3(L, S, nnx, nny, oq);
     }
   }
-  return bounce_value(L, q, d, Fn_oq, Fn_q, X, eu, (d > 0.) ? (real)0 : A_value(L, x, y, q));
+  return bounce_value(L, q, d, Fn_oq, Fn_q, X, eu, (d > 0.) ? (real)0 : A_value(L, S, x, y, q));
 }
 
 /* the streamed value: what the two swap passes leave in f[x][y][q] (:1224-1242) */
 template <typename real>
-LBM_HD real pull_value(const Lattice<real> &L, int x, int y, int q) {
-  if (q == 0) return G_value(L, x, y, 0);
+LBM_HD real pull_value(const Lattice<real> &L, const Stored<real> &S, int x, int y, int q) {
+  if (q == 0) return G_value(L, S, x, y, 0);
   const int sx = x - ex_of(q), sy = y - ey_of(q);
-  if (!in_array(L, sx, sy)) return G_value(L, x, y, opp_of(q));
-  return G_value(L, sx, sy, q);
+  if (!in_array(L, sx, sy)) return G_value(L, S, x, y, opp_of(q));
+  return G_value(L, S, sx, sy, q);
 }
 
 /* One boundary link of forces_fluid (src/main.c:1313-1320).  fs_oq = f_new[s][opp q] and

@@ -5,14 +5,19 @@
  *
  * Device layout (DESIGN.md "data layout"):
  *   f[2]     double-buffered populations, structure of arrays [q][x - x0][y], y contiguous, rows
- *            padded to a multiple of 32 elements (128-byte aligned rows, TMA-legal strides)
- *   cell[2]  obstacle map [x - x0][y] (int32: -1 fluid, grain index, nbgrains = wall ring);
- *            the buffer written by this step's rasteriser is "new", the other one is the "old"
- *            map reinit_obst_density reads (src/main.c:970)
+ *            padded to a multiple of 32 elements (128-byte aligned rows, TMA-legal strides).
+ *            Between LBM steps f[cur] holds "A": the populations of the last step after its
+ *            re-init and collide sweeps (holds_A); the reference's observable f[x][y][q] -- the
+ *            same step after bounce-back and streaming -- is materialised into the other buffer
+ *            only when somebody asks for it (get_f, fields, density).
+ *   cell[2]  obstacle map [x - x0][y] (int32: -1 fluid, grain index | act bit, nbgrains = wall
+ *            ring) of the last two steps, with the grain records rec[2]/R2[2]/boxes[2] that
+ *            produced them: the fused kernel streams with the stored step's map and records
+ *            and collides with the new ones (reinit_obst_density reads the old map, :970)
  *   grains   structure of arrays of `real`, replicated on every rank
  * Strip decomposition: rank k of P owns the global rows [xlo, xhi); with P > 1 the local arrays
- * carry two extra rows on each side (x0 = xlo - 2): f needs one ghost row (exchanged before
- * every LBM step), the obstacle map two (recomputed locally, grains are replicated).
+ * carry three extra rows on each side (x0 = xlo - 3): A needs two ghost rows (exchanged after
+ * every LBM step), the obstacle map three (recomputed locally, grains are replicated).
  */
 #include <dlfcn.h>
 #include <math.h>
@@ -140,12 +145,15 @@ struct Sim : SimBase {
   real *f[2] = {nullptr, nullptr};
   int *cell[2] = {nullptr, nullptr};
   int cur = 0, cur_cell = 0;
-  CUtensorMap tmap[2];
+  bool holds_A = false;      /* f[cur] holds A of the last step (stream pending) instead of f */
+  bool scratch_valid = false; /* f[1 - cur] holds the materialised f of the pending stream */
+  CUtensorMap tmA[2], tmCo[2], tmCn[2];
   std::vector<real *> grain_bufs;
   GrainArrays<real> g{};
-  GrainRec<real> *rec = nullptr;
-  real *R2 = nullptr;
-  GrainBox *boxes = nullptr;
+  GrainRec<real> *rec[2] = {nullptr, nullptr}; /* indexed like cell[] */
+  real *R2[2] = {nullptr, nullptr};
+  GrainBox *boxes[2] = {nullptr, nullptr};
+  EncodeTiled_t encode = nullptr;
   long long *facc = nullptr;
   double *fpartial = nullptr;
   VerletBuffers vb{};
@@ -168,7 +176,8 @@ struct Sim : SimBase {
     for (auto &e : ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     for (int k = 0; k < 2; ++k) { cudaFree(f[k]); cudaFree(cell[k]); }
     for (real *p : grain_bufs) cudaFree(p);
-    cudaFree(rec); cudaFree(R2); cudaFree(boxes); cudaFree(facc); cudaFree(fpartial);
+    for (int k = 0; k < 2; ++k) { cudaFree(rec[k]); cudaFree(R2[k]); cudaFree(boxes[k]); }
+    cudaFree(facc); cudaFree(fpartial);
     cudaFree(vb.bucket_count); cudaFree(vb.bucket_cursor); cudaFree(vb.sorted); cudaFree(vb.gcx); cudaFree(vb.gcy);
     cudaFree(vb.nbr_count); cudaFree(vb.nbr); cudaFree(vb.wflags); cudaFree(vb.error);
     cudaFree(dens_partials); cudaFree(dens_out); cudaFree(stage);
@@ -177,6 +186,7 @@ struct Sim : SimBase {
   }
 
   static constexpr int DENS_BLOCKS = 1184; /* 8 x 148 SMs */
+  static constexpr int GHOST = 3;          /* extra rows per side of a strip (map); A uses 2 of them */
 
   int init_device() override {
     int ndev = 0;
@@ -196,7 +206,7 @@ struct Sim : SimBase {
     xlo = P.rank * base + std::min(P.rank, rem);
     xhi = xlo + base + (P.rank < rem ? 1 : 0);
     if (P.nranks > 1 && xhi - xlo < 4) return fail(LBMDEM_EINVAL, "strips must be at least 4 rows wide");
-    if (P.nranks > 1) { x0 = xlo - 2; nxl = xhi - xlo + 4; } else { x0 = 0; nxl = lx; }
+    if (P.nranks > 1) { x0 = xlo - GHOST; nxl = xhi - xlo + 2 * GHOST; } else { x0 = 0; nxl = lx; }
     pitch = (ly + 31) / 32 * 32;
     plane = (size_t)nxl * pitch;
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -207,21 +217,32 @@ struct Sim : SimBase {
     }
     CK(cudaMalloc(&dens_partials, sizeof(double) * DENS_BLOCKS));
     CK(cudaMalloc(&dens_out, sizeof(double)));
-    /* TMA descriptors: 3-D (y, x, q) view of each population buffer */
+    /* TMA descriptors: 3-D (y, x, q) view of each population buffer, one lattice row per box;
+     * 2-D (y, x) views of each obstacle map with and without the y halo */
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
     if (!fn || qres != cudaDriverEntryPointSuccess) return fail(LBMDEM_ECUDA, "cuTensorMapEncodeTiled not available");
-    EncodeTiled_t encode = (EncodeTiled_t)fn;
+    encode = (EncodeTiled_t)fn;
+    using C = RowCfg<real>;
     for (int k = 0; k < 2; ++k) {
       const cuuint64_t dims[3] = {(cuuint64_t)ly, (cuuint64_t)nxl, (cuuint64_t)NQ};
       const cuuint64_t strides[2] = {(cuuint64_t)pitch * sizeof(real), (cuuint64_t)plane * sizeof(real)};
-      const cuuint32_t box[3] = {(cuuint32_t)TileBox<real>::BY, (cuuint32_t)TileBox<real>::BX, (cuuint32_t)NQ};
+      const cuuint32_t box[3] = {(cuuint32_t)C::BY, 1, (cuuint32_t)NQ};
       const cuuint32_t estr[3] = {1, 1, 1};
-      const CUresult r = encode(&tmap[k], sizeof(real) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
-                                3, f[k], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (r != CUDA_SUCCESS) return fail(LBMDEM_ECUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+      CUresult r = encode(&tmA[k], sizeof(real) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                          f[k], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(LBMDEM_ECUDA, "cuTensorMapEncodeTiled(f) failed with code " + std::to_string((int)r));
+      const cuuint64_t cdims[2] = {(cuuint64_t)ly, (cuuint64_t)nxl};
+      const cuuint64_t cstr[1] = {(cuuint64_t)pitch * sizeof(int)};
+      const cuuint32_t cbox_o[2] = {(cuuint32_t)C::BC, 1}, cbox_n[2] = {(cuuint32_t)C::TY, 1};
+      r = encode(&tmCo[k], CU_TENSOR_MAP_DATA_TYPE_INT32, 2, cell[k], cdims, cstr, cbox_o, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r == CUDA_SUCCESS)
+        r = encode(&tmCn[k], CU_TENSOR_MAP_DATA_TYPE_INT32, 2, cell[k], cdims, cstr, cbox_n, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(LBMDEM_ECUDA, "cuTensorMapEncodeTiled(map) failed with code " + std::to_string((int)r));
     }
     CK(cudaStreamSynchronize(stream));
     return 0;
@@ -240,10 +261,13 @@ struct Sim : SimBase {
       CK(cudaMemsetAsync(*s, 0, sizeof(real) * n, stream));
       grain_bufs.push_back(*s);
     }
-    cudaFree(rec); cudaFree(R2); cudaFree(boxes); cudaFree(facc); cudaFree(fpartial);
-    CK(cudaMalloc(&rec, sizeof(GrainRec<real>) * n));
-    CK(cudaMalloc(&R2, sizeof(real) * n));
-    CK(cudaMalloc(&boxes, sizeof(GrainBox) * n));
+    cudaFree(facc); cudaFree(fpartial);
+    for (int k = 0; k < 2; ++k) {
+      cudaFree(rec[k]); cudaFree(R2[k]); cudaFree(boxes[k]);
+      CK(cudaMalloc(&rec[k], sizeof(GrainRec<real>) * n));
+      CK(cudaMalloc(&R2[k], sizeof(real) * n));
+      CK(cudaMalloc(&boxes[k], sizeof(GrainBox) * n));
+    }
     CK(cudaMalloc(&facc, sizeof(long long) * 3 * n));
     CK(cudaMemsetAsync(facc, 0, sizeof(long long) * 3 * n, stream));
     CK(cudaMalloc(&fpartial, sizeof(double) * 3 * n));
@@ -313,13 +337,15 @@ struct Sim : SimBase {
         (rc = upload(g.It, It)) || (rc = upload(g.rLB, rLB)))
       return rc;
     /* init_density (:716-724) and init_obst (:663-711) */
-    const Lattice<real> L = lattice(0);
+    const Lattice<real> L = lattice();
     CK(launch_fill_rest<real>(f[0], plane, L, stream));
     CK(launch_fill_rest<real>(f[1], plane, L, stream));
     for (int k = 0; k < 2; ++k) CK(launch_cell_frame(cell[k], lx, ly, x0, nxl, pitch, n, stream));
     cur = 0;
     cur_cell = 0;
-    CK(launch_raster<real>(raster_params(), n, g, rec, R2, boxes, cell[cur_cell], x0, nxl, pitch, stream));
+    holds_A = false;
+    scratch_valid = false;
+    if ((rc = raster_into(cur_cell))) return rc;
     CK(cudaStreamSynchronize(stream));
     nbsteps = 0;
     nFile = 0;
@@ -369,7 +395,7 @@ struct Sim : SimBase {
     R.lx = lx; R.ly = ly; R.dx = dx; R.Mgx = Mgx; R.Mby = Mby;
     return R;
   }
-  Lattice<real> lattice(int fbuf) const {
+  Lattice<real> lattice() const {
     Lattice<real> L;
     L.lx = lx; L.ly = ly; L.x0 = x0; L.nxl = nxl; L.pitch = pitch; L.plane = plane; L.ngrains = n;
     L.dx = dx; L.c = c; L.Mgx = Mgx; L.Mby = Mby;
@@ -378,11 +404,22 @@ struct Sim : SimBase {
     L.s2 = (real)P.s2; L.s3 = (real)P.s3; L.s5 = (real)P.s5; L.s7 = (real)P.s7; L.s8 = (real)P.s8; L.s9 = (real)P.s9;
     const real w0[NQ] = {4. / 9, 1. / 36, 1. / 9, 1. / 36, 1. / 9, 1. / 36, 1. / 9, 1. / 36, 1. / 9}; /* :53-54 */
     for (int q = 0; q < NQ; ++q) L.w[q] = w0[q];
-    L.f = f[fbuf];
-    L.cell_new = cell[cur_cell];
-    L.cell_old = cell[1 - cur_cell];
-    L.grains = rec; L.boxes = boxes; L.R2 = R2; L.act_folded = 0;
     return L;
+  }
+  /* the stored state: populations in f[fbuf] with the map / records of slot `cslot` */
+  Stored<real> stored(int fbuf, int cslot) const {
+    Stored<real> S;
+    S.A = f[fbuf];
+    S.cell = cell[cslot];
+    S.grains = rec[cslot]; S.boxes = boxes[cslot]; S.R2 = R2[cslot];
+    S.act_folded = act_folded[cslot] ? 1 : 0;
+    return S;
+  }
+  bool act_folded[2] = {false, false};
+  int raster_into(int cslot) {
+    CK(launch_raster<real>(raster_params(), n, g, rec[cslot], R2[cslot], boxes[cslot], cell[cslot], x0, nxl, pitch, stream));
+    act_folded[cslot] = true;
+    return 0;
   }
   dem::Params<real> dem_params() const {
     dem::Params<real> D;
@@ -398,7 +435,8 @@ struct Sim : SimBase {
     return fail(LBMDEM_ENCCL, std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
   }
 
-  /* one ghost row of pre-collision populations per side */
+  /* two ghost rows of A per side: the fused kernel of the next step pulls from
+   * one of them, the force kernel's short links reach into the second */
   int halo_exchange() {
     if (P.nranks == 1) return 0;
     if (!comm) return fail(LBMDEM_ESTATE, "nranks > 1 but no communicator attached (lbmdem_attach_nccl)");
@@ -406,16 +444,17 @@ struct Sim : SimBase {
     int r = g_nccl.GroupStart();
     if (r) return nccl_fail(r, "ncclGroupStart");
     real *F = f[cur];
+    const size_t two = (size_t)2 * pitch; /* two consecutive rows are contiguous */
     for (int q = 0; q < NQ && !r; ++q) {
       real *pl = F + (size_t)q * plane;
-      if (P.rank > 0) { /* left neighbour: send first owned row (local 2), receive into ghost row (local 1) */
-        r = g_nccl.Send(pl + (size_t)2 * pitch, ly, dtype, P.rank - 1, comm, stream);
-        if (!r) r = g_nccl.Recv(pl + (size_t)1 * pitch, ly, dtype, P.rank - 1, comm, stream);
+      if (P.rank > 0) { /* left neighbour: send the first two owned rows, receive into the ghost rows below them */
+        r = g_nccl.Send(pl + (size_t)GHOST * pitch, two, dtype, P.rank - 1, comm, stream);
+        if (!r) r = g_nccl.Recv(pl + (size_t)(GHOST - 2) * pitch, two, dtype, P.rank - 1, comm, stream);
       }
       if (!r && P.rank < P.nranks - 1) {
-        const int last = xhi - xlo + 1; /* local row of the last owned row */
-        r = g_nccl.Send(pl + (size_t)last * pitch, ly, dtype, P.rank + 1, comm, stream);
-        if (!r) r = g_nccl.Recv(pl + (size_t)(last + 1) * pitch, ly, dtype, P.rank + 1, comm, stream);
+        const int end = xhi - x0; /* local row just past the owned rows */
+        r = g_nccl.Send(pl + (size_t)(end - 2) * pitch, two, dtype, P.rank + 1, comm, stream);
+        if (!r) r = g_nccl.Recv(pl + (size_t)end * pitch, two, dtype, P.rank + 1, comm, stream);
       }
     }
     const int r2 = g_nccl.GroupEnd();
@@ -453,45 +492,95 @@ struct Sim : SimBase {
     return 0;
   }
 
+  FusedArgs<real> fused_args(int out_buf) const {
+    FusedArgs<real> a;
+    a.L = lattice();
+    a.S = stored(cur, 1 - cur_cell);
+    a.cell_new = cell[cur_cell];
+    a.grains_new = rec[cur_cell];
+    a.out = f[out_buf];
+    a.xlo = xlo; a.xhi = xhi;
+    return a;
+  }
+
   /* the LBM part of renderScene (:1711-1717), asynchronous on `stream` */
   int lbm_step_async() {
     if (!ready) return fail(LBMDEM_ESTATE, "no grains loaded");
-    int rc = halo_exchange();
-    if (rc) return rc;
-    cur_cell ^= 1; /* the rasteriser writes the other map; the previous one becomes "old" */
-    CK(launch_raster<real>(raster_params(), n, g, rec, R2, boxes, cell[cur_cell], x0, nxl, pitch, stream));
-    StepArgs<real> a;
-    a.L = lattice(cur);
-    a.f_new = f[1 - cur];
-    a.facc = P.strict_fp ? nullptr : facc;
-    a.xlo = xlo; a.xhi = xhi;
-    std::pair<cudaEvent_t, cudaEvent_t> *ev;
-    if ((rc = record_k1_begin(&ev))) return rc;
-    if (P.kernel == 1) {
-      CK(P.strict_fp ? k1_strict::launch_lbm_generic<real>(a, stream) : k1_fast::launch_lbm_generic<real>(a, stream));
-    } else {
-      CK(P.strict_fp ? k1_strict::launch_lbm_tiled<real>(tmap[cur], a, stream)
-                     : k1_fast::launch_lbm_tiled<real>(tmap[cur], a, stream));
-    }
-    if (ev) CK(cudaEventRecord(ev->second, stream));
-    ++k1_launches;
-    all_launches += 4; /* grain_prepare, raster, K1, force post-processing (memsets not counted) */
-    if (P.strict_fp) {
-      CK(launch_force_serial<real>(a.L, a.f_new, xlo, xhi, fpartial, stream));
+    int rc;
+    cur_cell ^= 1; /* the rasteriser writes the other map; the previous one stays with the stored state */
+    if ((rc = raster_into(cur_cell))) return rc;
+    all_launches += 3; /* grain_prepare, raster, act_fold (memsets not counted) */
+    scratch_valid = false;
+    if (!holds_A) {
+      /* populations came from outside (init_density, set_f): sweeps 1-2 alone, in place */
+      const Lattice<real> L = lattice();
+      CK(P.strict_fp ? k1_strict::launch_lbm_h1<real>(L, f[cur], cell[1 - cur_cell], cell[cur_cell], rec[cur_cell], xlo, xhi, stream)
+                     : k1_fast::launch_lbm_h1<real>(L, f[cur], cell[1 - cur_cell], cell[cur_cell], rec[cur_cell], xlo, xhi, stream));
       ++all_launches;
+      holds_A = true;
+    } else {
+      const FusedArgs<real> a = fused_args(1 - cur);
+      if (P.kernel == 1) {
+        CK(P.strict_fp ? k1_strict::launch_lbm_slow<real>(a, SLOW_ALL, stream) : k1_fast::launch_lbm_slow<real>(a, SLOW_ALL, stream));
+        ++all_launches;
+      } else {
+        std::pair<cudaEvent_t, cudaEvent_t> *ev;
+        if ((rc = record_k1_begin(&ev))) return rc;
+        CK(P.strict_fp ? k1_strict::launch_lbm_rows<real>(tmA[cur], tmCo[1 - cur_cell], tmCn[cur_cell], a, stream)
+                       : k1_fast::launch_lbm_rows<real>(tmA[cur], tmCo[1 - cur_cell], tmCn[cur_cell], a, stream));
+        if (ev) CK(cudaEventRecord(ev->second, stream));
+        ++k1_launches;
+        CK(P.strict_fp ? k1_strict::launch_lbm_slow<real>(a, SLOW_EDGE, stream) : k1_fast::launch_lbm_slow<real>(a, SLOW_EDGE, stream));
+        all_launches += 2;
+      }
+      cur ^= 1;
+    }
+    if ((rc = halo_exchange())) return rc;
+    /* forces_fluid of this step (:1285-1333), from the state just stored */
+    const Lattice<real> L = lattice();
+    const Stored<real> S = stored(cur, cur_cell);
+    if (P.strict_fp) {
+      CK(launch_force_serial<real>(L, S, xlo, xhi, fpartial, stream));
       if (P.nranks > 1) {
         const int r = g_nccl.AllReduce(fpartial, fpartial, (size_t)3 * n, NcclApi::Float64, NcclApi::Sum, comm, stream);
         if (r) return nccl_fail(r, "ncclAllReduce");
       }
       CK(launch_force_scale<real>(fpartial, n, k12, k3, g.fhf1, g.fhf2, g.fhf3, stream));
     } else {
+      CK(launch_force_warp<real>(L, S, xlo, xhi, facc, stream));
       if (P.nranks > 1) { /* integer sum: exact, identical on every rank, independent of the decomposition */
         const int r = g_nccl.AllReduce(facc, facc, (size_t)3 * n, NcclApi::Int64, NcclApi::Sum, comm, stream);
         if (r) return nccl_fail(r, "ncclAllReduce");
       }
       CK(launch_force_finish<real>(facc, n, k12, k3, g.fhf1, g.fhf2, g.fhf3, stream));
     }
+    all_launches += 2;
+    return 0;
+  }
+
+  /* The reference's f[x][y][q] as of now.  While a stream is pending it is materialised into the
+   * other population buffer (sweeps 3-5 of the stored step, nothing else); the state is untouched. */
+  int observable_f(const real **out) {
+    if (!holds_A) { *out = f[cur]; return 0; }
+    if (!scratch_valid) {
+      FusedArgs<real> a = fused_args(1 - cur);
+      a.S = stored(cur, cur_cell); /* the stored step IS the current one */
+      CK(P.strict_fp ? k1_strict::launch_lbm_slow<real>(a, SLOW_STREAM_ONLY, stream)
+                     : k1_fast::launch_lbm_slow<real>(a, SLOW_STREAM_ONLY, stream));
+      scratch_valid = true;
+    }
+    *out = f[1 - cur];
+    return 0;
+  }
+  /* make f[cur] hold plain populations again (before they or the map are overwritten from outside) */
+  int settle() {
+    if (!holds_A) return 0;
+    const real *obs;
+    int rc = observable_f(&obs);
+    if (rc) return rc;
     cur ^= 1;
+    holds_A = false;
+    scratch_valid = false;
     return 0;
   }
 
@@ -575,7 +664,10 @@ struct Sim : SimBase {
   int get_strip(int *a, int *b) override { *a = xlo; *b = xhi; return 0; }
 
   int total_density(double *sum) override {
-    CK(launch_density<real>(f[cur], ly, x0, xlo, xhi, pitch, plane, dens_partials, DENS_BLOCKS, dens_out, stream));
+    const real *obs;
+    int rc = observable_f(&obs);
+    if (rc) return rc;
+    CK(launch_density<real>(obs, ly, x0, xlo, xhi, pitch, plane, dens_partials, DENS_BLOCKS, dens_out, stream));
     CK(cudaMemcpyAsync(sum, dens_out, sizeof(double), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
     return 0;
@@ -594,9 +686,11 @@ struct Sim : SimBase {
     const int chunk = 64;
     int rc = ensure_stage((size_t)chunk * ly * NQ);
     if (rc) return rc;
+    const real *obs;
+    if ((rc = observable_f(&obs))) return rc;
     for (int r0 = xlo; r0 < xhi; r0 += chunk) {
       const int nr = std::min(chunk, xhi - r0);
-      CK(launch_f_to_host_layout<real>(f[cur], ly, pitch, plane, r0 - x0, nr, stage, stream));
+      CK(launch_f_to_host_layout<real>(obs, ly, pitch, plane, r0 - x0, nr, stage, stream));
       CK(cudaMemcpyAsync(out + (size_t)(r0 - xlo) * ly * NQ, stage, sizeof(double) * (size_t)nr * ly * NQ,
                          cudaMemcpyDeviceToHost, stream));
       CK(cudaStreamSynchronize(stream));
@@ -607,6 +701,8 @@ struct Sim : SimBase {
     const int chunk = 64;
     int rc = ensure_stage((size_t)chunk * ly * NQ);
     if (rc) return rc;
+    holds_A = false; /* every owned population is overwritten: a pending stream is moot */
+    scratch_valid = false;
     for (int r0 = xlo; r0 < xhi; r0 += chunk) {
       const int nr = std::min(chunk, xhi - r0);
       CK(cudaMemcpyAsync(stage, in + (size_t)(r0 - xlo) * ly * NQ, sizeof(double) * (size_t)nr * ly * NQ,
@@ -620,9 +716,14 @@ struct Sim : SimBase {
     CK(cudaMemcpy2DAsync(out, sizeof(int) * ly, cell[cur_cell] + (size_t)(xlo - x0) * pitch, sizeof(int) * pitch,
                          sizeof(int) * ly, xhi - xlo, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
+    const size_t cnt = (size_t)(xhi - xlo) * ly;
+    for (size_t k = 0; k < cnt; ++k) out[k] = cell_obst(out[k]); /* drop the act bit */
     return 0;
   }
   int set_obst(const int *in) override {
+    int rc = settle(); /* a pending stream belongs to the map that is about to be replaced */
+    if (rc) return rc;
+    act_folded[cur_cell] = false;
     CK(cudaMemcpy2DAsync(cell[cur_cell] + (size_t)(xlo - x0) * pitch, sizeof(int) * pitch, in, sizeof(int) * ly,
                          sizeof(int) * ly, xhi - xlo, cudaMemcpyHostToDevice, stream));
     CK(cudaStreamSynchronize(stream));
@@ -632,8 +733,7 @@ struct Sim : SimBase {
     if (!ready) return fail(LBMDEM_ESTATE, "no grains loaded");
     int *d = nullptr;
     CK(cudaMalloc(&d, sizeof(int) * (size_t)(xhi - xlo) * ly));
-    const Lattice<real> L = lattice(cur);
-    cudaError_t e = launch_act_map<real>(L, xlo, xhi, d, stream);
+    cudaError_t e = launch_act_map<real>(lattice(), stored(cur, cur_cell), xlo, xhi, d, stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d, sizeof(int) * (size_t)(xhi - xlo) * ly, cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
     cudaFree(d);
@@ -707,8 +807,10 @@ struct Sim : SimBase {
       if (e == cudaSuccess) e = cudaMemcpy(gp, tmp.data(), sizeof(real) * n, cudaMemcpyHostToDevice);
     }
     float *p0 = d, *p1 = d + nn, *p2 = d + 4 * nn, *p3 = d + 7 * nn, *p4 = d + 8 * nn;
+    const real *obs = nullptr;
+    if (e == cudaSuccess && observable_f(&obs)) e = cudaErrorUnknown;
     if (e == cudaSuccess)
-      e = launch_fields<real>(f[cur], cell[cur_cell], g, gp, n, ly, x0, xlo, xhi, pitch, plane, (real)P.rho_moy, p0, p1, p2,
+      e = launch_fields<real>(obs, cell[cur_cell], g, gp, n, ly, x0, xlo, xhi, pitch, plane, (real)P.rho_moy, p0, p1, p2,
                               p3, p4, stream);
     if (e == cudaSuccess && gpress) e = cudaMemcpyAsync(gpress, p0, sizeof(float) * nn, cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess && gvel) e = cudaMemcpyAsync(gvel, p1, sizeof(float) * nn * 3, cudaMemcpyDeviceToHost, stream);
@@ -744,7 +846,9 @@ struct Sim : SimBase {
       for (int k = 0; k < 3; ++k)
         CK(cudaMemcpyAsync(hs + (size_t)(9 + k) * n, fh[k], sizeof(real) * n, cudaMemcpyDeviceToHost, stream));
     if (dens) {
-      CK(launch_density<real>(f[cur], ly, x0, xlo, xhi, pitch, plane, dens_partials, DENS_BLOCKS, dens_out, stream));
+      const real *obs;
+      if ((rc = observable_f(&obs))) return rc;
+      CK(launch_density<real>(obs, ly, x0, xlo, xhi, pitch, plane, dens_partials, DENS_BLOCKS, dens_out, stream));
       CK(cudaMemcpyAsync(dens, dens_out, sizeof(double), cudaMemcpyDeviceToHost, stream));
     }
     if (built) {

@@ -3,7 +3,7 @@
  *
  * Compiles the product's host+device node headers (csrc/lbm_node.cuh, raster_node.cuh,
  * dem_node.cuh) with g++ and drives them with plain serial loops, so that the *formulation*
- * the CUDA kernels implement -- the pull / on-demand restatement of the LBM step, the
+ * the CUDA kernels implement -- the stored-state / on-demand restatement of the LBM step, the
  * atomicMax-style rasteriser with the act rule, the gather-form DEM step over a sorted full
  * neighbour list -- can be pinned against the oracle on a machine without a GPU
  * (tests/test_hostcheck.py).  It is not a CPU fallback: nothing under 2d-lbm-dem_b200/ loads it.
@@ -95,13 +95,26 @@ int lbm_step_host(int lx, int ly, int n, const double *scal, const double *grain
   L.s2 = 1.5; L.s3 = 1.4; L.s5 = 1.5; L.s7 = 1.5; L.s8 = 1.9841; L.s9 = 1.9841;
   const real w0[NQ] = {4. / 9, 1. / 36, 1. / 9, 1. / 36, 1. / 9, 1. / 36, 1. / 9, 1. / 36, 1. / 9};
   for (int q = 0; q < NQ; ++q) L.w[q] = w0[q];
-  L.f = fs.data(); L.cell_old = cell_old.data(); L.grains = rec.data();
-  L.cell_new = g_act_folded ? cell_new.data() : cell_bare.data();
-  L.boxes = box.data(); L.R2 = R2v.data(); L.act_folded = g_act_folded;
 
+  /* sweeps 1-2, node-local: what the device stores between steps */
+  std::vector<real> A(nn * NQ);
+  for (int x = 0; x < lx; ++x)
+    for (int y = 0; y < ly; ++y) {
+      const size_t k = (size_t)x * ly + y;
+      real p[NQ];
+      for (int q = 0; q < NQ; ++q) p[q] = fs[q * nn + k];
+      if (!is_ring(L, x, y)) reinit_collide(L, rec.data(), cell_old[k], cell_new[k], x, y, p);
+      for (int q = 0; q < NQ; ++q) A[q * nn + k] = p[q];
+    }
+  Stored<real> S;
+  S.A = A.data(); S.grains = rec.data();
+  S.cell = g_act_folded ? cell_new.data() : cell_bare.data();
+  S.boxes = box.data(); S.R2 = R2v.data(); S.act_folded = g_act_folded;
+
+  /* sweeps 3-5 on demand from the stored state */
   for (int x = 0; x < lx; ++x)
     for (int y = 0; y < ly; ++y)
-      for (int q = 0; q < NQ; ++q) fn[q * nn + (size_t)x * ly + y] = pull_value(L, x, y, q);
+      for (int q = 0; q < NQ; ++q) fn[q * nn + (size_t)x * ly + y] = pull_value(L, S, x, y, q);
 
   for (size_t k = 0; k < nn; ++k) {
     for (int q = 0; q < NQ; ++q) f_out[k * NQ + q] = fn[q * nn + k];
@@ -121,8 +134,10 @@ int lbm_step_host(int lx, int ly, int n, const double *scal, const double *grain
         for (int q = 1; q < NQ; ++q) {
           const int ax = x + ex_of(q), ay = y + ey_of(q);
           if (cell_obst(cell_new[(size_t)ax * ly + ay]) == i) continue;
-          force_link<real>(q, fn[opp_of(q) * nn + (size_t)x * ly + y], fn[q * nn + (size_t)ax * ly + ay], x, y, xc, yc,
-                           &h1, &h2, &h3);
+          /* f_new[s][opp q] = G[n][opp q] and f_new[n][q] = G[s][q]: evaluated before streaming, as the device does */
+          const real fs_oq = G_value(L, S, ax, ay, opp_of(q)), fn_q = G_value(L, S, x, y, q);
+          if (fs_oq != fn[opp_of(q) * nn + (size_t)x * ly + y] || fn_q != fn[q * nn + (size_t)ax * ly + ay]) return -2;
+          force_link<real>(q, fs_oq, fn_q, x, y, xc, yc, &h1, &h2, &h3);
         }
       }
     fhf[3 * (size_t)i] = h1; fhf[3 * (size_t)i + 1] = h2; fhf[3 * (size_t)i + 2] = h3;
