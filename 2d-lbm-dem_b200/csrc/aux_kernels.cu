@@ -128,9 +128,125 @@ cudaError_t launch_act_map(const Lattice<real> &L, const Stored<real> &S, int xl
 }
 
 /* ------------------------------------------------------------------------------------------
- * K1f: forces_fluid (src/main.c:1285-1333) from the stored state.  For a node s of grain i and a
+ * Sweep 3 in place: wall ring (src/main.c:1123-1145), two passes (lbm_node.cuh, ring_value), one
+ * thread per ring node of the rows [xa, xb).
+ * ---------------------------------------------------------------------------------------- */
+template <typename real>
+__global__ void ring_sweep_kernel(const __grid_constant__ Lattice<real> L, const __grid_constant__ Stored<real> S, real *A,
+                                  int pass, int xa, int xb, int rows_lo, int rows_hi) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int x, y;
+  if (pass == 0) { /* y = 0 and y = ly-1 of every row in range */
+    if (t >= 2ll * (xb - xa)) return;
+    x = xa + (int)(t >> 1);
+    y = (t & 1) ? L.ly - 1 : 0;
+  } else { /* the owned ring rows x = 0 / x = lx-1 in full (corners included) */
+    if (t >= (long long)(rows_lo + rows_hi) * L.ly) return;
+    const int r = (int)(t / L.ly);
+    y = (int)(t - (long long)r * L.ly);
+    x = (r < rows_lo) ? 0 : L.lx - 1;
+  }
+  const size_t k = node_index(L, x, y);
+  real v[NQ];
+#pragma unroll
+  for (int q = 1; q < NQ; ++q) v[q] = ring_value(L, S, pass, x, y, q);
+#pragma unroll
+  for (int q = 1; q < NQ; ++q) A[q * L.plane + k] = v[q];
+}
+template <typename real>
+cudaError_t launch_ring_sweep(const Lattice<real> &L, const Stored<real> &S, real *A, int xa, int xb, cudaStream_t s) {
+  if (xb <= xa) return cudaSuccess;
+  const int lo = (xa == 0) ? 1 : 0, hi = (xb == L.lx) ? 1 : 0;
+  const long long t0 = 2ll * (xb - xa), t1 = (long long)(lo + hi) * L.ly;
+  ring_sweep_kernel<real><<<(unsigned)((t0 + 127) / 128), 128, 0, s>>>(L, S, A, 0, xa, xb, lo, hi);
+  if (t1 > 0) ring_sweep_kernel<real><<<(unsigned)((t1 + 127) / 128), 128, 0, s>>>(L, S, A, 1, xa, xb, lo, hi);
+  return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Sweep 4 in place: interpolated bounce-back on active solid nodes (src/main.c:1154-1222).
+ * One warp per grain: the lanes scan the grain's bounding box, compact its active nodes into a
+ * per-warp list, then share the (node, link) pairs out, one link per lane, so that the expensive
+ * part (delta: one sqrt, the interpolation: divisions) runs with full lanes.
+ * ---------------------------------------------------------------------------------------- */
+constexpr int SWEEP_WARPS = 4;
+constexpr int SWEEP_LIST = 64;
+
+template <typename real>
+__device__ __forceinline__ void sweep_links(const Lattice<real> &L, const Stored<real> &S, real *A, const int *list, int cnt,
+                                            int xa0, int ny, int yi, int lane, const DeferList<real> &D) {
+  for (int u = lane; u < cnt * 8; u += 32) {
+    const int t = list[u >> 3], q = 1 + (u & 7);
+    const int x = xa0 + t / ny, y = yi + t % ny;
+    real v;
+    int r = sweep_link(L, S, x, y, q, false, &v);
+    const size_t e = q * L.plane + node_index(L, x, y);
+    if (r == SWEEP_WRITE) {
+      A[e] = v;
+    } else if (r == SWEEP_DEFER) {
+      r = sweep_link(L, S, x, y, q, true, &v);
+      if (r == SWEEP_WRITE) {
+        const int slot = atomicAdd(D.count, 1);
+        if (slot < D.capacity) { D.index[slot] = e; D.value[slot] = v; }
+        else *(volatile int *)D.overflow = 1; /* mapped host memory */
+      }
+    }
+  }
+}
+
+template <typename real>
+__global__ void __launch_bounds__(SWEEP_WARPS * 32) bounce_sweep_kernel(const __grid_constant__ Lattice<real> L,
+                                                                         const __grid_constant__ Stored<real> S, real *A,
+                                                                         int xa, int xb, const DeferList<real> D) {
+  __shared__ int lists[SWEEP_WARPS][SWEEP_LIST];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * SWEEP_WARPS + w;
+  if (i >= L.ngrains) return;
+  const GrainBox b = S.boxes[i];
+  const int xa0 = max(b.xi, xa), xb0 = min(b.xf, xb - 1);
+  const int ny = b.yf - b.yi + 1;
+  if (ny <= 0 || xb0 < xa0) return;
+  const int total = (xb0 - xa0 + 1) * ny;
+  int *list = lists[w];
+  int cnt = 0;
+  for (int base = 0; base < total; base += 32) {
+    const int t = base + lane;
+    bool act = false;
+    if (t < total) {
+      const int c = S.cell[node_index(L, xa0 + t / ny, b.yi + t % ny)];
+      act = cell_obst(c) == i && node_act(L, S, xa0 + t / ny, b.yi + t % ny, c);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, act);
+    if (act) list[cnt + __popc(m & ((1u << lane) - 1))] = t;
+    cnt += __popc(m);
+    __syncwarp();
+    if (cnt > SWEEP_LIST - 32 || base + 32 >= total) {
+      sweep_links(L, S, A, list, cnt, xa0, ny, b.yi, lane, D);
+      cnt = 0;
+      __syncwarp();
+    }
+  }
+}
+template <typename real>
+__global__ void defer_apply_kernel(real *A, const DeferList<real> D) {
+  const int n = min(*D.count, D.capacity);
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) A[D.index[k]] = D.value[k];
+}
+template <typename real>
+cudaError_t launch_bounce_sweep(const Lattice<real> &L, const Stored<real> &S, real *A, int xa, int xb,
+                                const DeferList<real> &D, cudaStream_t s) {
+  if (xb <= xa || L.ngrains <= 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(D.count, 0, sizeof(int), s);
+  if (e != cudaSuccess) return e;
+  bounce_sweep_kernel<real><<<(L.ngrains + SWEEP_WARPS - 1) / SWEEP_WARPS, SWEEP_WARPS * 32, 0, s>>>(L, S, A, xa, xb, D);
+  defer_apply_kernel<real><<<8, 256, 0, s>>>(A, D);
+  return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------------------------------
+ * K1f: forces_fluid (src/main.c:1285-1333) from the swept state.  For a node s of grain i and a
  * link q to a node n not owned by i the reference adds (f_new[s][opp q] + f_new[n][q]) e_{opp q}
- * AFTER streaming; by the pull identity these are G[n][opp q] and G[s][q] before streaming.
+ * AFTER streaming; by the pull identity these are A[n][opp q] and A[s][q] before streaming.
  * ---------------------------------------------------------------------------------------- */
 __device__ __forceinline__ long long warp_sum_ll(long long v) {
 #pragma unroll
@@ -156,13 +272,14 @@ __global__ void force_warp_kernel(const __grid_constant__ Lattice<real> L, const
     const int total = (xb - xa + 1) * ny;
     for (int t = lane; t < total; t += 32) {
       const int x = xa + t / ny, y = b.yi + t % ny;
-      if (cell_obst(S.cell[node_index(L, x, y)]) != i) continue;
-#pragma unroll 1
+      const size_t k = node_index(L, x, y);
+      if (cell_obst(S.cell[k]) != i) continue;
+#pragma unroll
       for (int q = 1; q < NQ; ++q) {
-        const int ax = x + ex_of(q), ay = y + ey_of(q);
-        if (cell_obst(S.cell[node_index(L, ax, ay)]) == i) continue;
+        const size_t kn = node_index(L, x + ex_of(q), y + ey_of(q));
+        if (cell_obst(S.cell[kn]) == i) continue;
         real h1 = 0, h2 = 0, h3 = 0;
-        force_link<real>(q, G_value(L, S, ax, ay, opp_of(q)), G_value(L, S, x, y, q), x, y, xc, yc, &h1, &h2, &h3);
+        force_link<real>(q, S.A[opp_of(q) * L.plane + kn], S.A[q * L.plane + k], x, y, xc, yc, &h1, &h2, &h3);
         s1 += __double2ll_rn((double)h1 * FORCE_FIX);
         s2 += __double2ll_rn((double)h2 * FORCE_FIX);
         s3 += __double2ll_rn((double)h3 * TORQUE_FIX);
@@ -212,12 +329,13 @@ __global__ void force_serial_kernel(const __grid_constant__ Lattice<real> L, con
   real h1 = 0, h2 = 0, h3 = 0;
   for (int x = max(b.xi, xlo); x <= min(b.xf, xhi - 1); ++x)
     for (int y = b.yi; y <= b.yf; ++y) {
-      if (cell_obst(S.cell[node_index(L, x, y)]) != i) continue;
+      const size_t k = node_index(L, x, y);
+      if (cell_obst(S.cell[k]) != i) continue;
 #pragma unroll 1
       for (int q = 1; q < NQ; ++q) {
-        const int ax = x + ex_of(q), ay = y + ey_of(q);
-        if (cell_obst(S.cell[node_index(L, ax, ay)]) == i) continue;
-        force_link<real>(q, G_value(L, S, ax, ay, opp_of(q)), G_value(L, S, x, y, q), x, y, xc, yc, &h1, &h2, &h3);
+        const size_t kn = node_index(L, x + ex_of(q), y + ey_of(q));
+        if (cell_obst(S.cell[kn]) == i) continue;
+        force_link<real>(q, S.A[opp_of(q) * L.plane + kn], S.A[q * L.plane + k], x, y, xc, yc, &h1, &h2, &h3);
       }
     }
   partial[i] = h1; partial[n + i] = h2; partial[2 * n + i] = h3;
@@ -334,7 +452,7 @@ __global__ void verlet_lists_kernel(dem::Params<real> P, int n, const real *x1, 
     }
   vb.nbr_count[i] = cnt;
   vb.wflags[i] = dem::wall_flags(P, xi1, xi2, ri);
-  if (overflow) atomicExch(vb.error, 1);
+  if (overflow) *(volatile int *)vb.error = 1; /* mapped host memory */
 }
 
 template <typename real>
@@ -570,6 +688,10 @@ cudaError_t launch_fill_rest(real *f, size_t plane, const Lattice<real> &Lw, cud
   template cudaError_t launch_raster<real>(const RasterParams<real> &, int, const GrainArrays<real> &, GrainRec<real> *,  \
                                            real *, GrainBox *, int *, int, int, int, cudaStream_t);                      \
   template cudaError_t launch_act_map<real>(const Lattice<real> &, const Stored<real> &, int, int, int *, cudaStream_t);  \
+  template cudaError_t launch_ring_sweep<real>(const Lattice<real> &, const Stored<real> &, real *, int, int,             \
+                                               cudaStream_t);                                                             \
+  template cudaError_t launch_bounce_sweep<real>(const Lattice<real> &, const Stored<real> &, real *, int, int,           \
+                                                 const DeferList<real> &, cudaStream_t);                                  \
   template cudaError_t launch_force_warp<real>(const Lattice<real> &, const Stored<real> &, int, int, long long *,        \
                                                cudaStream_t);                                                             \
   template cudaError_t launch_force_finish<real>(const long long *, int, double, double, real *, real *, real *,          \

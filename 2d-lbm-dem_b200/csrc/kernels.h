@@ -27,25 +27,23 @@ namespace lbmdem {
 
 /* Row pipeline of the fused LBM kernel.  A CTA owns TY consecutive y-columns and marches along
  * x; each TMA transaction brings ONE lattice row of the strip into a ring of NS shared-memory
- * slots: the nine population planes (TY nodes plus a halo of HY nodes per side), the matching
- * row of the stored step's obstacle map (halo HC) and of this step's map (no halo).
+ * slots: the nine population planes (TY nodes plus a halo of HY nodes per side) and the matching
+ * rows of the stored step's and of this step's obstacle map.
  * The TMA unit wants the byte offset of the box origin along the contiguous dimension to be a
  * multiple of 16 (measured on B200: any other inner coordinate raises "illegal instruction",
- * tools/tma_probe.cu), so the y halo is 16 / sizeof(element) nodes wide instead of one. */
+ * tools/tma_probe.cu), so the y halo is 16 / sizeof(real) nodes wide instead of one; a box is at
+ * most 256 elements wide. */
 template <typename real>
 struct RowCfg {
-  static constexpr int TY = 128;            /* nodes (= threads) per CTA row; a TMA box is at most 256 wide */
+  static constexpr int TY = 128;            /* nodes (= threads) per CTA row */
   static constexpr int HY = 16 / (int)sizeof(real);
-  static constexpr int HC = 4;
   static constexpr int NS = (sizeof(real) == 8) ? 6 : 8;   /* ring slots */
   static constexpr int BY = TY + 2 * HY;
-  static constexpr int BC = TY + 2 * HC;
   static constexpr int A_BYTES = lbm::NQ * BY * (int)sizeof(real);
-  static constexpr int CO_BYTES = BC * 4, CN_BYTES = TY * 4;
+  static constexpr int C_BYTES = TY * 4;
   static constexpr int A_PAD = (A_BYTES + 127) / 128 * 128;
-  static constexpr int CO_PAD = (CO_BYTES + 127) / 128 * 128;
-  static constexpr int CN_PAD = (CN_BYTES + 127) / 128 * 128;
-  static constexpr int SLOT = A_PAD + CO_PAD + CN_PAD;
+  static constexpr int C_PAD = (C_BYTES + 127) / 128 * 128;
+  static constexpr int SLOT = A_PAD + 2 * C_PAD;
   static constexpr int SMEM = NS * SLOT;
 };
 
@@ -54,18 +52,29 @@ struct RowCfg {
 constexpr double FORCE_FIX = 4503599627370496.0;   /* 2^52 : fhf1, fhf2 (|sum| < 2^11) */
 constexpr double TORQUE_FIX = 281474976710656.0;   /* 2^48 : fhf3       (|sum| < 2^15) */
 
-/* One fused launch: sweeps 3-5 of the stored step (ring, grain bounce-back, streaming), then
- * sweeps 1-2 of this step (re-init, collide).  out may alias nothing in S. */
+/* One fused launch: sweep 5 of the stored step (streaming, a plain pull from the array the ring
+ * and bounce-back sweeps left behind), then sweeps 1-2 of this step (re-init, collide). */
 template <typename real>
 struct FusedArgs {
   lbm::Lattice<real> L;
-  lbm::Stored<real> S;                     /* step n-1 */
-  const int *cell_new;                     /* obstacle map of step n */
-  const lbm::GrainRec<real> *grains_new;   /* grain records of step n */
+  const real *A;                           /* stored populations, sweeps 1-4 applied, [q][x-x0][y] */
+  const int *cell_prev;                    /* obstacle map of the stored step */
+  const int *cell_new;                     /* obstacle map of this step */
+  const lbm::GrainRec<real> *grains_new;   /* grain records of this step */
   real *out;                               /* [q][x-x0][y] */
   int xlo, xhi;                            /* owned global rows [xlo, xhi) */
+  int stream_only;                         /* 1: sweep 5 alone (materialises the reference's f) */
 };
-enum SlowMode { SLOW_EDGE = 0, SLOW_ALL = 1, SLOW_STREAM_ONLY = 2 };
+
+/* links of the bounce-back sweep that must not be written while others are evaluated */
+template <typename real>
+struct DeferList {
+  int *count;          /* device counter */
+  size_t *index;       /* flat element index into the population buffer */
+  real *value;
+  int capacity;
+  int *overflow;       /* device flag */
+};
 
 template <typename real>
 struct GrainArrays {
@@ -76,13 +85,14 @@ struct GrainArrays {
 /* ---- K1 (two builds of the same source: contraction on = fast, off = strict) ---- */
 #define LBMDEM_DECLARE_K1(NS)                                                                                          \
   namespace NS {                                                                                                       \
-  /* nodes at least two away from the array edge, TMA row pipeline; returns the grid it used */                        \
+  /* interior nodes, TMA row pipeline */                                                                               \
   template <typename real>                                                                                             \
-  cudaError_t launch_lbm_rows(const CUtensorMap &tmA, const CUtensorMap &tmCo, const CUtensorMap &tmCn,                \
+  cudaError_t launch_lbm_rows(const CUtensorMap &tmA, const CUtensorMap &tmCp, const CUtensorMap &tmCn,                \
                               const FusedArgs<real> &a, cudaStream_t s);                                               \
-  /* on-demand evaluation from global memory: edge nodes, or every node (cross-check / stream only) */                 \
+  /* same map from global memory, one thread per node: ring nodes only (ring_only = 1) or every owned node            \
+   * (cross-check of the row kernel, params.kernel = 1) */                                                             \
   template <typename real>                                                                                             \
-  cudaError_t launch_lbm_slow(const FusedArgs<real> &a, int mode, cudaStream_t s);                                     \
+  cudaError_t launch_lbm_plain(const FusedArgs<real> &a, int ring_only, cudaStream_t s);                               \
   /* sweeps 1-2 alone, in place (first step, or after the populations were set from outside) */                        \
   template <typename real>                                                                                             \
   cudaError_t launch_lbm_h1(const lbm::Lattice<real> &L, real *f, const int *cell_prev, const int *cell_now,           \
@@ -102,7 +112,17 @@ cudaError_t launch_cell_frame(int *cell, int lx, int ly, int x0, int nxl, int pi
 template <typename real>
 cudaError_t launch_act_map(const lbm::Lattice<real> &L, const lbm::Stored<real> &S, int xlo, int xhi, int *act_out,
                            cudaStream_t s);
-/* forces_fluid (src/main.c:1295-1325) from the stored state, one warp per grain, fixed-point sums
+/* sweep 3 in place: wall-ring copies (src/main.c:1123-1145), ring nodes of the rows [xa, xb) */
+template <typename real>
+cudaError_t launch_ring_sweep(const lbm::Lattice<real> &L, const lbm::Stored<real> &S, real *A, int xa, int xb,
+                              cudaStream_t s);
+/* sweep 4 in place: interpolated bounce-back on the active solid nodes of the rows [xa, xb)
+ * (src/main.c:1154-1222), one warp per grain; links facing another grain across a one-node gap
+ * go through the deferred list (lbm_node.cuh, sweep_link) */
+template <typename real>
+cudaError_t launch_bounce_sweep(const lbm::Lattice<real> &L, const lbm::Stored<real> &S, real *A, int xa, int xb,
+                                const DeferList<real> &D, cudaStream_t s);
+/* forces_fluid (src/main.c:1295-1325) from the swept state, one warp per grain, fixed-point sums
  * over the links whose solid node lies in the owned rows; overwrites facc[3][n] */
 template <typename real>
 cudaError_t launch_force_warp(const lbm::Lattice<real> &L, const lbm::Stored<real> &S, int xlo, int xhi, long long *facc,

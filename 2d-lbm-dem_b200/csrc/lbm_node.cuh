@@ -238,98 +238,125 @@ LBM_HD void reinit_collide(const Lattice<real> &L, const GrainRec<real> *grains,
 }
 
 /* ------------------------------------------------------------------------------------------
- * Sweeps 3-5 evaluated on demand from the stored state (exact, slow): used for every node by
- * the generic kernel / the host check, for nodes on or next to the wall ring by the edge kernel,
- * for the rare look-back links by the tiled kernel, and by the force kernels.
+ * Sweeps 3-4 (wall ring, grain bounce-back) rewrite a SPARSE set of populations in place: ring
+ * nodes and active solid nodes.  They run as separate small kernels on the stored state; after
+ * them the array holds exactly what the reference holds before its swap passes, and sweep 5
+ * (streaming) is a plain pull (pull_plain).
  * ---------------------------------------------------------------------------------------- */
 template <typename real>
 LBM_HD real A_value(const Lattice<real> &L, const Stored<real> &S, int x, int y, int q) {
   return S.A[q * L.plane + node_index(L, x, y)];
 }
 
-/* ring node content after the wall-ring sweep (:1123-1145).  Order of the reference: rows
- * y=0 / y=ly-1 for x=1..lx-2 reading the pre-sweep state, then columns x=0 / x=lx-1 for
- * y=1..ly-2 reading what the row loop left, then the corners.  The only column reads that hit
- * a row-loop result are the four spelled out below. */
+/* Sweep 3, the wall-ring copies (:1123-1145), in the reference's order and therefore in two
+ * passes that each run in place, one thread per ring node:
+ *   pass 0  rows y = 0 / y = ly-1, x = 1..lx-2  (reads interior nodes and, at the row ends,
+ *           column ring nodes that pass 0 does not write);
+ *   pass 1  columns x = 0 / x = lx-1, y = 1..ly-2 (reads interior nodes and, at the column
+ *           ends, row ring nodes as pass 0 left them), and the four corners.
+ * Returns the new content of population q of ring node (x,y); populations the sweep does not
+ * assign come back unchanged. */
 template <typename real>
-LBM_HD_SLOW real ring_value(const Lattice<real> &L, const Stored<real> &S, int x, int y, int q) {
+LBM_HD real ring_value(const Lattice<real> &L, const Stored<real> &S, int pass, int x, int y, int q) {
   const int lx = L.lx, ly = L.ly;
   const bool xin = x >= 1 && x <= lx - 2, yin = y >= 1 && y <= ly - 2;
-  if (y == 0 && xin) {
-    if (q == 8) return A_value(L, S, x, 1, 4);
-    if (q == 7) return A_value(L, S, x + 1, 1, 3);
-    if (q == 1) return A_value(L, S, x - 1, 1, 5);
-  } else if (y == ly - 1 && xin) {
-    if (q == 4) return A_value(L, S, x, ly - 2, 8);
-    if (q == 3) return A_value(L, S, x - 1, ly - 2, 7) - L.lid6;
-    if (q == 5) return A_value(L, S, x + 1, ly - 2, 1) + L.lid6;
-  } else if (x == 0 && yin) {
-    if (q == 6) return A_value(L, S, 1, y, 2);
-    if (q == 7) return (y + 1 == ly - 1) ? (real)(A_value(L, S, 0, ly - 2, 7) - L.lid6) : A_value(L, S, 1, y + 1, 3);
-    if (q == 5) return (y - 1 == 0) ? A_value(L, S, 0, 1, 5) : A_value(L, S, 1, y - 1, 1);
-  } else if (x == lx - 1 && yin) {
-    if (q == 2) return A_value(L, S, lx - 2, y, 6);
-    if (q == 3) return (y - 1 == 0) ? A_value(L, S, lx - 1, 1, 3) : A_value(L, S, lx - 2, y - 1, 7);
-    if (q == 1)
-      return (y + 1 == ly - 1) ? (real)(A_value(L, S, lx - 1, ly - 2, 1) + L.lid6) : A_value(L, S, lx - 2, y + 1, 5);
-  } else if (x == 0 && y == 0) {
-    if (q == 7) return A_value(L, S, 1, 1, 3);
-  } else if (x == lx - 1 && y == 0) {
-    if (q == 1) return A_value(L, S, lx - 2, 1, 5);
-  } else if (x == 0 && y == ly - 1) {
-    if (q == 5) return A_value(L, S, 1, ly - 2, 1);
-  } else if (x == lx - 1 && y == ly - 1) {
-    if (q == 3) return A_value(L, S, lx - 2, ly - 2, 7);
+  if (pass == 0) {
+    if (y == 0 && xin) {
+      if (q == 8) return A_value(L, S, x, 1, 4);
+      if (q == 7) return A_value(L, S, x + 1, 1, 3);
+      if (q == 1) return A_value(L, S, x - 1, 1, 5);
+    } else if (y == ly - 1 && xin) {
+      if (q == 4) return A_value(L, S, x, ly - 2, 8);
+      if (q == 3) return A_value(L, S, x - 1, ly - 2, 7) - L.lid6;
+      if (q == 5) return A_value(L, S, x + 1, ly - 2, 1) + L.lid6;
+    }
+  } else {
+    if (x == 0 && yin) {
+      if (q == 6) return A_value(L, S, 1, y, 2);
+      if (q == 7) return A_value(L, S, 1, y + 1, 3);
+      if (q == 5) return A_value(L, S, 1, y - 1, 1);
+    } else if (x == lx - 1 && yin) {
+      if (q == 2) return A_value(L, S, lx - 2, y, 6);
+      if (q == 3) return A_value(L, S, lx - 2, y - 1, 7);
+      if (q == 1) return A_value(L, S, lx - 2, y + 1, 5);
+    } else if (x == 0 && y == 0) {
+      if (q == 7) return A_value(L, S, 1, 1, 3);
+    } else if (x == lx - 1 && y == 0) {
+      if (q == 1) return A_value(L, S, lx - 2, 1, 5);
+    } else if (x == 0 && y == ly - 1) {
+      if (q == 5) return A_value(L, S, 1, ly - 2, 1);
+    } else if (x == lx - 1 && y == ly - 1) {
+      if (q == 3) return A_value(L, S, lx - 2, ly - 2, 7);
+    }
   }
   return A_value(L, S, x, y, q);
 }
 
-/* content of node (x,y), population q, after sweeps 1-3 (what the grain sweep reads) */
+/* is (x,y) an interior solid node with act == 1 ? */
 template <typename real>
-LBM_HD real state3(const Lattice<real> &L, const Stored<real> &S, int x, int y, int q) {
-  return is_ring(L, x, y) ? ring_value(L, S, x, y, q) : A_value(L, S, x, y, q);
+LBM_HD bool is_active_solid(const Lattice<real> &L, const Stored<real> &S, int x, int y) {
+  if (is_ring(L, x, y)) return false;
+  const int c = S.cell[node_index(L, x, y)];
+  return !cell_is_fluid(c) && node_act(L, S, x, y, c);
 }
 
-/* content of node (x,y), population q, after the grain bounce-back sweep (:1154-1222).
- * NESTED marks the one level of look-back the serial sweep allows: when the second fluid-
- * side node nn of a short link (delta < 1/2) is itself an active solid node that the x-outer,
- * y-inner sweep visited earlier, the reference reads its already-updated value. */
-template <typename real, bool NESTED = false>
-LBM_HD_SLOW real G_value(const Lattice<real> &L, const Stored<real> &S, int x, int y, int q) {
-  if (is_ring(L, x, y)) return ring_value(L, S, x, y, q);
-  const int cn = S.cell[node_index(L, x, y)];
-  if (cell_is_fluid(cn) || q == 0 || !node_act(L, S, x, y, cn)) return A_value(L, S, x, y, q);
+/* Sweep 4, one link (s = (x,y) an ACTIVE interior solid node, q = 1..8) of the grain bounce-back
+ * sweep (:1154-1222).  The reference runs it serially, x outer, y inner, in place; the only read
+ * that can see another link's result is X = f[nn][opp q] of a short link (delta < 1/2) whose
+ * second fluid-side node nn = s + 2 e_q is itself an active solid node (a one-node gap between
+ * two grains): the reference then reads the partner's NEW value if nn was swept earlier, its old
+ * value otherwise.
+ *
+ *   SWEEP_KEEP   the link leaves f[s][q] untouched (delta <= 0)
+ *   SWEEP_WRITE  *v is the new f[s][q]
+ *   SWEEP_DEFER  (only when resolve == false) the link faces an active solid node across a
+ *                one-node gap: its partner link (nn, opp q) may read f[s][q], so it must not be
+ *                written while other links are still being evaluated.  Calling again with
+ *                resolve == true evaluates it from the pre-sweep state alone (the partner's new
+ *                value, where the reference would have seen it, is recomputed from that state).
+ * Reads: A at fluid nodes, ring nodes (ring sweep already applied), and pre-sweep values of
+ * deferred links -- none of which a concurrent in-place pass over the other links modifies. */
+enum { SWEEP_KEEP = 0, SWEEP_WRITE = 1, SWEEP_DEFER = 2 };
+
+template <typename real>
+LBM_HD_SLOW int sweep_link(const Lattice<real> &L, const Stored<real> &S, int x, int y, int q, bool resolve, real *v) {
   const int ex = ex_of(q), ey = ey_of(q), oq = opp_of(q);
   const int nx = x + ex, ny = y + ey;
-  if (!cell_is_fluid(S.cell[node_index(L, nx, ny)])) return L.w[q];
-  const GrainRec<real> g = S.grains[cell_obst(cn)];
+  if (!cell_is_fluid(S.cell[node_index(L, nx, ny)])) { /* :1161-1162 */
+    *v = L.w[q];
+    return SWEEP_WRITE;
+  }
+  const int nnx = nx + ex, nny = ny + ey; /* inside the array: n is an interior node */
+  const bool gap = is_active_solid(L, S, nnx, nny);
+  if (gap && !resolve) return SWEEP_DEFER;
+  const GrainRec<real> g = S.grains[cell_obst(S.cell[node_index(L, x, y)])];
   const real d = link_delta(g, x, y, q);
+  if (!(d > 0.)) return SWEEP_KEEP;
   const real eu = ex * wall_ux(L, g, y) + ey * wall_uy(L, g, x);
   const real Fn_q = A_value(L, S, nx, ny, q), Fn_oq = A_value(L, S, nx, ny, oq);
   real X = 0;
-  if (d > 0. && d < 0.5) {
-    const int nnx = nx + ex, nny = ny + ey;
-    bool look_back = false;
-    if (!NESTED && !is_ring(L, nnx, nny)) {
-      const int cnn = S.cell[node_index(L, nnx, nny)];
-      look_back = (nnx < x || (nnx == x && nny < y)) && node_act(L, S, nnx, nny, cnn);
-    }
-    if constexpr (!NESTED) {
-      X = look_back ? G_value<real, true>(L, S, nnx, nny, oq) : state3(L, S, nnx, nny, oq);
-    } else {
-      X = state3(L, S, nnx, nny, oq);
+  if (d < 0.5) {
+    X = A_value(L, S, nnx, nny, oq);
+    if (gap && (nnx < x || (nnx == x && nny < y))) {
+      /* the partner link (nn, opp q) was swept earlier: its new value, from the pre-sweep state.
+       * Its fluid neighbour is n, its second fluid-side node is s itself. */
+      const GrainRec<real> gp = S.grains[cell_obst(S.cell[node_index(L, nnx, nny)])];
+      const real dp = link_delta(gp, nnx, nny, oq);
+      const real eup = ex_of(oq) * wall_ux(L, gp, nny) + ey_of(oq) * wall_uy(L, gp, nnx);
+      X = bounce_value(L, oq, dp, Fn_q, Fn_oq, A_value(L, S, x, y, q), eup, X);
     }
   }
-  return bounce_value(L, q, d, Fn_oq, Fn_q, X, eu, (d > 0.) ? (real)0 : A_value(L, S, x, y, q));
+  *v = bounce_value(L, q, d, Fn_oq, Fn_q, X, eu, (real)0);
+  return SWEEP_WRITE;
 }
 
-/* the streamed value: what the two swap passes leave in f[x][y][q] (:1224-1242) */
+/* Sweep 5, the streamed value: what the two swap passes leave in f[x][y][q] (:1224-1242), from
+ * the array as it stands after sweeps 1-4. */
 template <typename real>
-LBM_HD real pull_value(const Lattice<real> &L, const Stored<real> &S, int x, int y, int q) {
-  if (q == 0) return G_value(L, S, x, y, 0);
+LBM_HD real pull_plain(const Lattice<real> &L, const real *A, int x, int y, int q) {
   const int sx = x - ex_of(q), sy = y - ey_of(q);
-  if (!in_array(L, sx, sy)) return G_value(L, S, x, y, opp_of(q));
-  return G_value(L, S, sx, sy, q);
+  if (q == 0 || !in_array(L, sx, sy)) return A[opp_of(q) * L.plane + node_index(L, x, y)];
+  return A[q * L.plane + node_index(L, sx, sy)];
 }
 
 /* One boundary link of forces_fluid (src/main.c:1313-1320).  fs_oq = f_new[s][opp q] and

@@ -6,18 +6,21 @@
  * Device layout (DESIGN.md "data layout"):
  *   f[2]     double-buffered populations, structure of arrays [q][x - x0][y], y contiguous, rows
  *            padded to a multiple of 32 elements (128-byte aligned rows, TMA-legal strides).
- *            Between LBM steps f[cur] holds "A": the populations of the last step after its
- *            re-init and collide sweeps (holds_A); the reference's observable f[x][y][q] -- the
- *            same step after bounce-back and streaming -- is materialised into the other buffer
- *            only when somebody asks for it (get_f, fields, density).
+ *            Between LBM steps f[cur] holds the populations of the last step as the reference
+ *            holds them just before its swap passes (holds_A: re-init, collide, ring and
+ *            bounce-back sweeps applied); the reference's observable f[x][y][q] -- the same
+ *            array after streaming -- is materialised into the other buffer only when somebody
+ *            asks for it (get_f, fields, density).
  *   cell[2]  obstacle map [x - x0][y] (int32: -1 fluid, grain index | act bit, nbgrains = wall
  *            ring) of the last two steps, with the grain records rec[2]/R2[2]/boxes[2] that
  *            produced them: the fused kernel streams with the stored step's map and records
  *            and collides with the new ones (reinit_obst_density reads the old map, :970)
  *   grains   structure of arrays of `real`, replicated on every rank
  * Strip decomposition: rank k of P owns the global rows [xlo, xhi); with P > 1 the local arrays
- * carry three extra rows on each side (x0 = xlo - 3): A needs two ghost rows (exchanged after
- * every LBM step), the obstacle map three (recomputed locally, grains are replicated).
+ * carry GHOST = 4 extra rows on each side (x0 = xlo - 4).  The populations of the ghost rows are
+ * exchanged once per LBM step, right after the fused kernel; the obstacle map of the ghost rows
+ * is recomputed locally (grains are replicated).  Each rank then applies the ring and bounce-back
+ * sweeps to its owned rows plus one ghost row per side, which is all the next pull reads.
  */
 #include <dlfcn.h>
 #include <math.h>
@@ -147,7 +150,9 @@ struct Sim : SimBase {
   int cur = 0, cur_cell = 0;
   bool holds_A = false;      /* f[cur] holds A of the last step (stream pending) instead of f */
   bool scratch_valid = false; /* f[1 - cur] holds the materialised f of the pending stream */
-  CUtensorMap tmA[2], tmCo[2], tmCn[2];
+  CUtensorMap tmA[2], tmC[2];
+  DeferList<real> defer{};
+  int *hflags = nullptr;      /* mapped host memory: [0] Verlet capacity exceeded, [1] deferred-link list full */
   std::vector<real *> grain_bufs;
   GrainArrays<real> g{};
   GrainRec<real> *rec[2] = {nullptr, nullptr}; /* indexed like cell[] */
@@ -179,14 +184,16 @@ struct Sim : SimBase {
     for (int k = 0; k < 2; ++k) { cudaFree(rec[k]); cudaFree(R2[k]); cudaFree(boxes[k]); }
     cudaFree(facc); cudaFree(fpartial);
     cudaFree(vb.bucket_count); cudaFree(vb.bucket_cursor); cudaFree(vb.sorted); cudaFree(vb.gcx); cudaFree(vb.gcy);
-    cudaFree(vb.nbr_count); cudaFree(vb.nbr); cudaFree(vb.wflags); cudaFree(vb.error);
+    cudaFree(vb.nbr_count); cudaFree(vb.nbr); cudaFree(vb.wflags);
     cudaFree(dens_partials); cudaFree(dens_out); cudaFree(stage);
+    cudaFree(defer.count); cudaFree(defer.index); cudaFree(defer.value);
+    if (hflags) cudaFreeHost(hflags);
     if (hstage) cudaFreeHost(hstage);
     if (stream) cudaStreamDestroy(stream);
   }
 
   static constexpr int DENS_BLOCKS = 1184; /* 8 x 148 SMs */
-  static constexpr int GHOST = 3;          /* extra rows per side of a strip (map); A uses 2 of them */
+  static constexpr int GHOST = 4;          /* extra rows per side of a strip */
 
   int init_device() override {
     int ndev = 0;
@@ -236,14 +243,13 @@ struct Sim : SimBase {
       if (r != CUDA_SUCCESS) return fail(LBMDEM_ECUDA, "cuTensorMapEncodeTiled(f) failed with code " + std::to_string((int)r));
       const cuuint64_t cdims[2] = {(cuuint64_t)ly, (cuuint64_t)nxl};
       const cuuint64_t cstr[1] = {(cuuint64_t)pitch * sizeof(int)};
-      const cuuint32_t cbox_o[2] = {(cuuint32_t)C::BC, 1}, cbox_n[2] = {(cuuint32_t)C::TY, 1};
-      r = encode(&tmCo[k], CU_TENSOR_MAP_DATA_TYPE_INT32, 2, cell[k], cdims, cstr, cbox_o, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+      const cuuint32_t cbox[2] = {(cuuint32_t)C::TY, 1};
+      r = encode(&tmC[k], CU_TENSOR_MAP_DATA_TYPE_INT32, 2, cell[k], cdims, cstr, cbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (r == CUDA_SUCCESS)
-        r = encode(&tmCn[k], CU_TENSOR_MAP_DATA_TYPE_INT32, 2, cell[k], cdims, cstr, cbox_n, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return fail(LBMDEM_ECUDA, "cuTensorMapEncodeTiled(map) failed with code " + std::to_string((int)r));
     }
+    CK(cudaHostAlloc(&hflags, 2 * sizeof(int), cudaHostAllocMapped));
+    hflags[0] = hflags[1] = 0;
     CK(cudaStreamSynchronize(stream));
     return 0;
   }
@@ -272,7 +278,7 @@ struct Sim : SimBase {
     CK(cudaMemsetAsync(facc, 0, sizeof(long long) * 3 * n, stream));
     CK(cudaMalloc(&fpartial, sizeof(double) * 3 * n));
     cudaFree(vb.bucket_count); cudaFree(vb.bucket_cursor); cudaFree(vb.sorted); cudaFree(vb.gcx); cudaFree(vb.gcy);
-    cudaFree(vb.nbr_count); cudaFree(vb.nbr); cudaFree(vb.wflags); cudaFree(vb.error);
+    cudaFree(vb.nbr_count); cudaFree(vb.nbr); cudaFree(vb.wflags);
     int nb = 1024;
     while (nb < 2 * n) nb <<= 1;
     vb.nbuckets = nb;
@@ -287,8 +293,13 @@ struct Sim : SimBase {
     CK(cudaMalloc(&vb.nbr, sizeof(int) * (size_t)n * vb.cap));
     CK(cudaMalloc(&vb.wflags, sizeof(int) * n));
     CK(cudaMemsetAsync(vb.wflags, 0, sizeof(int) * n, stream));
-    CK(cudaMalloc(&vb.error, sizeof(int)));
-    CK(cudaMemsetAsync(vb.error, 0, sizeof(int), stream));
+    CK(cudaHostGetDevicePointer(&vb.error, hflags, 0));
+    cudaFree(defer.count); cudaFree(defer.index); cudaFree(defer.value);
+    defer.capacity = std::max(65536, 64 * n);
+    CK(cudaMalloc(&defer.count, sizeof(int)));
+    CK(cudaMalloc(&defer.index, sizeof(size_t) * defer.capacity));
+    CK(cudaMalloc(&defer.value, sizeof(real) * defer.capacity));
+    CK(cudaHostGetDevicePointer(&defer.overflow, hflags + 1, 0));
     if (hstage) cudaFreeHost(hstage);
     hstage_elems = (size_t)n * 16;
     CK(cudaMallocHost(&hstage, sizeof(double) * hstage_elems));
@@ -435,8 +446,8 @@ struct Sim : SimBase {
     return fail(LBMDEM_ENCCL, std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
   }
 
-  /* two ghost rows of A per side: the fused kernel of the next step pulls from
-   * one of them, the force kernel's short links reach into the second */
+  /* GHOST rows of populations per side, as the fused kernel left them: the ring
+   * and bounce-back sweeps that follow reach that far beyond the rows they write */
   int halo_exchange() {
     if (P.nranks == 1) return 0;
     if (!comm) return fail(LBMDEM_ESTATE, "nranks > 1 but no communicator attached (lbmdem_attach_nccl)");
@@ -444,17 +455,17 @@ struct Sim : SimBase {
     int r = g_nccl.GroupStart();
     if (r) return nccl_fail(r, "ncclGroupStart");
     real *F = f[cur];
-    const size_t two = (size_t)2 * pitch; /* two consecutive rows are contiguous */
+    const size_t cnt = (size_t)GHOST * pitch; /* consecutive rows are contiguous */
     for (int q = 0; q < NQ && !r; ++q) {
       real *pl = F + (size_t)q * plane;
-      if (P.rank > 0) { /* left neighbour: send the first two owned rows, receive into the ghost rows below them */
-        r = g_nccl.Send(pl + (size_t)GHOST * pitch, two, dtype, P.rank - 1, comm, stream);
-        if (!r) r = g_nccl.Recv(pl + (size_t)(GHOST - 2) * pitch, two, dtype, P.rank - 1, comm, stream);
+      if (P.rank > 0) { /* left neighbour: send the first owned rows, receive into the ghost rows below them */
+        r = g_nccl.Send(pl + (size_t)GHOST * pitch, cnt, dtype, P.rank - 1, comm, stream);
+        if (!r) r = g_nccl.Recv(pl, cnt, dtype, P.rank - 1, comm, stream);
       }
       if (!r && P.rank < P.nranks - 1) {
         const int end = xhi - x0; /* local row just past the owned rows */
-        r = g_nccl.Send(pl + (size_t)(end - 2) * pitch, two, dtype, P.rank + 1, comm, stream);
-        if (!r) r = g_nccl.Recv(pl + (size_t)end * pitch, two, dtype, P.rank + 1, comm, stream);
+        r = g_nccl.Send(pl + (size_t)(end - GHOST) * pitch, cnt, dtype, P.rank + 1, comm, stream);
+        if (!r) r = g_nccl.Recv(pl + (size_t)end * pitch, cnt, dtype, P.rank + 1, comm, stream);
       }
     }
     const int r2 = g_nccl.GroupEnd();
@@ -492,22 +503,43 @@ struct Sim : SimBase {
     return 0;
   }
 
-  FusedArgs<real> fused_args(int out_buf) const {
+  FusedArgs<real> fused_args(int out_buf, int stream_only) const {
     FusedArgs<real> a;
     a.L = lattice();
-    a.S = stored(cur, 1 - cur_cell);
+    a.A = f[cur];
+    a.cell_prev = cell[1 - cur_cell];
     a.cell_new = cell[cur_cell];
     a.grains_new = rec[cur_cell];
     a.out = f[out_buf];
     a.xlo = xlo; a.xhi = xhi;
+    a.stream_only = stream_only;
     return a;
+  }
+  /* sweep 5 of the stored array (+ sweeps 1-2 of the new step unless stream_only) into f[1 - cur] */
+  int launch_fused(int stream_only, bool timed) {
+    const FusedArgs<real> a = fused_args(1 - cur, stream_only);
+    if (P.kernel == 1) {
+      CK(P.strict_fp ? k1_strict::launch_lbm_plain<real>(a, 0, stream) : k1_fast::launch_lbm_plain<real>(a, 0, stream));
+      ++all_launches;
+      return 0;
+    }
+    std::pair<cudaEvent_t, cudaEvent_t> *ev = nullptr;
+    int rc;
+    if (timed && (rc = record_k1_begin(&ev))) return rc;
+    CK(P.strict_fp ? k1_strict::launch_lbm_rows<real>(tmA[cur], tmC[1 - cur_cell], tmC[cur_cell], a, stream)
+                   : k1_fast::launch_lbm_rows<real>(tmA[cur], tmC[1 - cur_cell], tmC[cur_cell], a, stream));
+    if (ev) CK(cudaEventRecord(ev->second, stream));
+    if (timed) ++k1_launches;
+    CK(P.strict_fp ? k1_strict::launch_lbm_plain<real>(a, 1, stream) : k1_fast::launch_lbm_plain<real>(a, 1, stream));
+    all_launches += 2;
+    return 0;
   }
 
   /* the LBM part of renderScene (:1711-1717), asynchronous on `stream` */
   int lbm_step_async() {
     if (!ready) return fail(LBMDEM_ESTATE, "no grains loaded");
     int rc;
-    cur_cell ^= 1; /* the rasteriser writes the other map; the previous one stays with the stored state */
+    cur_cell ^= 1; /* the rasteriser writes the other map; the previous one stays with the stored array */
     if ((rc = raster_into(cur_cell))) return rc;
     all_launches += 3; /* grain_prepare, raster, act_fold (memsets not counted) */
     scratch_valid = false;
@@ -519,36 +551,28 @@ struct Sim : SimBase {
       ++all_launches;
       holds_A = true;
     } else {
-      const FusedArgs<real> a = fused_args(1 - cur);
-      if (P.kernel == 1) {
-        CK(P.strict_fp ? k1_strict::launch_lbm_slow<real>(a, SLOW_ALL, stream) : k1_fast::launch_lbm_slow<real>(a, SLOW_ALL, stream));
-        ++all_launches;
-      } else {
-        std::pair<cudaEvent_t, cudaEvent_t> *ev;
-        if ((rc = record_k1_begin(&ev))) return rc;
-        CK(P.strict_fp ? k1_strict::launch_lbm_rows<real>(tmA[cur], tmCo[1 - cur_cell], tmCn[cur_cell], a, stream)
-                       : k1_fast::launch_lbm_rows<real>(tmA[cur], tmCo[1 - cur_cell], tmCn[cur_cell], a, stream));
-        if (ev) CK(cudaEventRecord(ev->second, stream));
-        ++k1_launches;
-        CK(P.strict_fp ? k1_strict::launch_lbm_slow<real>(a, SLOW_EDGE, stream) : k1_fast::launch_lbm_slow<real>(a, SLOW_EDGE, stream));
-        all_launches += 2;
-      }
+      if ((rc = launch_fused(0, true))) return rc;
       cur ^= 1;
     }
     if ((rc = halo_exchange())) return rc;
-    /* forces_fluid of this step (:1285-1333), from the state just stored */
+    /* sweeps 3-4 in place (ring :1123-1145, grain bounce-back :1154-1222), then forces_fluid (:1285-1333) */
     const Lattice<real> L = lattice();
     const Stored<real> S = stored(cur, cur_cell);
+    const bool multi = P.nranks > 1;
+    CK(launch_ring_sweep<real>(L, S, f[cur], multi ? std::max(xlo - 3, 0) : 0, multi ? std::min(xhi + 3, lx) : lx, stream));
+    CK(launch_bounce_sweep<real>(L, S, f[cur], std::max(multi ? xlo - 1 : xlo, 1), std::min(multi ? xhi + 1 : xhi, lx - 1), defer,
+                                 stream));
+    all_launches += 3;
     if (P.strict_fp) {
       CK(launch_force_serial<real>(L, S, xlo, xhi, fpartial, stream));
-      if (P.nranks > 1) {
+      if (multi) {
         const int r = g_nccl.AllReduce(fpartial, fpartial, (size_t)3 * n, NcclApi::Float64, NcclApi::Sum, comm, stream);
         if (r) return nccl_fail(r, "ncclAllReduce");
       }
       CK(launch_force_scale<real>(fpartial, n, k12, k3, g.fhf1, g.fhf2, g.fhf3, stream));
     } else {
       CK(launch_force_warp<real>(L, S, xlo, xhi, facc, stream));
-      if (P.nranks > 1) { /* integer sum: exact, identical on every rank, independent of the decomposition */
+      if (multi) { /* integer sum: exact, identical on every rank, independent of the decomposition */
         const int r = g_nccl.AllReduce(facc, facc, (size_t)3 * n, NcclApi::Int64, NcclApi::Sum, comm, stream);
         if (r) return nccl_fail(r, "ncclAllReduce");
       }
@@ -559,14 +583,12 @@ struct Sim : SimBase {
   }
 
   /* The reference's f[x][y][q] as of now.  While a stream is pending it is materialised into the
-   * other population buffer (sweeps 3-5 of the stored step, nothing else); the state is untouched. */
+   * other population buffer (sweep 5 of the stored array, nothing else); the state is untouched. */
   int observable_f(const real **out) {
     if (!holds_A) { *out = f[cur]; return 0; }
     if (!scratch_valid) {
-      FusedArgs<real> a = fused_args(1 - cur);
-      a.S = stored(cur, cur_cell); /* the stored step IS the current one */
-      CK(P.strict_fp ? k1_strict::launch_lbm_slow<real>(a, SLOW_STREAM_ONLY, stream)
-                     : k1_fast::launch_lbm_slow<real>(a, SLOW_STREAM_ONLY, stream));
+      int rc = launch_fused(1, false);
+      if (rc) return rc;
       scratch_valid = true;
     }
     *out = f[1 - cur];
@@ -581,6 +603,14 @@ struct Sim : SimBase {
     cur ^= 1;
     holds_A = false;
     scratch_valid = false;
+    return 0;
+  }
+
+  /* error flags the kernels raise in mapped host memory; valid after a stream synchronise */
+  int check_flags() {
+    CK(cudaStreamSynchronize(stream));
+    if (hflags[0]) { hflags[0] = 0; return fail(LBMDEM_ECAP, "a grain has more Verlet neighbours than neighbour_capacity"); }
+    if (hflags[1]) { hflags[1] = 0; return fail(LBMDEM_ECAP, "deferred bounce-back link list is full"); }
     return 0;
   }
 
@@ -600,13 +630,7 @@ struct Sim : SimBase {
     return 0;
   }
 
-  int check_verlet_overflow() {
-    int flag = 0;
-    CK(cudaMemcpyAsync(&flag, vb.error, sizeof(int), cudaMemcpyDeviceToHost, stream));
-    CK(cudaStreamSynchronize(stream));
-    if (flag) return fail(LBMDEM_ECAP, "a grain has more Verlet neighbours than neighbour_capacity");
-    return 0;
-  }
+  int check_verlet_overflow() { return check_flags(); }
 
   int step_async(long nsteps, bool *built) {
     for (long k = 0; k < nsteps; ++k) {
@@ -630,23 +654,20 @@ struct Sim : SimBase {
     bool built = false;
     int rc = step_async(nsteps, &built);
     if (rc) return rc;
-    if (built) return check_verlet_overflow();
-    CK(cudaStreamSynchronize(stream));
-    return 0;
+    (void)built;
+    return check_flags();
   }
   int lbm_step() override {
     int rc = lbm_step_async();
     if (rc) return rc;
-    CK(cudaStreamSynchronize(stream));
-    return 0;
+    return check_flags();
   }
   int lbm_steps(long k) override {
     for (long i = 0; i < k; ++i) {
       int rc = lbm_step_async();
       if (rc) return rc;
     }
-    CK(cudaStreamSynchronize(stream));
-    return 0;
+    return check_flags();
   }
   int build_verlet() override {
     int rc = verlet_async();
@@ -851,11 +872,8 @@ struct Sim : SimBase {
       CK(launch_density<real>(obs, ly, x0, xlo, xhi, pitch, plane, dens_partials, DENS_BLOCKS, dens_out, stream));
       CK(cudaMemcpyAsync(dens, dens_out, sizeof(double), cudaMemcpyDeviceToHost, stream));
     }
-    if (built) {
-      if ((rc = check_verlet_overflow())) return rc;
-    } else {
-      CK(cudaStreamSynchronize(stream));
-    }
+    (void)built;
+    if ((rc = check_flags())) return rc;
     if (state_out)
       for (int k = 0; k < 9; ++k)
         for (int i = 0; i < n; ++i) state_out[(size_t)i * 9 + k] = hs[(size_t)k * n + i];

@@ -23,6 +23,7 @@ using namespace lbm;
 
 namespace {
 
+int g_last_deferred = 0;
 int g_act_folded = 1; /* 0: hand the on-demand path a bare obstacle map (what the device kernels get) */
 
 /* K2 on the host: owner = highest-index covering grain, then the act rule. */
@@ -111,10 +112,36 @@ int lbm_step_host(int lx, int ly, int n, const double *scal, const double *grain
   S.cell = g_act_folded ? cell_new.data() : cell_bare.data();
   S.boxes = box.data(); S.R2 = R2v.data(); S.act_folded = g_act_folded;
 
-  /* sweeps 3-5 on demand from the stored state */
+  /* sweep 3 in place, two passes, one "thread" per ring node, nodes in reverse order */
+  for (int pass = 0; pass < 2; ++pass)
+    for (int x = lx - 1; x >= 0; --x)
+      for (int y = ly - 1; y >= 0; --y) {
+        if (!is_ring(L, x, y)) continue;
+        real v[NQ];
+        for (int q = 1; q < NQ; ++q) v[q] = ring_value(L, S, pass, x, y, q);
+        for (int q = 1; q < NQ; ++q) A[q * nn + (size_t)x * ly + y] = v[q];
+      }
+  /* sweep 4 in place, the way the device does it: links in ARBITRARY order (here: reversed, the
+   * opposite of the reference's sweep), gap links through the deferred list */
+  std::vector<std::pair<size_t, real>> deferred;
+  for (int x = lx - 2; x >= 1; --x)
+    for (int y = ly - 2; y >= 1; --y) {
+      if (!is_active_solid(L, S, x, y)) continue;
+      for (int q = NQ - 1; q >= 1; --q) {
+        real v;
+        int r = sweep_link(L, S, x, y, q, false, &v);
+        const size_t e = q * nn + (size_t)x * ly + y;
+        if (r == SWEEP_WRITE) A[e] = v;
+        else if (r == SWEEP_DEFER && sweep_link(L, S, x, y, q, true, &v) == SWEEP_WRITE) deferred.emplace_back(e, v);
+      }
+    }
+  for (auto &d : deferred) A[d.first] = d.second;
+  g_last_deferred = (int)deferred.size();
+
+  /* sweep 5: plain pull */
   for (int x = 0; x < lx; ++x)
     for (int y = 0; y < ly; ++y)
-      for (int q = 0; q < NQ; ++q) fn[q * nn + (size_t)x * ly + y] = pull_value(L, S, x, y, q);
+      for (int q = 0; q < NQ; ++q) fn[q * nn + (size_t)x * ly + y] = pull_plain(L, A.data(), x, y, q);
 
   for (size_t k = 0; k < nn; ++k) {
     for (int q = 0; q < NQ; ++q) f_out[k * NQ + q] = fn[q * nn + k];
@@ -134,8 +161,8 @@ int lbm_step_host(int lx, int ly, int n, const double *scal, const double *grain
         for (int q = 1; q < NQ; ++q) {
           const int ax = x + ex_of(q), ay = y + ey_of(q);
           if (cell_obst(cell_new[(size_t)ax * ly + ay]) == i) continue;
-          /* f_new[s][opp q] = G[n][opp q] and f_new[n][q] = G[s][q]: evaluated before streaming, as the device does */
-          const real fs_oq = G_value(L, S, ax, ay, opp_of(q)), fn_q = G_value(L, S, x, y, q);
+          /* f_new[s][opp q] = A[n][opp q] and f_new[n][q] = A[s][q]: read before streaming, as the device does */
+          const real fs_oq = A[opp_of(q) * nn + (size_t)ax * ly + ay], fn_q = A[q * nn + (size_t)x * ly + y];
           if (fs_oq != fn[opp_of(q) * nn + (size_t)x * ly + y] || fn_q != fn[q * nn + (size_t)ax * ly + ay]) return -2;
           force_link<real>(q, fs_oq, fn_q, x, y, xc, yc, &h1, &h2, &h3);
         }
@@ -215,6 +242,7 @@ int dem_step_host(int n, const double *par /* see below */, int film, double *st
 extern "C" {
 #define EXPORT __attribute__((visibility("default")))
 EXPORT void hc_set_act_folded(int v) { g_act_folded = v; }
+EXPORT int hc_last_deferred(void) { return g_last_deferred; }
 /* scal: dx c Mgx Mby lid */
 EXPORT int hc_lbm_step_f64(int lx, int ly, int n, const double *scal, const double *grains, const double *f_in,
                            const int *obst_old, double *f_out, int *obst_new, int *act_new, double *fhf) {

@@ -90,6 +90,8 @@ def test_lbm_step_formulation_dense_scaled():
     # many small grains: one-node gaps between reduced discs, short links reading ring / solid nodes
     info = _lbm_case("f64", 96, 80, 1.0, seed=30, steps=3, n_target=120)
     assert info["n"] >= 60
+    # links across one-node gaps went through the deferred list (evaluated in reverse sweep order)
+    assert load_hostcheck().hc_last_deferred() > 100
 
 
 def _dem_params(sc):
