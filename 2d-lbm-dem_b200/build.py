@@ -3,7 +3,8 @@
     python 2d-lbm-dem_b200/build.py [-v] [--force]
 
 Translation units:
-  csrc/lbm_kernels.cu   twice: -DK1_NS=k1_fast (contraction on) and -DK1_NS=k1_strict (-fmad=false)
+  csrc/lbm_kernels.cu   twice: -DK1_NS=k1_fast -DLBM_RELAXED (contraction on, shared reciprocals) and
+                        -DK1_NS=k1_strict (-fmad=false, the reference's expressions verbatim)
   csrc/aux_kernels.cu   -fmad=false (bit-exact obstacle map and DEM step)
   csrc/sim.cu           host orchestration + C ABI (include/lbmdem_gpu.h)
 """
@@ -23,7 +24,7 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", *ARCH, "-Xcompiler", "-fPIC,-fvisibi
 HEADERS = ["kernels.h", "lbm_node.cuh", "raster_node.cuh", "dem_node.cuh"]
 
 UNITS = [
-    ("lbm_kernels_fast.o", "lbm_kernels.cu", ["-DK1_NS=k1_fast"]),
+    ("lbm_kernels_fast.o", "lbm_kernels.cu", ["-DK1_NS=k1_fast", "-DLBM_RELAXED"]),
     ("lbm_kernels_strict.o", "lbm_kernels.cu", ["-DK1_NS=k1_strict", "-fmad=false"]),
     ("aux_kernels.o", "aux_kernels.cu", ["-fmad=false"]),
     ("sim.o", "sim.cu", ["-fmad=false"]),

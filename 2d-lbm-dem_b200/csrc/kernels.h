@@ -37,7 +37,7 @@ template <typename real>
 struct RowCfg {
   static constexpr int TY = 128;            /* nodes (= threads) per CTA row */
   static constexpr int HY = 16 / (int)sizeof(real);
-  static constexpr int NS = (sizeof(real) == 8) ? 6 : 8;   /* ring slots */
+  static constexpr int NS = 6;              /* ring slots */
   static constexpr int BY = TY + 2 * HY;
   static constexpr int A_BYTES = lbm::NQ * BY * (int)sizeof(real);
   static constexpr int C_BYTES = TY * 4;

@@ -11,13 +11,15 @@
  * node is collided twice.
  *
  * lbm_rows_kernel (the hot kernel; every interior node).  A CTA owns TY consecutive y-columns
- * and a contiguous range of rows and marches along x.  One elected thread feeds a ring of NS
- * shared-memory slots with TMA (cp.async.bulk.tensor): per lattice row one 3-D box of the nine
+ * and a contiguous range of rows and marches along x.  A ring of NS shared-memory slots is fed
+ * with TMA (cp.async.bulk.tensor): per lattice row one 3-D box of the nine
  * population planes (TY nodes + halo) and one 2-D box each of the stored step's and of this
  * step's obstacle map, all completing on the slot's mbarrier.  Thread j computes node
  * (x, y0 + j): it waits for row x+1, pulls its nine populations from rows x-1, x, x+1 in shared
- * memory, re-initialises / collides in registers and stores nine coalesced values.  After a CTA
- * barrier the slot of row x-1 is refilled with row x-1+NS, so NS-3 rows per CTA are in flight.
+ * memory, re-initialises / collides in registers and stores nine coalesced values.  The queue
+ * is warp-specialised: a producer warp issues the TMA loads as slots are released (one "empty"
+ * mbarrier per slot, one arrival per consumer warp), so consumer warps never meet at a CTA
+ * barrier and up to NS-3 rows per CTA are in flight.
  *
  * lbm_plain_kernel is the same map from global memory, one thread per node: the ring nodes
  * every step (array-edge rule of the swap passes), or every node as the cross-check of the row
@@ -74,19 +76,23 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
       : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+/* TY consumer threads (one node of the row each) + one producer warp that owns the TMA queue */
 template <typename real>
-__global__ void __launch_bounds__(RowCfg<real>::TY) lbm_rows_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                    const __grid_constant__ CUtensorMap tmCp,
-                                                                    const __grid_constant__ CUtensorMap tmCn,
-                                                                    const __grid_constant__ FusedArgs<real> a) {
+__global__ void __launch_bounds__(RowCfg<real>::TY + 32) lbm_rows_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                         const __grid_constant__ CUtensorMap tmCp,
+                                                                         const __grid_constant__ CUtensorMap tmCn,
+                                                                         const __grid_constant__ FusedArgs<real> a) {
   using C = RowCfg<real>;
+  constexpr int NCW = C::TY / 32; /* consumer warps */
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ uint64_t full[C::NS];
+  __shared__ uint64_t full[C::NS], empty[C::NS];
 
   const Lattice<real> &L = a.L;
-  const int jy = threadIdx.x;
   const int y0 = blockIdx.x * C::TY;
-  const int gy = y0 + jy;
   /* rows of this CTA: a balanced share of the interior rows [R0, R1) of the strip */
   const int R0 = max(a.xlo, 1), R1 = min(a.xhi, L.lx - 1);
   const int r0 = R0 + (int)((long long)(R1 - R0) * blockIdx.y / gridDim.y);
@@ -94,36 +100,52 @@ __global__ void __launch_bounds__(RowCfg<real>::TY) lbm_rows_kernel(const __grid
   if (r1 <= r0) return;
   const int nload = r1 - r0 + 2; /* rows r0-1 .. r1; loaded row t is global row r0 - 1 + t */
 
-  auto issue = [&](int t) {
-    const int slot = t % C::NS;
-    unsigned char *base = smem + (size_t)slot * C::SLOT;
-    const int row = r0 - 1 + t - L.x0; /* local row */
-    mbar_expect_tx(&full[slot], (uint32_t)(C::A_BYTES + 2 * C::C_BYTES));
-    tma_load_3d(base, &tmA, &full[slot], y0 - C::HY, row, 0);
-    tma_load_2d(base + C::A_PAD, &tmCp, &full[slot], y0, row);
-    tma_load_2d(base + C::A_PAD + C::C_PAD, &tmCn, &full[slot], y0, row);
-  };
-
-  if (jy == 0) {
+  if (threadIdx.x == 0) {
 #pragma unroll
-    for (int s = 0; s < C::NS; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < C::NS; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], NCW);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    for (int t = 0; t < C::NS && t < nload; ++t) issue(t);
   }
   __syncthreads();
 
+  if (threadIdx.x >= C::TY) {
+    /* ---- producer warp: one lane keeps the ring full ---- */
+    if (threadIdx.x == C::TY) {
+      int slot = 0;
+      uint32_t round = 0; /* how many times the ring has wrapped */
+      for (int t = 0; t < nload; ++t) {
+        if (round > 0) mbar_wait(&empty[slot], (round - 1) & 1); /* all consumer warps are done with row t - NS */
+        unsigned char *base = smem + (size_t)slot * C::SLOT;
+        const int row = r0 - 1 + t - L.x0; /* local row */
+        mbar_expect_tx(&full[slot], (uint32_t)(C::A_BYTES + 2 * C::C_BYTES));
+        tma_load_3d(base, &tmA, &full[slot], y0 - C::HY, row, 0);
+        tma_load_2d(base + C::A_PAD, &tmCp, &full[slot], y0, row);
+        tma_load_2d(base + C::A_PAD + C::C_PAD, &tmCn, &full[slot], y0, row);
+        if (++slot == C::NS) { slot = 0; ++round; }
+      }
+    }
+    return;
+  }
+
+  /* ---- consumer warps ---- */
+  const int jy = threadIdx.x;
+  const int gy = y0 + jy;
   const bool active = gy >= 1 && gy <= L.ly - 2;
   const int by = jy + C::HY;
+  real *out = a.out + node_index(L, r0, gy);
   mbar_wait(&full[0], 0);
   mbar_wait(&full[1], 0);
 
   int slot_m = 0, slot_0 = 1; /* slots of rows t-1 and t */
+  uint32_t round_p = 0;       /* ring round of row t+1 */
   for (int t = 1; t <= nload - 2; ++t) {
-    const int slot_p = (slot_0 + 1 == C::NS) ? 0 : slot_0 + 1;
-    mbar_wait(&full[slot_p], ((t + 1) / C::NS) & 1);
+    int slot_p = slot_0 + 1;
+    if (slot_p == C::NS) { slot_p = 0; ++round_p; }
+    mbar_wait(&full[slot_p], round_p & 1);
     if (active) {
-      const int gx = r0 - 1 + t;
       const real *Am = reinterpret_cast<const real *>(smem + (size_t)slot_m * C::SLOT);
       const real *A0 = reinterpret_cast<const real *>(smem + (size_t)slot_0 * C::SLOT);
       const real *Ap = reinterpret_cast<const real *>(smem + (size_t)slot_p * C::SLOT);
@@ -141,13 +163,14 @@ __global__ void __launch_bounds__(RowCfg<real>::TY) lbm_rows_kernel(const __grid
           f[q] = As[q * C::BY + by - ey];
         }
       }
-      if (!a.stream_only) reinit_collide(L, a.grains_new, cprev, cnow, gx, gy, f);
-      const size_t k = node_index(L, gx, gy);
+      if (!a.stream_only) reinit_collide(L, a.grains_new, cprev, cnow, r0 - 1 + t, gy, f);
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) a.out[q * L.plane + k] = f[q];
+      for (int q = 0; q < NQ; ++q) out[q * L.plane] = f[q];
     }
-    __syncthreads(); /* every thread is done with row t-1 */
-    if (jy == 0 && t - 1 + C::NS < nload) issue(t - 1 + C::NS);
+    out += L.pitch;
+    /* this warp is done with row t-1 */
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[slot_m]);
     slot_m = slot_0;
     slot_0 = slot_p;
   }
@@ -219,7 +242,7 @@ cudaError_t launch_lbm_rows(const CUtensorMap &tmA, const CUtensorMap &tmCp, con
     int dev = 0, sms = 0, per_sm = 0;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbm_rows_kernel<real>, C::TY, C::SMEM)) != cudaSuccess)
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbm_rows_kernel<real>, C::TY + 32, C::SMEM)) != cudaSuccess)
       return e;
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     resident = sms * per_sm;
@@ -232,7 +255,7 @@ cudaError_t launch_lbm_rows(const CUtensorMap &tmA, const CUtensorMap &tmCp, con
   if (chunks < 1) chunks = 1;
   if (chunks > R1 - R0) chunks = R1 - R0;
   dim3 grid(strips, chunks);
-  lbm_rows_kernel<real><<<grid, C::TY, C::SMEM, s>>>(tmA, tmCp, tmCn, a);
+  lbm_rows_kernel<real><<<grid, C::TY + 32, C::SMEM, s>>>(tmA, tmCp, tmCn, a);
   return cudaGetLastError();
 }
 

@@ -165,12 +165,23 @@ LBM_HD real wall_uy(const Lattice<real> &L, const GrainRec<real> &g, int x) {
 template <typename real>
 LBM_HD void equilibrium(const Lattice<real> &L, const GrainRec<real> &g, int x, int y, real *out) {
   const real ux = wall_ux(L, g, y), uy = wall_uy(L, g, x);
+#if defined(LBM_RELAXED)
+  /* default device build: one reciprocal instead of ten divisions, polynomial in `real` */
+  const real ic = 1 / L.c;
+  const real u_squ = (ux * ux + uy * uy) * (ic * ic);
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const real eu = (ex_of(q) * ux + ey_of(q) * uy) * ic;
+    out[q] = L.w[q] * ((real)1 + 3 * eu + (real)4.5 * eu * eu - (real)1.5 * u_squ);
+  }
+#else
   const real u_squ = (ux * ux + uy * uy) / (L.c * L.c);
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
     const real eu = (ex_of(q) * ux + ey_of(q) * uy) / L.c;
     out[q] = L.w[q] * (1. + 3 * eu + 4.5 * eu * eu - 1.5 * u_squ);
   }
+#endif
 }
 
 /* src/main.c:1082-1116 */
@@ -187,12 +198,21 @@ LBM_HD void mrt_collide(const Lattice<real> &L, real *p) {
   real p_xx = p[2] - p[4] + p[6] - p[8];
   real p_xy = -p[1] + p[3] - p[5] + p[7];
   real j_x2 = j_x * j_x, j_y2 = j_y * j_y;
+#if defined(LBM_RELAXED)
+  /* default device build: the four divisions by rho share one reciprocal (1e-16 / 1e-7 relative) */
+  const real ir = 1 / rho;
+  real eO = e - L.s2 * (e + 2 * rho - 3 * (j_x2 + j_y2) * ir);
+  real epsO = eps - L.s3 * (eps - rho + 3 * (j_x2 + j_y2) * ir);
+  real p_xxO = p_xx - L.s8 * (p_xx - (j_x2 - j_y2) * ir);
+  real p_xyO = p_xy - L.s9 * (p_xy - j_x * j_y * ir);
+#else
   real eO = e - L.s2 * (e + 2 * rho - 3 * (j_x2 + j_y2) / rho);
   real epsO = eps - L.s3 * (eps - rho + 3 * (j_x2 + j_y2) / rho);
-  real q_xO = q_x - L.s5 * (q_x + j_x);
-  real q_yO = q_y - L.s7 * (q_y + j_y);
   real p_xxO = p_xx - L.s8 * (p_xx - (j_x2 - j_y2) / rho);
   real p_xyO = p_xy - L.s9 * (p_xy - j_x * j_y / rho);
+#endif
+  real q_xO = q_x - L.s5 * (q_x + j_x);
+  real q_yO = q_y - L.s7 * (q_y + j_y);
   p[0] = a * (4 * rho - 4 * eO + 4 * epsO);
   p[2] = a * (4 * rho - eO - 2 * epsO - 6 * j_x + 6 * q_xO + 9 * p_xxO);
   p[4] = a * (4 * rho - eO - 2 * epsO - 6 * j_y + 6 * q_yO - 9 * p_xxO);
