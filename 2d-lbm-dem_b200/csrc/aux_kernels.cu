@@ -32,10 +32,11 @@ __global__ void grain_prepare_kernel(RasterParams<real> P, int n, GrainArrays<re
 }
 
 /* one warp per grain; the owner of a node is the highest-index grain covering it (:1028 run
- * in index order), hence atomicMax over the fluid value -1 */
+ * in index order), hence atomicMax over the fluid value -1.  Grains whose reduced discs share a
+ * node are flagged: only they can have foreign neighbours deep inside their disc. */
 template <typename real>
 __global__ void raster_kernel(int n, const GrainRec<real> *rec, const real *R2, const GrainBox *boxes, int *cell, int x0,
-                              int nxl, int pitch) {
+                              int nxl, int pitch, int *overlap) {
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (i >= n) return;
@@ -44,35 +45,154 @@ __global__ void raster_kernel(int n, const GrainRec<real> *rec, const real *R2, 
   const int xa = max(b.xi, x0), xb = min(b.xf, x0 + nxl - 1);
   for (int x = xa; x <= xb; ++x)
     for (int y = b.yi + lane; y <= b.yf; y += 32)
-      if (disc_covers(xc, yc, r2, RR, x, y)) atomicMax(&cell[(size_t)(x - x0) * pitch + y], i);
+      if (disc_covers(xc, yc, r2, RR, x, y)) {
+        const int old = atomicMax(&cell[(size_t)(x - x0) * pitch + y], i);
+        if (old >= 0 && old != i) { overlap[i] = 1; overlap[old] = 1; }
+      }
 }
 
-/* act[x][y] (:1036-1052), one warp per grain, after ALL grains are rasterised: a node of grain i
- * is active iff one of its eight neighbours was fluid when the reference's loop reached grain i
- * (lbm_node.cuh, fluid_when_grain_ran).  The flag is folded into the map as CELL_ACT; readers
- * of a neighbour mask it off, so concurrent folding of other nodes is harmless. */
+constexpr int BND_WARPS = 4;     /* warps (= grains) per CTA */
+constexpr int BND_CAND = 256;    /* per-warp staging: candidate nodes, node entries, link entries */
+constexpr int BND_NODES = 256;
+constexpr int BND_LINKS = 768;
+
+__device__ __forceinline__ void list_flush(uint2 *dst, int *counter, int capacity, int *overflow, const uint2 *buf, int cnt,
+                                           int lane) {
+  int slot0 = 0;
+  if (lane == 0) slot0 = atomicAdd(counter, cnt);
+  slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+  for (int k = lane; k < cnt; k += 32) {
+    if (slot0 + k < capacity) dst[slot0 + k] = buf[k];
+    else *(volatile int *)overflow = 1; /* mapped host memory */
+  }
+}
+
+/* act[x][y] (:1036-1052), the boundary-node list and the bounce-back link list, one warp per
+ * grain, after ALL grains are rasterised.  A node of grain i is active iff one of its eight
+ * neighbours was fluid when the reference's loop reached grain i (lbm_node.cuh,
+ * fluid_when_grain_ran); the flag is folded into the map as CELL_ACT (readers of a neighbour mask
+ * it off, so concurrent folding of other nodes is harmless).
+ * Pass 1 classifies the bounding box on geometry alone: nodes outside the disc cannot be owned,
+ * nodes deep inside the disc of a grain that overlaps no other grain have all eight neighbours
+ * inside the same disc; what remains (the rim) is compacted into a per-warp list.  Pass 2 looks
+ * at the map, one rim node per lane. */
 template <typename real>
-__global__ void act_fold_kernel(int n, const GrainRec<real> *rec, const real *R2, const GrainBox *boxes, int *cell, int x0,
-                                int nxl, int pitch) {
-  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(BND_WARPS * 32) boundary_kernel(int n, const GrainRec<real> *rec, const real *R2,
+                                                                   const GrainBox *boxes, int *cell, int x0, int nxl, int pitch,
+                                                                   int lx, int ly, const int *overlap, BoundaryList B,
+                                                                   LinkList K) {
+  __shared__ int s_cand[BND_WARPS][BND_CAND];
+  __shared__ uint2 s_nodes[BND_WARPS][BND_NODES];
+  __shared__ uint2 s_links[BND_WARPS][BND_LINKS];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1;
+  const int i = blockIdx.x * BND_WARPS + w;
   if (i >= n) return;
   const GrainBox b = boxes[i];
   const real xc = rec[i].xc, yc = rec[i].yc, r2 = rec[i].r2, RR = R2[i];
   /* rows whose neighbours are held locally */
   const int xa = max(b.xi, x0 + 1), xb = min(b.xf, x0 + nxl - 2);
-  for (int x = xa; x <= xb; ++x)
-    for (int y = b.yi + lane; y <= b.yf; y += 32) {
-      const size_t k = (size_t)(x - x0) * pitch + y;
-      if (cell_obst(cell[k]) != i) continue;
-      bool act = false;
-#pragma unroll
-      for (int q = 1; q < NQ; ++q) {
-        const int nx = x + ex_of(q), ny = y + ey_of(q);
-        if (fluid_when_grain_ran(cell[(size_t)(nx - x0) * pitch + ny], i, n, xc, yc, r2, RR, b, nx, ny)) act = true;
+  const int ny = b.yf - b.yi + 1;
+  if (ny <= 0 || xb < xa) return;
+  const int total = (xb - xa + 1) * ny;
+  const float inv_ny = 1.0f / (float)ny;
+  real inner2 = -1;
+  if (!overlap[i]) {
+    const real rin = (real)sqrt((double)r2) - 2; /* neighbours of a node at most rin from the centre are inside the disc */
+    if (rin > 0) inner2 = rin * rin;
+  }
+  int *cand = s_cand[w];
+  uint2 *nodes = s_nodes[w], *links = s_links[w];
+  int ncand = 0, nnodes = 0, nlinks = 0;
+
+  for (int base = 0; base < total || ncand > 0; base += 32) {
+    /* ---- pass 1: geometry ---- */
+    if (base < total) {
+      const int t = base + lane;
+      bool rim = false;
+      int xy = 0;
+      if (t < total) {
+        int row = (int)(((float)t + 0.5f) * inv_ny); /* t / ny for the small integers that occur; fixed up below */
+        int y = t - row * ny;
+        if (y < 0) { --row; y += ny; } else if (y >= ny) { ++row; y -= ny; }
+        const int x = xa + row;
+        y += b.yi;
+        const real dist2 = (x - xc) * (x - xc) + (y - yc) * (y - yc);
+        const bool deep = dist2 < inner2 && x >= 2 && y >= 2 && x <= lx - 3 && y <= ly - 3;
+        rim = !deep && dist2 <= RR && dist2 <= r2;
+        xy = (row << 16) | (y - b.yi); /* position inside the bounding box */
       }
-      if (act) atomicOr(&cell[k], CELL_ACT);
+      const unsigned m = __ballot_sync(0xffffffffu, rim);
+      if (rim) cand[ncand + __popc(m & lt)] = xy;
+      ncand += __popc(m);
+      __syncwarp();
+      if (ncand <= BND_CAND - 32 && base + 32 < total) continue;
     }
+    /* ---- pass 2: the map, one rim node per lane ---- */
+    for (int c0 = 0; c0 < ncand; c0 += 32) {
+      bool emit = false;
+      uint2 e = make_uint2(0u, 0u);
+      unsigned bounce = 0, wl = 0; /* links for the sweep list */
+      if (c0 + lane < ncand) {
+        const int xy = cand[c0 + lane];
+        const int x = xa + (xy >> 16), y = b.yi + (xy & 0xffff);
+        const size_t k = (size_t)(x - x0) * pitch + y;
+        if (cell_obst(cell[k]) == i) {
+          bool act = false;
+          unsigned foreign = 0, fluid = 0;
+#pragma unroll
+          for (int q = 1; q < NQ; ++q) {
+            const int nx = x + ex_of(q), nyy = y + ey_of(q);
+            const int cn = cell[(size_t)(nx - x0) * pitch + nyy];
+            if (cell_is_fluid(cn)) fluid |= 1u << (q - 1);
+            if (cell_obst(cn) != i) {
+              foreign |= 1u << (q - 1);
+              if (fluid_when_grain_ran(cn, i, n, xc, yc, r2, RR, b, nx, nyy)) act = true;
+            }
+          }
+          if (act) {
+            atomicOr(&cell[k], CELL_ACT);
+            bounce = fluid;
+            if (!(x >= 2 && y >= 2 && x <= lx - 3 && y <= ly - 3)) wl = ~fluid & 0xffu; /* next to the ring */
+          }
+          if (foreign) {
+            emit = true;
+            e = make_uint2((unsigned)k, (foreign << 24) | (act ? BL_ACT : 0u) | (unsigned)i);
+          }
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, emit);
+      if (emit) nodes[nnodes + __popc(m & lt)] = e;
+      nnodes += __popc(m);
+      /* links: exclusive scan of the per-lane counts */
+      const int mine = __popc(bounce) + __popc(wl);
+      int incl = mine;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+      }
+      int pos = nlinks + incl - mine;
+      for (unsigned bits = bounce; bits; bits &= bits - 1)
+        links[pos++] = make_uint2(e.x, (unsigned)i | ((unsigned)__ffs(bits) << 24));
+      for (unsigned bits = wl; bits; bits &= bits - 1)
+        links[pos++] = make_uint2(e.x, (unsigned)i | ((unsigned)__ffs(bits) << 24) | LL_W);
+      nlinks += __shfl_sync(0xffffffffu, incl, 31);
+      __syncwarp();
+      if (nnodes > BND_NODES - 32) {
+        list_flush(B.entry, B.count, B.capacity, B.overflow, nodes, nnodes, lane);
+        nnodes = 0;
+      }
+      if (nlinks > BND_LINKS - 256) {
+        list_flush(K.entry, K.count, K.capacity, K.overflow, links, nlinks, lane);
+        nlinks = 0;
+      }
+      __syncwarp();
+    }
+    ncand = 0;
+  }
+  if (nnodes) list_flush(B.entry, B.count, B.capacity, B.overflow, nodes, nnodes, lane);
+  if (nlinks) list_flush(K.entry, K.count, K.capacity, K.overflow, links, nlinks, lane);
 }
 
 /* init_obst's frame (:674-687): ring = nbgrains, interior = -1 */
@@ -88,17 +208,22 @@ __global__ void cell_frame_kernel(int *cell, int lx, int ly, int x0, int nxl, in
 
 template <typename real>
 cudaError_t launch_raster(const RasterParams<real> &P, int n, const GrainArrays<real> &g, GrainRec<real> *rec, real *R2,
-                          GrainBox *boxes, int *cell, int x0, int nxl, int pitch, cudaStream_t s) {
+                          GrainBox *boxes, int *cell, int x0, int nxl, int pitch, int *overlap, const BoundaryList &B,
+                          const LinkList &K, cudaStream_t s) {
   grain_prepare_kernel<real><<<(n + 127) / 128, 128, 0, s>>>(P, n, g, rec, R2, boxes);
   /* clear the interior: rows with global x in [1, lx-2], columns [1, ly-2] (:997-1005) */
   const int ra = max(1 - x0, 0), rb = min(P.lx - 2 - x0, nxl - 1);
+  cudaError_t e;
   if (rb >= ra) {
-    cudaError_t e = cudaMemset2DAsync(cell + (size_t)ra * pitch + 1, sizeof(int) * pitch, 0xFF, sizeof(int) * (P.ly - 2),
-                                      rb - ra + 1, s);
+    e = cudaMemset2DAsync(cell + (size_t)ra * pitch + 1, sizeof(int) * pitch, 0xFF, sizeof(int) * (P.ly - 2), rb - ra + 1, s);
     if (e != cudaSuccess) return e;
   }
-  raster_kernel<real><<<(n * 32 + 255) / 256, 256, 0, s>>>(n, rec, R2, boxes, cell, x0, nxl, pitch);
-  act_fold_kernel<real><<<(n * 32 + 255) / 256, 256, 0, s>>>(n, rec, R2, boxes, cell, x0, nxl, pitch);
+  if ((e = cudaMemsetAsync(overlap, 0, sizeof(int) * n, s)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(B.count, 0, sizeof(int), s)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(K.count, 0, sizeof(int), s)) != cudaSuccess) return e;
+  raster_kernel<real><<<(n * 32 + 255) / 256, 256, 0, s>>>(n, rec, R2, boxes, cell, x0, nxl, pitch, overlap);
+  boundary_kernel<real><<<(n + BND_WARPS - 1) / BND_WARPS, BND_WARPS * 32, 0, s>>>(n, rec, R2, boxes, cell, x0, nxl, pitch,
+                                                                                    P.lx, P.ly, overlap, B, K);
   return cudaGetLastError();
 }
 
@@ -169,61 +294,38 @@ cudaError_t launch_ring_sweep(const Lattice<real> &L, const Stored<real> &S, rea
  * per-warp list, then share the (node, link) pairs out, one link per lane, so that the expensive
  * part (delta: one sqrt, the interpolation: divisions) runs with full lanes.
  * ---------------------------------------------------------------------------------------- */
-constexpr int SWEEP_WARPS = 4;
-constexpr int SWEEP_LIST = 64;
-
 template <typename real>
-__device__ __forceinline__ void sweep_links(const Lattice<real> &L, const Stored<real> &S, real *A, const int *list, int cnt,
-                                            int xa0, int ny, int yi, int lane, const DeferList<real> &D) {
-  for (int u = lane; u < cnt * 8; u += 32) {
-    const int t = list[u >> 3], q = 1 + (u & 7);
-    const int x = xa0 + t / ny, y = yi + t % ny;
+__global__ void __launch_bounds__(256) bounce_sweep_kernel(const __grid_constant__ Lattice<real> L,
+                                                           const __grid_constant__ Stored<real> S, real *A, int xa, int xb,
+                                                           const LinkList K, const DeferList<real> D) {
+  const int items = min(*K.count, K.capacity);
+  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < items; u += gridDim.x * blockDim.x) {
+    const uint2 en = K.entry[u];
+    const int q = (int)((en.y >> 24) & 15u);
+    const int row = (int)(en.x / (unsigned)L.pitch);
+    const int x = L.x0 + row, y = (int)(en.x - (unsigned)row * (unsigned)L.pitch);
+    if (x < xa || x >= xb) continue;
+    const size_t e = q * L.plane + en.x;
+    if (en.y & LL_W) { /* rest value next to the wall ring (the fused kernel does the others) */
+      A[e] = L.w[q];
+      continue;
+    }
     real v;
     int r = sweep_link(L, S, x, y, q, false, &v);
-    const size_t e = q * L.plane + node_index(L, x, y);
     if (r == SWEEP_WRITE) {
       A[e] = v;
     } else if (r == SWEEP_DEFER) {
       r = sweep_link(L, S, x, y, q, true, &v);
       if (r == SWEEP_WRITE) {
-        const int slot = atomicAdd(D.count, 1);
+        /* one counter update per group of lanes that got here together */
+        const unsigned grp = __activemask();
+        const int leader = __ffs(grp) - 1, lane = threadIdx.x & 31;
+        int slot = 0;
+        if (lane == leader) slot = atomicAdd(D.count, __popc(grp));
+        slot = __shfl_sync(grp, slot, leader) + __popc(grp & ((1u << lane) - 1));
         if (slot < D.capacity) { D.index[slot] = e; D.value[slot] = v; }
         else *(volatile int *)D.overflow = 1; /* mapped host memory */
       }
-    }
-  }
-}
-
-template <typename real>
-__global__ void __launch_bounds__(SWEEP_WARPS * 32) bounce_sweep_kernel(const __grid_constant__ Lattice<real> L,
-                                                                         const __grid_constant__ Stored<real> S, real *A,
-                                                                         int xa, int xb, const DeferList<real> D) {
-  __shared__ int lists[SWEEP_WARPS][SWEEP_LIST];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i = blockIdx.x * SWEEP_WARPS + w;
-  if (i >= L.ngrains) return;
-  const GrainBox b = S.boxes[i];
-  const int xa0 = max(b.xi, xa), xb0 = min(b.xf, xb - 1);
-  const int ny = b.yf - b.yi + 1;
-  if (ny <= 0 || xb0 < xa0) return;
-  const int total = (xb0 - xa0 + 1) * ny;
-  int *list = lists[w];
-  int cnt = 0;
-  for (int base = 0; base < total; base += 32) {
-    const int t = base + lane;
-    bool act = false;
-    if (t < total) {
-      const int c = S.cell[node_index(L, xa0 + t / ny, b.yi + t % ny)];
-      act = cell_obst(c) == i && node_act(L, S, xa0 + t / ny, b.yi + t % ny, c);
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, act);
-    if (act) list[cnt + __popc(m & ((1u << lane) - 1))] = t;
-    cnt += __popc(m);
-    __syncwarp();
-    if (cnt > SWEEP_LIST - 32 || base + 32 >= total) {
-      sweep_links(L, S, A, list, cnt, xa0, ny, b.yi, lane, D);
-      cnt = 0;
-      __syncwarp();
     }
   }
 }
@@ -233,12 +335,12 @@ __global__ void defer_apply_kernel(real *A, const DeferList<real> D) {
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) A[D.index[k]] = D.value[k];
 }
 template <typename real>
-cudaError_t launch_bounce_sweep(const Lattice<real> &L, const Stored<real> &S, real *A, int xa, int xb,
+cudaError_t launch_bounce_sweep(const Lattice<real> &L, const Stored<real> &S, real *A, int xa, int xb, const LinkList &K,
                                 const DeferList<real> &D, cudaStream_t s) {
   if (xb <= xa || L.ngrains <= 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(D.count, 0, sizeof(int), s);
   if (e != cudaSuccess) return e;
-  bounce_sweep_kernel<real><<<(L.ngrains + SWEEP_WARPS - 1) / SWEEP_WARPS, SWEEP_WARPS * 32, 0, s>>>(L, S, A, xa, xb, D);
+  bounce_sweep_kernel<real><<<148 * 8, 256, 0, s>>>(L, S, A, xa, xb, K, D);
   defer_apply_kernel<real><<<8, 256, 0, s>>>(A, D);
   return cudaGetLastError();
 }
@@ -254,47 +356,56 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
   return v;
 }
 
-/* one warp per grain; every link is rounded to 64-bit fixed point before it is added, so the
- * result is independent of the lane order and of the strip decomposition */
+/* one thread per (boundary node, link); every link is rounded to 64-bit fixed point before it is
+ * added, so the result is independent of the order of the adds and of the strip decomposition.
+ * The eight lanes of a node are summed with shuffles, then one lane adds to the grain's sums. */
 template <typename real>
-__global__ void force_warp_kernel(const __grid_constant__ Lattice<real> L, const __grid_constant__ Stored<real> S, int xlo,
-                                  int xhi, long long *facc) {
-  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(256) force_links_kernel(const __grid_constant__ Lattice<real> L,
+                                                          const __grid_constant__ Stored<real> S, int xlo, int xhi,
+                                                          const BoundaryList B, long long *facc) {
   const int n = L.ngrains;
-  if (i >= n) return;
-  const GrainBox b = S.boxes[i];
-  const real xc = S.grains[i].xc, yc = S.grains[i].yc;
-  const int xa = max(b.xi, xlo), xb = min(b.xf, xhi - 1);
-  const int ny = b.yf - b.yi + 1;
-  long long s1 = 0, s2 = 0, s3 = 0;
-  if (ny > 0 && xb >= xa) {
-    const int total = (xb - xa + 1) * ny;
-    for (int t = lane; t < total; t += 32) {
-      const int x = xa + t / ny, y = b.yi + t % ny;
-      const size_t k = node_index(L, x, y);
-      if (cell_obst(S.cell[k]) != i) continue;
-#pragma unroll
-      for (int q = 1; q < NQ; ++q) {
-        const size_t kn = node_index(L, x + ex_of(q), y + ey_of(q));
-        if (cell_obst(S.cell[kn]) == i) continue;
-        real h1 = 0, h2 = 0, h3 = 0;
-        force_link<real>(q, S.A[opp_of(q) * L.plane + kn], S.A[q * L.plane + k], x, y, xc, yc, &h1, &h2, &h3);
-        s1 += __double2ll_rn((double)h1 * FORCE_FIX);
-        s2 += __double2ll_rn((double)h2 * FORCE_FIX);
-        s3 += __double2ll_rn((double)h3 * TORQUE_FIX);
+  const long long items = 8ll * min(*B.count, B.capacity);
+  const long long padded = (items + 31) & ~31ll; /* whole warps stay in the loop: shuffles below */
+  for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < padded; u += (long long)gridDim.x * blockDim.x) {
+    long long s1 = 0, s2 = 0, s3 = 0;
+    int i = -1;
+    if (u < items) {
+      const uint2 en = B.entry[u >> 3];
+      const int q = 1 + (int)(u & 7);
+      const int row = (int)(en.x / (unsigned)L.pitch);
+      const int x = L.x0 + row, y = (int)(en.x - (unsigned)row * (unsigned)L.pitch);
+      if (x >= xlo && x < xhi) {
+        i = (int)(en.y & BL_GRAIN);
+        if ((en.y >> 24) & (1u << (q - 1))) {
+          const size_t kn = node_index(L, x + ex_of(q), y + ey_of(q));
+          real h1 = 0, h2 = 0, h3 = 0;
+          force_link<real>(q, S.A[opp_of(q) * L.plane + kn], S.A[q * L.plane + en.x], x, y, S.grains[i].xc, S.grains[i].yc,
+                           &h1, &h2, &h3);
+          s1 = __double2ll_rn((double)h1 * FORCE_FIX);
+          s2 = __double2ll_rn((double)h2 * FORCE_FIX);
+          s3 = __double2ll_rn((double)h3 * TORQUE_FIX);
+        }
       }
     }
+#pragma unroll
+    for (int d = 4; d > 0; d >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+      s3 += __shfl_xor_sync(0xffffffffu, s3, d);
+    }
+    if ((u & 7) == 0 && i >= 0) {
+      atomicAdd((unsigned long long *)&facc[i], (unsigned long long)s1);
+      atomicAdd((unsigned long long *)&facc[n + i], (unsigned long long)s2);
+      atomicAdd((unsigned long long *)&facc[2 * n + i], (unsigned long long)s3);
+    }
   }
-  s1 = warp_sum_ll(s1);
-  s2 = warp_sum_ll(s2);
-  s3 = warp_sum_ll(s3);
-  if (lane == 0) { facc[i] = s1; facc[n + i] = s2; facc[2 * n + i] = s3; }
 }
 template <typename real>
-cudaError_t launch_force_warp(const Lattice<real> &L, const Stored<real> &S, int xlo, int xhi, long long *facc,
-                              cudaStream_t s) {
-  force_warp_kernel<real><<<(L.ngrains * 32 + 127) / 128, 128, 0, s>>>(L, S, xlo, xhi, facc);
+cudaError_t launch_force_links(const Lattice<real> &L, const Stored<real> &S, int xlo, int xhi, const BoundaryList &B,
+                               long long *facc, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(facc, 0, sizeof(long long) * 3 * L.ngrains, s);
+  if (e != cudaSuccess) return e;
+  force_links_kernel<real><<<148 * 8, 256, 0, s>>>(L, S, xlo, xhi, B, facc);
   return cudaGetLastError();
 }
 
@@ -686,14 +797,15 @@ cudaError_t launch_fill_rest(real *f, size_t plane, const Lattice<real> &Lw, cud
 
 #define INSTANTIATE(real)                                                                                               \
   template cudaError_t launch_raster<real>(const RasterParams<real> &, int, const GrainArrays<real> &, GrainRec<real> *,  \
-                                           real *, GrainBox *, int *, int, int, int, cudaStream_t);                      \
+                                           real *, GrainBox *, int *, int, int, int, int *, const BoundaryList &,         \
+                                           const LinkList &, cudaStream_t);                                               \
   template cudaError_t launch_act_map<real>(const Lattice<real> &, const Stored<real> &, int, int, int *, cudaStream_t);  \
   template cudaError_t launch_ring_sweep<real>(const Lattice<real> &, const Stored<real> &, real *, int, int,             \
                                                cudaStream_t);                                                             \
   template cudaError_t launch_bounce_sweep<real>(const Lattice<real> &, const Stored<real> &, real *, int, int,           \
-                                                 const DeferList<real> &, cudaStream_t);                                  \
-  template cudaError_t launch_force_warp<real>(const Lattice<real> &, const Stored<real> &, int, int, long long *,        \
-                                               cudaStream_t);                                                             \
+                                                 const LinkList &, const DeferList<real> &, cudaStream_t);                \
+  template cudaError_t launch_force_links<real>(const Lattice<real> &, const Stored<real> &, int, int,                    \
+                                                const BoundaryList &, long long *, cudaStream_t);                         \
   template cudaError_t launch_force_finish<real>(const long long *, int, double, double, real *, real *, real *,          \
                                                  cudaStream_t);                                                           \
   template cudaError_t launch_force_serial<real>(const Lattice<real> &, const Stored<real> &, int, int, double *,         \

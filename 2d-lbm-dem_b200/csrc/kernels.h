@@ -7,7 +7,7 @@
  *   K1  lbm_rows        fused wall ring + grain bounce-back + pull stream of the stored step, then
  *                       re-init + MRT collide of this step  (src/main.c:966-986, :1071-1243)
  *   K1f force           momentum exchange per grain     (src/main.c:1285-1333)
- *   K2  raster          grain records + obstacle map + act bits (src/main.c:991-1065)
+ *   K2  raster          grain records + obstacle map + act bits + boundary-node list (src/main.c:991-1065)
  *   K3  verlet          hash-grid cell list -> sorted full neighbour lists + wall flags
  *                                                       (src/main.c:1519-1594)
  *   K4  dem             kick-drift, contact forces, kick (src/main.c:1733-1763, :1336-1516)
@@ -27,8 +27,8 @@ namespace lbmdem {
 
 /* Row pipeline of the fused LBM kernel.  A CTA owns TY consecutive y-columns and marches along
  * x; each TMA transaction brings ONE lattice row of the strip into a ring of NS shared-memory
- * slots: the nine population planes (TY nodes plus a halo of HY nodes per side) and the matching
- * rows of the stored step's and of this step's obstacle map.
+ * slots: the nine population planes (TY nodes plus a halo of HY nodes per side), the matching row
+ * of this step's obstacle map (halo HC) and of the stored step's map (no halo).
  * The TMA unit wants the byte offset of the box origin along the contiguous dimension to be a
  * multiple of 16 (measured on B200: any other inner coordinate raises "illegal instruction",
  * tools/tma_probe.cu), so the y halo is 16 / sizeof(real) nodes wide instead of one; a box is at
@@ -39,11 +39,14 @@ struct RowCfg {
   static constexpr int HY = 16 / (int)sizeof(real);
   static constexpr int NS = 6;              /* ring slots */
   static constexpr int BY = TY + 2 * HY;
+  static constexpr int HC = 4;
+  static constexpr int BC = TY + 2 * HC;
   static constexpr int A_BYTES = lbm::NQ * BY * (int)sizeof(real);
-  static constexpr int C_BYTES = TY * 4;
+  static constexpr int CN_BYTES = BC * 4, CP_BYTES = TY * 4;
   static constexpr int A_PAD = (A_BYTES + 127) / 128 * 128;
-  static constexpr int C_PAD = (C_BYTES + 127) / 128 * 128;
-  static constexpr int SLOT = A_PAD + 2 * C_PAD;
+  static constexpr int CN_PAD = (CN_BYTES + 127) / 128 * 128;
+  static constexpr int CP_PAD = (CP_BYTES + 127) / 128 * 128;
+  static constexpr int SLOT = A_PAD + CN_PAD + CP_PAD;
   static constexpr int SMEM = NS * SLOT;
 };
 
@@ -102,11 +105,33 @@ LBMDEM_DECLARE_K1(k1_fast)
 LBMDEM_DECLARE_K1(k1_strict)
 
 /* ---- everything below lives in the contraction-free translation unit (aux_kernels.cu) ---- */
-/* grain records + obstacle map + act bits of one step (K2) */
+/* Boundary nodes of one step's obstacle map: solid nodes with at least one neighbour that is not
+ * owned by the same grain.  entry.x = local node index (row * pitch + y), entry.y = grain index
+ * | BL_ACT if act[x][y] == 1 | mask << 24 where bit q-1 of mask marks link q as leaving the grain. */
+struct BoundaryList {
+  uint2 *entry;
+  int *count;          /* device counter */
+  int capacity;
+  int *overflow;       /* flag in mapped host memory */
+};
+constexpr unsigned BL_ACT = 1u << 23;
+constexpr unsigned BL_GRAIN = BL_ACT - 1;
+/* Links of the bounce-back sweep that the fused kernel cannot do on its own: entry.x = local node
+ * index of the active solid node, entry.y = grain index | q << 24 | LL_W if the link just takes
+ * the rest value (a w-link next to the wall ring, lbm_node.cuh w_links_with_collide). */
+struct LinkList {
+  uint2 *entry;
+  int *count;
+  int capacity;
+  int *overflow;       /* flag in mapped host memory */
+};
+constexpr unsigned LL_W = 1u << 28;
+
+/* grain records + obstacle map + act bits + boundary list of one step (K2) */
 template <typename real>
 cudaError_t launch_raster(const lbm::RasterParams<real> &P, int ngrains, const GrainArrays<real> &g,
                           lbm::GrainRec<real> *rec, real *R2, lbm::GrainBox *boxes, int *cell, int x0, int nxl, int pitch,
-                          cudaStream_t s);
+                          int *overlap, const BoundaryList &B, const LinkList &K, cudaStream_t s);
 cudaError_t launch_cell_frame(int *cell, int lx, int ly, int x0, int nxl, int pitch, int ring_value, cudaStream_t s);
 /* act[x][y] as the reference would hold it (tests / diagnostics) */
 template <typename real>
@@ -117,16 +142,16 @@ template <typename real>
 cudaError_t launch_ring_sweep(const lbm::Lattice<real> &L, const lbm::Stored<real> &S, real *A, int xa, int xb,
                               cudaStream_t s);
 /* sweep 4 in place: interpolated bounce-back on the active solid nodes of the rows [xa, xb)
- * (src/main.c:1154-1222), one warp per grain; links facing another grain across a one-node gap
- * go through the deferred list (lbm_node.cuh, sweep_link) */
+ * (src/main.c:1154-1222), one thread per listed link; links facing another grain across a
+ * one-node gap go through the deferred list (lbm_node.cuh, sweep_link) */
 template <typename real>
 cudaError_t launch_bounce_sweep(const lbm::Lattice<real> &L, const lbm::Stored<real> &S, real *A, int xa, int xb,
-                                const DeferList<real> &D, cudaStream_t s);
-/* forces_fluid (src/main.c:1295-1325) from the swept state, one warp per grain, fixed-point sums
- * over the links whose solid node lies in the owned rows; overwrites facc[3][n] */
+                                const LinkList &K, const DeferList<real> &D, cudaStream_t s);
+/* forces_fluid (src/main.c:1295-1325) from the swept state, one thread per (boundary node, link),
+ * fixed-point sums over the links whose solid node lies in the owned rows; overwrites facc[3][n] */
 template <typename real>
-cudaError_t launch_force_warp(const lbm::Lattice<real> &L, const lbm::Stored<real> &S, int xlo, int xhi, long long *facc,
-                              cudaStream_t s);
+cudaError_t launch_force_links(const lbm::Lattice<real> &L, const lbm::Stored<real> &S, int xlo, int xhi,
+                               const BoundaryList &B, long long *facc, cudaStream_t s);
 /* fixed-point sums -> fhf (scaled, src/main.c:1329-1331) */
 template <typename real>
 cudaError_t launch_force_finish(const long long *facc, int ngrains, double k12, double k3, real *fhf1, real *fhf2,

@@ -13,8 +13,8 @@
  * lbm_rows_kernel (the hot kernel; every interior node).  A CTA owns TY consecutive y-columns
  * and a contiguous range of rows and marches along x.  A ring of NS shared-memory slots is fed
  * with TMA (cp.async.bulk.tensor): per lattice row one 3-D box of the nine
- * population planes (TY nodes + halo) and one 2-D box each of the stored step's and of this
- * step's obstacle map, all completing on the slot's mbarrier.  Thread j computes node
+ * population planes (TY nodes + halo) and one 2-D box each of this step's (+ halo) and of the
+ * stored step's obstacle map, all completing on the slot's mbarrier.  Thread j computes node
  * (x, y0 + j): it waits for row x+1, pulls its nine populations from rows x-1, x, x+1 in shared
  * memory, re-initialises / collides in registers and stores nine coalesced values.  The queue
  * is warp-specialised: a producer warp issues the TMA loads as slots are released (one "empty"
@@ -120,10 +120,10 @@ __global__ void __launch_bounds__(RowCfg<real>::TY + 32) lbm_rows_kernel(const _
         if (round > 0) mbar_wait(&empty[slot], (round - 1) & 1); /* all consumer warps are done with row t - NS */
         unsigned char *base = smem + (size_t)slot * C::SLOT;
         const int row = r0 - 1 + t - L.x0; /* local row */
-        mbar_expect_tx(&full[slot], (uint32_t)(C::A_BYTES + 2 * C::C_BYTES));
+        mbar_expect_tx(&full[slot], (uint32_t)(C::A_BYTES + C::CN_BYTES + C::CP_BYTES));
         tma_load_3d(base, &tmA, &full[slot], y0 - C::HY, row, 0);
-        tma_load_2d(base + C::A_PAD, &tmCp, &full[slot], y0, row);
-        tma_load_2d(base + C::A_PAD + C::C_PAD, &tmCn, &full[slot], y0, row);
+        tma_load_2d(base + C::A_PAD, &tmCn, &full[slot], y0 - C::HC, row);
+        tma_load_2d(base + C::A_PAD + C::CN_PAD, &tmCp, &full[slot], y0, row);
         if (++slot == C::NS) { slot = 0; ++round; }
       }
     }
@@ -149,8 +149,9 @@ __global__ void __launch_bounds__(RowCfg<real>::TY + 32) lbm_rows_kernel(const _
       const real *Am = reinterpret_cast<const real *>(smem + (size_t)slot_m * C::SLOT);
       const real *A0 = reinterpret_cast<const real *>(smem + (size_t)slot_0 * C::SLOT);
       const real *Ap = reinterpret_cast<const real *>(smem + (size_t)slot_p * C::SLOT);
-      const int *cells = reinterpret_cast<const int *>(smem + (size_t)slot_0 * C::SLOT + C::A_PAD);
-      const int cprev = cells[jy], cnow = cells[C::C_PAD / 4 + jy];
+      const int *Cn0 = reinterpret_cast<const int *>(smem + (size_t)slot_0 * C::SLOT + C::A_PAD);
+      const int cnow = Cn0[jy + C::HC], cprev = Cn0[C::CN_PAD / 4 + jy];
+      const int gx = r0 - 1 + t;
       real f[NQ];
       /* a node that is solid under the stored step's map is overwritten by the re-init sweep,
        * whatever streams into it: skip the pull */
@@ -163,7 +164,20 @@ __global__ void __launch_bounds__(RowCfg<real>::TY + 32) lbm_rows_kernel(const _
           f[q] = As[q * C::BY + by - ey];
         }
       }
-      if (!a.stream_only) reinit_collide(L, a.grains_new, cprev, cnow, r0 - 1 + t, gy, f);
+      if (!a.stream_only) {
+        reinit_collide(L, a.grains_new, cprev, cnow, gx, gy, f);
+        if (cell_is_act(cnow) && w_links_with_collide(L, gx, gy)) {
+          /* active solid node: links into non-fluid neighbours take the rest value (:1161-1162) */
+          const int *Cnm = reinterpret_cast<const int *>(smem + (size_t)slot_m * C::SLOT + C::A_PAD);
+          const int *Cnp = reinterpret_cast<const int *>(smem + (size_t)slot_p * C::SLOT + C::A_PAD);
+#pragma unroll
+          for (int q = 1; q < NQ; ++q) {
+            const int ex = ex_of(q), ey = ey_of(q);
+            const int *Cs = ex > 0 ? Cnp : (ex < 0 ? Cnm : Cn0); /* neighbour row x + ex */
+            if (!cell_is_fluid(Cs[jy + C::HC + ey])) f[q] = L.w[q];
+          }
+        }
+      }
 #pragma unroll
       for (int q = 0; q < NQ; ++q) out[q * L.plane] = f[q];
     }
@@ -174,6 +188,15 @@ __global__ void __launch_bounds__(RowCfg<real>::TY + 32) lbm_rows_kernel(const _
     slot_m = slot_0;
     slot_0 = slot_p;
   }
+}
+
+/* the w-links of an active solid node (see lbm_rows_kernel), map read from global memory */
+template <typename real>
+__device__ __forceinline__ void w_links_global(const Lattice<real> &L, const int *cell_now, int x, int y, real *f) {
+  if (!cell_is_act(cell_now[node_index(L, x, y)]) || !w_links_with_collide(L, x, y)) return;
+#pragma unroll
+  for (int q = 1; q < NQ; ++q)
+    if (!cell_is_fluid(cell_now[node_index(L, x + ex_of(q), y + ey_of(q))])) f[q] = L.w[q];
 }
 
 /* one thread per node from global memory: ring nodes (ring_only) or all owned nodes */
@@ -208,7 +231,10 @@ __global__ void __launch_bounds__(128) lbm_plain_kernel(const __grid_constant__ 
   real f[NQ];
 #pragma unroll
   for (int q = 0; q < NQ; ++q) f[q] = pull_plain(L, a.A, x, y, q);
-  if (!a.stream_only && !is_ring(L, x, y)) reinit_collide(L, a.grains_new, a.cell_prev[k], a.cell_new[k], x, y, f);
+  if (!a.stream_only && !is_ring(L, x, y)) {
+    reinit_collide(L, a.grains_new, a.cell_prev[k], a.cell_new[k], x, y, f);
+    w_links_global(L, a.cell_new, x, y, f);
+  }
 #pragma unroll
   for (int q = 0; q < NQ; ++q) a.out[q * L.plane + k] = f[q];
 }
@@ -222,11 +248,12 @@ __global__ void __launch_bounds__(128) lbm_h1_kernel(const Lattice<real> L, real
   if (y >= L.ly || x >= xhi || is_ring(L, x, y)) return;
   const size_t k = node_index(L, x, y);
   const int cprev = cell_prev[k], cnow = cell_now[k];
-  if (cell_is_fluid(cprev) && !cell_is_fluid(cnow)) return; /* neither sweep touches the node */
+  if (cell_is_fluid(cprev) && !cell_is_act(cnow) && !cell_is_fluid(cnow)) return; /* nothing touches the node */
   real p[NQ];
 #pragma unroll
   for (int q = 0; q < NQ; ++q) p[q] = f[q * L.plane + k];
   reinit_collide(L, grains_new, cprev, cnow, x, y, p);
+  w_links_global(L, cell_now, x, y, p);
 #pragma unroll
   for (int q = 0; q < NQ; ++q) f[q * L.plane + k] = p[q];
 }

@@ -257,6 +257,16 @@ LBM_HD void reinit_collide(const Lattice<real> &L, const GrainRec<real> *grains,
   if (cell_is_fluid(cell_now)) mrt_collide(L, p);
 }
 
+/* The part of sweep 4 that needs no neighbour population: at an active solid node every link
+ * whose neighbour is not fluid gets the rest value, f[s][q] = w[q] (:1161-1162, :1192-1193).  The
+ * fused kernel applies it while the node is in registers -- except next to the wall ring, where
+ * the ring sweep (which the reference runs BEFORE the grain sweep) still has to read the old
+ * value; those few links go through the sweep kernel's list instead. */
+template <typename real>
+LBM_HD bool w_links_with_collide(const Lattice<real> &L, int x, int y) {
+  return x >= 2 && y >= 2 && x <= L.lx - 3 && y <= L.ly - 3;
+}
+
 /* ------------------------------------------------------------------------------------------
  * Sweeps 3-4 (wall ring, grain bounce-back) rewrite a SPARSE set of populations in place: ring
  * nodes and active solid nodes.  They run as separate small kernels on the stored state; after

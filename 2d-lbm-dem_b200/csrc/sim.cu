@@ -150,9 +150,12 @@ struct Sim : SimBase {
   int cur = 0, cur_cell = 0;
   bool holds_A = false;      /* f[cur] holds A of the last step (stream pending) instead of f */
   bool scratch_valid = false; /* f[1 - cur] holds the materialised f of the pending stream */
-  CUtensorMap tmA[2], tmC[2];
+  CUtensorMap tmA[2], tmC[2], tmCh[2]; /* populations; map rows without / with the y halo */
+  LinkList llist{};
   DeferList<real> defer{};
-  int *hflags = nullptr;      /* mapped host memory: [0] Verlet capacity exceeded, [1] deferred-link list full */
+  BoundaryList blist{};
+  int *overlap = nullptr;
+  int *hflags = nullptr;      /* mapped host memory: [0] Verlet capacity exceeded, [1] deferred-link list full, [2] boundary list full */
   std::vector<real *> grain_bufs;
   GrainArrays<real> g{};
   GrainRec<real> *rec[2] = {nullptr, nullptr}; /* indexed like cell[] */
@@ -187,6 +190,7 @@ struct Sim : SimBase {
     cudaFree(vb.nbr_count); cudaFree(vb.nbr); cudaFree(vb.wflags);
     cudaFree(dens_partials); cudaFree(dens_out); cudaFree(stage);
     cudaFree(defer.count); cudaFree(defer.index); cudaFree(defer.value);
+    cudaFree(blist.entry); cudaFree(blist.count); cudaFree(overlap); cudaFree(llist.entry); cudaFree(llist.count);
     if (hflags) cudaFreeHost(hflags);
     if (hstage) cudaFreeHost(hstage);
     if (stream) cudaStreamDestroy(stream);
@@ -246,10 +250,14 @@ struct Sim : SimBase {
       const cuuint32_t cbox[2] = {(cuuint32_t)C::TY, 1};
       r = encode(&tmC[k], CU_TENSOR_MAP_DATA_TYPE_INT32, 2, cell[k], cdims, cstr, cbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      const cuuint32_t cboxh[2] = {(cuuint32_t)C::BC, 1};
+      if (r == CUDA_SUCCESS)
+        r = encode(&tmCh[k], CU_TENSOR_MAP_DATA_TYPE_INT32, 2, cell[k], cdims, cstr, cboxh, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return fail(LBMDEM_ECUDA, "cuTensorMapEncodeTiled(map) failed with code " + std::to_string((int)r));
     }
-    CK(cudaHostAlloc(&hflags, 2 * sizeof(int), cudaHostAllocMapped));
-    hflags[0] = hflags[1] = 0;
+    CK(cudaHostAlloc(&hflags, 4 * sizeof(int), cudaHostAllocMapped));
+    hflags[0] = hflags[1] = hflags[2] = hflags[3] = 0;
     CK(cudaStreamSynchronize(stream));
     return 0;
   }
@@ -300,6 +308,19 @@ struct Sim : SimBase {
     CK(cudaMalloc(&defer.index, sizeof(size_t) * defer.capacity));
     CK(cudaMalloc(&defer.value, sizeof(real) * defer.capacity));
     CK(cudaHostGetDevicePointer(&defer.overflow, hflags + 1, 0));
+    cudaFree(blist.entry); cudaFree(blist.count); cudaFree(overlap);
+    blist.capacity = (int)std::min<size_t>(plane / 2 + 1024, (size_t)1 << 30);
+    CK(cudaMalloc(&blist.entry, sizeof(uint2) * blist.capacity));
+    CK(cudaMalloc(&blist.count, sizeof(int)));
+    CK(cudaMemsetAsync(blist.count, 0, sizeof(int), stream));
+    CK(cudaHostGetDevicePointer(&blist.overflow, hflags + 2, 0));
+    CK(cudaMalloc(&overlap, sizeof(int) * n));
+    cudaFree(llist.entry); cudaFree(llist.count);
+    llist.capacity = (int)std::min<size_t>(plane + 4096, (size_t)1 << 30);
+    CK(cudaMalloc(&llist.entry, sizeof(uint2) * llist.capacity));
+    CK(cudaMalloc(&llist.count, sizeof(int)));
+    CK(cudaMemsetAsync(llist.count, 0, sizeof(int), stream));
+    CK(cudaHostGetDevicePointer(&llist.overflow, hflags + 3, 0));
     if (hstage) cudaFreeHost(hstage);
     hstage_elems = (size_t)n * 16;
     CK(cudaMallocHost(&hstage, sizeof(double) * hstage_elems));
@@ -428,7 +449,8 @@ struct Sim : SimBase {
   }
   bool act_folded[2] = {false, false};
   int raster_into(int cslot) {
-    CK(launch_raster<real>(raster_params(), n, g, rec[cslot], R2[cslot], boxes[cslot], cell[cslot], x0, nxl, pitch, stream));
+    CK(launch_raster<real>(raster_params(), n, g, rec[cslot], R2[cslot], boxes[cslot], cell[cslot], x0, nxl, pitch, overlap, blist,
+                            llist, stream));
     act_folded[cslot] = true;
     return 0;
   }
@@ -526,8 +548,8 @@ struct Sim : SimBase {
     std::pair<cudaEvent_t, cudaEvent_t> *ev = nullptr;
     int rc;
     if (timed && (rc = record_k1_begin(&ev))) return rc;
-    CK(P.strict_fp ? k1_strict::launch_lbm_rows<real>(tmA[cur], tmC[1 - cur_cell], tmC[cur_cell], a, stream)
-                   : k1_fast::launch_lbm_rows<real>(tmA[cur], tmC[1 - cur_cell], tmC[cur_cell], a, stream));
+    CK(P.strict_fp ? k1_strict::launch_lbm_rows<real>(tmA[cur], tmC[1 - cur_cell], tmCh[cur_cell], a, stream)
+                   : k1_fast::launch_lbm_rows<real>(tmA[cur], tmC[1 - cur_cell], tmCh[cur_cell], a, stream));
     if (ev) CK(cudaEventRecord(ev->second, stream));
     if (timed) ++k1_launches;
     CK(P.strict_fp ? k1_strict::launch_lbm_plain<real>(a, 1, stream) : k1_fast::launch_lbm_plain<real>(a, 1, stream));
@@ -541,7 +563,7 @@ struct Sim : SimBase {
     int rc;
     cur_cell ^= 1; /* the rasteriser writes the other map; the previous one stays with the stored array */
     if ((rc = raster_into(cur_cell))) return rc;
-    all_launches += 3; /* grain_prepare, raster, act_fold (memsets not counted) */
+    all_launches += 3; /* grain_prepare, raster, boundary (memsets not counted) */
     scratch_valid = false;
     if (!holds_A) {
       /* populations came from outside (init_density, set_f): sweeps 1-2 alone, in place */
@@ -560,8 +582,8 @@ struct Sim : SimBase {
     const Stored<real> S = stored(cur, cur_cell);
     const bool multi = P.nranks > 1;
     CK(launch_ring_sweep<real>(L, S, f[cur], multi ? std::max(xlo - 3, 0) : 0, multi ? std::min(xhi + 3, lx) : lx, stream));
-    CK(launch_bounce_sweep<real>(L, S, f[cur], std::max(multi ? xlo - 1 : xlo, 1), std::min(multi ? xhi + 1 : xhi, lx - 1), defer,
-                                 stream));
+    CK(launch_bounce_sweep<real>(L, S, f[cur], std::max(multi ? xlo - 1 : xlo, 1), std::min(multi ? xhi + 1 : xhi, lx - 1), llist,
+                                 defer, stream));
     all_launches += 3;
     if (P.strict_fp) {
       CK(launch_force_serial<real>(L, S, xlo, xhi, fpartial, stream));
@@ -571,7 +593,7 @@ struct Sim : SimBase {
       }
       CK(launch_force_scale<real>(fpartial, n, k12, k3, g.fhf1, g.fhf2, g.fhf3, stream));
     } else {
-      CK(launch_force_warp<real>(L, S, xlo, xhi, facc, stream));
+      CK(launch_force_links<real>(L, S, xlo, xhi, blist, facc, stream));
       if (multi) { /* integer sum: exact, identical on every rank, independent of the decomposition */
         const int r = g_nccl.AllReduce(facc, facc, (size_t)3 * n, NcclApi::Int64, NcclApi::Sum, comm, stream);
         if (r) return nccl_fail(r, "ncclAllReduce");
@@ -611,6 +633,8 @@ struct Sim : SimBase {
     CK(cudaStreamSynchronize(stream));
     if (hflags[0]) { hflags[0] = 0; return fail(LBMDEM_ECAP, "a grain has more Verlet neighbours than neighbour_capacity"); }
     if (hflags[1]) { hflags[1] = 0; return fail(LBMDEM_ECAP, "deferred bounce-back link list is full"); }
+    if (hflags[2]) { hflags[2] = 0; return fail(LBMDEM_ECAP, "boundary-node list is full"); }
+    if (hflags[3]) { hflags[3] = 0; return fail(LBMDEM_ECAP, "bounce-back link list is full"); }
     return 0;
   }
 

@@ -104,7 +104,13 @@ int lbm_step_host(int lx, int ly, int n, const double *scal, const double *grain
       const size_t k = (size_t)x * ly + y;
       real p[NQ];
       for (int q = 0; q < NQ; ++q) p[q] = fs[q * nn + k];
-      if (!is_ring(L, x, y)) reinit_collide(L, rec.data(), cell_old[k], cell_new[k], x, y, p);
+      if (!is_ring(L, x, y)) {
+        reinit_collide(L, rec.data(), cell_old[k], cell_new[k], x, y, p);
+        /* the fused kernel also applies the w-links of active solid nodes away from the ring */
+        if (cell_is_act(cell_new[k]) && w_links_with_collide(L, x, y))
+          for (int q = 1; q < NQ; ++q)
+            if (!cell_is_fluid(cell_new[(size_t)(x + ex_of(q)) * ly + y + ey_of(q)])) p[q] = L.w[q];
+      }
       for (int q = 0; q < NQ; ++q) A[q * nn + k] = p[q];
     }
   Stored<real> S;
@@ -128,6 +134,8 @@ int lbm_step_host(int lx, int ly, int n, const double *scal, const double *grain
     for (int y = ly - 2; y >= 1; --y) {
       if (!is_active_solid(L, S, x, y)) continue;
       for (int q = NQ - 1; q >= 1; --q) {
+        /* the link list holds bounce links, and w-links only next to the ring */
+        if (!cell_is_fluid(S.cell[(size_t)(x + ex_of(q)) * ly + y + ey_of(q)]) && w_links_with_collide(L, x, y)) continue;
         real v;
         int r = sweep_link(L, S, x, y, q, false, &v);
         const size_t e = q * nn + (size_t)x * ly + y;
