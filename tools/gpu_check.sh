@@ -14,6 +14,10 @@ timeout 600 python bench.py --workload $WORK > $OUT/${TAG}_bench.json 2> $OUT/${
 cat $OUT/${TAG}_bench.json
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --workload $WORK --steps 3 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_launches.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:$KREGEX -s 6 -c 3 -f -o $OUT/${TAG}_k1 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:lbm_rows -s 4 -c 2 -f -o $OUT/${TAG}_k1 \
     python bench.py --workload $WORK --steps 3 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_k1.log 2>&1
+if [ "$KREGEX" != "lbm_rows" ]; then
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:$KREGEX -s 8 -c 4 -f -o $OUT/${TAG}_aux \
+    python bench.py --workload $WORK --steps 3 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_aux.log 2>&1
+fi
 ls -la $OUT
