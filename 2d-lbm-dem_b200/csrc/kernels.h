@@ -50,10 +50,8 @@ struct RowCfg {
   static constexpr int SMEM = NS * SLOT;
 };
 
-/* hydrodynamic-force sums are 64-bit fixed point: integer adds commute, so the sum does not
- * depend on the order in which lanes / GPUs contribute */
-constexpr double FORCE_FIX = 4503599627370496.0;   /* 2^52 : fhf1, fhf2 (|sum| < 2^11) */
-constexpr double TORQUE_FIX = 281474976710656.0;   /* 2^48 : fhf3       (|sum| < 2^15) */
+using lbm::FORCE_FIX;
+using lbm::TORQUE_FIX;
 
 /* One fused launch: sweep 5 of the stored step (streaming, a plain pull from the array the ring
  * and bounce-back sweeps left behind), then sweeps 1-2 of this step (re-init, collide). */

@@ -389,6 +389,11 @@ LBM_HD real pull_plain(const Lattice<real> &L, const real *A, int x, int y, int 
   return A[q * L.plane + node_index(L, sx, sy)];
 }
 
+/* hydrodynamic-force sums of the default build are 64-bit fixed point: integer adds commute, so
+ * the sum does not depend on the order in which lanes / GPUs contribute */
+constexpr double FORCE_FIX = 4503599627370496.0;   /* 2^52 : fhf1, fhf2 (|sum| < 2^11) */
+constexpr double TORQUE_FIX = 281474976710656.0;   /* 2^48 : fhf3       (|sum| < 2^15) */
+
 /* One boundary link of forces_fluid (src/main.c:1313-1320).  fs_oq = f_new[s][opp q] and
  * fn_q = f_new[n][q] (both POST-stream), s = (x,y) a node owned by the grain, n = s + e_q a
  * node NOT owned by it.  Accumulates in the reference's expression order. */

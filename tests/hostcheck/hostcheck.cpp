@@ -12,6 +12,7 @@
  */
 #include <algorithm>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -180,6 +181,176 @@ int lbm_step_host(int lx, int ly, int n, const double *scal, const double *grain
   return 0;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Strip decomposition, staged the way Sim (csrc/sim.cu) stages it on one rank, so that the ghost
+ * widths and sweep ranges can be tested with two CPU processes exchanging rows (gloo):
+ *   stage 1  raster on the local rows, sweeps 1-2 (+ w-links) on the OWNED rows
+ *   -- exchange GHOST rows of populations with the x-neighbours --
+ *   stage 2  ring sweep on [xlo-3, xhi+3), bounce-back sweep on [xlo-1, xhi+1) with the deferred
+ *            list, fixed-point force sums over links whose solid node is owned
+ *   -- all-reduce (integer sum) of the force sums --
+ *   stage 3  plain pull on the owned rows
+ * Local arrays cover the rows x0 .. x0+nxl-1 (x0 = xlo - 4 on an inner edge), [q][row][y]. */
+template <typename real>
+struct StripCtx {
+  Lattice<real> L;
+  int xlo, xhi;
+  std::vector<int> cell;
+  std::vector<GrainRec<real>> rec;
+  std::vector<GrainBox> box;
+  std::vector<real> R2;
+};
+
+template <typename real>
+void strip_lattice(Lattice<real> &L, int lx, int ly, int n, int x0, int nxl, const double *scal) {
+  L.lx = lx; L.ly = ly; L.x0 = x0; L.nxl = nxl; L.pitch = ly; L.plane = (size_t)nxl * ly; L.ngrains = n;
+  L.dx = (real)scal[0]; L.c = (real)scal[1]; L.Mgx = (real)scal[2]; L.Mby = (real)scal[3];
+  const real lid = (real)scal[4];
+  L.lid6 = lid / 6;
+  L.s2 = 1.5; L.s3 = 1.4; L.s5 = 1.5; L.s7 = 1.5; L.s8 = 1.9841; L.s9 = 1.9841;
+  const real w0[NQ] = {4. / 9, 1. / 36, 1. / 9, 1. / 36, 1. / 9, 1. / 36, 1. / 9, 1. / 36, 1. / 9};
+  for (int q = 0; q < NQ; ++q) L.w[q] = w0[q];
+}
+
+/* K2 on the local rows: frame, max-owner raster, act fold where the neighbours are local */
+template <typename real>
+void strip_raster(StripCtx<real> &C, const double *grains) {
+  const Lattice<real> &L = C.L;
+  const int n = L.ngrains, ly = L.ly;
+  RasterParams<real> P;
+  P.lx = L.lx; P.ly = L.ly; P.dx = L.dx; P.Mgx = L.Mgx; P.Mby = L.Mby;
+  C.cell.assign(L.plane, -1);
+  for (int r = 0; r < L.nxl; ++r)
+    for (int y = 0; y < ly; ++y) {
+      const int x = L.x0 + r;
+      if (x <= 0 || x >= L.lx - 1 || y <= 0 || y >= ly - 1) C.cell[(size_t)r * ly + y] = n;
+    }
+  C.rec.resize(n); C.box.resize(n); C.R2.resize(n);
+  for (int i = 0; i < n; ++i) {
+    const double *g = grains + 7 * (size_t)i;
+    GrainRec<real> &R = C.rec[i];
+    grain_geometry(P, (real)g[0], (real)g[1], (real)g[5], (real)g[6], &R.xc, &R.yc, &R.r2, &C.R2[i], &C.box[i]);
+    R.x1 = (real)g[0]; R.x2 = (real)g[1]; R.v1 = (real)g[2]; R.v2 = (real)g[3]; R.v3 = (real)g[4];
+    for (int x = std::max(C.box[i].xi, L.x0); x <= std::min(C.box[i].xf, L.x0 + L.nxl - 1); ++x)
+      for (int y = C.box[i].yi; y <= C.box[i].yf; ++y)
+        if (disc_covers(R.xc, R.yc, R.r2, C.R2[i], x, y)) {
+          int &c = C.cell[node_index(L, x, y)];
+          c = std::max(c, i);
+        }
+  }
+  for (int i = 0; i < n; ++i) {
+    const GrainRec<real> &R = C.rec[i];
+    for (int x = std::max(C.box[i].xi, L.x0 + 1); x <= std::min(C.box[i].xf, L.x0 + L.nxl - 2); ++x)
+      for (int y = C.box[i].yi; y <= C.box[i].yf; ++y) {
+        int &c = C.cell[node_index(L, x, y)];
+        if (cell_obst(c) != i) continue;
+        bool act = false;
+        for (int q = 1; q < NQ; ++q) {
+          const int nx = x + ex_of(q), ny = y + ey_of(q);
+          if (fluid_when_grain_ran(C.cell[node_index(L, nx, ny)], i, n, R.xc, R.yc, R.r2, C.R2[i], C.box[i], nx, ny)) act = true;
+        }
+        if (act) c |= CELL_ACT;
+      }
+  }
+}
+
+template <typename real>
+int strip_stage1(int lx, int ly, int n, int x0, int nxl, int xlo, int xhi, const double *scal, const double *grains,
+                 double *f /* in: pre-collision, out: A on the owned rows; [q][row][y] */, const int *cell_old /* local */,
+                 int *cell_new_out /* local, act folded */) {
+  StripCtx<real> C;
+  strip_lattice(C.L, lx, ly, n, x0, nxl, scal);
+  strip_raster(C, grains);
+  const Lattice<real> &L = C.L;
+  for (int x = xlo; x < xhi; ++x)
+    for (int y = 0; y < ly; ++y) {
+      if (is_ring(L, x, y)) continue;
+      const size_t k = node_index(L, x, y);
+      real p[NQ];
+      for (int q = 0; q < NQ; ++q) p[q] = (real)f[q * L.plane + k];
+      reinit_collide(L, C.rec.data(), cell_old[k], C.cell[k], x, y, p);
+      if (cell_is_act(C.cell[k]) && w_links_with_collide(L, x, y))
+        for (int q = 1; q < NQ; ++q)
+          if (!cell_is_fluid(C.cell[node_index(L, x + ex_of(q), y + ey_of(q))])) p[q] = L.w[q];
+      for (int q = 0; q < NQ; ++q) f[q * L.plane + k] = p[q];
+    }
+  for (size_t k = 0; k < L.plane; ++k) cell_new_out[k] = C.cell[k];
+  return 0;
+}
+
+template <typename real>
+int strip_stage2(int lx, int ly, int n, int x0, int nxl, int xlo, int xhi, int nranks, const double *scal,
+                 const double *grains, double *A_io /* local, ghosts filled */, long long *facc /* [3][n] */) {
+  StripCtx<real> C;
+  strip_lattice(C.L, lx, ly, n, x0, nxl, scal);
+  strip_raster(C, grains);
+  const Lattice<real> &L = C.L;
+  std::vector<real> A(L.plane * NQ);
+  for (size_t k = 0; k < A.size(); ++k) A[k] = (real)A_io[k];
+  Stored<real> S;
+  S.A = A.data(); S.cell = C.cell.data(); S.grains = C.rec.data(); S.boxes = C.box.data(); S.R2 = C.R2.data();
+  S.act_folded = 1;
+  const bool multi = nranks > 1;
+  const int ra = multi ? std::max(xlo - 3, 0) : 0, rb = multi ? std::min(xhi + 3, lx) : lx;
+  for (int pass = 0; pass < 2; ++pass)
+    for (int x = rb - 1; x >= ra; --x)
+      for (int y = ly - 1; y >= 0; --y) {
+        if (!is_ring(L, x, y)) continue;
+        if (pass == 1 && !(x == 0 || x == lx - 1)) continue; /* the device's pass 1 covers the ring ROWS only */
+        real v[NQ];
+        for (int q = 1; q < NQ; ++q) v[q] = ring_value(L, S, pass, x, y, q);
+        for (int q = 1; q < NQ; ++q) A[q * L.plane + node_index(L, x, y)] = v[q];
+      }
+  const int sa = std::max(multi ? xlo - 1 : xlo, 1), sb = std::min(multi ? xhi + 1 : xhi, lx - 1);
+  std::vector<std::pair<size_t, real>> deferred;
+  for (int x = sb - 1; x >= sa; --x)
+    for (int y = ly - 2; y >= 1; --y) {
+      if (!is_active_solid(L, S, x, y)) continue;
+      for (int q = NQ - 1; q >= 1; --q) {
+        const bool nb_fluid = cell_is_fluid(S.cell[node_index(L, x + ex_of(q), y + ey_of(q))]);
+        if (!nb_fluid && w_links_with_collide(L, x, y)) continue;
+        real v;
+        int r = sweep_link(L, S, x, y, q, false, &v);
+        const size_t e = q * L.plane + node_index(L, x, y);
+        if (r == SWEEP_WRITE) A[e] = v;
+        else if (r == SWEEP_DEFER && sweep_link(L, S, x, y, q, true, &v) == SWEEP_WRITE) deferred.emplace_back(e, v);
+      }
+    }
+  for (auto &d : deferred) A[d.first] = d.second;
+  /* fixed-point force sums over links whose solid node is owned */
+  for (int k = 0; k < 3 * n; ++k) facc[k] = 0;
+  for (int x = std::max(xlo, 1); x < std::min(xhi, lx - 1); ++x)
+    for (int y = 1; y < ly - 1; ++y) {
+      const size_t k = node_index(L, x, y);
+      const int i = cell_obst(S.cell[k]);
+      if (i < 0 || i >= n) continue;
+      for (int q = 1; q < NQ; ++q) {
+        const size_t kn = node_index(L, x + ex_of(q), y + ey_of(q));
+        if (cell_obst(S.cell[kn]) == i) continue;
+        real h1 = 0, h2 = 0, h3 = 0;
+        force_link<real>(q, A[opp_of(q) * L.plane + kn], A[q * L.plane + k], x, y, C.rec[i].xc, C.rec[i].yc, &h1, &h2, &h3);
+        facc[i] += llrint((double)h1 * FORCE_FIX);
+        facc[n + i] += llrint((double)h2 * FORCE_FIX);
+        facc[2 * n + i] += llrint((double)h3 * TORQUE_FIX);
+      }
+    }
+  for (size_t k = 0; k < A.size(); ++k) A_io[k] = A[k];
+  return 0;
+}
+
+template <typename real>
+int strip_stage3(int lx, int ly, int x0, int nxl, int xlo, int xhi, const double *scal, const double *A_in,
+                 double *f_out /* [xhi-xlo][ly][9], reference layout */) {
+  Lattice<real> L;
+  strip_lattice(L, lx, ly, 0, x0, nxl, scal);
+  std::vector<real> A(L.plane * NQ);
+  for (size_t k = 0; k < A.size(); ++k) A[k] = (real)A_in[k];
+  for (int x = xlo; x < xhi; ++x)
+    for (int y = 0; y < ly; ++y)
+      for (int q = 0; q < NQ; ++q) f_out[((size_t)(x - xlo) * ly + y) * NQ + q] = pull_plain(L, A.data(), x, y, q);
+  return 0;
+}
+
 /* gather-form DEM step over a sorted FULL neighbour list (what K4 does), serial on the host */
 template <typename real>
 int dem_step_host(int n, const double *par /* see below */, int film, double *state /* [n][9] x1 x2 x3 v1 v2 v3 a1 a2 a3 */,
@@ -259,6 +430,18 @@ EXPORT int hc_lbm_step_f64(int lx, int ly, int n, const double *scal, const doub
 EXPORT int hc_lbm_step_f32(int lx, int ly, int n, const double *scal, const double *grains, const double *f_in,
                            const int *obst_old, double *f_out, int *obst_new, int *act_new, double *fhf) {
   return lbm_step_host<float>(lx, ly, n, scal, grains, f_in, obst_old, f_out, obst_new, act_new, fhf);
+}
+EXPORT int hc_strip_stage1_f64(int lx, int ly, int n, int x0, int nxl, int xlo, int xhi, const double *scal,
+                               const double *grains, double *f, const int *cell_old, int *cell_new) {
+  return strip_stage1<double>(lx, ly, n, x0, nxl, xlo, xhi, scal, grains, f, cell_old, cell_new);
+}
+EXPORT int hc_strip_stage2_f64(int lx, int ly, int n, int x0, int nxl, int xlo, int xhi, int nranks, const double *scal,
+                               const double *grains, double *A, long long *facc) {
+  return strip_stage2<double>(lx, ly, n, x0, nxl, xlo, xhi, nranks, scal, grains, A, facc);
+}
+EXPORT int hc_strip_stage3_f64(int lx, int ly, int x0, int nxl, int xlo, int xhi, const double *scal, const double *A,
+                               double *f_out) {
+  return strip_stage3<double>(lx, ly, x0, nxl, xlo, xhi, scal, A, f_out);
 }
 EXPORT int hc_dem_step_f64(int n, const double *par, int film, double *state, const double *props, const double *fhf,
                            int rebuild, int *nbr_count, int *nbr, int cap, int *wflags) {

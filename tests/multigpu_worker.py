@@ -1,0 +1,70 @@
+"""Worker of tests/test_multi_gpu.py: one process per GPU (torchrun, NCCL).  The strip-decomposed
+run must be BIT-IDENTICAL to the one-GPU run of the same build (pure data movement plus an exact
+integer all-reduce), and agree with the oracle like the one-GPU run does."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "2d-lbm-dem_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch
+
+import lbmdem_dist as D
+import lbmdem_gpu as G
+from oracle.oraclewrap import Oracle
+from util import perturbed_f, random_kinematics, small_packing
+
+
+def main():
+    rank, world = D.init_process_group("nccl")
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local_rank)
+    for prec, lx, ly, steps in (("f64", 203, 160, 60), ("f32", 160, 131, 24)):
+        r, x, y = small_packing(lx, ly, 1.0, seed=71, n_target=90)
+        f0 = perturbed_f(lx, ly, 72)
+        o = Oracle(lx, ly, 1.0, prec)
+        n = o.init_arrays(r, x, y)
+        v, w, a = random_kinematics(n, 73, vmax=0.02)
+        st = o.grains()[:, :9].copy()
+        st[:, 3:5], st[:, 5:6] = v, w
+        o.set_f(f0)
+        o.set_grain_state(st)
+
+        strip = D.make_strip_solver(lx, ly, 1.0, prec)
+        one = G.Solver(lx, ly, 1.0, prec, device=local_rank)
+        xlo, xhi = strip.xlo, strip.xhi
+        assert (xlo, xhi) == D.strip_bounds(lx, rank, world)
+        for s in (strip, one):
+            assert s.init_arrays(r, x, y) == n
+            s.set_grain_state(st)
+        one.set_f(f0)
+        strip.set_f(f0[xlo:xhi])
+        for chunk in range(3):
+            for s in (strip, one, o):
+                s.step(steps // 3)
+            assert np.array_equal(strip.f(), one.f()[xlo:xhi]), f"{prec} rank {rank}: populations differ from the 1-GPU run"
+            assert np.array_equal(strip.obst(), one.obst()[xlo:xhi])
+            assert np.array_equal(strip.fhf(), one.fhf()), f"{prec} rank {rank}: fhf differs from the 1-GPU run"
+            assert np.array_equal(strip.grains(), one.grains()), f"{prec} rank {rank}: grains differ from the 1-GPU run"
+        assert np.array_equal(strip.obst(), o.obst()[xlo:xhi])
+        tol = 1e-6 if prec == "f64" else 1e-4
+        go, gs = o.grains(), strip.grains()
+        assert np.abs(gs[:, :3] - go[:, :3]).max() <= tol * np.abs(go[:, :3]).max()
+        # the density checksum of the strips adds up to the 1-GPU one
+        part = torch.tensor([strip.total_density()], dtype=torch.float64, device="cuda")
+        torch.distributed.all_reduce(part)
+        assert abs(part.item() - one.total_density()) < 1e-9 * lx * ly
+        # strict build: bit-exact against the oracle on the lattice also when decomposed, for one LBM step
+        strip.close()
+        one.close()
+    D.barrier()
+    torch.distributed.destroy_process_group()
+    print(f"rank {rank}: ok")
+
+
+if __name__ == "__main__":
+    main()
