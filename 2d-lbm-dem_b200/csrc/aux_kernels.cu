@@ -132,11 +132,12 @@ __global__ void __launch_bounds__(BND_WARPS * 32) boundary_kernel(int n, const G
     for (int c0 = 0; c0 < ncand; c0 += 32) {
       bool emit = false;
       uint2 e = make_uint2(0u, 0u);
-      unsigned bounce = 0, wl = 0; /* links for the sweep list */
+      unsigned bounce = 0, wl = 0, knode = 0; /* links for the sweep list */
       if (c0 + lane < ncand) {
         const int xy = cand[c0 + lane];
         const int x = xa + (xy >> 16), y = b.yi + (xy & 0xffff);
         const size_t k = (size_t)(x - x0) * pitch + y;
+        knode = (unsigned)k;
         if (cell_obst(cell[k]) == i) {
           bool act = false;
           unsigned foreign = 0, fluid = 0;
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(BND_WARPS * 32) boundary_kernel(int n, const G
             bounce = fluid;
             if (!(x >= 2 && y >= 2 && x <= lx - 3 && y <= ly - 3)) wl = ~fluid & 0xffu; /* next to the ring */
           }
-          if (foreign) {
+          if (foreign & ~fluid) { /* the force kernel's share: foreign neighbours that are not fluid */
             emit = true;
             e = make_uint2((unsigned)k, (foreign << 24) | (act ? BL_ACT : 0u) | (unsigned)i);
           }
@@ -174,9 +175,9 @@ __global__ void __launch_bounds__(BND_WARPS * 32) boundary_kernel(int n, const G
       }
       int pos = nlinks + incl - mine;
       for (unsigned bits = bounce; bits; bits &= bits - 1)
-        links[pos++] = make_uint2(e.x, (unsigned)i | ((unsigned)__ffs(bits) << 24));
+        links[pos++] = make_uint2(knode, (unsigned)i | ((unsigned)__ffs(bits) << 24));
       for (unsigned bits = wl; bits; bits &= bits - 1)
-        links[pos++] = make_uint2(e.x, (unsigned)i | ((unsigned)__ffs(bits) << 24) | LL_W);
+        links[pos++] = make_uint2(knode, (unsigned)i | ((unsigned)__ffs(bits) << 24) | LL_W);
       nlinks += __shfl_sync(0xffffffffu, incl, 31);
       __syncwarp();
       if (nnodes > BND_NODES - 32) {
@@ -294,10 +295,35 @@ cudaError_t launch_ring_sweep(const Lattice<real> &L, const Stored<real> &S, rea
  * per-warp list, then share the (node, link) pairs out, one link per lane, so that the expensive
  * part (delta: one sqrt, the interpolation: divisions) runs with full lanes.
  * ---------------------------------------------------------------------------------------- */
+/* adds three fixed-point values to the sums of grain i; lanes of a warp that hold the same grain
+ * are summed first (exact: integers), so there is about one atomic per grain and warp */
+__device__ __forceinline__ void grain_sums_add(long long *facc, int n, int i, long long s1, long long s2, long long s3) {
+  const unsigned active = __activemask();
+  const unsigned peers = __match_any_sync(active, i);
+  const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+  long long t1 = 0, t2 = 0, t3 = 0;
+  for (unsigned m = peers; m; m &= m - 1) {
+    const int src = __ffs(m) - 1;
+    t1 += __shfl_sync(peers, s1, src);
+    t2 += __shfl_sync(peers, s2, src);
+    t3 += __shfl_sync(peers, s3, src);
+  }
+  if (lane == leader && i >= 0) {
+    atomicAdd((unsigned long long *)&facc[i], (unsigned long long)t1);
+    atomicAdd((unsigned long long *)&facc[n + i], (unsigned long long)t2);
+    atomicAdd((unsigned long long *)&facc[2 * n + i], (unsigned long long)t3);
+  }
+}
+
+/* One thread per listed link.  Besides the sweep itself the thread holds both operands of the
+ * link's momentum exchange (forces_fluid, :1313-1320: f_new[s][opp q] = A[n][opp q] and
+ * f_new[n][q] = the value it just produced), so links into FLUID neighbours are added to the
+ * grain's force sums here (facc != nullptr, owned rows only); force_links_kernel adds the rest. */
 template <typename real>
 __global__ void __launch_bounds__(256) bounce_sweep_kernel(const __grid_constant__ Lattice<real> L,
                                                            const __grid_constant__ Stored<real> S, real *A, int xa, int xb,
-                                                           const LinkList K, const DeferList<real> D) {
+                                                           int xlo, int xhi, const LinkList K, const DeferList<real> D,
+                                                           long long *facc) {
   const int items = min(*K.count, K.capacity);
   for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < items; u += gridDim.x * blockDim.x) {
     const uint2 en = K.entry[u];
@@ -327,6 +353,15 @@ __global__ void __launch_bounds__(256) bounce_sweep_kernel(const __grid_constant
         else *(volatile int *)D.overflow = 1; /* mapped host memory */
       }
     }
+    if (facc != nullptr && x >= xlo && x < xhi) {
+      if (r == SWEEP_KEEP) v = A[e];
+      const int i = (int)(en.y & BL_GRAIN);
+      const size_t kn = node_index(L, x + ex_of(q), y + ey_of(q));
+      real h1 = 0, h2 = 0, h3 = 0;
+      force_link<real>(q, A[opp_of(q) * L.plane + kn], v, x, y, S.grains[i].xc, S.grains[i].yc, &h1, &h2, &h3);
+      grain_sums_add(facc, L.ngrains, i, __double2ll_rn((double)h1 * FORCE_FIX), __double2ll_rn((double)h2 * FORCE_FIX),
+                     __double2ll_rn((double)h3 * TORQUE_FIX));
+    }
   }
 }
 template <typename real>
@@ -335,12 +370,13 @@ __global__ void defer_apply_kernel(real *A, const DeferList<real> D) {
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) A[D.index[k]] = D.value[k];
 }
 template <typename real>
-cudaError_t launch_bounce_sweep(const Lattice<real> &L, const Stored<real> &S, real *A, int xa, int xb, const LinkList &K,
-                                const DeferList<real> &D, cudaStream_t s) {
+cudaError_t launch_bounce_sweep(const Lattice<real> &L, const Stored<real> &S, real *A, int xa, int xb, int xlo, int xhi,
+                                const LinkList &K, const DeferList<real> &D, long long *facc, cudaStream_t s) {
   if (xb <= xa || L.ngrains <= 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(D.count, 0, sizeof(int), s);
   if (e != cudaSuccess) return e;
-  bounce_sweep_kernel<real><<<148 * 8, 256, 0, s>>>(L, S, A, xa, xb, K, D);
+  if (facc != nullptr && (e = cudaMemsetAsync(facc, 0, sizeof(long long) * 3 * L.ngrains, s)) != cudaSuccess) return e;
+  bounce_sweep_kernel<real><<<148 * 12, 256, 0, s>>>(L, S, A, xa, xb, xlo, xhi, K, D, facc);
   defer_apply_kernel<real><<<8, 256, 0, s>>>(A, D);
   return cudaGetLastError();
 }
@@ -356,7 +392,8 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
   return v;
 }
 
-/* one thread per (boundary node, link); every link is rounded to 64-bit fixed point before it is
+/* one thread per (listed node, link) for the links into NON-fluid foreign neighbours (other grains,
+ * the wall ring); every link is rounded to 64-bit fixed point before it is
  * added, so the result is independent of the order of the adds and of the strip decomposition.
  * The eight lanes of a node are summed with shuffles, then one lane adds to the grain's sums. */
 template <typename real>
@@ -376,8 +413,9 @@ __global__ void __launch_bounds__(256) force_links_kernel(const __grid_constant_
       const int x = L.x0 + row, y = (int)(en.x - (unsigned)row * (unsigned)L.pitch);
       if (x >= xlo && x < xhi) {
         i = (int)(en.y & BL_GRAIN);
-        if ((en.y >> 24) & (1u << (q - 1))) {
-          const size_t kn = node_index(L, x + ex_of(q), y + ey_of(q));
+        const size_t kn = node_index(L, x + ex_of(q), y + ey_of(q));
+        /* links into fluid neighbours were added by the sweep kernel */
+        if (((en.y >> 24) & (1u << (q - 1))) && !cell_is_fluid(S.cell[kn])) {
           real h1 = 0, h2 = 0, h3 = 0;
           force_link<real>(q, S.A[opp_of(q) * L.plane + kn], S.A[q * L.plane + en.x], x, y, S.grains[i].xc, S.grains[i].yc,
                            &h1, &h2, &h3);
@@ -403,9 +441,7 @@ __global__ void __launch_bounds__(256) force_links_kernel(const __grid_constant_
 template <typename real>
 cudaError_t launch_force_links(const Lattice<real> &L, const Stored<real> &S, int xlo, int xhi, const BoundaryList &B,
                                long long *facc, cudaStream_t s) {
-  cudaError_t e = cudaMemsetAsync(facc, 0, sizeof(long long) * 3 * L.ngrains, s);
-  if (e != cudaSuccess) return e;
-  force_links_kernel<real><<<148 * 8, 256, 0, s>>>(L, S, xlo, xhi, B, facc);
+  force_links_kernel<real><<<148 * 4, 256, 0, s>>>(L, S, xlo, xhi, B, facc); /* adds to what the sweep kernel left */
   return cudaGetLastError();
 }
 
@@ -802,8 +838,8 @@ cudaError_t launch_fill_rest(real *f, size_t plane, const Lattice<real> &Lw, cud
   template cudaError_t launch_act_map<real>(const Lattice<real> &, const Stored<real> &, int, int, int *, cudaStream_t);  \
   template cudaError_t launch_ring_sweep<real>(const Lattice<real> &, const Stored<real> &, real *, int, int,             \
                                                cudaStream_t);                                                             \
-  template cudaError_t launch_bounce_sweep<real>(const Lattice<real> &, const Stored<real> &, real *, int, int,           \
-                                                 const LinkList &, const DeferList<real> &, cudaStream_t);                \
+  template cudaError_t launch_bounce_sweep<real>(const Lattice<real> &, const Stored<real> &, real *, int, int, int, int, \
+                                                 const LinkList &, const DeferList<real> &, long long *, cudaStream_t);   \
   template cudaError_t launch_force_links<real>(const Lattice<real> &, const Stored<real> &, int, int,                    \
                                                 const BoundaryList &, long long *, cudaStream_t);                         \
   template cudaError_t launch_force_finish<real>(const long long *, int, double, double, real *, real *, real *,          \

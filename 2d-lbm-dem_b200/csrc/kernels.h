@@ -104,7 +104,7 @@ LBMDEM_DECLARE_K1(k1_strict)
 
 /* ---- everything below lives in the contraction-free translation unit (aux_kernels.cu) ---- */
 /* Boundary nodes of one step's obstacle map: solid nodes with at least one neighbour that is not
- * owned by the same grain.  entry.x = local node index (row * pitch + y), entry.y = grain index
+ * owned by the same grain and not fluid.  entry.x = local node index (row * pitch + y), entry.y = grain index
  * | BL_ACT if act[x][y] == 1 | mask << 24 where bit q-1 of mask marks link q as leaving the grain. */
 struct BoundaryList {
   uint2 *entry;
@@ -141,12 +141,14 @@ cudaError_t launch_ring_sweep(const lbm::Lattice<real> &L, const lbm::Stored<rea
                               cudaStream_t s);
 /* sweep 4 in place: interpolated bounce-back on the active solid nodes of the rows [xa, xb)
  * (src/main.c:1154-1222), one thread per listed link; links facing another grain across a
- * one-node gap go through the deferred list (lbm_node.cuh, sweep_link) */
+ * one-node gap go through the deferred list (lbm_node.cuh, sweep_link).  With facc != nullptr the
+ * kernel first zeroes facc[3][n] and adds the momentum exchange of every link into a fluid
+ * neighbour whose solid node lies in [xlo, xhi) */
 template <typename real>
-cudaError_t launch_bounce_sweep(const lbm::Lattice<real> &L, const lbm::Stored<real> &S, real *A, int xa, int xb,
-                                const LinkList &K, const DeferList<real> &D, cudaStream_t s);
-/* forces_fluid (src/main.c:1295-1325) from the swept state, one thread per (boundary node, link),
- * fixed-point sums over the links whose solid node lies in the owned rows; overwrites facc[3][n] */
+cudaError_t launch_bounce_sweep(const lbm::Lattice<real> &L, const lbm::Stored<real> &S, real *A, int xa, int xb, int xlo,
+                                int xhi, const LinkList &K, const DeferList<real> &D, long long *facc, cudaStream_t s);
+/* the rest of forces_fluid (src/main.c:1295-1325): links into non-fluid foreign neighbours (other
+ * grains, the wall ring), one thread per (listed node, link); ADDS to facc[3][n] */
 template <typename real>
 cudaError_t launch_force_links(const lbm::Lattice<real> &L, const lbm::Stored<real> &S, int xlo, int xhi,
                                const BoundaryList &B, long long *facc, cudaStream_t s);

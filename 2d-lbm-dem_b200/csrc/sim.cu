@@ -582,8 +582,8 @@ struct Sim : SimBase {
     const Stored<real> S = stored(cur, cur_cell);
     const bool multi = P.nranks > 1;
     CK(launch_ring_sweep<real>(L, S, f[cur], multi ? std::max(xlo - 3, 0) : 0, multi ? std::min(xhi + 3, lx) : lx, stream));
-    CK(launch_bounce_sweep<real>(L, S, f[cur], std::max(multi ? xlo - 1 : xlo, 1), std::min(multi ? xhi + 1 : xhi, lx - 1), llist,
-                                 defer, stream));
+    CK(launch_bounce_sweep<real>(L, S, f[cur], std::max(multi ? xlo - 1 : xlo, 1), std::min(multi ? xhi + 1 : xhi, lx - 1), xlo,
+                                 xhi, llist, defer, P.strict_fp ? nullptr : facc, stream));
     all_launches += 3;
     if (P.strict_fp) {
       CK(launch_force_serial<real>(L, S, xlo, xhi, fpartial, stream));
