@@ -43,12 +43,32 @@ __global__ void raster_kernel(int n, const GrainRec<real> *rec, const real *R2, 
   const GrainBox b = boxes[i];
   const real xc = rec[i].xc, yc = rec[i].yc, r2 = rec[i].r2, RR = R2[i];
   const int xa = max(b.xi, x0), xb = min(b.xf, x0 + nxl - 1);
-  for (int x = xa; x <= xb; ++x)
-    for (int y = b.yi + lane; y <= b.yf; y += 32)
-      if (disc_covers(xc, yc, r2, RR, x, y)) {
-        const int old = atomicMax(&cell[(size_t)(x - x0) * pitch + y], i);
-        if (old >= 0 && old != i) { overlap[i] = 1; overlap[old] = 1; }
+  const int ny = b.yf - b.yi + 1;
+  if (ny <= 0 || xb < xa) return;
+  const int total = (xb - xa + 1) * ny;
+  const float inv_ny = 1.0f / (float)ny;
+  bool shared_node = false;
+  /* four nodes per lane and trip, so that the atomics are in flight together */
+  for (int base = 0; base < total; base += 128) {
+    int old[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      old[u] = -1;
+      const int t = base + u * 32 + lane;
+      if (t < total) {
+        int row = (int)(((float)t + 0.5f) * inv_ny); /* t / ny for the small integers that occur; fixed up below */
+        int y = t - row * ny;
+        if (y < 0) { --row; y += ny; } else if (y >= ny) { ++row; y -= ny; }
+        const int x = xa + row;
+        y += b.yi;
+        if (disc_covers(xc, yc, r2, RR, x, y)) old[u] = atomicMax(&cell[(size_t)(x - x0) * pitch + y], i);
       }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (old[u] >= 0 && old[u] != i) { shared_node = true; overlap[old[u]] = 1; }
+  }
+  if (shared_node) overlap[i] = 1;
 }
 
 constexpr int BND_WARPS = 4;     /* warps (= grains) per CTA */
@@ -320,7 +340,7 @@ __device__ __forceinline__ void grain_sums_add(long long *facc, int n, int i, lo
  * f_new[n][q] = the value it just produced), so links into FLUID neighbours are added to the
  * grain's force sums here (facc != nullptr, owned rows only); force_links_kernel adds the rest. */
 template <typename real>
-__global__ void __launch_bounds__(256) bounce_sweep_kernel(const __grid_constant__ Lattice<real> L,
+__global__ void __launch_bounds__(256, 4) bounce_sweep_kernel(const __grid_constant__ Lattice<real> L,
                                                            const __grid_constant__ Stored<real> S, real *A, int xa, int xb,
                                                            int xlo, int xhi, const LinkList K, const DeferList<real> D,
                                                            long long *facc) {
@@ -376,7 +396,7 @@ cudaError_t launch_bounce_sweep(const Lattice<real> &L, const Stored<real> &S, r
   cudaError_t e = cudaMemsetAsync(D.count, 0, sizeof(int), s);
   if (e != cudaSuccess) return e;
   if (facc != nullptr && (e = cudaMemsetAsync(facc, 0, sizeof(long long) * 3 * L.ngrains, s)) != cudaSuccess) return e;
-  bounce_sweep_kernel<real><<<148 * 12, 256, 0, s>>>(L, S, A, xa, xb, xlo, xhi, K, D, facc);
+  bounce_sweep_kernel<real><<<148 * 16, 256, 0, s>>>(L, S, A, xa, xb, xlo, xhi, K, D, facc);
   defer_apply_kernel<real><<<8, 256, 0, s>>>(A, D);
   return cudaGetLastError();
 }
