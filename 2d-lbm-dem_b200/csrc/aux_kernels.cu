@@ -706,9 +706,16 @@ __global__ void dem_kick_kernel(dem::Params<real> P, int n, GrainArrays<real> g)
 
 template <typename real>
 cudaError_t launch_dem_step(const dem::Params<real> &P, int n, bool film, const GrainArrays<real> &g,
-                            const VerletBuffers &vb, cudaStream_t s) {
+                            const VerletBuffers &vb, real *mid, cudaStream_t s) {
   const int nb = (n + 127) / 128;
   dem_kick_drift_kernel<real><<<nb, 128, 0, s>>>(P, n, g);
+  if (mid != nullptr) {
+    const real *src[6] = {g.x1, g.x2, g.x3, g.v1, g.v2, g.v3};
+    for (int k = 0; k < 6; ++k) {
+      cudaError_t e = cudaMemcpyAsync(mid + (size_t)k * n, src[k], sizeof(real) * n, cudaMemcpyDeviceToDevice, s);
+      if (e != cudaSuccess) return e;
+    }
+  }
   dem_forces_kernel<real><<<(n * 32 + 127) / 128, 128, 0, s>>>(P, n, film, g, vb);
   dem_kick_kernel<real><<<nb, 128, 0, s>>>(P, n, g);
   return cudaGetLastError();
@@ -871,7 +878,7 @@ cudaError_t launch_fill_rest(real *f, size_t plane, const Lattice<real> &Lw, cud
   template cudaError_t launch_verlet<real>(const dem::Params<real> &, int, const GrainArrays<real> &, real,               \
                                            const VerletBuffers &, cudaStream_t);                                         \
   template cudaError_t launch_dem_step<real>(const dem::Params<real> &, int, bool, const GrainArrays<real> &,             \
-                                             const VerletBuffers &, cudaStream_t);                                       \
+                                             const VerletBuffers &, real *, cudaStream_t);                               \
   template cudaError_t launch_density<real>(const real *, int, int, int, int, int, size_t, double *, int, double *,       \
                                             cudaStream_t);                                                                \
   template cudaError_t launch_fields<real>(const real *, const int *, const GrainArrays<real> &, const real *, int, int,  \

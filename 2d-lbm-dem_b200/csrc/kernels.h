@@ -181,7 +181,8 @@ cudaError_t launch_verlet(const dem::Params<real> &P, int n, const GrainArrays<r
                           const VerletBuffers &vb, cudaStream_t s);
 template <typename real>
 cudaError_t launch_dem_step(const dem::Params<real> &P, int n, bool film, const GrainArrays<real> &g,
-                            const VerletBuffers &vb, cudaStream_t s);
+                            const VerletBuffers &vb, real *mid /* nullptr, or [6][n]: x1 x2 x3 v1 v2 v3 after the
+                            kick-drift, i.e. as acceleration_grains() sees them */, cudaStream_t s);
 
 template <typename real>
 cudaError_t launch_density(const real *f, int ly, int x0, int xlo, int xhi, int pitch, size_t plane, double *partials,

@@ -106,6 +106,7 @@ struct SimBase {
   virtual int load_sample(const char *path) = 0;
   virtual int set_grains(int n, const double *r, const double *x1, const double *x2) = 0;
   virtual int step(long n) = 0;
+  virtual int step_capture(double *mid) = 0;
   virtual int lbm_step() = 0;
   virtual int lbm_steps(long n) = 0;
   virtual int build_verlet() = 0;
@@ -188,7 +189,7 @@ struct Sim : SimBase {
     cudaFree(facc); cudaFree(fpartial);
     cudaFree(vb.bucket_count); cudaFree(vb.bucket_cursor); cudaFree(vb.sorted); cudaFree(vb.gcx); cudaFree(vb.gcy);
     cudaFree(vb.nbr_count); cudaFree(vb.nbr); cudaFree(vb.wflags);
-    cudaFree(dens_partials); cudaFree(dens_out); cudaFree(stage);
+    cudaFree(dens_partials); cudaFree(dens_out); cudaFree(stage); cudaFree(mid_dev);
     cudaFree(defer.count); cudaFree(defer.index); cudaFree(defer.value);
     cudaFree(blist.entry); cudaFree(blist.count); cudaFree(overlap); cudaFree(llist.entry); cudaFree(llist.count);
     if (hflags) cudaFreeHost(hflags);
@@ -267,6 +268,8 @@ struct Sim : SimBase {
     if (n_ <= 0) return fail(LBMDEM_EINVAL, "need at least one grain (the reference reads g[0], src/main.c:220)");
     for (real *p : grain_bufs) cudaFree(p);
     grain_bufs.clear();
+    cudaFree(mid_dev);
+    mid_dev = nullptr;
     n = n_;
     real **slots[] = {&g.x1, &g.x2, &g.x3, &g.v1, &g.v2, &g.v3, &g.a1, &g.a2, &g.a3, &g.r, &g.m, &g.It, &g.rLB,
                       &g.fhf1, &g.fhf2, &g.fhf3};
@@ -656,7 +659,8 @@ struct Sim : SimBase {
 
   int check_verlet_overflow() { return check_flags(); }
 
-  int step_async(long nsteps, bool *built) {
+  real *mid_dev = nullptr; /* [6][n], lbmdem_step_capture */
+  int step_async(long nsteps, bool *built, bool capture = false) {
     for (long k = 0; k < nsteps; ++k) {
       int rc;
       if (nbsteps % npDEM == 0 && (rc = lbm_step_async())) return rc;
@@ -665,7 +669,7 @@ struct Sim : SimBase {
         *built = true;
       }
       const bool film = (nbsteps % P.stepFilm == 0);
-      CK(launch_dem_step<real>(dem_params(), n, film, g, vb, stream));
+      CK(launch_dem_step<real>(dem_params(), n, film, g, vb, capture ? mid_dev : nullptr, stream));
       all_launches += 3;
       ++nbsteps;
       if (nbsteps % P.stepFilm == 0) ++nFile;
@@ -680,6 +684,20 @@ struct Sim : SimBase {
     if (rc) return rc;
     (void)built;
     return check_flags();
+  }
+  int step_capture(double *mid) override {
+    if (!ready) return fail(LBMDEM_ESTATE, "no grains loaded");
+    if (!mid) return fail(LBMDEM_EINVAL, "step_capture: null output");
+    if (!mid_dev) CK(cudaMalloc(&mid_dev, sizeof(real) * 6 * n));
+    bool built = false;
+    int rc = step_async(1, &built, true);
+    if (rc) return rc;
+    std::vector<real> tmp((size_t)6 * n);
+    CK(cudaMemcpyAsync(tmp.data(), mid_dev, sizeof(real) * 6 * n, cudaMemcpyDeviceToHost, stream));
+    if ((rc = check_flags())) return rc;
+    for (int k = 0; k < 6; ++k)
+      for (int i = 0; i < n; ++i) mid[(size_t)i * 6 + k] = tmp[(size_t)k * n + i];
+    return 0;
   }
   int lbm_step() override {
     int rc = lbm_step_async();
@@ -998,6 +1016,7 @@ API int lbmdem_set_grains(lbmdem_ctx *ctx, int n, const double *r, const double 
   CTX_OR_FAIL; return ctx->sim->set_grains(n, r, x1, x2);
 }
 API int lbmdem_step(lbmdem_ctx *ctx, long n) { CTX_OR_FAIL; return ctx->sim->step(n); }
+API int lbmdem_step_capture(lbmdem_ctx *ctx, double *mid) { CTX_OR_FAIL; return ctx->sim->step_capture(mid); }
 API int lbmdem_lbm_step(lbmdem_ctx *ctx) { CTX_OR_FAIL; return ctx->sim->lbm_step(); }
 API int lbmdem_lbm_steps(lbmdem_ctx *ctx, long n) { CTX_OR_FAIL; return ctx->sim->lbm_steps(n); }
 API int lbmdem_build_verlet(lbmdem_ctx *ctx) { CTX_OR_FAIL; return ctx->sim->build_verlet(); }

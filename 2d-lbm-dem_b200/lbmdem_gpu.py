@@ -69,6 +69,7 @@ def load_library():
         "lbmdem_load_sample": ([vp, C.c_char_p], C.c_int),
         "lbmdem_set_grains": ([vp, C.c_int, _dp, _dp, _dp], C.c_int),
         "lbmdem_step": ([vp, C.c_long], C.c_int),
+        "lbmdem_step_capture": ([vp, _dp], C.c_int),
         "lbmdem_lbm_step": ([vp], C.c_int),
         "lbmdem_lbm_steps": ([vp, C.c_long], C.c_int),
         "lbmdem_build_verlet": ([vp], C.c_int),
@@ -187,6 +188,12 @@ class Solver:
 
     def build_verlet(self):
         self._ck(self.L.lbmdem_build_verlet(self.h))
+
+    def step_capture(self):
+        """one renderScene() call; returns [n][6] x1 x2 x3 v1 v2 v3 as acceleration_grains() saw them"""
+        mid = np.empty((self.n, 6))
+        self._ck(self.L.lbmdem_step_capture(self.h, mid))
+        return mid
 
     def step_host(self, state_in, n_dem_steps, want_state=True, want_fhf=True, want_density=True):
         """lbmdem_step_host: host arrays in, host arrays out (the end-to-end call)."""

@@ -81,6 +81,11 @@ int lbmdem_set_grains(lbmdem_ctx *ctx, int n, const double *r, const double *x1,
 /* renderScene() n times (src/main.c:1697-1765): LBM step every npDEM-th call, Verlet lists
  * every UpdateVerlet-th, kick-drift, forces, kick.  No file output. */
 int lbmdem_step(lbmdem_ctx *ctx, long n_dem_steps);
+/* ONE renderScene() call that also returns the grain positions and velocities as
+ * acceleration_grains() saw them (after the kick-drift of src/main.c:1748-1753, before the
+ * forces): mid[n][6] = x1 x2 x3 v1 v2 v3.  The host replays the reference's contact diagnostics
+ * (p, s, slip, ... of write_DEM, src/main.c:340-438) from it on output steps. */
+int lbmdem_step_capture(lbmdem_ctx *ctx, double *mid);
 /* The LBM part of one renderScene() call (src/main.c:1711-1717): reinit_obst_density,
  * obst_construction, collision_streaming, forces_fluid. */
 int lbmdem_lbm_step(lbmdem_ctx *ctx);

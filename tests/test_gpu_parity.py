@@ -345,3 +345,27 @@ def test_golden_packings_strict_build_is_bit_exact(name, prec):
     assert np.array_equal(s.fhf(), gold["end_fhf"])
     assert _sha(s.obst()) == str(gold["end_obst_sha256"])
     assert _sha(s.f()) == str(gold["end_f_sha256"])
+
+
+def test_lbmdem_executable_writes_the_reference_files(tmp_path):
+    """The drop-in binary (2d-lbm-dem_b200/host/lbmdem_main.c): 8000 renderScene() calls of the 64 x 48
+    packing from rest, strict build.  stats.data, DEM000000.dat, DEM000001.dat and the five VTK files of
+    frame 0 must be byte-identical to what the compiled reference wrote (tests/golden/outputs_64x48)."""
+    import importlib.util
+    import subprocess
+    spec = importlib.util.spec_from_file_location("host_build", os.path.join(os.path.dirname(GOLD), "..", "2d-lbm-dem_b200",
+                                                                             "host", "build.py"))
+    hb = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(hb)
+    exe = hb.build_exe()
+    ref_dir = os.path.join(GOLD, "outputs_64x48")
+    p = subprocess.run([exe, os.path.join(GOLD, "pack_64x48_f64.data"), "--lx", "64", "--ly", "48", "--strict", "--steps", "8000",
+                        "--outdir", str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert "Nb grains 7" in p.stdout and "Iteration Number 0, Total density in the system" in p.stdout
+    assert "final_density:" in p.stderr
+    for name in sorted(os.listdir(ref_dir)):
+        if name.endswith(".npz"):
+            continue
+        mine, ref = open(tmp_path / name, "rb").read(), open(os.path.join(ref_dir, name), "rb").read()
+        assert mine == ref, f"{name} differs from the reference's file"

@@ -140,8 +140,61 @@ def case_packing(lx, ly, prec, seed, steps, n_target, full):
     print(name, "n =", n, "density", out["end_density"])
 
 
+def case_outputs():
+    """The reference's own output files for 8000 renderScene() calls of the 64 x 48 packing from
+    rest: DEM000000.dat (call 4000), DEM000001.dat + five VTK files (call 8000), stats.data.
+    Stored verbatim under tests/golden/outputs_64x48/ with the state the writers saw."""
+    ref = Reference(64, 48, "1.", "f64")
+    out_dir = os.path.join(GOLD, "outputs_64x48")
+    os.makedirs(out_dir, exist_ok=True)
+    tmp = tempfile.mkdtemp(prefix="golden_out_")
+    cwd = os.getcwd()
+    os.chdir(tmp)
+    try:
+        n = ref.init(os.path.join(GOLD, "pack_64x48_f64.data"))
+        # the reference's main() truncates stats.data and writes the header before the loop (:1867-1877)
+        with open("stats.data", "w") as fh:
+            fh.write("#1_t 2_xfront 3_xgrainmax 4_height 5_zmean 6_energie_x 7_energie_y "
+                     "8_energie_teta 9_energie_cin 10_N0 11_N1 12_N2 13_N3 14_N4 15_N5 "
+                     "16_energy_Potential 17_Strain_Energy 18_Frictional_Work "
+                     "19_Internal_Friction 20_Inelastic_Collision 21_Slip "
+                     "22_Rotational_Work\n")
+        replay = {}
+        done = 0
+        for mark in (3998, 3999, 7998, 7999):
+            ref.step(mark - done)
+            done = mark
+            replay[f"grains_{mark}"] = ref.grains()
+            replay[f"fhf_{mark}"] = ref.fhf()
+            cum, half = ref.verlet()
+            replay[f"cumul_{mark}"], replay[f"half_{mark}"] = cum, half
+            for nm, lst in zip("BTLR", ref.wall_lists()):
+                replay[f"wall{nm}_{mark}"] = lst
+            sc = ref.scalars()
+            replay[f"d11_{mark}"] = np.array([sc[k] for k in ("dx", "dtLB", "dt", "dt2", "c", "Mgx", "Mdx", "Mby", "Mhy", "xG", "yG")])
+            if mark in (3999, 7999):
+                ref.step(1)
+                done = mark + 1
+                replay[f"grains_{done}"] = ref.grains()
+                replay[f"fhf_{done}"] = ref.fhf()
+                replay[f"diag_{done}"] = ref.grain_diag()
+        np.savez_compressed(os.path.join(out_dir, "replay_states.npz"), **replay)
+        assert done == 8000
+        state = dict(f=ref.f(), obst=ref.obst(), grains=ref.grains(), diag=ref.grain_diag(), fhf=ref.fhf(),
+                     density=np.float64(ref.total_density()))
+        scalars_of(ref, state)
+    finally:
+        os.chdir(cwd)
+    for name in sorted(os.listdir(tmp)):
+        if name.endswith((".vtk", ".dat", ".data")) and not name.startswith("pack"):
+            shutil.copyfile(os.path.join(tmp, name), os.path.join(out_dir, name))
+    np.savez_compressed(os.path.join(out_dir, "state_8000.npz"), **state)
+    print("outputs_64x48:", sorted(os.listdir(out_dir)))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    case_outputs()
     case_a08d83()
     case_packing(64, 48, "f64", 3, 30, None, True)
     case_packing(64, 48, "f32", 3, 30, None, True)
