@@ -349,31 +349,39 @@ LBM_HD bool is_active_solid(const Lattice<real> &L, const Stored<real> &S, int x
 enum { SWEEP_KEEP = 0, SWEEP_WRITE = 1, SWEEP_DEFER = 2 };
 
 template <typename real>
-LBM_HD_SLOW int sweep_link(const Lattice<real> &L, const Stored<real> &S, int x, int y, int q, bool resolve, real *v) {
+LBM_HD_SLOW int sweep_link(const Lattice<real> &L, const Stored<real> &S, int x, int y, int q, bool resolve, real *v,
+                           int grain = -1 /* owner of (x,y) if the caller knows it */) {
   const int ex = ex_of(q), ey = ey_of(q), oq = opp_of(q);
   const int nx = x + ex, ny = y + ey;
-  if (!cell_is_fluid(S.cell[node_index(L, nx, ny)])) { /* :1161-1162 */
+  const int nnx = nx + ex, nny = ny + ey;
+  const size_t ks = node_index(L, x, y), kn = node_index(L, nx, ny);
+  /* nn lies inside the array whenever n is fluid (an interior node); clamp the address for the other case */
+  const bool nn_in = in_array(L, nnx, nny);
+  const size_t knn = nn_in ? node_index(L, nnx, nny) : kn;
+  /* every load below has an address that depends on (x, y, q) alone: they are issued together */
+  const int cn = S.cell[kn], cnn = S.cell[knn];
+  if (grain < 0) grain = cell_obst(S.cell[ks]);
+  const GrainRec<real> g = S.grains[grain];
+  const real Fn_q = S.A[q * L.plane + kn], Fn_oq = S.A[oq * L.plane + kn], Xnn = S.A[oq * L.plane + knn];
+  if (!cell_is_fluid(cn)) { /* :1161-1162 */
     *v = L.w[q];
     return SWEEP_WRITE;
   }
-  const int nnx = nx + ex, nny = ny + ey; /* inside the array: n is an interior node */
-  const bool gap = is_active_solid(L, S, nnx, nny);
+  const bool gap = !is_ring(L, nnx, nny) && !cell_is_fluid(cnn) && node_act(L, S, nnx, nny, cnn);
   if (gap && !resolve) return SWEEP_DEFER;
-  const GrainRec<real> g = S.grains[cell_obst(S.cell[node_index(L, x, y)])];
   const real d = link_delta(g, x, y, q);
   if (!(d > 0.)) return SWEEP_KEEP;
   const real eu = ex * wall_ux(L, g, y) + ey * wall_uy(L, g, x);
-  const real Fn_q = A_value(L, S, nx, ny, q), Fn_oq = A_value(L, S, nx, ny, oq);
   real X = 0;
   if (d < 0.5) {
-    X = A_value(L, S, nnx, nny, oq);
+    X = Xnn;
     if (gap && (nnx < x || (nnx == x && nny < y))) {
       /* the partner link (nn, opp q) was swept earlier: its new value, from the pre-sweep state.
        * Its fluid neighbour is n, its second fluid-side node is s itself. */
-      const GrainRec<real> gp = S.grains[cell_obst(S.cell[node_index(L, nnx, nny)])];
+      const GrainRec<real> gp = S.grains[cell_obst(cnn)];
       const real dp = link_delta(gp, nnx, nny, oq);
       const real eup = ex_of(oq) * wall_ux(L, gp, nny) + ey_of(oq) * wall_uy(L, gp, nnx);
-      X = bounce_value(L, oq, dp, Fn_q, Fn_oq, A_value(L, S, x, y, q), eup, X);
+      X = bounce_value(L, oq, dp, Fn_q, Fn_oq, S.A[q * L.plane + ks], eup, X);
     }
   }
   *v = bounce_value(L, q, d, Fn_oq, Fn_q, X, eu, (real)0);

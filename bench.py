@@ -37,6 +37,8 @@ WORKLOADS = {
              "BASELINE configs[3]: 4096x4096 lattice per GPU, scale 2.7, fp32, 6355 synthetic grains per 4096 rows"),
     "cfg3": (2048, 2048, 1.0, "f64", "a08d83",
              "BASELINE configs[2]: 2048x2048 lattice, scale 1, fp64, 726 synthetic grains"),
+    "cfg5": (1024, 8192, 2.6, "f64", "50000_strip",
+             "BASELINE configs[4]: 1024 rows x 8192 columns per GPU (8192x8192 on 8 GPUs), scale 2.6, fp64, 4000 synthetic grains per strip"),
     "cfg2": (1024, 1024, 1.0, "f64", None,
              "BASELINE configs[1]: 1024x1024 lattice, fp64, one grain outside the lattice (pure LBM stencil)"),
 }

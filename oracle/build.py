@@ -11,7 +11,7 @@ Two things are built here, both into git-ignored locations:
    with the snapshot are used.
 2. ``oracle/_build/liboracle.so`` -- the plain-C restatement ``oracle/lbmdem_oracle.c``
    (runtime lx/ly/scale, both precisions), pinned against (1) by
-   ``tests/test_oracle_vs_reference.py``.
+   ``tests/test_oracle_pin.py``.
 
 Flags.  The *correctness* oracle is ``-std=c99 -O2 -ffp-contract=off``, serial:
 the reference's own release flags (``-Ofast -march=native ...``, CMakeLists.txt:17)
@@ -52,6 +52,7 @@ PREBUILT = [
     (4096, 4096, "2.7", "f64", False, True),
     (2048, 2048, "1.", "f64", True, True),    # BASELINE cfg 3 / cfg 2 timed baselines (bench.py --workload)
     (1024, 1024, "1.", "f64", True, True),
+    (1024, 8192, "2.6", "f64", True, True),   # BASELINE cfg 5, one strip
 ]
 
 
