@@ -38,7 +38,13 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(verbose=False, force=False) -> str:
+def build(verbose=False, force=False, tag="", defines=()) -> str:
+    """tag / defines: experimental variants (tools/k1_variants.sh): objects and library get the tag as a suffix"""
+    global OBJ, LIB
+    if tag:
+        OBJ = os.path.join(HERE, "_obj_" + tag)
+        LIB = os.path.join(HERE, f"liblbmdem_gpu_{tag}.so")
+        force = force or not os.path.exists(LIB)
     os.makedirs(OBJ, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.join(HERE, "..", "include", "lbmdem_gpu.h"),
                                                          os.path.abspath(__file__)]
@@ -46,7 +52,7 @@ def build(verbose=False, force=False) -> str:
     for obj, src, flags in UNITS:
         o, s = os.path.join(OBJ, obj), os.path.join(CSRC, src)
         if force or _stale(o, [s] + hdrs):
-            jobs.append(["nvcc", *COMMON, *flags, "-c", s, "-o", o])
+            jobs.append(["nvcc", *COMMON, *flags, *defines, "-c", s, "-o", o])
 
     def run(cmd):
         if verbose:
@@ -62,4 +68,5 @@ def build(verbose=False, force=False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(verbose="-v" in sys.argv, force="--force" in sys.argv))
+    tag = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--tag=")), "")
+    print(build(verbose="-v" in sys.argv, force="--force" in sys.argv, tag=tag, defines=[a for a in sys.argv if a.startswith("-D")]))

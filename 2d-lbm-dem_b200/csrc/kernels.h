@@ -37,7 +37,10 @@ template <typename real>
 struct RowCfg {
   static constexpr int TY = 128;            /* nodes (= threads) per CTA row */
   static constexpr int HY = 16 / (int)sizeof(real);
-  static constexpr int NS = 6;              /* ring slots */
+#ifndef LBMDEM_K1_NS
+#define LBMDEM_K1_NS 4   /* measured on B200: more resident CTAs beat a deeper ring (profiles/r01_k1_tuning.txt) */
+#endif
+  static constexpr int NS = LBMDEM_K1_NS;   /* ring slots */
   static constexpr int BY = TY + 2 * HY;
   static constexpr int HC = 4;
   static constexpr int BC = TY + 2 * HC;

@@ -81,8 +81,15 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 }
 
 /* TY consumer threads (one node of the row each) + one producer warp that owns the TMA queue */
+#ifndef LBMDEM_K1_MINB_F32
+#define LBMDEM_K1_MINB_F32 1
+#endif
+#ifndef LBMDEM_K1_MINB_F64
+#define LBMDEM_K1_MINB_F64 4   /* caps the fp64 build at 102 registers: 4 CTAs per SM (profiles/r01_k1_tuning.txt) */
+#endif
 template <typename real>
-__global__ void __launch_bounds__(RowCfg<real>::TY + 32) lbm_rows_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(RowCfg<real>::TY + 32, sizeof(real) == 8 ? LBMDEM_K1_MINB_F64 : LBMDEM_K1_MINB_F32)
+    lbm_rows_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                          const __grid_constant__ CUtensorMap tmCp,
                                                                          const __grid_constant__ CUtensorMap tmCn,
                                                                          const __grid_constant__ FusedArgs<real> a) {

@@ -271,13 +271,15 @@ struct Sim : SimBase {
     cudaFree(mid_dev);
     mid_dev = nullptr;
     n = n_;
-    real **slots[] = {&g.x1, &g.x2, &g.x3, &g.v1, &g.v2, &g.v3, &g.a1, &g.a2, &g.a3, &g.r, &g.m, &g.It, &g.rLB,
-                      &g.fhf1, &g.fhf2, &g.fhf3};
-    for (real **s : slots) {
-      CK(cudaMalloc(s, sizeof(real) * n));
-      CK(cudaMemsetAsync(*s, 0, sizeof(real) * n, stream));
-      grain_bufs.push_back(*s);
-    }
+    /* one slab, so that the kinematic state (9 arrays) and state + fhf (12 arrays) move in one copy each:
+     * x1 x2 x3 v1 v2 v3 a1 a2 a3 | fhf1 fhf2 fhf3 | r m It rLB */
+    real *slab = nullptr;
+    CK(cudaMalloc(&slab, sizeof(real) * 16 * (size_t)n));
+    CK(cudaMemsetAsync(slab, 0, sizeof(real) * 16 * (size_t)n, stream));
+    grain_bufs.push_back(slab);
+    real **slots[] = {&g.x1, &g.x2, &g.x3, &g.v1, &g.v2, &g.v3, &g.a1, &g.a2, &g.a3, &g.fhf1, &g.fhf2, &g.fhf3,
+                      &g.r, &g.m, &g.It, &g.rLB};
+    for (size_t k = 0; k < 16; ++k) *slots[k] = slab + k * (size_t)n;
     cudaFree(facc); cudaFree(fpartial);
     for (int k = 0; k < 2; ++k) {
       cudaFree(rec[k]); cudaFree(R2[k]); cudaFree(boxes[k]);
@@ -890,38 +892,32 @@ struct Sim : SimBase {
   /* end-to-end step with host buffers: pinned staging, async copies on the work stream */
   int step_host(const double *state_in, long nsteps, double *state_out, double *fhf_out, double *dens) override {
     if (!ready) return fail(LBMDEM_ESTATE, "no grains loaded");
-    real *st[9] = {g.x1, g.x2, g.x3, g.v1, g.v2, g.v3, g.a1, g.a2, g.a3};
-    real *fh[3] = {g.fhf1, g.fhf2, g.fhf3};
-    real *hs = reinterpret_cast<real *>(hstage); /* 16 n doubles >= 12 n reals */
-    if (state_in) {
-      for (int k = 0; k < 9; ++k)
-        for (int i = 0; i < n; ++i) hs[(size_t)k * n + i] = (real)state_in[(size_t)i * 9 + k];
-      for (int k = 0; k < 9; ++k)
-        CK(cudaMemcpyAsync(st[k], hs + (size_t)k * n, sizeof(real) * n, cudaMemcpyHostToDevice, stream));
+    real *hs = reinterpret_cast<real *>(hstage); /* 16 n doubles >= 12 n reals; pinned */
+    const size_t N = (size_t)n;
+    if (state_in) { /* [n][9] doubles -> [9][n] reals, one copy into the grain slab */
+      for (size_t i = 0; i < N; ++i)
+        for (int k = 0; k < 9; ++k) hs[k * N + i] = (real)state_in[i * 9 + k];
+      CK(cudaMemcpyAsync(g.x1, hs, sizeof(real) * 9 * N, cudaMemcpyHostToDevice, stream));
     }
     bool built = false;
     int rc = step_async(nsteps, &built);
     if (rc) return rc;
-    if (state_out)
-      for (int k = 0; k < 9; ++k)
-        CK(cudaMemcpyAsync(hs + (size_t)k * n, st[k], sizeof(real) * n, cudaMemcpyDeviceToHost, stream));
-    if (fhf_out)
-      for (int k = 0; k < 3; ++k)
-        CK(cudaMemcpyAsync(hs + (size_t)(9 + k) * n, fh[k], sizeof(real) * n, cudaMemcpyDeviceToHost, stream));
+    (void)built;
+    if (state_out || fhf_out) /* state and fhf are contiguous in the slab */
+      CK(cudaMemcpyAsync(hs, g.x1, sizeof(real) * 12 * N, cudaMemcpyDeviceToHost, stream));
     if (dens) {
       const real *obs;
       if ((rc = observable_f(&obs))) return rc;
       CK(launch_density<real>(obs, ly, x0, xlo, xhi, pitch, plane, dens_partials, DENS_BLOCKS, dens_out, stream));
       CK(cudaMemcpyAsync(dens, dens_out, sizeof(double), cudaMemcpyDeviceToHost, stream));
     }
-    (void)built;
     if ((rc = check_flags())) return rc;
     if (state_out)
-      for (int k = 0; k < 9; ++k)
-        for (int i = 0; i < n; ++i) state_out[(size_t)i * 9 + k] = hs[(size_t)k * n + i];
+      for (size_t i = 0; i < N; ++i)
+        for (int k = 0; k < 9; ++k) state_out[i * 9 + k] = hs[k * N + i];
     if (fhf_out)
-      for (int k = 0; k < 3; ++k)
-        for (int i = 0; i < n; ++i) fhf_out[(size_t)i * 3 + k] = hs[(size_t)(9 + k) * n + i];
+      for (size_t i = 0; i < N; ++i)
+        for (int k = 0; k < 3; ++k) fhf_out[i * 3 + k] = hs[(9 + k) * N + i];
     return 0;
   }
 

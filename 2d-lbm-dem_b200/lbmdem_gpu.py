@@ -16,7 +16,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liblbmdem_gpu.so")
+LIB_PATH = os.environ.get("LBMDEM_LIB") or os.path.join(HERE, "liblbmdem_gpu.so")   # LBMDEM_LIB: tuning variants
 
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 _fp = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
