@@ -31,13 +31,16 @@ __global__ void grain_prepare_kernel(RasterParams<real> P, int n, GrainArrays<re
   boxes[i] = b;
 }
 
-/* one warp per grain; the owner of a node is the highest-index grain covering it (:1028 run
+constexpr int GSPLIT = 4; /* warps per grain in the rasteriser and the boundary pass */
+
+/* GSPLIT warps per grain; the owner of a node is the highest-index grain covering it (:1028 run
  * in index order), hence atomicMax over the fluid value -1.  Grains whose reduced discs share a
  * node are flagged: only they can have foreign neighbours deep inside their disc. */
 template <typename real>
 __global__ void raster_kernel(int n, const GrainRec<real> *rec, const real *R2, const GrainBox *boxes, int *cell, int x0,
                               int nxl, int pitch, int *overlap) {
-  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int i = wg / GSPLIT, part = wg % GSPLIT; /* GSPLIT warps share one grain's bounding box */
   const int lane = threadIdx.x & 31;
   if (i >= n) return;
   const GrainBox b = boxes[i];
@@ -49,7 +52,7 @@ __global__ void raster_kernel(int n, const GrainRec<real> *rec, const real *R2, 
   const float inv_ny = 1.0f / (float)ny;
   bool shared_node = false;
   /* four nodes per lane and trip, so that the atomics are in flight together */
-  for (int base = 0; base < total; base += 128) {
+  for (int base = part * 128; base < total; base += 128 * GSPLIT) {
     int old[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -106,14 +109,21 @@ __global__ void __launch_bounds__(BND_WARPS * 32) boundary_kernel(int n, const G
   __shared__ uint2 s_links[BND_WARPS][BND_LINKS];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1;
-  const int i = blockIdx.x * BND_WARPS + w;
+  const int wg = blockIdx.x * BND_WARPS + w;
+  const int i = wg / GSPLIT, part = wg % GSPLIT; /* GSPLIT warps share one grain: a contiguous share of its rows each */
   if (i >= n) return;
   const GrainBox b = boxes[i];
   const real xc = rec[i].xc, yc = rec[i].yc, r2 = rec[i].r2, RR = R2[i];
   /* rows whose neighbours are held locally */
-  const int xa = max(b.xi, x0 + 1), xb = min(b.xf, x0 + nxl - 2);
+  int xa = max(b.xi, x0 + 1), xb = min(b.xf, x0 + nxl - 2);
   const int ny = b.yf - b.yi + 1;
   if (ny <= 0 || xb < xa) return;
+  {
+    const int rows = xb - xa + 1, lo = rows * part / GSPLIT, hi = rows * (part + 1) / GSPLIT;
+    xb = xa + hi - 1;
+    xa = xa + lo;
+    if (xb < xa) return;
+  }
   const int total = (xb - xa + 1) * ny;
   const float inv_ny = 1.0f / (float)ny;
   real inner2 = -1;
@@ -242,8 +252,8 @@ cudaError_t launch_raster(const RasterParams<real> &P, int n, const GrainArrays<
   if ((e = cudaMemsetAsync(overlap, 0, sizeof(int) * n, s)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(B.count, 0, sizeof(int), s)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(K.count, 0, sizeof(int), s)) != cudaSuccess) return e;
-  raster_kernel<real><<<(n * 32 + 255) / 256, 256, 0, s>>>(n, rec, R2, boxes, cell, x0, nxl, pitch, overlap);
-  boundary_kernel<real><<<(n + BND_WARPS - 1) / BND_WARPS, BND_WARPS * 32, 0, s>>>(n, rec, R2, boxes, cell, x0, nxl, pitch,
+  raster_kernel<real><<<(n * GSPLIT * 32 + 255) / 256, 256, 0, s>>>(n, rec, R2, boxes, cell, x0, nxl, pitch, overlap);
+  boundary_kernel<real><<<(n * GSPLIT + BND_WARPS - 1) / BND_WARPS, BND_WARPS * 32, 0, s>>>(n, rec, R2, boxes, cell, x0, nxl, pitch,
                                                                                     P.lx, P.ly, overlap, B, K);
   return cudaGetLastError();
 }
