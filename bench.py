@@ -88,7 +88,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -163,13 +163,13 @@ def cpu_reference(workload, steps, warmup, sample_path, tmpdir, as_line):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--strict", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-steps", type=int, default=6)
+    ap.add_argument("--cpu-steps", type=int, default=40)
     a = ap.parse_args()
     rows, ly, scale, prec, preset, desc = WORKLOADS[a.workload]
     rank, local_rank, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
@@ -186,8 +186,12 @@ def main():
             return 0
         n_grains = make_sample_file(preset, 1, rows, sample_path)
         W = max(1, min(a.warmup, 2))
+        # every coupled step of the full lattice costs the host ~0.25 s: time at most REF_CAP of the K steps
+        REF_CAP = 120
+        timed = max(1, min(a.steps, REF_CAP))
         with quiet_stdout():
-            cb = cpu_reference(a.workload, a.steps, W, sample_path, tmpdir, True)
+            cb = cpu_reference(a.workload, timed, W, sample_path, tmpdir, True)
+        config["reference_steps_timed"] = timed
         config["grains"] = n_grains
         line = {"impl": "reference", "metric": "MLUPS", "value": cb["value"], "unit": "MLUPS", "n_gpus": n_gpus,
                 "steps": a.steps, "warmup": W, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
