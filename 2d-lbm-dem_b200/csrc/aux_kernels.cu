@@ -38,7 +38,7 @@ constexpr int GSPLIT = 4; /* warps per grain in the rasteriser and the boundary 
  * node are flagged: only they can have foreign neighbours deep inside their disc. */
 template <typename real>
 __global__ void raster_kernel(int n, const GrainRec<real> *rec, const real *R2, const GrainBox *boxes, int *cell, int x0,
-                              int nxl, int pitch, int *overlap) {
+                              int nxl, int pitch, int *overlap, int *min_owner, int genkey) {
   const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int i = wg / GSPLIT, part = wg % GSPLIT; /* GSPLIT warps share one grain's bounding box */
   const int lane = threadIdx.x & 31;
@@ -54,9 +54,11 @@ __global__ void raster_kernel(int n, const GrainRec<real> *rec, const real *R2, 
   /* four nodes per lane and trip, so that the atomics are in flight together */
   for (int base = part * 128; base < total; base += 128 * GSPLIT) {
     int old[4];
+    size_t at[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       old[u] = -1;
+      at[u] = 0;
       const int t = base + u * 32 + lane;
       if (t < total) {
         int row = (int)(((float)t + 0.5f) * inv_ny); /* t / ny for the small integers that occur; fixed up below */
@@ -64,12 +66,20 @@ __global__ void raster_kernel(int n, const GrainRec<real> *rec, const real *R2, 
         if (y < 0) { --row; y += ny; } else if (y >= ny) { ++row; y -= ny; }
         const int x = xa + row;
         y += b.yi;
-        if (disc_covers(xc, yc, r2, RR, x, y)) old[u] = atomicMax(&cell[(size_t)(x - x0) * pitch + y], i);
+        if (disc_covers(xc, yc, r2, RR, x, y)) {
+          at[u] = (size_t)(x - x0) * pitch + y;
+          old[u] = atomicMax(&cell[at[u]], i);
+        }
       }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u)
-      if (old[u] >= 0 && old[u] != i) { shared_node = true; overlap[old[u]] = 1; }
+      if (old[u] >= 0 && old[u] != i) {
+        /* a node under more than one reduced disc: keep the lowest covering index as well */
+        shared_node = true;
+        overlap[old[u]] = 1;
+        atomicMin(&min_owner[at[u]], (genkey << MINOWNER_SHIFT) | min(old[u], i));
+      }
   }
   if (shared_node) overlap[i] = 1;
 }
@@ -102,8 +112,8 @@ __device__ __forceinline__ void list_flush(uint2 *dst, int *counter, int capacit
 template <typename real>
 __global__ void __launch_bounds__(BND_WARPS * 32) boundary_kernel(int n, const GrainRec<real> *rec, const real *R2,
                                                                    const GrainBox *boxes, int *cell, int x0, int nxl, int pitch,
-                                                                   int lx, int ly, const int *overlap, BoundaryList B,
-                                                                   LinkList K) {
+                                                                   int lx, int ly, const int *overlap, const int *min_owner,
+                                                                   int genkey, BoundaryList B, LinkList K) {
   __shared__ int s_cand[BND_WARPS][BND_CAND];
   __shared__ uint2 s_nodes[BND_WARPS][BND_NODES];
   __shared__ uint2 s_links[BND_WARPS][BND_LINKS];
@@ -174,11 +184,16 @@ __global__ void __launch_bounds__(BND_WARPS * 32) boundary_kernel(int n, const G
 #pragma unroll
           for (int q = 1; q < NQ; ++q) {
             const int nx = x + ex_of(q), nyy = y + ey_of(q);
-            const int cn = cell[(size_t)(nx - x0) * pitch + nyy];
+            const size_t kq = (size_t)(nx - x0) * pitch + nyy;
+            const int cn = cell[kq];
             if (cell_is_fluid(cn)) fluid |= 1u << (q - 1);
-            if (cell_obst(cn) != i) {
+            const int kown = cell_obst(cn);
+            if (kown != i) {
               foreign |= 1u << (q - 1);
-              if (fluid_when_grain_ran(cn, i, n, xc, yc, r2, RR, b, nx, nyy)) act = true;
+              /* a neighbour owned by a LATER grain counted as fluid when grain i ran unless a grain
+               * j <= i lies under it as well: only then is the min-owner map consulted */
+              const int mo = (kown > i && kown < n) ? min_owner_decode(min_owner[kq], genkey) : -1;
+              if (fluid_when_grain_ran_exact(cn, i, n, mo)) act = true;
             }
           }
           if (act) {
@@ -239,8 +254,8 @@ __global__ void cell_frame_kernel(int *cell, int lx, int ly, int x0, int nxl, in
 
 template <typename real>
 cudaError_t launch_raster(const RasterParams<real> &P, int n, const GrainArrays<real> &g, GrainRec<real> *rec, real *R2,
-                          GrainBox *boxes, int *cell, int x0, int nxl, int pitch, int *overlap, const BoundaryList &B,
-                          const LinkList &K, cudaStream_t s) {
+                          GrainBox *boxes, int *cell, int x0, int nxl, int pitch, int *overlap, int *min_owner, int genkey,
+                          const BoundaryList &B, const LinkList &K, cudaStream_t s) {
   grain_prepare_kernel<real><<<(n + 127) / 128, 128, 0, s>>>(P, n, g, rec, R2, boxes);
   /* clear the interior: rows with global x in [1, lx-2], columns [1, ly-2] (:997-1005) */
   const int ra = max(1 - x0, 0), rb = min(P.lx - 2 - x0, nxl - 1);
@@ -252,9 +267,10 @@ cudaError_t launch_raster(const RasterParams<real> &P, int n, const GrainArrays<
   if ((e = cudaMemsetAsync(overlap, 0, sizeof(int) * n, s)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(B.count, 0, sizeof(int), s)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(K.count, 0, sizeof(int), s)) != cudaSuccess) return e;
-  raster_kernel<real><<<(n * GSPLIT * 32 + 255) / 256, 256, 0, s>>>(n, rec, R2, boxes, cell, x0, nxl, pitch, overlap);
+  raster_kernel<real><<<(n * GSPLIT * 32 + 255) / 256, 256, 0, s>>>(n, rec, R2, boxes, cell, x0, nxl, pitch, overlap,
+                                                                 min_owner, genkey);
   boundary_kernel<real><<<(n * GSPLIT + BND_WARPS - 1) / BND_WARPS, BND_WARPS * 32, 0, s>>>(n, rec, R2, boxes, cell, x0, nxl, pitch,
-                                                                                    P.lx, P.ly, overlap, B, K);
+                                                                                    P.lx, P.ly, overlap, min_owner, genkey, B, K);
   return cudaGetLastError();
 }
 
@@ -871,8 +887,8 @@ cudaError_t launch_fill_rest(real *f, size_t plane, const Lattice<real> &Lw, cud
 
 #define INSTANTIATE(real)                                                                                               \
   template cudaError_t launch_raster<real>(const RasterParams<real> &, int, const GrainArrays<real> &, GrainRec<real> *,  \
-                                           real *, GrainBox *, int *, int, int, int, int *, const BoundaryList &,         \
-                                           const LinkList &, cudaStream_t);                                               \
+                                           real *, GrainBox *, int *, int, int, int, int *, int *, int,                   \
+                                           const BoundaryList &, const LinkList &, cudaStream_t);                         \
   template cudaError_t launch_act_map<real>(const Lattice<real> &, const Stored<real> &, int, int, int *, cudaStream_t);  \
   template cudaError_t launch_ring_sweep<real>(const Lattice<real> &, const Stored<real> &, real *, int, int,             \
                                                cudaStream_t);                                                             \

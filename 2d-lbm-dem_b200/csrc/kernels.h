@@ -132,7 +132,8 @@ constexpr unsigned LL_W = 1u << 28;
 template <typename real>
 cudaError_t launch_raster(const lbm::RasterParams<real> &P, int ngrains, const GrainArrays<real> &g,
                           lbm::GrainRec<real> *rec, real *R2, lbm::GrainBox *boxes, int *cell, int x0, int nxl, int pitch,
-                          int *overlap, const BoundaryList &B, const LinkList &K, cudaStream_t s);
+                          int *overlap, int *min_owner /* [x-x0][y], lbm_node.cuh MINOWNER_* */, int genkey,
+                          const BoundaryList &B, const LinkList &K, cudaStream_t s);
 cudaError_t launch_cell_frame(int *cell, int lx, int ly, int x0, int nxl, int pitch, int ring_value, cudaStream_t s);
 /* act[x][y] as the reference would hold it (tests / diagnostics) */
 template <typename real>

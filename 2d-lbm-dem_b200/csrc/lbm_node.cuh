@@ -79,9 +79,11 @@ LBM_HD bool disc_covers(real xc, real yc, real r2, real R2, int x, int y) {
 
 /* Was node n "fluid" when the reference's grain loop reached grain i (:1047)?  At that moment
  * the map holds grains 0..i only.  n is fluid then iff no grain j <= i covers it: final map
- * -1, or final owner k > i while grain i itself does not cover n.  (A node covered by k > i
- * AND by some j < i but not by i -- three mutually overlapping reduced discs -- would be
- * misjudged; reduced discs are 0.85 r, so even a pair only overlaps at > 15 % interpenetration.)
+ * -1, or final owner k > i while grain i itself does not cover n.  This form needs nothing but
+ * the map and is used for maps that come from outside (lbmdem_set_obst); a node covered by k > i
+ * AND by some j < i but not by i -- three mutually overlapping reduced discs -- is misjudged by
+ * it (reduced discs are 0.85 r: even a pair only overlaps at > 15 % interpenetration).  The
+ * device's own rasteriser uses fluid_when_grain_ran_exact below.
  */
 template <typename real>
 LBM_HD bool fluid_when_grain_ran(int cell_n, int i, int ngrains, real xc, real yc, real r2, real R2,
@@ -93,6 +95,27 @@ LBM_HD bool fluid_when_grain_ran(int cell_n, int i, int ngrains, real xc, real y
 }
 
 /* geometry and constants of the lattice (strip-local storage: rows x0 .. x0+nxl-1) */
+/* The exact form of the same question, for maps the rasteriser built itself: it also records,
+ * for every node that more than one reduced disc covers, the LOWEST covering index (min_owner;
+ * -1 = the node is covered by its owner alone).  n was fluid when grain i ran iff no grain
+ * j <= i covers it, i.e. iff the lowest covering index is greater than i -- whatever the number
+ * of mutually overlapping discs. */
+LBM_HD bool fluid_when_grain_ran_exact(int cell_n, int i, int ngrains, int min_owner) {
+  if (cell_is_fluid(cell_n)) return true;
+  const int k = cell_obst(cell_n);
+  if (k >= ngrains || k <= i) return false;
+  return (min_owner >= 0 ? min_owner : k) > i;
+}
+/* min-owner map entries: (generation key << 23) | grain index, written with atomicMin; the key
+ * DEcreases from step to step, so that entries of older steps lose against this step's and the
+ * map needs clearing only when the key wraps (csrc/sim.cu) */
+constexpr int MINOWNER_SHIFT = 23;
+constexpr int MINOWNER_GRAIN = (1 << MINOWNER_SHIFT) - 1;
+constexpr int MINOWNER_EMPTY = 0x7f7f7f7f;
+LBM_HD int min_owner_decode(int entry, int genkey) {
+  return (entry >> MINOWNER_SHIFT) == genkey ? (entry & MINOWNER_GRAIN) : -1;
+}
+
 template <typename real>
 struct Lattice {
   int lx, ly;             /* global lattice size */

@@ -156,6 +156,8 @@ struct Sim : SimBase {
   DeferList<real> defer{};
   BoundaryList blist{};
   int *overlap = nullptr;
+  int *min_owner = nullptr; /* [x-x0][y]: lowest covering grain of multiply covered nodes (lbm_node.cuh MINOWNER_*) */
+  int genkey = 0;           /* generation key of this step's entries; counts down, the map is cleared when it wraps */
   int *hflags = nullptr;      /* mapped host memory: [0] Verlet capacity exceeded, [1] deferred-link list full, [2] boundary list full */
   std::vector<real *> grain_bufs;
   GrainArrays<real> g{};
@@ -192,6 +194,7 @@ struct Sim : SimBase {
     cudaFree(dens_partials); cudaFree(dens_out); cudaFree(stage); cudaFree(mid_dev);
     cudaFree(defer.count); cudaFree(defer.index); cudaFree(defer.value);
     cudaFree(blist.entry); cudaFree(blist.count); cudaFree(overlap); cudaFree(llist.entry); cudaFree(llist.count);
+    cudaFree(min_owner);
     if (hflags) cudaFreeHost(hflags);
     if (hstage) cudaFreeHost(hstage);
     if (stream) cudaStreamDestroy(stream);
@@ -454,8 +457,15 @@ struct Sim : SimBase {
   }
   bool act_folded[2] = {false, false};
   int raster_into(int cslot) {
-    CK(launch_raster<real>(raster_params(), n, g, rec[cslot], R2[cslot], boxes[cslot], cell[cslot], x0, nxl, pitch, overlap, blist,
-                            llist, stream));
+    if (!min_owner) CK(cudaMalloc(&min_owner, sizeof(int) * plane));
+    if (genkey <= 1) { /* first use, or the key wrapped: forget every older entry */
+      CK(cudaMemsetAsync(min_owner, 0x7f, sizeof(int) * plane, stream));
+      genkey = 0x7e;
+    } else {
+      --genkey;
+    }
+    CK(launch_raster<real>(raster_params(), n, g, rec[cslot], R2[cslot], boxes[cslot], cell[cslot], x0, nxl, pitch, overlap, min_owner,
+                            genkey, blist, llist, stream));
     act_folded[cslot] = true;
     return 0;
   }

@@ -33,6 +33,7 @@ void raster_host(int lx, int ly, int n, const RasterParams<real> &P, const real 
                  const real *rLB, const real *v1, const real *v2, const real *v3, std::vector<int> &cell,
                  std::vector<GrainRec<real>> &rec, std::vector<GrainBox> &box, std::vector<real> &R2) {
   cell.assign((size_t)lx * ly, -1);
+  std::vector<int> min_owner((size_t)lx * ly, -1); /* lowest covering index of multiply covered nodes */
   for (int x = 0; x < lx; ++x) cell[(size_t)x * ly] = cell[(size_t)x * ly + ly - 1] = n;
   for (int y = 0; y < ly; ++y) cell[y] = cell[(size_t)(lx - 1) * ly + y] = n;
   rec.resize(n);
@@ -44,7 +45,11 @@ void raster_host(int lx, int ly, int n, const RasterParams<real> &P, const real 
     g.x1 = x1[i]; g.x2 = x2[i]; g.v1 = v1[i]; g.v2 = v2[i]; g.v3 = v3[i];
     for (int x = box[i].xi; x <= box[i].xf; ++x)
       for (int y = box[i].yi; y <= box[i].yf; ++y)
-        if (disc_covers(g.xc, g.yc, g.r2, R2[i], x, y)) cell[(size_t)x * ly + y] = std::max(cell[(size_t)x * ly + y], i);
+        if (disc_covers(g.xc, g.yc, g.r2, R2[i], x, y)) {
+          int &c = cell[(size_t)x * ly + y];
+          if (c >= 0) { int &m = min_owner[(size_t)x * ly + y]; m = (m < 0) ? std::min(c, i) : std::min(m, i); }
+          c = std::max(c, i);
+        }
   }
   for (int i = 0; i < n; ++i) {
     const GrainRec<real> &g = rec[i];
@@ -54,7 +59,7 @@ void raster_host(int lx, int ly, int n, const RasterParams<real> &P, const real 
         bool act = false;
         for (int q = 1; q < NQ; ++q) {
           const int nx = x + ex_of(q), ny = y + ey_of(q);
-          if (fluid_when_grain_ran(cell[(size_t)nx * ly + ny], i, n, g.xc, g.yc, g.r2, R2[i], box[i], nx, ny)) act = true;
+          if (fluid_when_grain_ran_exact(cell[(size_t)nx * ly + ny], i, n, min_owner[(size_t)nx * ly + ny])) act = true;
         }
         if (act) cell[(size_t)x * ly + y] = i | CELL_ACT;
       }
@@ -220,6 +225,7 @@ void strip_raster(StripCtx<real> &C, const double *grains) {
   RasterParams<real> P;
   P.lx = L.lx; P.ly = L.ly; P.dx = L.dx; P.Mgx = L.Mgx; P.Mby = L.Mby;
   C.cell.assign(L.plane, -1);
+  std::vector<int> min_owner(L.plane, -1);
   for (int r = 0; r < L.nxl; ++r)
     for (int y = 0; y < ly; ++y) {
       const int x = L.x0 + r;
@@ -235,6 +241,7 @@ void strip_raster(StripCtx<real> &C, const double *grains) {
       for (int y = C.box[i].yi; y <= C.box[i].yf; ++y)
         if (disc_covers(R.xc, R.yc, R.r2, C.R2[i], x, y)) {
           int &c = C.cell[node_index(L, x, y)];
+          if (c >= 0) { int &m = min_owner[node_index(L, x, y)]; m = (m < 0) ? std::min(c, i) : std::min(m, i); }
           c = std::max(c, i);
         }
   }
@@ -247,7 +254,7 @@ void strip_raster(StripCtx<real> &C, const double *grains) {
         bool act = false;
         for (int q = 1; q < NQ; ++q) {
           const int nx = x + ex_of(q), ny = y + ey_of(q);
-          if (fluid_when_grain_ran(C.cell[node_index(L, nx, ny)], i, n, R.xc, R.yc, R.r2, C.R2[i], C.box[i], nx, ny)) act = true;
+          if (fluid_when_grain_ran_exact(C.cell[node_index(L, nx, ny)], i, n, min_owner[node_index(L, nx, ny)])) act = true;
         }
         if (act) c |= CELL_ACT;
       }

@@ -369,3 +369,110 @@ def test_lbmdem_executable_writes_the_reference_files(tmp_path):
             continue
         mine, ref = open(tmp_path / name, "rb").read(), open(os.path.join(ref_dir, name), "rb").read()
         assert mine == ref, f"{name} differs from the reference's file"
+
+
+# ---- edge cases and full-size properties ---------------------------------------------------------
+def test_far_grain_lid_driven_cavity():
+    """BASELINE configs[1]: no grain inside the lattice (the reference cannot run with zero grains: one
+    grain outside the lattice, inside the DEM walls), moving lid.  No contacts, hence no chaos: the
+    strict build stays bit-exact and the default build within 1e-9 over 300 renderScene() calls."""
+    lx = ly = 128
+    for strict in (1, 0):
+        o = Oracle(lx, ly, 1.0, "f64")
+        s = G.Solver(lx, ly, 1.0, "f64", lid_u=0.05, strict_fp=strict)
+        r, x, y = np.array([1.0e-3]), np.array([0.5 * lx * 1e-3]), np.array([1.0e-3])
+        assert o.init_arrays(r, x, y) == s.init_arrays(r, x, y) == 1
+        o.set_lid(0.05)
+        o.step(300)
+        s.step(300)
+        fo, fs = o.f(), s.f()
+        assert (o.obst() >= 0).sum() == 2 * lx + 2 * ly - 4          # only the wall ring is solid
+        assert np.array_equal(o.obst(), s.obst())
+        jx = (fo * np.array([0, -1, -1, -1, 0, 1, 1, 1, 0.0])).sum(-1)
+        assert np.abs(jx).max() > 1e-3                                # the lid does drive a flow
+        if strict:
+            assert np.array_equal(fo, fs) and np.array_equal(o.grains(), s.grains())
+        else:
+            assert _relerr(fs, fo) < 1e-9
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_overlapping_discs_and_discs_on_the_ring_strict(prec):
+    """Reduced discs that overlap each other (> 15 % interpenetration), discs that reach into the wall
+    ring and a disc partly outside the lattice: owner = highest index, links into other grains and into
+    the ring count in forces_fluid, deep nodes of overlapping grains are not skipped."""
+    lx, ly = 96, 72
+    dx = 1e-4 * lx / (lx - 1)
+    r = np.array([10, 9, 8, 7, 9, 6.5]) * dx
+    x = np.array([30, 39, 34, 3.0, 80, 95.0]) * dx            # 0-1-2 overlap pairwise; 3 on the left ring; 5 sticks out on the right
+    y = np.array([30, 31, 38, 40, 2.5, 20]) * dx              # 4 on the bottom ring
+    o = Oracle(lx, ly, 1.0, prec)
+    s = G.Solver(lx, ly, 1.0, prec, strict_fp=1)
+    n = o.init_arrays(r, x, y)
+    assert s.init_arrays(r, x, y) == n
+    _same_start(o, s, n, 77, vmax=0.03)
+    ob = o.obst()
+    assert ((ob >= 0) & (ob < n)).sum() > 500 and len(np.unique(ob)) == n + 2
+    for step in range(4):
+        o.lbm_step()
+        s.lbm_step()
+        assert np.array_equal(o.obst(), s.obst())
+        solid = (o.obst() >= 0) & (o.obst() < n)
+        assert np.array_equal(o.act()[solid], s.act()[solid])
+        assert np.array_equal(o.f(), s.f()), f"step {step}"
+        assert np.array_equal(o.fhf(), s.fhf()), f"step {step}"
+        st = o.grains()[:, :9].copy()
+        st[:, 0:2] += np.random.default_rng(step).uniform(-0.5, 0.5, size=(n, 2)) * dx
+        o.set_grain_state(st)
+        s.set_grain_state(st)
+    # the default build agrees too (fixed-point force sums, list-driven kernels)
+    d = G.Solver(lx, ly, 1.0, prec)
+    d.init_arrays(r, x, y)
+    d.set_obst(o.obst())          # the map reinit_obst_density will treat as "old"
+    d.set_f(o.f())
+    d.set_grain_state(o.grains()[:, :9])
+    o.lbm_step()
+    d.lbm_step()
+    assert np.array_equal(o.obst(), d.obst())
+    assert _relerr(d.f(), o.f()) < REL_STEP[prec]
+    assert _relerr(d.fhf(), o.fhf()) < (1e-9 if prec == "f64" else 5e-3)
+
+
+def test_full_size_row_kernel_equals_plain_kernel_fp64():
+    """BASELINE configs[2] size (2048 x 2048, fp64, 726 grains): the TMA row pipeline and the plain
+    one-thread-per-node kernel are the same map; every population identical after 3 coupled steps."""
+    import make_sample as ms
+    lx = ly = 2048
+    n, r_min, r_max, width = ms.PRESETS["a08d83"]
+    r, x, y = ms.packed_sample(n, r_min, r_max, width, seed=12345)
+    a = G.Solver(lx, ly, 1.0, "f64", kernel=0)
+    b = G.Solver(lx, ly, 1.0, "f64", kernel=1)
+    for slv in (a, b):
+        assert slv.init_arrays(r * 1e-3, x * 1e-3, y * 1e-3) == n
+        slv.step(3 * slv.scalars()["npDEM"] + 1)
+    assert np.array_equal(a.obst(), b.obst())
+    assert np.array_equal(a.fhf(), b.fhf()) and np.array_equal(a.grains(), b.grains())
+    fa = a.f()
+    assert np.array_equal(fa, b.f())
+    assert np.isfinite(fa).all() and abs(fa.sum() / (lx * ly) - 1.0) < 1e-6
+
+
+def test_full_size_fp32_properties():
+    """BASELINE configs[3] size (4096 x 4096, fp32, 6355 grains): row kernel == plain kernel through
+    the order-free checksums (fixed-shape density reduction, fixed-point force sums), and the lattice
+    mass stays put."""
+    import make_sample as ms
+    lx = ly = 4096
+    n, r_min, r_max, width = ms.PRESETS["a08_7000"]
+    r, x, y = ms.packed_sample(n, r_min, r_max, width, seed=12345)
+    a = G.Solver(lx, ly, 2.7, "f32", kernel=0)
+    b = G.Solver(lx, ly, 2.7, "f32", kernel=1)
+    dens = []
+    for slv in (a, b):
+        assert slv.init_arrays(r * 1e-3, x * 1e-3, y * 1e-3) == n
+        slv.step(4 * slv.scalars()["npDEM"] + 1)
+        dens.append(slv.total_density())
+    assert dens[0] == dens[1]
+    assert np.array_equal(a.fhf(), b.fhf()) and np.array_equal(a.grains(), b.grains())
+    assert abs(dens[0] / (lx * ly) - 1.0) < 1e-5
+    assert np.abs(a.fhf()).max() > 0

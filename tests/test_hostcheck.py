@@ -21,12 +21,12 @@ def _grain_table(g):
     return np.ascontiguousarray(g[:, [0, 1, 3, 4, 5, 9, 12]])
 
 
-def _lbm_case(prec, lx, ly, scale, seed, lid=0.0, steps=4, n_target=None):
+def _lbm_case(prec, lx, ly, scale, seed, lid=0.0, steps=4, n_target=None, discs=None):
     hc = load_hostcheck()
     fn = getattr(hc, f"hc_lbm_step_{prec}")
     real = np.float64 if prec == "f64" else np.float32
     o = Oracle(lx, ly, scale, prec)
-    r, x, y = small_packing(lx, ly, scale, seed, n_target=n_target)
+    r, x, y = discs if discs is not None else small_packing(lx, ly, scale, seed, n_target=n_target)
     n = o.init_arrays(r, x, y)
     if lid:
         o.set_lid(lid)
@@ -92,6 +92,19 @@ def test_lbm_step_formulation_dense_scaled():
     assert info["n"] >= 60
     # links across one-node gaps went through the deferred list (evaluated in reverse sweep order)
     assert load_hostcheck().hc_last_deferred() > 100
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_lbm_step_overlapping_discs_and_discs_on_the_ring(prec):
+    # three mutually overlapping reduced discs (the act rule needs the lowest covering index there),
+    # discs reaching into the wall ring, a disc partly outside the lattice
+    lx, ly = 96, 72
+    dx = 1e-4 * lx / (lx - 1)
+    r = np.array([10, 9, 8, 7, 9, 6.5]) * dx
+    x = np.array([30, 39, 34, 3.0, 80, 95.0]) * dx
+    y = np.array([30, 31, 38, 40, 2.5, 20]) * dx
+    info = _lbm_case(prec, lx, ly, 1.0, seed=40, steps=3, discs=(r, x, y))
+    assert info["n"] == 6 and info["solid"] > 500
 
 
 def _dem_params(sc):
