@@ -141,6 +141,7 @@ struct Sim : SimBase {
   bool ready = false;
   /* reference globals, kept in `real` like the reference keeps them (src/main.c:52-165) */
   real dx = 0, dtLB = 0, c = 0, dt = 0, dt2 = 0, Mgx = 0, Mdx = 0, Mby = 0, Mhy = 0, xG = 0, yG = 0, rmax = 0;
+  real t = 0; /* src/main.c:165, advanced only while the walls vibrate */
   int npDEM = 1;
   long nbsteps = 0, nFile = 0;
   double k12 = 0, k3 = 0; /* fhf scale factors (:1329-1331) */
@@ -389,6 +390,7 @@ struct Sim : SimBase {
     CK(cudaStreamSynchronize(stream));
     nbsteps = 0;
     nFile = 0;
+    t = 0;
     ready = true;
     return n;
   }
@@ -473,7 +475,7 @@ struct Sim : SimBase {
     dem::Params<real> D;
     D.kg = (real)P.kg; D.kt = (real)P.kt; D.km = (real)P.km; D.ktm = (real)P.ktm; D.nug = (real)P.nug;
     D.num = (real)P.num; D.numb = (real)P.numb; D.nugt = (real)P.nugt; D.mu = (real)P.mu; D.mum = (real)P.mum;
-    D.mumb = (real)P.mumb; D.murf = (real)P.murf; D.freq = (real)P.freq; D.amp = (real)P.amp; D.t = 0;
+    D.mumb = (real)P.mumb; D.murf = (real)P.murf; D.freq = (real)P.freq; D.amp = (real)P.amp; D.t = t;
     D.distVerlet = (real)P.distVerlet; D.dt = dt; D.dt2 = dt2; D.xG = xG; D.yG = yG;
     D.Mgx = Mgx; D.Mdx = Mdx; D.Mby = Mby; D.Mhy = Mhy;
     return D;
@@ -675,6 +677,12 @@ struct Sim : SimBase {
   int step_async(long nsteps, bool *built, bool capture = false) {
     for (long k = 0; k < nsteps; ++k) {
       int rc;
+      if (P.vib == 1) { /* vibrating walls (:1701-1706) */
+        const real freq = (real)P.freq, amp = (real)P.amp;
+        t = t + dt;
+        Mgx = Mgx + amp * sin((double)(freq * t));
+        Mdx = Mdx + amp * sin((double)(freq * t));
+      }
       if (nbsteps % npDEM == 0 && (rc = lbm_step_async())) return rc;
       if (nbsteps % P.UpdateVerlet == 0) {
         if ((rc = verlet_async())) return rc;
@@ -988,7 +996,7 @@ API int lbmdem_default_params(lbmdem_params *p) {
   p->rscale = 1e-3; p->distVerlet = 5e-4; p->dtt = 0.; p->iterDEM = 100.;
   p->freq = 5; p->amp = 4.e-4; p->rhoS = 2650;
   p->UpdateVerlet = 100; p->stepFilm = 8000;
-  p->lid_u = 0; p->strict_fp = 0; p->kernel = 0; p->neighbour_capacity = 32;
+  p->lid_u = 0; p->strict_fp = 0; p->kernel = 0; p->neighbour_capacity = 32; p->vib = 0;
   return 0;
 }
 

@@ -9,6 +9,7 @@
  *   --duration T                         #define duration (src/main.c:47)          LBMDEM_DURATION
  *   --steps N                            stop after N renderScene() calls          LBMDEM_STEPS
  *   --strict                             bit-exact build (lbmdem_params.strict_fp) LBMDEM_STRICT
+ *   --vib                                vibrating walls, int vib = 1 (:162)       LBMDEM_VIB
  *   --device D, --outdir DIR             CUDA device, directory of the output files (default: cwd)
  * Outputs, as the reference writes them: stdout banner and progress lines, stderr
  * "final_density: %f", stats.data, DEM%06d.dat every 4000 calls, five VTK files every 8000 calls.
@@ -81,6 +82,7 @@ int main(int argc, char **argv) {
   if ((v = opt_or_env(argc, argv, "--device", "LBMDEM_DEVICE"))) p.device = atoi(v);
   p.single_precision = flag_or_env(argc, argv, "--single", "LBMDEM_SINGLE");
   p.strict_fp = flag_or_env(argc, argv, "--strict", "LBMDEM_STRICT");
+  p.vib = flag_or_env(argc, argv, "--vib", "LBMDEM_VIB"); /* int vib (src/main.c:162) */
   double duration = 1.5; /* src/main.c:47 */
   long max_steps = -1;
   if ((v = opt_or_env(argc, argv, "--duration", "LBMDEM_DURATION"))) duration = atof(v);

@@ -44,7 +44,7 @@ class Params(C.Structure):
         ("rscale", C.c_double), ("distVerlet", C.c_double), ("dtt", C.c_double), ("iterDEM", C.c_double),
         ("freq", C.c_double), ("amp", C.c_double), ("rhoS", C.c_double),
         ("UpdateVerlet", C.c_long), ("stepFilm", C.c_long),
-        ("lid_u", C.c_double), ("strict_fp", C.c_int), ("kernel", C.c_int), ("neighbour_capacity", C.c_int),
+        ("lid_u", C.c_double), ("strict_fp", C.c_int), ("kernel", C.c_int), ("neighbour_capacity", C.c_int), ("vib", C.c_int),
     ]
 
 

@@ -58,6 +58,7 @@ typedef struct lbmdem_params {
                               the reference's serial order -> bit-identical to the reference build */
   int kernel;              /* 0: tiled TMA kernel (default); 1: generic on-demand kernel (cross-check) */
   int neighbour_capacity;  /* per-grain Verlet capacity, default 32 */
+  int vib;                 /* 1: shake the left/right walls, src/main.c:162, :1701-1706 (default 0) */
 } lbmdem_params;
 
 /* Fills *p with the reference's defaults: lx=7826, ly=2325, scale=1, fp64 and every constant

@@ -68,6 +68,7 @@ struct oracle {
   real pf, pft, pff, ic; /* src/main.c:130-131 */
   real Mby, Mgx, Mhy, Mdx; /* src/main.c:201-204 */
   real lid; /* extension, 0 = reference behaviour */
+  int vib;  /* src/main.c:162 */
   grain_t *g;
   real *rLB, *fhf1, *fhf2, *fhf3;
   int *cumul, *neigh, *wallB, *wallT, *wallL, *wallR;
@@ -170,6 +171,7 @@ API int SFX(oracle_set_grains)(oracle *o, int n, const double *r, const double *
 }
 
 API void SFX(oracle_set_lid)(oracle *o, double uw) { o->lid = (real)uw; }
+API void SFX(oracle_set_vib)(oracle *o, int vib) { o->vib = vib; }
 
 /* src/main.c:663-711 */
 static void init_obst(oracle *o) {
@@ -700,9 +702,14 @@ API void SFX(oracle_init_verlet)(oracle *o) {
   for (int i = 0; i < o->n; ++i) if (-g[i].x1 - g[i].r + o->Mdx < o->distVerlet) o->wallR[o->nR++] = i;
 }
 
-/* src/main.c:1697-1765 (vib = 0; outputs are the caller's business) */
+/* src/main.c:1697-1765 (outputs are the caller's business) */
 static void render_scene(oracle *o) {
   grain_t *g = o->g;
+  if (o->vib == 1) { /* :1701-1706 */
+    o->t = o->t + o->dt;
+    o->Mgx = o->Mgx + o->amp * sin(o->freq * o->t);
+    o->Mdx = o->Mdx + o->amp * sin(o->freq * o->t);
+  }
   if (o->nbsteps % o->npDEM == 0) SFX(oracle_lbm_step)(o);
   if (o->nbsteps % o->UpdateVerlet == 0) SFX(oracle_init_verlet)(o);
   for (long i = 0; i <= o->n - 1; i++) {

@@ -35,6 +35,7 @@ typedef struct oracle oracle; /* opaque; one per precision-specific entry point 
   void oracle_init_##SFX(oracle *o);                                                         \
   /* non-reference extension: moving lid, the commented-out uw terms at src/main.c:1129-1130 */\
   void oracle_set_lid_##SFX(oracle *o, double uw);                                           \
+  void oracle_set_vib_##SFX(oracle *o, int vib);                                             \
   /* src/main.c:1697-1765 renderScene, n times (no file output) */                           \
   void oracle_step_##SFX(oracle *o, long n);                                                 \
   /* src/main.c:1711-1717 without the density print */                                       \

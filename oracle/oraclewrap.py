@@ -73,6 +73,9 @@ class Oracle:
     def set_lid(self, uw):
         self._fn("oracle_set_lid", [C.c_void_p, C.c_double])(self.o, float(uw))
 
+    def set_vib(self, vib):
+        self._fn("oracle_set_vib", [C.c_void_p, C.c_int])(self.o, int(vib))
+
     def step(self, n=1):
         self._fn("oracle_step", [C.c_void_p, C.c_long])(self.o, n)
 

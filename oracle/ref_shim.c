@@ -53,7 +53,7 @@ static void ref_free_all(void) {
 REF_API int ref_init(const char *sample_path) {
   ref_free_all();
   /* globals that main() relies on being in their load-time state */
-  nbsteps = 0; nFile = 0; start = 0; t = 0;
+  nbsteps = 0; nFile = 0; start = 0; t = 0; vib = 0;
   pf = 0.; pft = 0.; pff = 0.; ic = 0;
   TSE = 0.0; TBW = 0.0; INCE = 0.0; TSLIP = 0.0; TRW = 0.0;
   nNeighWallb = nNeighWallt = nNeighWallL = nNeighWallR = 0;
@@ -133,6 +133,7 @@ REF_API void ref_get_scalars(double *d, long *l) {
   l[0] = npDEM; l[1] = nbsteps; l[2] = nFile; l[3] = nbgrains;
 }
 REF_API void ref_set_nbsteps(long n) { nbsteps = n; }
+REF_API void ref_set_vib(int v) { vib = v; } /* src/main.c:162 */
 
 /* serial sum exactly as check_density (src/main.c:1249-1258), value returned */
 REF_API double ref_total_density(void) {

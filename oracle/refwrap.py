@@ -58,6 +58,9 @@ class Reference:
             raise MemoryError("reference allocation failed")
         return self.n
 
+    def set_vib(self, vib):
+        self.lib.ref_set_vib(int(vib))
+
     def step(self, n=1):
         self.lib.ref_step(n)
 

@@ -476,3 +476,22 @@ def test_full_size_fp32_properties():
     assert np.array_equal(a.fhf(), b.fhf()) and np.array_equal(a.grains(), b.grains())
     assert abs(dens[0] / (lx * ly) - 1.0) < 1e-5
     assert np.abs(a.fhf()).max() > 0
+
+
+def test_vibrating_walls_strict_is_bit_exact():
+    """int vib = 1 (src/main.c:162, :1701-1706)"""
+    o = Oracle(96, 80, 1.0, "f64")
+    s = G.Solver(96, 80, 1.0, "f64", strict_fp=1, vib=1)
+    r, x, y = small_packing(96, 80, 1.0, 91, n_target=60)
+    n = o.init_arrays(r, x, y)
+    assert s.init_arrays(r, x, y) == n
+    o.set_vib(1)
+    _same_start(o, s, n, 92, vmax=0.02)
+    for chunk in range(3):
+        o.step(41)
+        s.step(41)
+        assert o.scalars() == s.scalars()
+        assert np.array_equal(o.grains()[:, :9], s.grains()[:, :9])
+        assert np.array_equal(o.obst(), s.obst())
+    assert np.array_equal(o.f(), s.f()) and np.array_equal(o.fhf(), s.fhf())
+    assert o.scalars()["Mgx"] != 0.0

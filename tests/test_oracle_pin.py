@@ -173,3 +173,22 @@ def test_oracle_equals_reference_film_step(tmp_path, monkeypatch):
     ref.step(6)
     o.step(6)
     _assert_same(ref, o, "across step 8000:")
+
+
+def test_oracle_equals_reference_with_vibrating_walls(tmp_path, monkeypatch):
+    """int vib = 1 (src/main.c:162, :1701-1706): the left / right walls and the lattice origin move every call"""
+    monkeypatch.chdir(tmp_path)
+    ref, o, n = _both(64, 48, "f64", os.path.join(GOLD, "pack_64x48_f64.data"))
+    v, w, a = random_kinematics(n, 12, vmax=0.02)
+    st = ref.grains()[:, :9].copy()
+    st[:, 3:5], st[:, 5:6] = v, w
+    for z in (ref, o):
+        z.set_grain_state(st)
+        z.set_vib(1)
+    for chunk in range(3):
+        ref.step(45)
+        o.step(45)
+        _assert_same(ref, o, f"vib, after {(chunk + 1) * 45} calls:")
+        assert ref.scalars() == o.scalars()
+    assert ref.scalars()["Mgx"] != 0.0
+    ref.set_vib(0)
