@@ -871,6 +871,31 @@ cudaError_t launch_f_from_host_layout(real *f, int ly, int pitch, size_t plane, 
   return cudaGetLastError();
 }
 
+template <typename real>
+__global__ void grain_unpack_kernel(const double *rows, int n, int ncols, real *cols) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * ncols) return;
+  const int i = t / ncols, k = t - i * ncols;
+  cols[(size_t)k * n + i] = (real)rows[t];
+}
+template <typename real>
+__global__ void grain_pack_kernel(const real *cols, int n, int ncols, double *rows) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * ncols) return;
+  const int i = t / ncols, k = t - i * ncols;
+  rows[t] = (double)cols[(size_t)k * n + i];
+}
+template <typename real>
+cudaError_t launch_grain_unpack(const double *rows, int n, int ncols, real *cols, cudaStream_t s) {
+  grain_unpack_kernel<real><<<(n * ncols + 255) / 256, 256, 0, s>>>(rows, n, ncols, cols);
+  return cudaGetLastError();
+}
+template <typename real>
+cudaError_t launch_grain_pack(const real *cols, int n, int ncols, double *rows, cudaStream_t s) {
+  grain_pack_kernel<real><<<(n * ncols + 255) / 256, 256, 0, s>>>(cols, n, ncols, rows);
+  return cudaGetLastError();
+}
+
 /* init_density (src/main.c:716-724): f = w everywhere */
 template <typename real>
 __global__ void fill_rest_kernel(real *f, size_t plane, Lattice<real> Lw) {
@@ -913,6 +938,8 @@ cudaError_t launch_fill_rest(real *f, size_t plane, const Lattice<real> &Lw, cud
                                            cudaStream_t);                                                                 \
   template cudaError_t launch_f_to_host_layout<real>(const real *, int, int, size_t, int, int, double *, cudaStream_t);   \
   template cudaError_t launch_f_from_host_layout<real>(real *, int, int, size_t, int, int, const double *, cudaStream_t); \
+  template cudaError_t launch_grain_unpack<real>(const double *, int, int, real *, cudaStream_t);                         \
+  template cudaError_t launch_grain_pack<real>(const real *, int, int, double *, cudaStream_t);                           \
   template cudaError_t launch_fill_rest<real>(real *, size_t, const Lattice<real> &, cudaStream_t);
 INSTANTIATE(float)
 INSTANTIATE(double)

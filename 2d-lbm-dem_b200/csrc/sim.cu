@@ -192,7 +192,7 @@ struct Sim : SimBase {
     cudaFree(facc); cudaFree(fpartial);
     cudaFree(vb.bucket_count); cudaFree(vb.bucket_cursor); cudaFree(vb.sorted); cudaFree(vb.gcx); cudaFree(vb.gcy);
     cudaFree(vb.nbr_count); cudaFree(vb.nbr); cudaFree(vb.wflags);
-    cudaFree(dens_partials); cudaFree(dens_out); cudaFree(stage); cudaFree(mid_dev);
+    cudaFree(dens_partials); cudaFree(dens_out); cudaFree(stage); cudaFree(mid_dev); cudaFree(gstage);
     cudaFree(defer.count); cudaFree(defer.index); cudaFree(defer.value);
     cudaFree(blist.entry); cudaFree(blist.count); cudaFree(overlap); cudaFree(llist.entry); cudaFree(llist.count);
     cudaFree(min_owner);
@@ -274,6 +274,8 @@ struct Sim : SimBase {
     grain_bufs.clear();
     cudaFree(mid_dev);
     mid_dev = nullptr;
+    cudaFree(gstage);
+    gstage = nullptr;
     n = n_;
     /* one slab, so that the kinematic state (9 arrays) and state + fhf (12 arrays) move in one copy each:
      * x1 x2 x3 v1 v2 v3 a1 a2 a3 | fhf1 fhf2 fhf3 | r m It rLB */
@@ -908,21 +910,28 @@ struct Sim : SimBase {
   }
 
   /* end-to-end step with host buffers: pinned staging, async copies on the work stream */
+  /* End-to-end step with host buffers.  The rows of doubles travel as they are (one memcpy into /
+   * out of pinned memory, one copy over PCIe each way); the device does the transposition and
+   * the double <-> real conversion. */
+  double *gstage = nullptr; /* device: [n][9] in, then [n][9] + [n][3] out */
   int step_host(const double *state_in, long nsteps, double *state_out, double *fhf_out, double *dens) override {
     if (!ready) return fail(LBMDEM_ESTATE, "no grains loaded");
-    real *hs = reinterpret_cast<real *>(hstage); /* 16 n doubles >= 12 n reals; pinned */
     const size_t N = (size_t)n;
-    if (state_in) { /* [n][9] doubles -> [9][n] reals, one copy into the grain slab */
-      for (size_t i = 0; i < N; ++i)
-        for (int k = 0; k < 9; ++k) hs[k * N + i] = (real)state_in[i * 9 + k];
-      CK(cudaMemcpyAsync(g.x1, hs, sizeof(real) * 9 * N, cudaMemcpyHostToDevice, stream));
+    if (!gstage) CK(cudaMalloc(&gstage, sizeof(double) * 12 * N));
+    if (state_in) {
+      memcpy(hstage, state_in, sizeof(double) * 9 * N); /* hstage: 16 n doubles of pinned memory */
+      CK(cudaMemcpyAsync(gstage, hstage, sizeof(double) * 9 * N, cudaMemcpyHostToDevice, stream));
+      CK(launch_grain_unpack<real>(gstage, n, 9, g.x1, stream)); /* x1 .. a3 are contiguous in the slab */
     }
     bool built = false;
     int rc = step_async(nsteps, &built);
     if (rc) return rc;
     (void)built;
-    if (state_out || fhf_out) /* state and fhf are contiguous in the slab */
-      CK(cudaMemcpyAsync(hs, g.x1, sizeof(real) * 12 * N, cudaMemcpyDeviceToHost, stream));
+    if (state_out || fhf_out) {
+      CK(launch_grain_pack<real>(g.x1, n, 9, gstage, stream));
+      CK(launch_grain_pack<real>(g.fhf1, n, 3, gstage + 9 * N, stream));
+      CK(cudaMemcpyAsync(hstage, gstage, sizeof(double) * 12 * N, cudaMemcpyDeviceToHost, stream));
+    }
     if (dens) {
       const real *obs;
       if ((rc = observable_f(&obs))) return rc;
@@ -930,12 +939,8 @@ struct Sim : SimBase {
       CK(cudaMemcpyAsync(dens, dens_out, sizeof(double), cudaMemcpyDeviceToHost, stream));
     }
     if ((rc = check_flags())) return rc;
-    if (state_out)
-      for (size_t i = 0; i < N; ++i)
-        for (int k = 0; k < 9; ++k) state_out[i * 9 + k] = hs[k * N + i];
-    if (fhf_out)
-      for (size_t i = 0; i < N; ++i)
-        for (int k = 0; k < 3; ++k) fhf_out[i * 3 + k] = hs[(9 + k) * N + i];
+    if (state_out) memcpy(state_out, hstage, sizeof(double) * 9 * N);
+    if (fhf_out) memcpy(fhf_out, hstage + 9 * N, sizeof(double) * 3 * N);
     return 0;
   }
 

@@ -160,7 +160,20 @@ def cpu_reference(workload, steps, warmup, sample_path, tmpdir, as_line):
         os.chdir(cwd)
 
 
+def emit(line: dict):
+    """the ONE line of this process's real stdout (fd 1 is pointed at stderr while the run lasts: NCCL and
+    the reference print banners there)"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
@@ -199,7 +212,7 @@ def main():
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": cb["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import numpy as np
@@ -303,7 +316,7 @@ def main():
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": "MLUPS", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     s.close()
     if world > 1:
         import torch.distributed as dist
