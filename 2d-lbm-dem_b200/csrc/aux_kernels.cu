@@ -31,7 +31,8 @@ __global__ void grain_prepare_kernel(RasterParams<real> P, int n, GrainArrays<re
   boxes[i] = b;
 }
 
-constexpr int GSPLIT = 4; /* warps per grain in the rasteriser and the boundary pass */
+constexpr int GSPLIT = 4;  /* warps per grain in the rasteriser */
+constexpr int BSPLIT = 2;  /* warps per grain in the boundary pass */
 
 /* GSPLIT warps per grain; the owner of a node is the highest-index grain covering it (:1028 run
  * in index order), hence atomicMax over the fluid value -1.  Grains whose reduced discs share a
@@ -105,10 +106,10 @@ __device__ __forceinline__ void list_flush(uint2 *dst, int *counter, int capacit
  * neighbours was fluid when the reference's loop reached grain i (lbm_node.cuh,
  * fluid_when_grain_ran); the flag is folded into the map as CELL_ACT (readers of a neighbour mask
  * it off, so concurrent folding of other nodes is harmless).
- * Pass 1 classifies the bounding box on geometry alone: nodes outside the disc cannot be owned,
- * nodes deep inside the disc of a grain that overlaps no other grain have all eight neighbours
- * inside the same disc; what remains (the rim) is compacted into a per-warp list.  Pass 2 looks
- * at the map, one rim node per lane. */
+ * Pass 1 works on geometry alone: nodes outside the disc cannot be owned, nodes deep inside the
+ * disc of a grain that overlaps no other grain have all eight neighbours inside the same disc; what
+ * remains (the rim: the two ends of every row's chord) goes into a per-warp list.  Pass 2 looks at
+ * the map, one rim node per lane. */
 template <typename real>
 __global__ void __launch_bounds__(BND_WARPS * 32) boundary_kernel(int n, const GrainRec<real> *rec, const real *R2,
                                                                    const GrainBox *boxes, int *cell, int x0, int nxl, int pitch,
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(BND_WARPS * 32) boundary_kernel(int n, const G
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1;
   const int wg = blockIdx.x * BND_WARPS + w;
-  const int i = wg / GSPLIT, part = wg % GSPLIT; /* GSPLIT warps share one grain: a contiguous share of its rows each */
+  const int i = wg / BSPLIT, part = wg % BSPLIT; /* BSPLIT warps share one grain: a contiguous share of its rows each */
   if (i >= n) return;
   const GrainBox b = boxes[i];
   const real xc = rec[i].xc, yc = rec[i].yc, r2 = rec[i].r2, RR = R2[i];
@@ -129,45 +130,69 @@ __global__ void __launch_bounds__(BND_WARPS * 32) boundary_kernel(int n, const G
   const int ny = b.yf - b.yi + 1;
   if (ny <= 0 || xb < xa) return;
   {
-    const int rows = xb - xa + 1, lo = rows * part / GSPLIT, hi = rows * (part + 1) / GSPLIT;
+    const int rows = xb - xa + 1, lo = rows * part / BSPLIT, hi = rows * (part + 1) / BSPLIT;
     xb = xa + hi - 1;
     xa = xa + lo;
     if (xb < xa) return;
   }
-  const int total = (xb - xa + 1) * ny;
-  const float inv_ny = 1.0f / (float)ny;
   real inner2 = -1;
   if (!overlap[i]) {
     const real rin = (real)sqrt((double)r2) - 2; /* neighbours of a node at most rin from the centre are inside the disc */
     if (rin > 0) inner2 = rin * rin;
   }
+  const real rmin2 = r2 < RR ? r2 : RR;
   int *cand = s_cand[w];
   uint2 *nodes = s_nodes[w], *links = s_links[w];
-  int ncand = 0, nnodes = 0, nlinks = 0;
+  int nnodes = 0, nlinks = 0;
 
-  for (int base = 0; base < total || ncand > 0; base += 32) {
-    /* ---- pass 1: geometry ---- */
-    if (base < total) {
-      const int t = base + lane;
-      bool rim = false;
-      int xy = 0;
-      if (t < total) {
-        int row = (int)(((float)t + 0.5f) * inv_ny); /* t / ny for the small integers that occur; fixed up below */
-        int y = t - row * ny;
-        if (y < 0) { --row; y += ny; } else if (y >= ny) { ++row; y -= ny; }
-        const int x = xa + row;
-        y += b.yi;
-        const real dist2 = (x - xc) * (x - xc) + (y - yc) * (y - yc);
-        const bool deep = dist2 < inner2 && x >= 2 && y >= 2 && x <= lx - 3 && y <= ly - 3;
-        rim = !deep && dist2 <= RR && dist2 <= r2;
-        xy = (row << 16) | (y - b.yi); /* position inside the bounding box */
+  for (int rb = xa; rb <= xb; rb += 32) {
+    /* ---- pass 1: geometry.  Lane = one row of the bounding box: the covered nodes of a row are a
+     * chord of the disc, the deep ones a shorter chord inside it; what may be rim is the two ends
+     * (bracketed generously with float square roots -- pass 2 repeats the exact tests) ---- */
+    const int row = rb + lane;
+    int ya1 = 0, c1 = 0, ya2 = 0, c2 = 0;
+    if (row <= xb) {
+      const real dxr = row - xc;
+      const real h2 = rmin2 - dxr * dxr;
+      if (h2 >= 0) {
+        const float h = sqrtf((float)h2);
+        const int ylo = max((int)floorf((float)yc - h) - 1, b.yi), yhi = min((int)ceilf((float)yc + h) + 1, b.yf);
+        int dlo = 1, dhi = 0; /* rows of certainly deep nodes: empty unless ... */
+        if (inner2 > 0 && row >= 2 && row <= lx - 3) {
+          const real g2 = inner2 - dxr * dxr;
+          if (g2 > 0) {
+            const float gi = sqrtf((float)g2);
+            dlo = max((int)ceilf((float)yc - gi) + 1, 2);
+            dhi = min((int)floorf((float)yc + gi) - 1, ly - 3);
+          }
+        }
+        if (dlo <= dhi) {
+          ya1 = ylo; c1 = min(dlo - 1, yhi) - ylo + 1;
+          ya2 = max(dhi + 1, ylo); c2 = yhi - ya2 + 1;
+        } else {
+          ya1 = ylo; c1 = yhi - ylo + 1;
+        }
+        if (c1 < 0) c1 = 0;
+        if (c2 < 0) c2 = 0;
       }
-      const unsigned m = __ballot_sync(0xffffffffu, rim);
-      if (rim) cand[ncand + __popc(m & lt)] = xy;
-      ncand += __popc(m);
-      __syncwarp();
-      if (ncand <= BND_CAND - 32 && base + 32 < total) continue;
     }
+    const int mine_c = c1 + c2;
+    int incl_c = mine_c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl_c, d);
+      if (lane >= d) incl_c += v;
+    }
+    const int off = incl_c - mine_c, total = __shfl_sync(0xffffffffu, incl_c, 31);
+    for (int wbase = 0; wbase < total; wbase += BND_CAND) {
+      /* this window of the candidate sequence into the staging list */
+      const int j0 = max(0, wbase - off), j1 = min(mine_c, wbase + BND_CAND - off);
+      for (int j = j0; j < j1; ++j) {
+        const int y = (j < c1) ? ya1 + j : ya2 + (j - c1);
+        cand[off + j - wbase] = ((row - xa) << 16) | (y - b.yi);
+      }
+      const int ncand = min(BND_CAND, total - wbase);
+      __syncwarp();
     /* ---- pass 2: the map, one rim node per lane ---- */
     for (int c0 = 0; c0 < ncand; c0 += 32) {
       bool emit = false;
@@ -178,7 +203,10 @@ __global__ void __launch_bounds__(BND_WARPS * 32) boundary_kernel(int n, const G
         const int x = xa + (xy >> 16), y = b.yi + (xy & 0xffff);
         const size_t k = (size_t)(x - x0) * pitch + y;
         knode = (unsigned)k;
-        if (cell_obst(cell[k]) == i) {
+        /* the exact tests: covered by the disc (src/main.c:1026-1029) and not deep inside it */
+        const real dist2 = (x - xc) * (x - xc) + (y - yc) * (y - yc);
+        const bool deep = dist2 < inner2 && x >= 2 && y >= 2 && x <= lx - 3 && y <= ly - 3;
+        if (!deep && dist2 <= RR && dist2 <= r2 && cell_obst(cell[k]) == i) {
           bool act = false;
           unsigned foreign = 0, fluid = 0;
 #pragma unroll
@@ -235,7 +263,7 @@ __global__ void __launch_bounds__(BND_WARPS * 32) boundary_kernel(int n, const G
       }
       __syncwarp();
     }
-    ncand = 0;
+    }
   }
   if (nnodes) list_flush(B.entry, B.count, B.capacity, B.overflow, nodes, nnodes, lane);
   if (nlinks) list_flush(K.entry, K.count, K.capacity, K.overflow, links, nlinks, lane);
@@ -269,7 +297,7 @@ cudaError_t launch_raster(const RasterParams<real> &P, int n, const GrainArrays<
   if ((e = cudaMemsetAsync(K.count, 0, sizeof(int), s)) != cudaSuccess) return e;
   raster_kernel<real><<<(n * GSPLIT * 32 + 255) / 256, 256, 0, s>>>(n, rec, R2, boxes, cell, x0, nxl, pitch, overlap,
                                                                  min_owner, genkey);
-  boundary_kernel<real><<<(n * GSPLIT + BND_WARPS - 1) / BND_WARPS, BND_WARPS * 32, 0, s>>>(n, rec, R2, boxes, cell, x0, nxl, pitch,
+  boundary_kernel<real><<<(n * BSPLIT + BND_WARPS - 1) / BND_WARPS, BND_WARPS * 32, 0, s>>>(n, rec, R2, boxes, cell, x0, nxl, pitch,
                                                                                     P.lx, P.ly, overlap, min_owner, genkey, B, K);
   return cudaGetLastError();
 }
