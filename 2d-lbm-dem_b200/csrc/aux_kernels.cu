@@ -412,11 +412,11 @@ __global__ void __launch_bounds__(256, 4) bounce_sweep_kernel(const __grid_const
     }
     real v;
     const int owner = (int)(en.y & BL_GRAIN);
-    int r = sweep_link(L, S, x, y, q, false, &v, owner);
+    int r = sweep_link(L, S, x, y, q, false, &v, owner, true); /* listed bounce links have a fluid neighbour */
     if (r == SWEEP_WRITE) {
       A[e] = v;
     } else if (r == SWEEP_DEFER) {
-      r = sweep_link(L, S, x, y, q, true, &v, owner);
+      r = sweep_link(L, S, x, y, q, true, &v, owner, true);
       if (r == SWEEP_WRITE) {
         /* one counter update per group of lanes that got here together */
         const unsigned grp = __activemask();

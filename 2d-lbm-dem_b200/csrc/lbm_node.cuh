@@ -373,35 +373,35 @@ enum { SWEEP_KEEP = 0, SWEEP_WRITE = 1, SWEEP_DEFER = 2 };
 
 template <typename real>
 LBM_HD_SLOW int sweep_link(const Lattice<real> &L, const Stored<real> &S, int x, int y, int q, bool resolve, real *v,
-                           int grain = -1 /* owner of (x,y) if the caller knows it */) {
+                           int grain = -1 /* owner of (x,y) if the caller knows it */,
+                           bool n_is_fluid = false /* the caller knows that the neighbour is fluid */) {
   const int ex = ex_of(q), ey = ey_of(q), oq = opp_of(q);
   const int nx = x + ex, ny = y + ey;
   const int nnx = nx + ex, nny = ny + ey;
   const size_t ks = node_index(L, x, y), kn = node_index(L, nx, ny);
-  /* nn lies inside the array whenever n is fluid (an interior node); clamp the address for the other case */
-  const bool nn_in = in_array(L, nnx, nny);
-  const size_t knn = nn_in ? node_index(L, nnx, nny) : kn;
-  /* every load below has an address that depends on (x, y, q) alone: they are issued together */
-  const int cn = S.cell[kn], cnn = S.cell[knn];
+  /* the loads whose address depends on (x, y, q) alone are issued together */
+  const real Fn_q = S.A[q * L.plane + kn], Fn_oq = S.A[oq * L.plane + kn];
   if (grain < 0) grain = cell_obst(S.cell[ks]);
   const GrainRec<real> g = S.grains[grain];
-  const real Fn_q = S.A[q * L.plane + kn], Fn_oq = S.A[oq * L.plane + kn], Xnn = S.A[oq * L.plane + knn];
-  if (!cell_is_fluid(cn)) { /* :1161-1162 */
+  if (!n_is_fluid && !cell_is_fluid(S.cell[kn])) { /* :1161-1162 */
     *v = L.w[q];
     return SWEEP_WRITE;
   }
-  const bool gap = !is_ring(L, nnx, nny) && !cell_is_fluid(cnn) && node_act(L, S, nnx, nny, cnn);
+  /* n fluid => n is an interior node => nn lies inside the array.  An interior solid nn is active:
+   * its neighbour n is fluid */
+  const bool gap = !is_ring(L, nnx, nny) && !cell_is_fluid(S.cell[node_index(L, nnx, nny)]);
   if (gap && !resolve) return SWEEP_DEFER;
   const real d = link_delta(g, x, y, q);
   if (!(d > 0.)) return SWEEP_KEEP;
   const real eu = ex * wall_ux(L, g, y) + ey * wall_uy(L, g, x);
   real X = 0;
   if (d < 0.5) {
-    X = Xnn;
+    const size_t knn = node_index(L, nnx, nny);
+    X = S.A[oq * L.plane + knn];
     if (gap && (nnx < x || (nnx == x && nny < y))) {
       /* the partner link (nn, opp q) was swept earlier: its new value, from the pre-sweep state.
        * Its fluid neighbour is n, its second fluid-side node is s itself. */
-      const GrainRec<real> gp = S.grains[cell_obst(cnn)];
+      const GrainRec<real> gp = S.grains[cell_obst(S.cell[knn])];
       const real dp = link_delta(gp, nnx, nny, oq);
       const real eup = ex_of(oq) * wall_ux(L, gp, nny) + ey_of(oq) * wall_uy(L, gp, nnx);
       X = bounce_value(L, oq, dp, Fn_q, Fn_oq, S.A[q * L.plane + ks], eup, X);
