@@ -124,6 +124,8 @@ struct SimBase {
   virtual int get_fhf(double *out) = 0;
   virtual int set_fhf(const double *in) = 0;
   virtual int get_verlet(int *count, int *nbr, int capacity, int *wall_flags) = 0;
+  virtual int save_state(const char *path) = 0;
+  virtual int load_state(const char *path) = 0;
   virtual int get_fields(const double *gp, float *a, float *b, float *c, float *d, float *e) = 0;
   virtual int step_host(const double *state_in, long n, double *state_out, double *fhf_out, double *dens) = 0;
   virtual int attach_nccl(const void *id) = 0;
@@ -878,6 +880,91 @@ struct Sim : SimBase {
     return 0;
   }
 
+  /* ---- checkpoint / restart (absent upstream): everything the next renderScene() call reads ----
+   * header, grain slab (x v a fhf r m It rLB as stored), Verlet lists, the obstacle map of the last LBM step
+   * (the next one treats it as "old") and the reference's f[x][y][q] of the owned rows.  Restarting from the file
+   * continues bit for bit (tests/test_gpu_parity.py::test_checkpoint_restart_is_bit_exact). */
+  struct CkHeader {
+    char magic[8];
+    int version, lx, ly, single, n, nranks, rank, cap;
+    double scale;
+    long nbsteps, nFile;
+    double t, Mgx, Mdx, Mby, Mhy;
+  };
+  int save_state(const char *path) override {
+    if (!ready) return fail(LBMDEM_ESTATE, "no grains loaded");
+    FILE *fp = fopen(path, "wb");
+    if (!fp) return fail(LBMDEM_EIO, std::string("cannot write ") + path);
+    CkHeader h;
+    memset(&h, 0, sizeof h);
+    memcpy(h.magic, "LBMDEMCK", 8);
+    h.version = 1; h.lx = lx; h.ly = ly; h.single = sizeof(real) == 4; h.n = n; h.nranks = P.nranks; h.rank = P.rank;
+    h.cap = vb.cap; h.scale = P.scale; h.nbsteps = nbsteps; h.nFile = nFile;
+    h.t = t; h.Mgx = Mgx; h.Mdx = Mdx; h.Mby = Mby; h.Mhy = Mhy;
+    int rc = 0;
+    const size_t rows = (size_t)(xhi - xlo);
+    std::vector<real> slab((size_t)16 * n);
+    std::vector<int> cnt(n), nbr((size_t)n * vb.cap), wf(n), ob(rows * ly);
+    std::vector<double> fb(rows * ly * NQ);
+    cudaError_t e = cudaMemcpyAsync(slab.data(), g.x1, sizeof(real) * 16 * n, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(cnt.data(), vb.nbr_count, sizeof(int) * n, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(nbr.data(), vb.nbr, sizeof(int) * nbr.size(), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(wf.data(), vb.wflags, sizeof(int) * n, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) { fclose(fp); CK(e); }
+    if ((rc = get_obst(ob.data())) || (rc = get_f(fb.data()))) { fclose(fp); return rc; }
+    bool ok = fwrite(&h, sizeof h, 1, fp) == 1 && fwrite(slab.data(), sizeof(real), slab.size(), fp) == slab.size() &&
+              fwrite(cnt.data(), sizeof(int), cnt.size(), fp) == cnt.size() &&
+              fwrite(nbr.data(), sizeof(int), nbr.size(), fp) == nbr.size() &&
+              fwrite(wf.data(), sizeof(int), wf.size(), fp) == wf.size() &&
+              fwrite(ob.data(), sizeof(int), ob.size(), fp) == ob.size() &&
+              fwrite(fb.data(), sizeof(double), fb.size(), fp) == fb.size();
+    ok = (fclose(fp) == 0) && ok;
+    return ok ? 0 : fail(LBMDEM_EIO, std::string("short write to ") + path);
+  }
+  int load_state(const char *path) override {
+    FILE *fp = fopen(path, "rb");
+    if (!fp) return fail(LBMDEM_EIO, std::string("cannot open ") + path);
+    CkHeader h;
+    if (fread(&h, sizeof h, 1, fp) != 1 || memcmp(h.magic, "LBMDEMCK", 8) || h.version != 1) {
+      fclose(fp);
+      return fail(LBMDEM_EIO, std::string("not a checkpoint: ") + path);
+    }
+    if (h.lx != lx || h.ly != ly || h.single != (int)(sizeof(real) == 4) || h.nranks != P.nranks || h.rank != P.rank ||
+        h.scale != P.scale || h.n <= 0) {
+      fclose(fp);
+      return fail(LBMDEM_EINVAL, "checkpoint was written with another lattice / precision / decomposition");
+    }
+    const size_t rows = (size_t)(xhi - xlo);
+    std::vector<real> slab((size_t)16 * h.n);
+    std::vector<int> cnt(h.n), nbr((size_t)h.n * h.cap), wf(h.n), ob(rows * ly);
+    std::vector<double> fb(rows * ly * NQ);
+    const bool ok = fread(slab.data(), sizeof(real), slab.size(), fp) == slab.size() &&
+                    fread(cnt.data(), sizeof(int), cnt.size(), fp) == cnt.size() &&
+                    fread(nbr.data(), sizeof(int), nbr.size(), fp) == nbr.size() &&
+                    fread(wf.data(), sizeof(int), wf.size(), fp) == wf.size() &&
+                    fread(ob.data(), sizeof(int), ob.size(), fp) == ob.size() &&
+                    fread(fb.data(), sizeof(double), fb.size(), fp) == fb.size();
+    fclose(fp);
+    if (!ok) return fail(LBMDEM_EIO, std::string("short read from ") + path);
+    /* main()'s set-up from the radii (derived constants, m, It, rLB), then the saved state on top of it */
+    const size_t N = (size_t)h.n;
+    std::vector<real> r(slab.begin() + 12 * N, slab.begin() + 13 * N), x1(slab.begin(), slab.begin() + N),
+        x2(slab.begin() + N, slab.begin() + 2 * N);
+    P.neighbour_capacity = h.cap;
+    int rc = finish_setup(r, x1, x2);
+    if (rc < 0) return rc;
+    CK(cudaMemcpyAsync(g.x1, slab.data(), sizeof(real) * 16 * N, cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(vb.nbr_count, cnt.data(), sizeof(int) * N, cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(vb.nbr, nbr.data(), sizeof(int) * nbr.size(), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(vb.wflags, wf.data(), sizeof(int) * N, cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+    nbsteps = h.nbsteps; nFile = h.nFile;
+    t = (real)h.t; Mgx = (real)h.Mgx; Mdx = (real)h.Mdx; Mby = (real)h.Mby; Mhy = (real)h.Mhy;
+    if ((rc = set_obst(ob.data())) || (rc = set_f(fb.data()))) return rc;
+    return n;
+  }
+
   int get_fields(const double *gp_in, float *gpress, float *gvel, float *gacc, float *fpress, float *fvel) override {
     if (!ready) return fail(LBMDEM_ESTATE, "no grains loaded");
     const size_t nn = (size_t)(xhi - xlo) * ly;
@@ -1055,6 +1142,8 @@ API int lbmdem_set_fhf(lbmdem_ctx *ctx, const double *in) { CTX_OR_FAIL; return 
 API int lbmdem_get_verlet(lbmdem_ctx *ctx, int *count, int *nbr, int capacity, int *wf) {
   CTX_OR_FAIL; return ctx->sim->get_verlet(count, nbr, capacity, wf);
 }
+API int lbmdem_save_state(lbmdem_ctx *ctx, const char *path) { CTX_OR_FAIL; return ctx->sim->save_state(path); }
+API int lbmdem_load_state(lbmdem_ctx *ctx, const char *path) { CTX_OR_FAIL; return ctx->sim->load_state(path); }
 API int lbmdem_get_fields(lbmdem_ctx *ctx, const double *gp, float *a, float *b, float *c, float *d, float *e) {
   CTX_OR_FAIL; return ctx->sim->get_fields(gp, a, b, c, d, e);
 }

@@ -11,6 +11,8 @@
  *   --strict                             bit-exact build (lbmdem_params.strict_fp) LBMDEM_STRICT
  *   --vib                                vibrating walls, int vib = 1 (:162)       LBMDEM_VIB
  *   --device D, --outdir DIR             CUDA device, directory of the output files (default: cwd)
+ *   --restart FILE                       continue from a checkpoint instead of reading positions from <inputfile>
+ *   --checkpoint FILE                    write a checkpoint when the run ends (lbmdem_save_state)
  * Outputs, as the reference writes them: stdout banner and progress lines, stderr
  * "final_density: %f", stats.data, DEM%06d.dat every 4000 calls, five VTK files every 8000 calls.
  * (The PostScript contact plot DEM%06d.ps of write_forces() is not produced.)
@@ -107,8 +109,10 @@ int main(int argc, char **argv) {
     printf("%s\n", com);
     printf("Nb grains %d\n", cnt);
   }
-  const int n = lbmdem_load_sample(ctx, argv[1]);
-  if (n < 0) die("read_sample");
+  const char *restart = opt_or_env(argc, argv, "--restart", "LBMDEM_RESTART");
+  const char *checkpoint = opt_or_env(argc, argv, "--checkpoint", "LBMDEM_CHECKPOINT");
+  const int n = restart ? lbmdem_load_state(ctx, restart) : lbmdem_load_sample(ctx, argv[1]);
+  if (n < 0) die(restart ? "restart" : "read_sample");
 
   double d11[11];
   long l4[4];
@@ -133,13 +137,13 @@ int main(int argc, char **argv) {
   }
   time(&now);
   printf("Current local time and date: %s", asctime(localtime(&now)));
-  if (lbmdem_write_stats_header(outdir)) { fprintf(stderr, "lbmdem: cannot write stats.data\n"); return EXIT_FAILURE; }
+  if (!restart && lbmdem_write_stats_header(outdir)) { fprintf(stderr, "lbmdem: cannot write stats.data\n"); return EXIT_FAILURE; }
   lbmdem_diag *dg = lbmdem_diag_create(n, &p);
 
   const size_t nn = (size_t)p.lx * p.ly;
   float *f_gp = NULL, *f_gv = NULL, *f_ga = NULL, *f_fp = NULL, *f_fv = NULL;
-  long nbsteps = 0;
-  int nFile = 0;
+  long nbsteps = l4[1]; /* 0, or where the checkpoint was taken */
+  int nFile = (int)l4[2];
   double summary[7] = {0, 0, 0, 0, 0, 0, 0};
   /* main loop: do { renderScene(); ... } while (nbsteps * dt <= duration)  (src/main.c:1880-1890) */
   int more = 1;
@@ -210,6 +214,7 @@ int main(int argc, char **argv) {
     CK(lbmdem_total_density(ctx, &sum));
     fprintf(stderr, "final_density: %f\n", sum);
   }
+  if (checkpoint) CK(lbmdem_save_state(ctx, checkpoint));
   time(&now);
   printf("End local time and date: %s", asctime(localtime(&now)));
   lbmdem_diag_destroy(dg);

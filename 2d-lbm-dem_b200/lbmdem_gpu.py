@@ -88,6 +88,8 @@ def load_library():
         "lbmdem_set_fhf": ([vp, _dp], C.c_int),
         "lbmdem_get_verlet": ([vp, _ip, _ip, C.c_int, _ip], C.c_int),
         "lbmdem_get_fields": ([vp, vp, _fp, _fp, _fp, _fp, _fp], C.c_int),
+        "lbmdem_save_state": ([vp, C.c_char_p], C.c_int),
+        "lbmdem_load_state": ([vp, C.c_char_p], C.c_int),
         "lbmdem_step_host": ([vp, vp, C.c_long, vp, vp, vp], C.c_int),
         "lbmdem_nccl_unique_id": ([vp], C.c_int),
         "lbmdem_attach_nccl": ([vp, vp], C.c_int),
@@ -170,6 +172,13 @@ class Solver:
     def init_arrays(self, r, x1, x2) -> int:
         r, x1, x2 = (np.ascontiguousarray(a, dtype=np.float64) for a in (r, x1, x2))
         self.n = self._ck(self.L.lbmdem_set_grains(self.h, len(r), r, x1, x2))
+        return self.n
+
+    def save_state(self, path: str):
+        self._ck(self.L.lbmdem_save_state(self.h, os.fsencode(path)))
+
+    def load_state(self, path: str) -> int:
+        self.n = self._ck(self.L.lbmdem_load_state(self.h, os.fsencode(path)))
         return self.n
 
     def attach_nccl(self, uid: bytes):

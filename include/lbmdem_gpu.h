@@ -118,6 +118,13 @@ int lbmdem_set_fhf(lbmdem_ctx *ctx, const double *in);
  * (bit 0 B, 1 T, 2 L, 3 R).  The reference's half list is the j > i part. */
 int lbmdem_get_verlet(lbmdem_ctx *ctx, int *count, int *nbr, int capacity, int *wall_flags);
 
+/* Checkpoint / restart (the reference has none): everything the next renderScene()
+ * call reads, in one file per rank.  lbmdem_load_state replaces lbmdem_load_sample on a context
+ * created with the same lattice, precision and decomposition; returns nbgrains.  A run continued
+ * from the file is bit-identical to the uninterrupted one. */
+int lbmdem_save_state(lbmdem_ctx *ctx, const char *path);
+int lbmdem_load_state(lbmdem_ctx *ctx, const char *path);
+
 /* write_vtk's five point fields (src/main.c:284-323) for the owned rows, float32, [y][x-xlo]
  * order (x fastest), vectors with 3 components; grain_p may be NULL on input side (pressure of
  * grains is a contact diagnostic kept by the caller): pass per-grain values or NULL for zeros. */

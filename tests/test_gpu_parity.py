@@ -495,3 +495,34 @@ def test_vibrating_walls_strict_is_bit_exact():
         assert np.array_equal(o.obst(), s.obst())
     assert np.array_equal(o.f(), s.f()) and np.array_equal(o.fhf(), s.fhf())
     assert o.scalars()["Mgx"] != 0.0
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_checkpoint_restart_is_bit_exact(prec, tmp_path):
+    """lbmdem_save_state / lbmdem_load_state: a run continued from the file equals the uninterrupted
+    one bit for bit, in the default build, also when the file is written between two LBM steps and
+    between two Verlet rebuilds."""
+    lx, ly = 120, 96
+    r, x, y = small_packing(lx, ly, 1.0, seed=101, n_target=70)
+    a = G.Solver(lx, ly, 1.0, prec)
+    n = a.init_arrays(r, x, y)
+    v, w, acc = random_kinematics(n, 102, vmax=0.02)
+    st = a.grains()[:, :9].copy()
+    st[:, 3:5], st[:, 5:6] = v, w
+    a.set_f(perturbed_f(lx, ly, 103))
+    a.set_grain_state(st)
+    a.step(137)                                   # not a multiple of npDEM nor of UpdateVerlet
+    ck = str(tmp_path / "state.ck")
+    a.save_state(ck)
+    a.step(150)
+    b = G.Solver(lx, ly, 1.0, prec)
+    assert b.load_state(ck) == n
+    assert b.scalars()["nbsteps"] == 137
+    b.step(150)
+    assert a.scalars() == b.scalars()
+    assert np.array_equal(a.grains(), b.grains())
+    assert np.array_equal(a.fhf(), b.fhf())
+    assert np.array_equal(a.obst(), b.obst())
+    assert np.array_equal(a.f(), b.f())
+    with pytest.raises(G.LbmdemError):
+        G.Solver(lx + 1, ly, 1.0, prec).load_state(ck)
