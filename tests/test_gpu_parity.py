@@ -526,3 +526,31 @@ def test_checkpoint_restart_is_bit_exact(prec, tmp_path):
     assert np.array_equal(a.f(), b.f())
     with pytest.raises(G.LbmdemError):
         G.Solver(lx + 1, ly, 1.0, prec).load_state(ck)
+
+
+def test_reference_default_build_size_strict(tmp_path):
+    """BASELINE configs[0]: the reference's DEFAULT build (7826 x 2325, fp64) on the 47 980-grain synthetic
+    stand-in for bin/50000-test.data, 37 renderScene() calls.  The strict build reproduces the compiled
+    reference's bits (hashes in tests/golden/default_build_50000.npz); grains beyond the lattice are legal."""
+    import make_sample as ms
+    gold = np.load(os.path.join(GOLD, "default_build_50000.npz"))
+    n, r_min, r_max, width = ms.PRESETS["50000-test"]
+    r, x, y = ms.packed_sample(n, r_min, r_max, width, seed=12345)
+    path = str(tmp_path / "s50k.data")
+    ms.write_sample(path, r, x, y, comment="# synthetic 50000-test seed=12345")
+    assert hashlib.sha256(open(path, "rb").read()).hexdigest() == str(gold["sample_sha256"])
+    s = G.Solver(7826, 2325, 1.0, "f64", strict_fp=1)
+    assert s.init(path) == n
+    sc = s.scalars()
+    for k in sc:
+        assert sc[k] == gold[f"scalar_{k}"], k
+    s.step(int(gold["steps"]))
+    g = s.grains()
+    assert np.array_equal(g[::97, :9], gold["grains_sample"])
+    assert _sha(g[:, :9]) == str(gold["grains_sha256"])
+    assert _sha(s.fhf()) == str(gold["fhf_sha256"])
+    assert _sha(s.obst()) == str(gold["obst_sha256"])
+    assert _sha(s.f()) == str(gold["f_sha256"])
+    # the reference adds 1.6e8 terms serially; the device reduces pairwise: the SUMS differ in the 9th digit
+    # although every addend is identical (f hash above)
+    assert abs(s.total_density() - float(gold["density"])) < 1e-8 * 7826 * 2325

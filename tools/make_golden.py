@@ -192,8 +192,39 @@ def case_outputs():
     print("outputs_64x48:", sorted(os.listdir(out_dir)))
 
 
+def case_default_build():
+    """The reference's DEFAULT build (lx = 7826, ly = 2325, fp64) on the synthetic 47 980-grain packing that
+    stands in for bin/50000-test.data (BASELINE configs[0]; tools/make_sample.py, seed 12345): 37 calls of
+    renderScene() = 4 LBM steps, one Verlet build.  Hashes only (the populations alone are 1.3 GB)."""
+    n, r_min, r_max, width = make_sample.PRESETS["50000-test"]
+    r, x, y = make_sample.packed_sample(n, r_min, r_max, width, seed=12345)
+    tmp = tempfile.mkdtemp(prefix="golden_def_")
+    path = os.path.join(tmp, "s50k.data")
+    make_sample.write_sample(path, r, x, y, comment="# synthetic 50000-test seed=12345")
+    ref = Reference(7826, 2325, "1.", "f64")
+    cwd = os.getcwd()
+    os.chdir(tmp)
+    try:
+        assert ref.init(path) == n
+        out = {}
+        scalars_of(ref, out)
+        ref.step(37)
+        g = ref.grains()
+        out.update(steps=np.int64(37), grains_sha256=np.array(sha(g[:, :9])), fhf_sha256=np.array(sha(ref.fhf())),
+                   obst_sha256=np.array(sha(ref.obst())), f_sha256=np.array(sha(ref.f())),
+                   density=np.float64(ref.total_density()), grains_sample=g[::97, :9], fhf_sample=ref.fhf()[::97],
+                   sample_sha256=np.array(hashlib.sha256(open(path, "rb").read()).hexdigest()))
+    finally:
+        os.chdir(cwd)
+    np.savez_compressed(os.path.join(GOLD, "default_build_50000.npz"), **out)
+    print("default_build_50000: density", out["density"])
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    if "--default-build" in sys.argv:
+        case_default_build()
+        return
     case_outputs()
     case_a08d83()
     case_packing(64, 48, "f64", 3, 30, None, True)
