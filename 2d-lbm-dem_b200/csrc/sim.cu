@@ -891,8 +891,13 @@ struct Sim : SimBase {
     long nbsteps, nFile;
     double t, Mgx, Mdx, Mby, Mhy;
   };
-  int save_state(const char *path) override {
+  std::string rank_path(const char *path) const { /* one file per rank of a strip-decomposed run */
+    return P.nranks > 1 ? std::string(path) + ".rank" + std::to_string(P.rank) : std::string(path);
+  }
+  int save_state(const char *path_) override {
     if (!ready) return fail(LBMDEM_ESTATE, "no grains loaded");
+    const std::string rp = rank_path(path_);
+    const char *path = rp.c_str();
     FILE *fp = fopen(path, "wb");
     if (!fp) return fail(LBMDEM_EIO, std::string("cannot write ") + path);
     CkHeader h;
@@ -922,7 +927,9 @@ struct Sim : SimBase {
     ok = (fclose(fp) == 0) && ok;
     return ok ? 0 : fail(LBMDEM_EIO, std::string("short write to ") + path);
   }
-  int load_state(const char *path) override {
+  int load_state(const char *path_) override {
+    const std::string rp = rank_path(path_);
+    const char *path = rp.c_str();
     FILE *fp = fopen(path, "rb");
     if (!fp) return fail(LBMDEM_EIO, std::string("cannot open ") + path);
     CkHeader h;

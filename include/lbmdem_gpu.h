@@ -119,7 +119,7 @@ int lbmdem_set_fhf(lbmdem_ctx *ctx, const double *in);
 int lbmdem_get_verlet(lbmdem_ctx *ctx, int *count, int *nbr, int capacity, int *wall_flags);
 
 /* Checkpoint / restart (the reference has none): everything the next renderScene()
- * call reads, in one file per rank.  lbmdem_load_state replaces lbmdem_load_sample on a context
+ * call reads, in one file per rank ("<path>.rank<k>" when nranks > 1).  lbmdem_load_state replaces lbmdem_load_sample on a context
  * created with the same lattice, precision and decomposition; returns nbgrains.  A run continued
  * from the file is bit-identical to the uninterrupted one. */
 int lbmdem_save_state(lbmdem_ctx *ctx, const char *path);
