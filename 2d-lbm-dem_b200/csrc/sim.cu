@@ -411,7 +411,7 @@ struct Sim : SimBase {
     std::vector<real> r(cnt), x1(cnt), x2(cnt);
     const real rs = (real)P.rscale;
     for (int i = 0; i < cnt; ++i) {
-      double a, b, cc; /* %le into double then rounded == %e into float for the values that occur? no: parse in `real` */
+      double a, b, cc; /* the reference scans with "%le" into double or "%e" into float (FLOAT_FORMAT, :34-40): parse in `real` */
       if (sizeof(real) == 8) {
         if (fscanf(fp, "%le %le %le;\n", &a, &b, &cc) != 3) { fclose(fp); return fail(LBMDEM_EIO, "short sample file"); }
         r[i] = (real)a; x1[i] = (real)b; x2[i] = (real)cc;
