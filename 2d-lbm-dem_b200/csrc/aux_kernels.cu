@@ -137,7 +137,9 @@ __global__ void __launch_bounds__(BND_WARPS * 32) boundary_kernel(int n, const G
   }
   real inner2 = -1;
   if (!overlap[i]) {
-    const real rin = (real)sqrt((double)r2) - 2; /* neighbours of a node at most rin from the centre are inside the disc */
+    /* the eight neighbours of a node lie within sqrt(2) of it: a node at most rin from the centre has them all
+     * inside the disc (0.03 of slack for the rounding of the distance tests) */
+    const real rin = (real)(sqrt((double)r2) - 1.45);
     if (rin > 0) inner2 = rin * rin;
   }
   const real rmin2 = r2 < RR ? r2 : RR;
@@ -238,20 +240,15 @@ __global__ void __launch_bounds__(BND_WARPS * 32) boundary_kernel(int n, const G
       const unsigned m = __ballot_sync(0xffffffffu, emit);
       if (emit) nodes[nnodes + __popc(m & lt)] = e;
       nnodes += __popc(m);
-      /* links: exclusive scan of the per-lane counts */
-      const int mine = __popc(bounce) + __popc(wl);
-      int incl = mine;
+      /* links: one round per direction, the lanes that own such a link take consecutive slots */
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += v;
+      for (int q = 1; q < NQ; ++q) {
+        const bool isb = (bounce >> (q - 1)) & 1u, isw = (wl >> (q - 1)) & 1u;
+        const unsigned mq = __ballot_sync(0xffffffffu, isb || isw);
+        if (isb || isw)
+          links[nlinks + __popc(mq & lt)] = make_uint2(knode, (unsigned)i | ((unsigned)q << 24) | (isw ? LL_W : 0u));
+        nlinks += __popc(mq);
       }
-      int pos = nlinks + incl - mine;
-      for (unsigned bits = bounce; bits; bits &= bits - 1)
-        links[pos++] = make_uint2(knode, (unsigned)i | ((unsigned)__ffs(bits) << 24));
-      for (unsigned bits = wl; bits; bits &= bits - 1)
-        links[pos++] = make_uint2(knode, (unsigned)i | ((unsigned)__ffs(bits) << 24) | LL_W);
-      nlinks += __shfl_sync(0xffffffffu, incl, 31);
       __syncwarp();
       if (nnodes > BND_NODES - 32) {
         list_flush(B.entry, B.count, B.capacity, B.overflow, nodes, nnodes, lane);
