@@ -31,6 +31,9 @@ __global__ void grain_prepare_kernel(RasterParams<real> P, int n, GrainArrays<re
   boxes[i] = b;
 }
 
+#ifndef LBMDEM_SWEEP_MINB
+#define LBMDEM_SWEEP_MINB 4
+#endif
 constexpr int GSPLIT = 4;  /* warps per grain in the rasteriser */
 constexpr int BSPLIT = 2;  /* warps per grain in the boundary pass */
 
@@ -391,7 +394,7 @@ __device__ __forceinline__ void grain_sums_add(long long *facc, int n, int i, lo
  * f_new[n][q] = the value it just produced), so links into FLUID neighbours are added to the
  * grain's force sums here (facc != nullptr, owned rows only); force_links_kernel adds the rest. */
 template <typename real>
-__global__ void __launch_bounds__(256, 4) bounce_sweep_kernel(const __grid_constant__ Lattice<real> L,
+__global__ void __launch_bounds__(256, LBMDEM_SWEEP_MINB) bounce_sweep_kernel(const __grid_constant__ Lattice<real> L,
                                                            const __grid_constant__ Stored<real> S, real *A, int xa, int xb,
                                                            int xlo, int xhi, const LinkList K, const DeferList<real> D,
                                                            long long *facc) {
