@@ -7,25 +7,25 @@
  * (:1077-1119), (3) wall-ring copies (:1123-1145), (4) interpolated bounce-back on active solid
  * nodes (:1154-1222) and (5) two swap passes that stream (:1224-1242).
  *
- * Sweeps 1-2 are node-local (reinit_collide below).  Sweeps 3-5 are restated as a pure
- * function of the state "A" that sweeps 1-2 leave behind:
+ * Sweeps 1-2 are node-local (reinit_collide below).  Sweeps 3-4 rewrite a sparse set of
+ * populations -- ring nodes, the rim of the grains -- and run as small in-place kernels
+ * (ring_value, sweep_link below).  After them the array "A" holds exactly what the reference
+ * holds before its swap passes, and sweep 5 is a plain pull:
  *
- *      f_next[q](p) = G[q](p - e_q)        if p - e_q lies inside the array,
- *                   = G[opp q](p)          otherwise                      (swap passes, :1224-1242)
+ *      f_next[q](p) = A[q](p - e_q)        if p - e_q lies inside the array,
+ *                   = A[opp q](p)          otherwise                      (swap passes, :1224-1242)
  *
- * where G(s) is the content of node s after sweeps 3-4, evaluated on demand from A, the
- * obstacle map and the grain records of that step (ring_value, G_value, pull_value).  The
- * device therefore stores A between steps and one fused kernel does "sweeps 3-5 of step n-1,
+ * The device therefore stores A between steps and one fused kernel does "sweep 5 of step n-1,
  * then sweeps 1-2 of step n" per node (lbm_kernels.cu); the hydrodynamic force of step n
- * (forces_fluid, :1285-1333) is a function of G as well (force_link).  Operand order and
+ * (forces_fluid, :1285-1333) reads A as well (force_link).  Operand order and
  * int/float/double promotions follow the reference source expression by expression (they
  * decide the last bit, and in the -DSINGLE_PRECISION build the `1.`/`4.5`/`fabs`/`sqrt`
  * promotions to double are part of the result).
  *
  * Two users:
- *   - lbm_kernels.cu / aux_kernels.cu: the tiled TMA kernel uses the arithmetic helpers on
- *     shared-memory rows and calls G_value() (global memory) only for the rare look-back links;
- *     the edge / generic / stream kernels and the force kernels call pull_value() / G_value().
+ *   - lbm_kernels.cu / aux_kernels.cu: the TMA row kernel uses reinit_collide on registers and
+ *     pulls from shared-memory rows; the ring, sweep and force kernels call ring_value,
+ *     sweep_link and force_link on global memory.
  *   - tests/hostcheck: the same header compiled by g++ to pin the formulation against the
  *     oracle on the CPU, bit for bit (test infrastructure only; not a product path).
  */
@@ -35,7 +35,7 @@
 
 #if defined(__CUDACC__)
 #define LBM_HD __host__ __device__ __forceinline__
-#define LBM_HD_SLOW __host__ __device__ __noinline__ /* on-demand path: one copy, called */
+#define LBM_HD_SLOW __host__ __device__ __noinline__ /* sparse paths: one copy, called */
 #else
 #define LBM_HD inline
 #define LBM_HD_SLOW inline

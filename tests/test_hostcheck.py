@@ -3,8 +3,9 @@
 The product's node headers (csrc/lbm_node.cuh, raster_node.cuh, dem_node.cuh) are compiled by
 g++ (tests/hostcheck) and driven serially; results must be BIT-IDENTICAL to the oracle
 (oracle/lbmdem_oracle.c, itself pinned bit-identical to the compiled reference):
-  - the pull / on-demand restatement of reinit + collide + ring + grain bounce-back + swap
-    streaming (SURVEY.md 3.3, App. A.1) incl. ring nodes, solid nodes, moving grains;
+  - the stored-state restatement of the LBM step: node-local reinit + collide (+ w-links), ring
+    sweep in two in-place passes, grain bounce-back sweep in arbitrary link order with the
+    deferred list, plain pull (SURVEY.md 3.3, App. A.1) incl. ring nodes, solid nodes, moving grains;
   - the max-owner rasteriser with the act rule (src/main.c:991-1065);
   - forces_fluid from post-stream values (src/main.c:1285-1333);
   - the gather-form DEM step over a sorted full neighbour list (src/main.c:1336-1516, :1733-1763).
