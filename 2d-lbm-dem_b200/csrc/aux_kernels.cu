@@ -776,6 +776,68 @@ cudaError_t launch_dem_step(const dem::Params<real> &P, int n, bool film, const 
   return cudaGetLastError();
 }
 
+/* Small samples: the same sub-step, nsub times, by one CTA (thread i = grain i).  The contributions of the
+ * neighbours are added in list order, like the warp kernel's shuffle loop and the reference's scatter loop. */
+template <typename real>
+__global__ void __launch_bounds__(DEM_BATCH_MAX) dem_batch_kernel(dem::Params<real> P, int n, int nsub, GrainArrays<real> g,
+                                                                  VerletBuffers vb) {
+  const int i = threadIdx.x;
+  const bool on = i < n;
+  real x1 = 0, x2 = 0, x3 = 0, v1 = 0, v2 = 0, v3 = 0, a1 = 0, a2 = 0, a3 = 0, ri = 0, mi = 1, Iti = 1, f1 = 0, f2 = 0, f3 = 0;
+  int cnt = 0, wfl = 0;
+  if (on) {
+    x1 = g.x1[i]; x2 = g.x2[i]; x3 = g.x3[i]; v1 = g.v1[i]; v2 = g.v2[i]; v3 = g.v3[i];
+    a1 = g.a1[i]; a2 = g.a2[i]; a3 = g.a3[i]; ri = g.r[i]; mi = g.m[i]; Iti = g.It[i];
+    f1 = g.fhf1[i]; f2 = g.fhf2[i]; f3 = g.fhf3[i];
+    cnt = vb.nbr_count[i]; wfl = vb.wflags[i];
+  }
+  for (int s = 0; s < nsub; ++s) {
+    if (on) {
+      dem::kick_drift(P, &x1, &v1, a1);
+      dem::kick_drift(P, &x2, &v2, a2);
+      dem::kick_drift(P, &x3, &v3, a3);
+      g.x1[i] = x1; g.x2[i] = x2; g.v1[i] = v1; g.v2[i] = v2; g.v3[i] = v3; /* what the neighbours read */
+    }
+    __syncthreads();
+    if (on) {
+      a1 = f1; a2 = f2; a3 = f3;
+      for (int k = 0; k < cnt; ++k) {
+        const int j = vb.nbr[(size_t)i * vb.cap + k];
+        const real xj1 = g.x1[j], xj2 = g.x2[j], vj1 = g.v1[j], vj2 = g.v2[j], vj3 = g.v3[j], rj = g.r[j];
+        dem::Force<real> F;
+        if (i < j) {
+          if (dem::pair_force(P, false, x1, x2, v1, v2, v3, ri, xj1, xj2, vj1, vj2, vj3, rj, &F)) {
+            a1 = a1 + F.f1; a2 = a2 + F.f2; a3 = a3 + F.f3;
+          }
+        } else {
+          if (dem::pair_force(P, false, xj1, xj2, vj1, vj2, vj3, rj, x1, x2, v1, v2, v3, ri, &F)) {
+            a1 = a1 + (-F.f1); a2 = a2 + (-F.f2); a3 = a3 + F.f3;
+          }
+        }
+      }
+      dem::add_wall_forces(P, wfl, x1, x2, v1, v2, v3, ri, &a1, &a2, &a3);
+      dem::finish_acceleration(P, mi, Iti, &a1, &a2, &a3);
+    }
+    __syncthreads(); /* everybody has read the mid-step velocities before they move on */
+    if (on) {
+      dem::kick(P, &v1, a1);
+      dem::kick(P, &v2, a2);
+      dem::kick(P, &v3, a3);
+    }
+  }
+  if (on) {
+    g.x3[i] = x3; g.v1[i] = v1; g.v2[i] = v2; g.v3[i] = v3; g.a1[i] = a1; g.a2[i] = a2; g.a3[i] = a3;
+  }
+}
+template <typename real>
+cudaError_t launch_dem_batch(const dem::Params<real> &P, int n, int nsub, const GrainArrays<real> &g, const VerletBuffers &vb,
+                             cudaStream_t s) {
+  if (n > DEM_BATCH_MAX) return cudaErrorInvalidValue;
+  const int threads = (n + 31) / 32 * 32;
+  dem_batch_kernel<real><<<1, threads, 0, s>>>(P, n, nsub, g, vb);
+  return cudaGetLastError();
+}
+
 /* ------------------------------------------------------------------------------------------
  * K5: check_density / final_density (src/main.c:1249-1273), fixed-shape two-stage sum in fp64
  * ---------------------------------------------------------------------------------------- */
@@ -959,6 +1021,8 @@ cudaError_t launch_fill_rest(real *f, size_t plane, const Lattice<real> &Lw, cud
                                            const VerletBuffers &, cudaStream_t);                                         \
   template cudaError_t launch_dem_step<real>(const dem::Params<real> &, int, bool, const GrainArrays<real> &,             \
                                              const VerletBuffers &, real *, cudaStream_t);                               \
+  template cudaError_t launch_dem_batch<real>(const dem::Params<real> &, int, int, const GrainArrays<real> &,             \
+                                              const VerletBuffers &, cudaStream_t);                                      \
   template cudaError_t launch_density<real>(const real *, int, int, int, int, int, size_t, double *, int, double *,       \
                                             cudaStream_t);                                                                \
   template cudaError_t launch_fields<real>(const real *, const int *, const GrainArrays<real> &, const real *, int, int,  \

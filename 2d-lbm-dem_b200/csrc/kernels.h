@@ -188,6 +188,13 @@ cudaError_t launch_dem_step(const dem::Params<real> &P, int n, bool film, const 
                             const VerletBuffers &vb, real *mid /* nullptr, or [6][n]: x1 x2 x3 v1 v2 v3 after the
                             kick-drift, i.e. as acceleration_grains() sees them */, cudaStream_t s);
 
+/* nsub consecutive DEM sub-steps (normal contact law, fixed lists and fhf) in ONE launch: a single CTA, one
+ * thread per grain, for small samples (n <= DEM_BATCH_MAX) where three launches per sub-step are all latency */
+constexpr int DEM_BATCH_MAX = 1024;
+template <typename real>
+cudaError_t launch_dem_batch(const dem::Params<real> &P, int n, int nsub, const GrainArrays<real> &g, const VerletBuffers &vb,
+                             cudaStream_t s);
+
 template <typename real>
 cudaError_t launch_density(const real *f, int ly, int x0, int xlo, int xhi, int pitch, size_t plane, double *partials,
                            int npartials, double *out, cudaStream_t s);

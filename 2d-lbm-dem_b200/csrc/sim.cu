@@ -693,10 +693,23 @@ struct Sim : SimBase {
         *built = true;
       }
       const bool film = (nbsteps % P.stepFilm == 0);
-      CK(launch_dem_step<real>(dem_params(), n, film, g, vb, capture ? mid_dev : nullptr, stream));
-      all_launches += 3;
-      ++nbsteps;
-      if (nbsteps % P.stepFilm == 0) ++nFile;
+      /* small samples: this call's sub-step and those of the following calls that do nothing else go in one launch */
+      long nb = 1;
+      if (n <= DEM_BATCH_MAX && !film && !capture && P.vib != 1) {
+        while (k + nb < nsteps && (nbsteps + nb) % npDEM != 0 && (nbsteps + nb) % P.UpdateVerlet != 0 &&
+               (nbsteps + nb) % P.stepFilm != 0)
+          ++nb;
+        CK(launch_dem_batch<real>(dem_params(), n, (int)nb, g, vb, stream));
+        all_launches += 1;
+      } else {
+        CK(launch_dem_step<real>(dem_params(), n, film, g, vb, capture ? mid_dev : nullptr, stream));
+        all_launches += 3;
+      }
+      for (long b = 0; b < nb; ++b) {
+        ++nbsteps;
+        if (nbsteps % P.stepFilm == 0) ++nFile;
+      }
+      k += nb - 1;
     }
     return 0;
   }
