@@ -444,14 +444,25 @@ __global__ void defer_apply_kernel(real *A, const DeferList<real> D) {
   const int n = min(*D.count, D.capacity);
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) A[D.index[k]] = D.value[k];
 }
+/* The sweep in three stages, so that a strip-decomposed run can sweep the rows that need no ghost data while
+ * the ghost rows are still in flight: begin (empty deferred list, zero force sums), any number of passes over
+ * disjoint row ranges, end (apply the deferred links -- only after EVERY pass, they read pre-sweep values). */
 template <typename real>
-cudaError_t launch_bounce_sweep(const Lattice<real> &L, const Stored<real> &S, real *A, int xa, int xb, int xlo, int xhi,
-                                const LinkList &K, const DeferList<real> &D, long long *facc, cudaStream_t s) {
-  if (xb <= xa || L.ngrains <= 0) return cudaSuccess;
+cudaError_t launch_bounce_begin(int ngrains, const DeferList<real> &D, long long *facc, cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(D.count, 0, sizeof(int), s);
   if (e != cudaSuccess) return e;
-  if (facc != nullptr && (e = cudaMemsetAsync(facc, 0, sizeof(long long) * 3 * L.ngrains, s)) != cudaSuccess) return e;
+  if (facc != nullptr) e = cudaMemsetAsync(facc, 0, sizeof(long long) * 3 * ngrains, s);
+  return e;
+}
+template <typename real>
+cudaError_t launch_bounce_pass(const Lattice<real> &L, const Stored<real> &S, real *A, int xa, int xb, int xlo, int xhi,
+                               const LinkList &K, const DeferList<real> &D, long long *facc, cudaStream_t s) {
+  if (xb <= xa || L.ngrains <= 0) return cudaSuccess;
   bounce_sweep_kernel<real><<<148 * 16, 256, 0, s>>>(L, S, A, xa, xb, xlo, xhi, K, D, facc);
+  return cudaGetLastError();
+}
+template <typename real>
+cudaError_t launch_bounce_end(real *A, const DeferList<real> &D, cudaStream_t s) {
   defer_apply_kernel<real><<<8, 256, 0, s>>>(A, D);
   return cudaGetLastError();
 }
@@ -1007,8 +1018,10 @@ cudaError_t launch_fill_rest(real *f, size_t plane, const Lattice<real> &Lw, cud
   template cudaError_t launch_act_map<real>(const Lattice<real> &, const Stored<real> &, int, int, int *, cudaStream_t);  \
   template cudaError_t launch_ring_sweep<real>(const Lattice<real> &, const Stored<real> &, real *, int, int,             \
                                                cudaStream_t);                                                             \
-  template cudaError_t launch_bounce_sweep<real>(const Lattice<real> &, const Stored<real> &, real *, int, int, int, int, \
-                                                 const LinkList &, const DeferList<real> &, long long *, cudaStream_t);   \
+  template cudaError_t launch_bounce_begin<real>(int, const DeferList<real> &, long long *, cudaStream_t);                \
+  template cudaError_t launch_bounce_pass<real>(const Lattice<real> &, const Stored<real> &, real *, int, int, int, int,  \
+                                                const LinkList &, const DeferList<real> &, long long *, cudaStream_t);    \
+  template cudaError_t launch_bounce_end<real>(real *, const DeferList<real> &, cudaStream_t);                            \
   template cudaError_t launch_force_links<real>(const Lattice<real> &, const Stored<real> &, int, int,                    \
                                                 const BoundaryList &, long long *, cudaStream_t);                         \
   template cudaError_t launch_force_finish<real>(const long long *, int, double, double, real *, real *, real *,          \

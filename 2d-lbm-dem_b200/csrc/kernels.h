@@ -143,14 +143,18 @@ cudaError_t launch_act_map(const lbm::Lattice<real> &L, const lbm::Stored<real> 
 template <typename real>
 cudaError_t launch_ring_sweep(const lbm::Lattice<real> &L, const lbm::Stored<real> &S, real *A, int xa, int xb,
                               cudaStream_t s);
-/* sweep 4 in place: interpolated bounce-back on the active solid nodes of the rows [xa, xb)
- * (src/main.c:1154-1222), one thread per listed link; links facing another grain across a
- * one-node gap go through the deferred list (lbm_node.cuh, sweep_link).  With facc != nullptr the
- * kernel first zeroes facc[3][n] and adds the momentum exchange of every link into a fluid
- * neighbour whose solid node lies in [xlo, xhi) */
+/* sweep 4 in place: interpolated bounce-back on the active solid nodes (src/main.c:1154-1222), one thread per
+ * listed link; links facing another grain across a one-node gap go through the deferred list (lbm_node.cuh,
+ * sweep_link).  Three stages: begin (empties the deferred list and, with facc != nullptr, zeroes facc[3][n]),
+ * passes over disjoint row ranges [xa, xb) (each also adds the momentum exchange of its links into fluid
+ * neighbours whose solid node lies in [xlo, xhi)), end (applies the deferred links; after every pass). */
 template <typename real>
-cudaError_t launch_bounce_sweep(const lbm::Lattice<real> &L, const lbm::Stored<real> &S, real *A, int xa, int xb, int xlo,
-                                int xhi, const LinkList &K, const DeferList<real> &D, long long *facc, cudaStream_t s);
+cudaError_t launch_bounce_begin(int ngrains, const DeferList<real> &D, long long *facc, cudaStream_t s);
+template <typename real>
+cudaError_t launch_bounce_pass(const lbm::Lattice<real> &L, const lbm::Stored<real> &S, real *A, int xa, int xb, int xlo,
+                               int xhi, const LinkList &K, const DeferList<real> &D, long long *facc, cudaStream_t s);
+template <typename real>
+cudaError_t launch_bounce_end(real *A, const DeferList<real> &D, cudaStream_t s);
 /* the rest of forces_fluid (src/main.c:1295-1325): links into non-fluid foreign neighbours (other
  * grains, the wall ring), one thread per (listed node, link); ADDS to facc[3][n] */
 template <typename real>

@@ -149,6 +149,8 @@ struct Sim : SimBase {
   double k12 = 0, k3 = 0; /* fhf scale factors (:1329-1331) */
   /* device */
   cudaStream_t stream = nullptr;
+  cudaStream_t comm_stream = nullptr;            /* halo exchange of a strip-decomposed run, overlapped with the interior sweep */
+  cudaEvent_t ev_state = nullptr, ev_halo = nullptr;
   real *f[2] = {nullptr, nullptr};
   int *cell[2] = {nullptr, nullptr};
   int cur = 0, cur_cell = 0;
@@ -200,6 +202,9 @@ struct Sim : SimBase {
     cudaFree(min_owner);
     if (hflags) cudaFreeHost(hflags);
     if (hstage) cudaFreeHost(hstage);
+    if (ev_state) cudaEventDestroy(ev_state);
+    if (ev_halo) cudaEventDestroy(ev_halo);
+    if (comm_stream) cudaStreamDestroy(comm_stream);
     if (stream) cudaStreamDestroy(stream);
   }
 
@@ -228,6 +233,13 @@ struct Sim : SimBase {
     pitch = (ly + 31) / 32 * 32;
     plane = (size_t)nxl * pitch;
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (P.nranks > 1) {
+      int lo = 0, hi = 0;
+      CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CK(cudaStreamCreateWithPriority(&comm_stream, cudaStreamNonBlocking, hi));
+      CK(cudaEventCreateWithFlags(&ev_state, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&ev_halo, cudaEventDisableTiming));
+    }
     for (int k = 0; k < 2; ++k) {
       CK(cudaMalloc(&f[k], sizeof(real) * plane * NQ));
       CK(cudaMemsetAsync(f[k], 0, sizeof(real) * plane * NQ, stream));
@@ -491,7 +503,7 @@ struct Sim : SimBase {
 
   /* GHOST rows of populations per side, as the fused kernel left them: the ring
    * and bounce-back sweeps that follow reach that far beyond the rows they write */
-  int halo_exchange() {
+  int halo_exchange(cudaStream_t st) {
     if (P.nranks == 1) return 0;
     if (!comm) return fail(LBMDEM_ESTATE, "nranks > 1 but no communicator attached (lbmdem_attach_nccl)");
     const int dtype = sizeof(real) == 8 ? NcclApi::Float64 : NcclApi::Float32;
@@ -502,13 +514,13 @@ struct Sim : SimBase {
     for (int q = 0; q < NQ && !r; ++q) {
       real *pl = F + (size_t)q * plane;
       if (P.rank > 0) { /* left neighbour: send the first owned rows, receive into the ghost rows below them */
-        r = g_nccl.Send(pl + (size_t)GHOST * pitch, cnt, dtype, P.rank - 1, comm, stream);
-        if (!r) r = g_nccl.Recv(pl, cnt, dtype, P.rank - 1, comm, stream);
+        r = g_nccl.Send(pl + (size_t)GHOST * pitch, cnt, dtype, P.rank - 1, comm, st);
+        if (!r) r = g_nccl.Recv(pl, cnt, dtype, P.rank - 1, comm, st);
       }
       if (!r && P.rank < P.nranks - 1) {
         const int end = xhi - x0; /* local row just past the owned rows */
-        r = g_nccl.Send(pl + (size_t)(end - GHOST) * pitch, cnt, dtype, P.rank + 1, comm, stream);
-        if (!r) r = g_nccl.Recv(pl + (size_t)end * pitch, cnt, dtype, P.rank + 1, comm, stream);
+        r = g_nccl.Send(pl + (size_t)(end - GHOST) * pitch, cnt, dtype, P.rank + 1, comm, st);
+        if (!r) r = g_nccl.Recv(pl + (size_t)end * pitch, cnt, dtype, P.rank + 1, comm, st);
       }
     }
     const int r2 = g_nccl.GroupEnd();
@@ -597,14 +609,36 @@ struct Sim : SimBase {
       if ((rc = launch_fused(0, true))) return rc;
       cur ^= 1;
     }
-    if ((rc = halo_exchange())) return rc;
     /* sweeps 3-4 in place (ring :1123-1145, grain bounce-back :1154-1222), then forces_fluid (:1285-1333) */
     const Lattice<real> L = lattice();
     const Stored<real> S = stored(cur, cur_cell);
     const bool multi = P.nranks > 1;
-    CK(launch_ring_sweep<real>(L, S, f[cur], multi ? std::max(xlo - 3, 0) : 0, multi ? std::min(xhi + 3, lx) : lx, stream));
-    CK(launch_bounce_sweep<real>(L, S, f[cur], std::max(multi ? xlo - 1 : xlo, 1), std::min(multi ? xhi + 1 : xhi, lx - 1), xlo,
-                                 xhi, llist, defer, P.strict_fp ? nullptr : facc, stream));
+    long long *fa = P.strict_fp ? nullptr : facc;
+    CK(launch_bounce_begin<real>(n, defer, fa, stream));
+    if (!multi) {
+      CK(launch_ring_sweep<real>(L, S, f[cur], 0, lx, stream));
+      CK(launch_bounce_pass<real>(L, S, f[cur], 1, lx - 1, xlo, xhi, llist, defer, fa, stream));
+    } else if (xhi - xlo < 8) {
+      if ((rc = halo_exchange(stream))) return rc;
+      CK(launch_ring_sweep<real>(L, S, f[cur], std::max(xlo - 3, 0), std::min(xhi + 3, lx), stream));
+      CK(launch_bounce_pass<real>(L, S, f[cur], std::max(xlo - 1, 1), std::min(xhi + 1, lx - 1), xlo, xhi, llist, defer, fa, stream));
+    } else {
+      /* The ghost rows travel on their own stream while this one sweeps the rows that do not need them: a link
+       * of row x reads rows x-2 .. x+2, a ring node of row x reads rows x-1 .. x+1. */
+      CK(cudaEventRecord(ev_state, stream));
+      CK(cudaStreamWaitEvent(comm_stream, ev_state, 0));
+      if ((rc = halo_exchange(comm_stream))) return rc;
+      CK(cudaEventRecord(ev_halo, comm_stream));
+      CK(launch_ring_sweep<real>(L, S, f[cur], xlo + 1, xhi - 1, stream));
+      CK(launch_bounce_pass<real>(L, S, f[cur], xlo + 3, xhi - 3, xlo, xhi, llist, defer, fa, stream));
+      CK(cudaStreamWaitEvent(stream, ev_halo, 0));
+      CK(launch_ring_sweep<real>(L, S, f[cur], std::max(xlo - 3, 0), xlo + 1, stream));
+      CK(launch_ring_sweep<real>(L, S, f[cur], xhi - 1, std::min(xhi + 3, lx), stream));
+      CK(launch_bounce_pass<real>(L, S, f[cur], std::max(xlo - 1, 1), xlo + 3, xlo, xhi, llist, defer, fa, stream));
+      CK(launch_bounce_pass<real>(L, S, f[cur], xhi - 3, std::min(xhi + 1, lx - 1), xlo, xhi, llist, defer, fa, stream));
+      all_launches += 4;
+    }
+    CK(launch_bounce_end<real>(f[cur], defer, stream));
     all_launches += 3;
     if (P.strict_fp) {
       CK(launch_force_serial<real>(L, S, xlo, xhi, fpartial, stream));

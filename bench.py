@@ -183,6 +183,8 @@ def main():
     ap.add_argument("--strict", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=40)
+    ap.add_argument("--sample-gpus", type=int, default=0,
+                    help="diagnostic: build the grain sample as for this many GPUs (replicated-grain cost on one GPU)")
     a = ap.parse_args()
     rows, ly, scale, prec, preset, desc = WORKLOADS[a.workload]
     rank, local_rank, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
@@ -229,7 +231,7 @@ def main():
         D.init_process_group("nccl")
     torch.cuda.set_device(local_rank)
     lx = rows * n_gpus
-    n_grains = make_sample_file(preset, n_gpus, rows, sample_path)
+    n_grains = make_sample_file(preset, a.sample_gpus or n_gpus, rows, sample_path)
     config["grains"] = n_grains
 
     s = D.make_strip_solver(lx, ly, scale, prec, strict_fp=a.strict)
