@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 HOST_LIB = os.path.join(PKG, "liblbmdem_host.so")
 EXE = os.path.join(PKG, "lbmdem")
-CFLAGS = ["-std=c99", "-O2", "-ffp-contract=off", "-Wall", "-Wextra", "-D_POSIX_C_SOURCE=200809L"]
+CFLAGS = ["-std=c99", "-O2", "-ffp-contract=off", "-Wall", "-Wextra", "-D_DEFAULT_SOURCE", "-D_POSIX_C_SOURCE=200809L"]
 WRITERS = ["vtk_writer.c", "dem_output.c"]
 
 

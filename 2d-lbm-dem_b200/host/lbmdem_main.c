@@ -11,6 +11,9 @@
  *   --strict                             bit-exact build (lbmdem_params.strict_fp) LBMDEM_STRICT
  *   --vib                                vibrating walls, int vib = 1 (:162)       LBMDEM_VIB
  *   --device D, --outdir DIR             CUDA device, directory of the output files (default: cwd)
+ *   --gpus N                             x-strip decomposition over N GPUs of this box: the process forks N-1
+ *                                        ranks (one process per GPU, devices D .. D+N-1), the ranks meet over
+ *                                        NCCL inside the library; rank 0 prints and writes every file       LBMDEM_GPUS
  *   --restart FILE                       continue from a checkpoint instead of reading positions from <inputfile>
  *   --checkpoint FILE                    write a checkpoint when the run ends (lbmdem_save_state)
  * Outputs, as the reference writes them: stdout banner and progress lines, stderr
@@ -21,7 +24,10 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/wait.h>
 #include <time.h>
+#include <unistd.h>
 
 #include "../../include/lbmdem_gpu.h"
 #include "dem_output.h"
@@ -33,8 +39,45 @@
 
 static lbmdem_ctx *ctx;
 
+/* ---- ranks of a multi-GPU run: forked processes that share one anonymous mapping ---- */
+typedef struct {
+  volatile int id_ready;          /* rank 0 has published the NCCL id */
+  char nccl_id[128];
+  volatile int arrived, sense;    /* sense-reversing barrier */
+  volatile int failed;            /* some rank died: everybody leaves */
+  double partial[64];             /* per-rank contribution to a sum (density checksum) */
+} shared_t;
+static shared_t *sh;
+static float *sh_fields;          /* the five VTK point fields of the WHOLE lattice, [y][x] order */
+static int rank, nranks = 1;
+
+static void barrier(void) {
+  if (nranks == 1) return;
+  const int my = !sh->sense;
+  if (__atomic_add_fetch(&sh->arrived, 1, __ATOMIC_ACQ_REL) == nranks) {
+    sh->arrived = 0;
+    __atomic_store_n(&sh->sense, my, __ATOMIC_RELEASE);
+  } else {
+    while (__atomic_load_n(&sh->sense, __ATOMIC_ACQUIRE) != my) {
+      if (sh->failed) exit(EXIT_FAILURE);
+      usleep(50);
+    }
+  }
+}
+/* sum over the ranks of one double each; every rank gets the result */
+static double rank_sum(double v) {
+  if (nranks == 1) return v;
+  sh->partial[rank] = v;
+  barrier();
+  double s = 0;
+  for (int r = 0; r < nranks; ++r) s += sh->partial[r];
+  barrier();
+  return s;
+}
+
 static void die(const char *what) {
-  fprintf(stderr, "lbmdem: %s: %s\n", what, lbmdem_last_error(ctx));
+  fprintf(stderr, "lbmdem: rank %d: %s: %s\n", rank, what, lbmdem_last_error(ctx));
+  if (sh) sh->failed = 1;
   exit(EXIT_FAILURE);
 }
 #define CK(call) do { if ((call) < 0) die(#call); } while (0)
@@ -91,11 +134,48 @@ int main(int argc, char **argv) {
   if ((v = opt_or_env(argc, argv, "--steps", "LBMDEM_STEPS"))) max_steps = atol(v);
   const char *outdir = opt_or_env(argc, argv, "--outdir", "LBMDEM_OUTDIR");
   if (!outdir) outdir = "";
+  if ((v = opt_or_env(argc, argv, "--gpus", "LBMDEM_GPUS"))) nranks = atoi(v);
+  if (nranks < 1 || nranks > 64) { fprintf(stderr, "lbmdem: --gpus must be between 1 and 64\n"); return EXIT_FAILURE; }
+  const size_t nn_all = (size_t)p.lx * p.ly;
+  if (nranks > 1) {
+    /* before any CUDA call: share a mapping, then fork one process per further GPU */
+    fflush(stdout);
+    sh = mmap(NULL, sizeof *sh, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+    sh_fields = mmap(NULL, sizeof(float) * 11 * nn_all, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    if (sh == MAP_FAILED || sh_fields == MAP_FAILED) { fprintf(stderr, "lbmdem: mmap failed\n"); return EXIT_FAILURE; }
+    memset(sh, 0, sizeof *sh);
+    for (int r = 1; r < nranks; ++r) {
+      const pid_t pid = fork();
+      if (pid < 0) { fprintf(stderr, "lbmdem: fork failed\n"); return EXIT_FAILURE; }
+      if (pid == 0) { rank = r; break; }
+    }
+    p.rank = rank; p.nranks = nranks; p.device += rank;
+    if (rank != 0) { /* only rank 0 talks */
+      if (!freopen("/dev/null", "w", stdout)) return EXIT_FAILURE;
+    }
+  }
 
   if (lbmdem_create(&p, &ctx)) {
-    fprintf(stderr, "lbmdem: %s\n", lbmdem_last_error(NULL));
+    fprintf(stderr, "lbmdem: rank %d: %s\n", rank, lbmdem_last_error(NULL));
+    if (sh) sh->failed = 1;
     return EXIT_FAILURE;
   }
+  if (nranks > 1) {
+    if (rank == 0) {
+      if (lbmdem_nccl_unique_id(sh->nccl_id)) { fprintf(stderr, "lbmdem: %s\n", lbmdem_last_error(NULL)); sh->failed = 1; return EXIT_FAILURE; }
+      __atomic_store_n(&sh->id_ready, 1, __ATOMIC_RELEASE);
+    } else {
+      while (!__atomic_load_n(&sh->id_ready, __ATOMIC_ACQUIRE)) {
+        if (sh->failed) return EXIT_FAILURE;
+        usleep(100);
+      }
+    }
+    char id[128];
+    memcpy(id, sh->nccl_id, 128);
+    CK(lbmdem_attach_nccl(ctx, id));
+  }
+  int xlo = 0, xhi = p.lx;
+  CK(lbmdem_get_strip(ctx, &xlo, &xhi));
   /* read_sample prints the comment line and the grain count (src/main.c:613-619) */
   {
     FILE *fp = fopen(argv[1], "r");
@@ -137,10 +217,10 @@ int main(int argc, char **argv) {
   }
   time(&now);
   printf("Current local time and date: %s", asctime(localtime(&now)));
-  if (!restart && lbmdem_write_stats_header(outdir)) { fprintf(stderr, "lbmdem: cannot write stats.data\n"); return EXIT_FAILURE; }
+  if (rank == 0 && !restart && lbmdem_write_stats_header(outdir)) { fprintf(stderr, "lbmdem: cannot write stats.data\n"); return EXIT_FAILURE; }
   lbmdem_diag *dg = lbmdem_diag_create(n, &p);
 
-  const size_t nn = (size_t)p.lx * p.ly;
+  const size_t nn = (size_t)(xhi - xlo) * p.ly; /* nodes of this rank's strip */
   float *f_gp = NULL, *f_gv = NULL, *f_ga = NULL, *f_fp = NULL, *f_fv = NULL;
   long nbsteps = l4[1]; /* 0, or where the checkpoint was taken */
   int nFile = (int)l4[2];
@@ -179,6 +259,7 @@ int main(int argc, char **argv) {
     if ((nbsteps - 1) % STEP_CONSOLE == 0 && (nbsteps - 1) % npDEM == 0) {
       double sum; /* check_density (:1249-1260) of the call that just ended */
       CK(lbmdem_total_density(ctx, &sum));
+      sum = rank_sum(sum);
       printf("Iteration Number %ld, Total density in the system %f\n", nbsteps - 1, sum);
     }
     if (nbsteps % STEP_FILM == 0) { /* write_vtk, nFile++ (:1767-1772) */
@@ -189,15 +270,30 @@ int main(int argc, char **argv) {
       lbmdem_diag_get(dg, diag);
       for (int i = 0; i < n; ++i) gp[i] = diag[17 * (size_t)i];
       CK(lbmdem_get_fields(ctx, gp, f_gp, f_gv, f_ga, f_fp, f_fv));
-      if (lbmdem_write_vtk_frame(outdir, nFile, p.lx, p.ly, f_gp, f_gv, f_ga, f_fp, f_fv)) {
+      const float *w_gp = f_gp, *w_gv = f_gv, *w_ga = f_ga, *w_fp = f_fp, *w_fv = f_fv;
+      if (nranks > 1) {
+        /* every rank drops its columns [xlo, xhi) of each [y][x] field into the shared arrays */
+        float *all[5] = {sh_fields, sh_fields + nn_all, sh_fields + 4 * nn_all, sh_fields + 7 * nn_all, sh_fields + 8 * nn_all};
+        const float *mine[5] = {f_gp, f_gv, f_ga, f_fp, f_fv};
+        const int comp[5] = {1, 3, 3, 1, 3};
+        const int w = xhi - xlo;
+        for (int k = 0; k < 5; ++k)
+          for (int y = 0; y < p.ly; ++y)
+            memcpy(all[k] + ((size_t)y * p.lx + xlo) * comp[k], mine[k] + (size_t)y * w * comp[k], sizeof(float) * w * comp[k]);
+        barrier();
+        w_gp = all[0]; w_gv = all[1]; w_ga = all[2]; w_fp = all[3]; w_fv = all[4];
+      }
+      if (rank == 0 && lbmdem_write_vtk_frame(outdir, nFile, p.lx, p.ly, w_gp, w_gv, w_ga, w_fp, w_fv)) {
         fprintf(stderr, "lbmdem: cannot write the VTK frame\n");
+        if (sh) sh->failed = 1;
         return EXIT_FAILURE;
       }
+      barrier(); /* the shared arrays are free again */
       nFile++;
     }
     if (nbsteps % STEP_STROB == 0) { /* write_DEM (:1773-1776) */
       CK(lbmdem_get_fhf(ctx, fhf));
-      if (lbmdem_write_dem(dg, outdir, nFile, nbsteps, grains, fhf, d11, summary)) {
+      if (rank == 0 && lbmdem_write_dem(dg, outdir, nFile, nbsteps, grains, fhf, d11, summary)) {
         fprintf(stderr, "lbmdem: cannot write DEM%06d.dat\n", nFile);
         return EXIT_FAILURE;
       }
@@ -212,12 +308,20 @@ int main(int argc, char **argv) {
   {
     double sum; /* final_density (:1262-1273) */
     CK(lbmdem_total_density(ctx, &sum));
-    fprintf(stderr, "final_density: %f\n", sum);
+    sum = rank_sum(sum);
+    if (rank == 0) fprintf(stderr, "final_density: %f\n", sum);
   }
   if (checkpoint) CK(lbmdem_save_state(ctx, checkpoint));
   time(&now);
   printf("End local time and date: %s", asctime(localtime(&now)));
   lbmdem_diag_destroy(dg);
+  barrier();
   lbmdem_destroy(ctx);
+  if (nranks > 1 && rank == 0) {
+    int status = 0, bad = 0;
+    while (wait(&status) > 0)
+      if (!WIFEXITED(status) || WEXITSTATUS(status) != 0) bad = 1;
+    if (bad) return EXIT_FAILURE;
+  }
   return 0;
 }

@@ -28,3 +28,32 @@ def test_strips_are_bit_identical_to_one_gpu():
     assert p.returncode == 0, (p.stdout + p.stderr)[-4000:]
     for rank in range(world):
         assert f"rank {rank}: ok" in p.stdout
+
+
+def test_executable_on_two_gpus_writes_the_same_files_as_on_one(tmp_path):
+    """`lbmdem <file> --gpus 2` (the executable forks one rank per GPU): the default build is bit-identical for any
+    number of strips, so every output file must equal the one-GPU run's byte for byte."""
+    import importlib.util
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least two GPUs")
+    root = os.path.dirname(HERE)
+    spec = importlib.util.spec_from_file_location("host_build", os.path.join(root, "2d-lbm-dem_b200", "host", "build.py"))
+    hb = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(hb)
+    exe = hb.build_exe()
+    sample = os.path.join(HERE, "golden", "pack_64x48_f64.data")
+    outs = []
+    for gpus in (1, 2):
+        out = tmp_path / f"g{gpus}"
+        out.mkdir()
+        p = subprocess.run([exe, sample, "--lx", "64", "--ly", "48", "--steps", "8000", "--gpus", str(gpus), "--outdir", str(out)],
+                           capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+        assert "final_density:" in p.stderr
+        outs.append((out, p))
+    names = sorted(os.listdir(outs[0][0]))
+    assert len(names) == 8 and names == sorted(os.listdir(outs[1][0]))
+    for name in names:
+        assert open(outs[0][0] / name, "rb").read() == open(outs[1][0] / name, "rb").read(), name
+    assert outs[0][1].stderr.strip().splitlines()[-1] == outs[1][1].stderr.strip().splitlines()[-1]   # final_density
