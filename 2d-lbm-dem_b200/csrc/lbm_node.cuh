@@ -207,9 +207,50 @@ LBM_HD void equilibrium(const Lattice<real> &L, const GrainRec<real> &g, int x, 
 #endif
 }
 
-/* src/main.c:1082-1116 */
+/* src/main.c:1082-1116.  The reference's expressions verbatim -- except in the default device build
+ * (LBM_RELAXED, below), which evaluates the same nine-moment map with shared sub-sums. */
 template <typename real>
 LBM_HD void mrt_collide(const Lattice<real> &L, real *p) {
+#if defined(LBM_RELAXED)
+  /* Same linear maps, regrouped (differences at rounding level, well inside the parity tolerance):
+   * the moments from the sums over the diagonal and over the axis populations, one reciprocal of rho
+   * for the four equilibria, the back-transform from two shared combinations per population class. */
+  const real sd = (p[1] + p[3]) + (p[5] + p[7]), sa = (p[2] + p[4]) + (p[6] + p[8]);
+  const real rho = p[0] + sd + sa;
+  const real e = -4 * p[0] + 2 * sd - sa;
+  const real eps = 4 * p[0] + sd - 2 * sa;
+  const real dxp = p[5] + p[7], dxm = p[1] + p[3], dyp = p[1] + p[7], dym = p[3] + p[5];
+  const real j_x = (dxp - dxm) + (p[6] - p[2]);
+  const real q_x = (dxp - dxm) - 2 * (p[6] - p[2]);
+  const real j_y = (dyp - dym) + (p[8] - p[4]);
+  const real q_y = (dyp - dym) - 2 * (p[8] - p[4]);
+  const real p_xx = (p[2] + p[6]) - (p[4] + p[8]);
+  const real p_xy = (p[3] + p[7]) - (p[1] + p[5]);
+  const real ir = 1 / rho;
+  const real j_x2 = j_x * j_x, j_y2 = j_y * j_y;
+  const real jj = 3 * (j_x2 + j_y2) * ir;
+  const real eO = e - L.s2 * (e + 2 * rho - jj);
+  const real epsO = eps - L.s3 * (eps - rho + jj);
+  const real q_xO = q_x - L.s5 * (q_x + j_x);
+  const real q_yO = q_y - L.s7 * (q_y + j_y);
+  const real p_xxO = p_xx - L.s8 * (p_xx - (j_x2 - j_y2) * ir);
+  const real p_xyO = p_xy - L.s9 * (p_xy - j_x * j_y * ir);
+  const real a = (real)(1. / 36);
+  const real r4 = 4 * rho;
+  const real A = a * (r4 - eO - 2 * epsO), B = a * (r4 + 2 * eO + epsO);
+  const real cx = (6 * a) * (j_x - q_xO), cy = (6 * a) * (j_y - q_yO);
+  const real gx = (3 * a) * (2 * j_x + q_xO), gy = (3 * a) * (2 * j_y + q_yO);
+  const real pxx9 = (9 * a) * p_xxO, pxy9 = (9 * a) * p_xyO;
+  p[0] = a * (r4 - 4 * eO + 4 * epsO);
+  p[2] = (A + pxx9) - cx;
+  p[6] = (A + pxx9) + cx;
+  p[4] = (A - pxx9) - cy;
+  p[8] = (A - pxx9) + cy;
+  p[1] = (B - pxy9) - (gx - gy);
+  p[5] = (B - pxy9) + (gx - gy);
+  p[3] = (B + pxy9) - (gx + gy);
+  p[7] = (B + pxy9) + (gx + gy);
+#else
   const real a = 1. / 36;
   real rho = p[0] + p[1] + p[2] + p[3] + p[4] + p[5] + p[6] + p[7] + p[8];
   real e = -4 * p[0] + 2 * p[1] - p[2] + 2 * p[3] - p[4] + 2 * p[5] - p[6] + 2 * p[7] - p[8];
@@ -221,19 +262,10 @@ LBM_HD void mrt_collide(const Lattice<real> &L, real *p) {
   real p_xx = p[2] - p[4] + p[6] - p[8];
   real p_xy = -p[1] + p[3] - p[5] + p[7];
   real j_x2 = j_x * j_x, j_y2 = j_y * j_y;
-#if defined(LBM_RELAXED)
-  /* default device build: the four divisions by rho share one reciprocal (1e-16 / 1e-7 relative) */
-  const real ir = 1 / rho;
-  real eO = e - L.s2 * (e + 2 * rho - 3 * (j_x2 + j_y2) * ir);
-  real epsO = eps - L.s3 * (eps - rho + 3 * (j_x2 + j_y2) * ir);
-  real p_xxO = p_xx - L.s8 * (p_xx - (j_x2 - j_y2) * ir);
-  real p_xyO = p_xy - L.s9 * (p_xy - j_x * j_y * ir);
-#else
   real eO = e - L.s2 * (e + 2 * rho - 3 * (j_x2 + j_y2) / rho);
   real epsO = eps - L.s3 * (eps - rho + 3 * (j_x2 + j_y2) / rho);
   real p_xxO = p_xx - L.s8 * (p_xx - (j_x2 - j_y2) / rho);
   real p_xyO = p_xy - L.s9 * (p_xy - j_x * j_y / rho);
-#endif
   real q_xO = q_x - L.s5 * (q_x + j_x);
   real q_yO = q_y - L.s7 * (q_y + j_y);
   p[0] = a * (4 * rho - 4 * eO + 4 * epsO);
@@ -245,6 +277,7 @@ LBM_HD void mrt_collide(const Lattice<real> &L, real *p) {
   p[3] = a * (4 * rho + 2 * eO + epsO - 6 * j_x - 3 * q_xO - 6 * j_y - 3 * q_yO + 9 * p_xyO);
   p[5] = a * (4 * rho + 2 * eO + epsO + 6 * j_x + 3 * q_xO - 6 * j_y - 3 * q_yO - 9 * p_xyO);
   p[7] = a * (4 * rho + 2 * eO + epsO + 6 * j_x + 3 * q_xO + 6 * j_y + 3 * q_yO + 9 * p_xyO);
+#endif
 }
 
 /* src/main.c:1053-1058: link fraction for the link from solid node (x,y) along q to its fluid
