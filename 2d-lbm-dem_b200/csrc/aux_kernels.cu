@@ -16,10 +16,14 @@ using namespace lbm;
 /* ------------------------------------------------------------------------------------------
  * K2: obst_construction (src/main.c:991-1065) without the delta[] array; act[] is a bit of the map
  * ---------------------------------------------------------------------------------------- */
+/* also empties what the step's later kernels fill: the overlap flags, the three list counters and (default build)
+ * the fixed-point force sums -- no memset nodes between the kernels of a step */
 template <typename real>
 __global__ void grain_prepare_kernel(RasterParams<real> P, int n, GrainArrays<real> g, GrainRec<real> *rec, real *R2,
-                                     GrainBox *boxes) {
+                                     GrainBox *boxes, int *overlap, int *count_a, int *count_b, int *count_c,
+                                     long long *facc) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) { *count_a = 0; *count_b = 0; *count_c = 0; }
   if (i >= n) return;
   GrainRec<real> r;
   GrainBox b;
@@ -29,13 +33,24 @@ __global__ void grain_prepare_kernel(RasterParams<real> P, int n, GrainArrays<re
   rec[i] = r;
   R2[i] = R2i;
   boxes[i] = b;
+  overlap[i] = 0;
+  if (facc != nullptr) { facc[i] = 0; facc[n + i] = 0; facc[2 * n + i] = 0; }
 }
 
 #ifndef LBMDEM_SWEEP_MINB
 #define LBMDEM_SWEEP_MINB 4
 #endif
-constexpr int GSPLIT = 4;  /* warps per grain in the rasteriser */
-constexpr int BSPLIT = 2;  /* warps per grain in the boundary pass */
+#ifndef LBMDEM_BSPLIT
+#define LBMDEM_BSPLIT 2
+#endif
+#ifndef LBMDEM_BND_MINB
+#define LBMDEM_BND_MINB 1
+#endif
+#ifndef LBMDEM_BND_STAGE
+#define LBMDEM_BND_STAGE 256
+#endif
+constexpr int GSPLIT = 4;              /* warps per grain in the rasteriser */
+constexpr int BSPLIT = LBMDEM_BSPLIT;  /* warps per grain in the boundary pass */
 
 /* GSPLIT warps per grain; the owner of a node is the highest-index grain covering it (:1028 run
  * in index order), hence atomicMax over the fluid value -1.  Grains whose reduced discs share a
@@ -89,9 +104,9 @@ __global__ void raster_kernel(int n, const GrainRec<real> *rec, const real *R2, 
 }
 
 constexpr int BND_WARPS = 4;     /* warps (= grains) per CTA */
-constexpr int BND_CAND = 256;    /* per-warp staging: candidate nodes, node entries, link entries */
-constexpr int BND_NODES = 256;
-constexpr int BND_LINKS = 768;
+constexpr int BND_CAND = LBMDEM_BND_STAGE;    /* per-warp staging: candidate nodes, node entries, link entries */
+constexpr int BND_NODES = LBMDEM_BND_STAGE;
+constexpr int BND_LINKS = 2 * LBMDEM_BND_STAGE + 256; /* a round of 32 nodes adds up to 256 links: flushed above 2 * STAGE */
 
 __device__ __forceinline__ void list_flush(uint2 *dst, int *counter, int capacity, int *overflow, const uint2 *buf, int cnt,
                                            int lane) {
@@ -108,13 +123,15 @@ __device__ __forceinline__ void list_flush(uint2 *dst, int *counter, int capacit
  * grain, after ALL grains are rasterised.  A node of grain i is active iff one of its eight
  * neighbours was fluid when the reference's loop reached grain i (lbm_node.cuh,
  * fluid_when_grain_ran); the flag is folded into the map as CELL_ACT (readers of a neighbour mask
- * it off, so concurrent folding of other nodes is harmless).
+ * it off, so concurrent folding of other nodes is harmless).  Nodes of the boundary list -- a NON-fluid
+ * neighbour under another owner -- get CELL_RIM: together the two bits tell the fused kernel which solid
+ * nodes anything will ever read (lbm_node.cuh, node_is_dead).
  * Pass 1 works on geometry alone: nodes outside the disc cannot be owned, nodes deep inside the
  * disc of a grain that overlaps no other grain have all eight neighbours inside the same disc; what
  * remains (the rim: the two ends of every row's chord) goes into a per-warp list.  Pass 2 looks at
  * the map, one rim node per lane. */
 template <typename real>
-__global__ void __launch_bounds__(BND_WARPS * 32) boundary_kernel(int n, const GrainRec<real> *rec, const real *R2,
+__global__ void __launch_bounds__(BND_WARPS * 32, LBMDEM_BND_MINB) boundary_kernel(int n, const GrainRec<real> *rec, const real *R2,
                                                                    const GrainBox *boxes, int *cell, int x0, int nxl, int pitch,
                                                                    int lx, int ly, const int *overlap, const int *min_owner,
                                                                    int genkey, BoundaryList B, LinkList K) {
@@ -153,7 +170,7 @@ __global__ void __launch_bounds__(BND_WARPS * 32) boundary_kernel(int n, const G
   for (int rb = xa; rb <= xb; rb += 32) {
     /* ---- pass 1: geometry.  Lane = one row of the bounding box: the covered nodes of a row are a
      * chord of the disc, the deep ones a shorter chord inside it; what may be rim is the two ends
-     * (bracketed generously with float square roots -- pass 2 repeats the exact tests) ---- */
+     * (bracketed with float square roots -- pass 2 repeats the exact tests) ---- */
     const int row = rb + lane;
     int ya1 = 0, c1 = 0, ya2 = 0, c2 = 0;
     if (row <= xb) {
@@ -161,14 +178,16 @@ __global__ void __launch_bounds__(BND_WARPS * 32) boundary_kernel(int n, const G
       const real h2 = rmin2 - dxr * dxr;
       if (h2 >= 0) {
         const float h = sqrtf((float)h2);
-        const int ylo = max((int)floorf((float)yc - h) - 1, b.yi), yhi = min((int)ceilf((float)yc + h) + 1, b.yf);
+        /* covered nodes have |y - yc| <= h: floor / ceil of the float bounds bracket them (the float error is far
+         * below one node); deep nodes have |y - yc| < gi: the bracket stays 0.05 node inside that */
+        const int ylo = max((int)floorf((float)yc - h), b.yi), yhi = min((int)ceilf((float)yc + h), b.yf);
         int dlo = 1, dhi = 0; /* rows of certainly deep nodes: empty unless ... */
         if (inner2 > 0 && row >= 2 && row <= lx - 3) {
           const real g2 = inner2 - dxr * dxr;
           if (g2 > 0) {
             const float gi = sqrtf((float)g2);
-            dlo = max((int)ceilf((float)yc - gi) + 1, 2);
-            dhi = min((int)floorf((float)yc + gi) - 1, ly - 3);
+            dlo = max((int)ceilf((float)yc - gi + 0.05f), 2);
+            dhi = min((int)floorf((float)yc + gi - 0.05f), ly - 3);
           }
         }
         if (dlo <= dhi) {
@@ -229,12 +248,13 @@ __global__ void __launch_bounds__(BND_WARPS * 32) boundary_kernel(int n, const G
               if (fluid_when_grain_ran_exact(cn, i, n, mo)) act = true;
             }
           }
+          const bool rim = (foreign & ~fluid) != 0;
+          if (act || rim) atomicOr(&cell[k], (act ? CELL_ACT : 0) | (rim ? CELL_RIM : 0));
           if (act) {
-            atomicOr(&cell[k], CELL_ACT);
             bounce = fluid;
             if (!(x >= 2 && y >= 2 && x <= lx - 3 && y <= ly - 3)) wl = ~fluid & 0xffu; /* next to the ring */
           }
-          if (foreign & ~fluid) { /* the force kernel's share: foreign neighbours that are not fluid */
+          if (rim) { /* the force kernel's share: foreign neighbours that are not fluid */
             emit = true;
             e = make_uint2((unsigned)k, (foreign << 24) | (act ? BL_ACT : 0u) | (unsigned)i);
           }
@@ -283,8 +303,8 @@ __global__ void cell_frame_kernel(int *cell, int lx, int ly, int x0, int nxl, in
 template <typename real>
 cudaError_t launch_raster(const RasterParams<real> &P, int n, const GrainArrays<real> &g, GrainRec<real> *rec, real *R2,
                           GrainBox *boxes, int *cell, int x0, int nxl, int pitch, int *overlap, int *min_owner, int genkey,
-                          const BoundaryList &B, const LinkList &K, cudaStream_t s) {
-  grain_prepare_kernel<real><<<(n + 127) / 128, 128, 0, s>>>(P, n, g, rec, R2, boxes);
+                          const BoundaryList &B, const LinkList &K, int *defer_count, long long *facc, cudaStream_t s) {
+  grain_prepare_kernel<real><<<(n + 127) / 128, 128, 0, s>>>(P, n, g, rec, R2, boxes, overlap, B.count, K.count, defer_count, facc);
   /* clear the interior: rows with global x in [1, lx-2], columns [1, ly-2] (:997-1005) */
   const int ra = max(1 - x0, 0), rb = min(P.lx - 2 - x0, nxl - 1);
   cudaError_t e;
@@ -292,9 +312,6 @@ cudaError_t launch_raster(const RasterParams<real> &P, int n, const GrainArrays<
     e = cudaMemset2DAsync(cell + (size_t)ra * pitch + 1, sizeof(int) * pitch, 0xFF, sizeof(int) * (P.ly - 2), rb - ra + 1, s);
     if (e != cudaSuccess) return e;
   }
-  if ((e = cudaMemsetAsync(overlap, 0, sizeof(int) * n, s)) != cudaSuccess) return e;
-  if ((e = cudaMemsetAsync(B.count, 0, sizeof(int), s)) != cudaSuccess) return e;
-  if ((e = cudaMemsetAsync(K.count, 0, sizeof(int), s)) != cudaSuccess) return e;
   raster_kernel<real><<<(n * GSPLIT * 32 + 255) / 256, 256, 0, s>>>(n, rec, R2, boxes, cell, x0, nxl, pitch, overlap,
                                                                  min_owner, genkey);
   boundary_kernel<real><<<(n * BSPLIT + BND_WARPS - 1) / BND_WARPS, BND_WARPS * 32, 0, s>>>(n, rec, R2, boxes, cell, x0, nxl, pitch,
@@ -369,23 +386,37 @@ cudaError_t launch_ring_sweep(const Lattice<real> &L, const Stored<real> &S, rea
  * per-warp list, then share the (node, link) pairs out, one link per lane, so that the expensive
  * part (delta: one sqrt, the interpolation: divisions) runs with full lanes.
  * ---------------------------------------------------------------------------------------- */
-/* adds three fixed-point values to the sums of grain i; lanes of a warp that hold the same grain
- * are summed first (exact: integers), so there is about one atomic per grain and warp */
+/* Adds three fixed-point values to the sums of grain i (i < 0: nothing to add).  EVERY lane of the warp calls it.
+ * Lanes that hold the same grain are summed first (exact: integers), so there is about one atomic per grain and
+ * warp.  The link list is grouped by grain, so the lanes of a grain normally form one contiguous run: a segmented
+ * shuffle reduction (five rounds); any other pattern takes the lane-by-lane loop. */
 __device__ __forceinline__ void grain_sums_add(long long *facc, int n, int i, long long s1, long long s2, long long s3) {
-  const unsigned active = __activemask();
-  const unsigned peers = __match_any_sync(active, i);
-  const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
-  long long t1 = 0, t2 = 0, t3 = 0;
-  for (unsigned m = peers; m; m &= m - 1) {
-    const int src = __ffs(m) - 1;
-    t1 += __shfl_sync(peers, s1, src);
-    t2 += __shfl_sync(peers, s2, src);
-    t3 += __shfl_sync(peers, s3, src);
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const unsigned peers = __match_any_sync(full, i);
+  const int first = __ffs(peers) - 1, cnt = __popc(peers);
+  const bool run = (peers >> first) == (cnt == 32 ? full : ((1u << cnt) - 1u));
+  if (__all_sync(full, run)) {
+    const int end = first + cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const long long t1 = __shfl_down_sync(full, s1, d), t2 = __shfl_down_sync(full, s2, d), t3 = __shfl_down_sync(full, s3, d);
+      if (lane + d < end) { s1 += t1; s2 += t2; s3 += t3; }
+    }
+  } else {
+    long long t1 = 0, t2 = 0, t3 = 0;
+    for (unsigned m = peers; m; m &= m - 1) {
+      const int src = __ffs(m) - 1;
+      t1 += __shfl_sync(peers, s1, src);
+      t2 += __shfl_sync(peers, s2, src);
+      t3 += __shfl_sync(peers, s3, src);
+    }
+    s1 = t1; s2 = t2; s3 = t3;
   }
-  if (lane == leader && i >= 0) {
-    atomicAdd((unsigned long long *)&facc[i], (unsigned long long)t1);
-    atomicAdd((unsigned long long *)&facc[n + i], (unsigned long long)t2);
-    atomicAdd((unsigned long long *)&facc[2 * n + i], (unsigned long long)t3);
+  if (lane == first && i >= 0) {
+    atomicAdd((unsigned long long *)&facc[i], (unsigned long long)s1);
+    atomicAdd((unsigned long long *)&facc[n + i], (unsigned long long)s2);
+    atomicAdd((unsigned long long *)&facc[2 * n + i], (unsigned long long)s3);
   }
 }
 
@@ -399,44 +430,54 @@ __global__ void __launch_bounds__(256, LBMDEM_SWEEP_MINB) bounce_sweep_kernel(co
                                                            int xlo, int xhi, const LinkList K, const DeferList<real> D,
                                                            long long *facc) {
   const int items = min(*K.count, K.capacity);
-  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < items; u += gridDim.x * blockDim.x) {
-    const uint2 en = K.entry[u];
-    const int q = (int)((en.y >> 24) & 15u);
-    const int row = (int)(en.x / (unsigned)L.pitch);
-    const int x = L.x0 + row, y = (int)(en.x - (unsigned)row * (unsigned)L.pitch);
-    if (x < xa || x >= xb) continue;
-    const size_t e = q * L.plane + en.x;
-    if (en.y & LL_W) { /* rest value next to the wall ring (the fused kernel does the others) */
-      A[e] = L.w[q];
-      continue;
-    }
-    real v;
-    const int owner = (int)(en.y & BL_GRAIN);
-    int r = sweep_link(L, S, x, y, q, false, &v, owner, true); /* listed bounce links have a fluid neighbour */
-    if (r == SWEEP_WRITE) {
-      A[e] = v;
-    } else if (r == SWEEP_DEFER) {
-      r = sweep_link(L, S, x, y, q, true, &v, owner, true);
-      if (r == SWEEP_WRITE) {
-        /* one counter update per group of lanes that got here together */
-        const unsigned grp = __activemask();
-        const int leader = __ffs(grp) - 1, lane = threadIdx.x & 31;
-        int slot = 0;
-        if (lane == leader) slot = atomicAdd(D.count, __popc(grp));
-        slot = __shfl_sync(grp, slot, leader) + __popc(grp & ((1u << lane) - 1));
-        if (slot < D.capacity) { D.index[slot] = e; D.value[slot] = v; }
-        else *(volatile int *)D.overflow = 1; /* mapped host memory */
+  const int padded = (items + 31) & ~31; /* whole warps stay in the loop: grain_sums_add shuffles */
+  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < padded; u += gridDim.x * blockDim.x) {
+    int fi = -1;
+    long long s1 = 0, s2 = 0, s3 = 0;
+    if (u < items) {
+      const uint2 en = K.entry[u];
+      const int q = (int)((en.y >> 24) & 15u);
+      const int row = (int)(en.x / (unsigned)L.pitch);
+      const int x = L.x0 + row, y = (int)(en.x - (unsigned)row * (unsigned)L.pitch);
+      if (x >= xa && x < xb) {
+        const size_t e = q * L.plane + en.x;
+        if (en.y & LL_W) { /* rest value next to the wall ring (the fused kernel does the others) */
+          A[e] = L.w[q];
+        } else {
+          const int owner = (int)(en.y & BL_GRAIN);
+          const GrainRec<real> g = S.grains[owner];
+          real v, Fn_oq;
+          bool gap;
+          /* listed bounce links have a fluid neighbour; a link across a one-node gap is evaluated from the
+           * pre-sweep state and filed in the deferred list (lbm_node.cuh, sweep_link) */
+          const int r = sweep_link_core(L, S, g, x, y, q, true, &v, true, &gap, &Fn_oq);
+          if (r == SWEEP_WRITE) {
+            if (!gap) {
+              A[e] = v;
+            } else {
+              /* one counter update per group of lanes that got here together */
+              const unsigned grp = __activemask();
+              const int leader = __ffs(grp) - 1, lane = threadIdx.x & 31;
+              int slot = 0;
+              if (lane == leader) slot = atomicAdd(D.count, __popc(grp));
+              slot = __shfl_sync(grp, slot, leader) + __popc(grp & ((1u << lane) - 1));
+              if (slot < D.capacity) { D.index[slot] = e; D.value[slot] = v; }
+              else *(volatile int *)D.overflow = 1; /* mapped host memory */
+            }
+          }
+          if (facc != nullptr && x >= xlo && x < xhi) {
+            if (r == SWEEP_KEEP) v = A[e];
+            real h1 = 0, h2 = 0, h3 = 0;
+            force_link<real>(q, Fn_oq, v, x, y, g.xc, g.yc, &h1, &h2, &h3);
+            fi = owner;
+            s1 = __double2ll_rn((double)h1 * FORCE_FIX);
+            s2 = __double2ll_rn((double)h2 * FORCE_FIX);
+            s3 = __double2ll_rn((double)h3 * TORQUE_FIX);
+          }
+        }
       }
     }
-    if (facc != nullptr && x >= xlo && x < xhi) {
-      if (r == SWEEP_KEEP) v = A[e];
-      const int i = (int)(en.y & BL_GRAIN);
-      const size_t kn = node_index(L, x + ex_of(q), y + ey_of(q));
-      real h1 = 0, h2 = 0, h3 = 0;
-      force_link<real>(q, A[opp_of(q) * L.plane + kn], v, x, y, S.grains[i].xc, S.grains[i].yc, &h1, &h2, &h3);
-      grain_sums_add(facc, L.ngrains, i, __double2ll_rn((double)h1 * FORCE_FIX), __double2ll_rn((double)h2 * FORCE_FIX),
-                     __double2ll_rn((double)h3 * TORQUE_FIX));
-    }
+    if (facc != nullptr) grain_sums_add(facc, L.ngrains, fi, s1, s2, s3);
   }
 }
 template <typename real>
@@ -447,13 +488,6 @@ __global__ void defer_apply_kernel(real *A, const DeferList<real> D) {
 /* The sweep in three stages, so that a strip-decomposed run can sweep the rows that need no ghost data while
  * the ghost rows are still in flight: begin (empty deferred list, zero force sums), any number of passes over
  * disjoint row ranges, end (apply the deferred links -- only after EVERY pass, they read pre-sweep values). */
-template <typename real>
-cudaError_t launch_bounce_begin(int ngrains, const DeferList<real> &D, long long *facc, cudaStream_t s) {
-  cudaError_t e = cudaMemsetAsync(D.count, 0, sizeof(int), s);
-  if (e != cudaSuccess) return e;
-  if (facc != nullptr) e = cudaMemsetAsync(facc, 0, sizeof(long long) * 3 * ngrains, s);
-  return e;
-}
 template <typename real>
 cudaError_t launch_bounce_pass(const Lattice<real> &L, const Stored<real> &S, real *A, int xa, int xb, int xlo, int xhi,
                                const LinkList &K, const DeferList<real> &D, long long *facc, cudaStream_t s) {
@@ -1014,11 +1048,10 @@ cudaError_t launch_fill_rest(real *f, size_t plane, const Lattice<real> &Lw, cud
 #define INSTANTIATE(real)                                                                                               \
   template cudaError_t launch_raster<real>(const RasterParams<real> &, int, const GrainArrays<real> &, GrainRec<real> *,  \
                                            real *, GrainBox *, int *, int, int, int, int *, int *, int,                   \
-                                           const BoundaryList &, const LinkList &, cudaStream_t);                         \
+                                           const BoundaryList &, const LinkList &, int *, long long *, cudaStream_t);     \
   template cudaError_t launch_act_map<real>(const Lattice<real> &, const Stored<real> &, int, int, int *, cudaStream_t);  \
   template cudaError_t launch_ring_sweep<real>(const Lattice<real> &, const Stored<real> &, real *, int, int,             \
                                                cudaStream_t);                                                             \
-  template cudaError_t launch_bounce_begin<real>(int, const DeferList<real> &, long long *, cudaStream_t);                \
   template cudaError_t launch_bounce_pass<real>(const Lattice<real> &, const Stored<real> &, real *, int, int, int, int,  \
                                                 const LinkList &, const DeferList<real> &, long long *, cudaStream_t);    \
   template cudaError_t launch_bounce_end<real>(real *, const DeferList<real> &, cudaStream_t);                            \

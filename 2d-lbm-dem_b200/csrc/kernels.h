@@ -101,6 +101,10 @@ struct GrainArrays {
   template <typename real>                                                                                             \
   cudaError_t launch_lbm_h1(const lbm::Lattice<real> &L, real *f, const int *cell_prev, const int *cell_now,           \
                             const lbm::GrainRec<real> *grains_new, int xlo, int xhi, cudaStream_t s);                  \
+  /* the populations the fused kernel leaves unwritten (lbm_node.cuh, node_is_dead), rows [xa, xb) of A */            \
+  template <typename real>                                                                                             \
+  cudaError_t launch_lbm_fill_dead(const lbm::Lattice<real> &L, real *A, const int *cell_prev, const int *cell_now,    \
+                                   const lbm::GrainRec<real> *grains_new, int xa, int xb, cudaStream_t s);             \
   }
 LBMDEM_DECLARE_K1(k1_fast)
 LBMDEM_DECLARE_K1(k1_strict)
@@ -133,7 +137,8 @@ template <typename real>
 cudaError_t launch_raster(const lbm::RasterParams<real> &P, int ngrains, const GrainArrays<real> &g,
                           lbm::GrainRec<real> *rec, real *R2, lbm::GrainBox *boxes, int *cell, int x0, int nxl, int pitch,
                           int *overlap, int *min_owner /* [x-x0][y], lbm_node.cuh MINOWNER_* */, int genkey,
-                          const BoundaryList &B, const LinkList &K, cudaStream_t s);
+                          const BoundaryList &B, const LinkList &K, int *defer_count /* emptied as well */,
+                          long long *facc /* nullptr, or [3][n] force sums to be zeroed */, cudaStream_t s);
 cudaError_t launch_cell_frame(int *cell, int lx, int ly, int x0, int nxl, int pitch, int ring_value, cudaStream_t s);
 /* act[x][y] as the reference would hold it (tests / diagnostics) */
 template <typename real>
@@ -145,11 +150,9 @@ cudaError_t launch_ring_sweep(const lbm::Lattice<real> &L, const lbm::Stored<rea
                               cudaStream_t s);
 /* sweep 4 in place: interpolated bounce-back on the active solid nodes (src/main.c:1154-1222), one thread per
  * listed link; links facing another grain across a one-node gap go through the deferred list (lbm_node.cuh,
- * sweep_link).  Three stages: begin (empties the deferred list and, with facc != nullptr, zeroes facc[3][n]),
+ * sweep_link).  Two stages (the deferred list and facc[3][n] were emptied by launch_raster):
  * passes over disjoint row ranges [xa, xb) (each also adds the momentum exchange of its links into fluid
  * neighbours whose solid node lies in [xlo, xhi)), end (applies the deferred links; after every pass). */
-template <typename real>
-cudaError_t launch_bounce_begin(int ngrains, const DeferList<real> &D, long long *facc, cudaStream_t s);
 template <typename real>
 cudaError_t launch_bounce_pass(const lbm::Lattice<real> &L, const lbm::Stored<real> &S, real *A, int xa, int xb, int xlo,
                                int xhi, const LinkList &K, const DeferList<real> &D, long long *facc, cudaStream_t s);

@@ -33,6 +33,9 @@
 #ifndef K1_NS
 #error "compile with -DK1_NS=k1_fast or -DK1_NS=k1_strict"
 #endif
+#ifndef LBMDEM_DEAD_GROUP
+#define LBMDEM_DEAD_GROUP 8   /* lanes per skip decision of the row kernel: 8 floats = one 32-byte sector (0: never skip) */
+#endif
 
 namespace lbmdem {
 namespace K1_NS {
@@ -142,6 +145,8 @@ __global__ void __launch_bounds__(RowCfg<real>::TY + 32, sizeof(real) == 8 ? LBM
   const int gy = y0 + jy;
   const bool active = gy >= 1 && gy <= L.ly - 2;
   const int by = jy + C::HY;
+  /* one 64-bit pointer + q * plane: 64 registers, 6 CTAs per SM.  (A 32-bit offset from uniform plane bases needs
+   * 48 registers and gives 8 CTAs per SM -- measured 4 % SLOWER, profiles/r01_k1_tuning.txt.) */
   real *out = a.out + node_index(L, r0, gy);
   mbar_wait(&full[0], 0);
   mbar_wait(&full[1], 0);
@@ -152,13 +157,31 @@ __global__ void __launch_bounds__(RowCfg<real>::TY + 32, sizeof(real) == 8 ? LBM
     int slot_p = slot_0 + 1;
     if (slot_p == C::NS) { slot_p = 0; ++round_p; }
     mbar_wait(&full[slot_p], round_p & 1);
+    const int *Cn0 = reinterpret_cast<const int *>(smem + (size_t)slot_0 * C::SLOT + C::A_PAD);
+    const int gx = r0 - 1 + t;
+    int cnow = 0, cprev = 0;
+    bool work = active;
     if (active) {
+      cnow = Cn0[jy + C::HC];
+      cprev = Cn0[C::CN_PAD / 4 + jy];
+    }
+    {
+      /* deep inside a grain under both maps: nothing reads what the re-init sweep would leave here (lbm_node.cuh,
+       * node_is_dead; the fill_dead kernel materialises it when the populations are observed).  Skipped in whole
+       * aligned groups of DEAD_GROUP lanes only, so that no 32-byte sector of the output is written in part. */
+      bool skip = !active || (!a.stream_only && node_is_dead(L, cprev, cnow, gx, gy));
+#if LBMDEM_DEAD_GROUP > 1
+      const unsigned all = __ballot_sync(0xffffffffu, skip);
+      const unsigned grp = (LBMDEM_DEAD_GROUP >= 32 ? 0xffffffffu : ((1u << (LBMDEM_DEAD_GROUP & 31)) - 1u))
+                           << (threadIdx.x & 31 & ~(LBMDEM_DEAD_GROUP - 1));
+      skip = (all & grp) == grp;
+#endif
+      if (skip) work = false;
+    }
+    if (work) {
       const real *Am = reinterpret_cast<const real *>(smem + (size_t)slot_m * C::SLOT);
       const real *A0 = reinterpret_cast<const real *>(smem + (size_t)slot_0 * C::SLOT);
       const real *Ap = reinterpret_cast<const real *>(smem + (size_t)slot_p * C::SLOT);
-      const int *Cn0 = reinterpret_cast<const int *>(smem + (size_t)slot_0 * C::SLOT + C::A_PAD);
-      const int cnow = Cn0[jy + C::HC], cprev = Cn0[C::CN_PAD / 4 + jy];
-      const int gx = r0 - 1 + t;
       real f[NQ];
       /* a node that is solid under the stored step's map is overwritten by the re-init sweep,
        * whatever streams into it: skip the pull */
@@ -235,6 +258,7 @@ __global__ void __launch_bounds__(128) lbm_plain_kernel(const __grid_constant__ 
     x = a.xlo + r;
   }
   const size_t k = node_index(L, x, y);
+  if (!a.stream_only && !is_ring(L, x, y) && node_is_dead(L, a.cell_prev[k], a.cell_new[k], x, y)) return;
   real f[NQ];
 #pragma unroll
   for (int q = 0; q < NQ; ++q) f[q] = pull_plain(L, a.A, x, y, q);
@@ -263,6 +287,24 @@ __global__ void __launch_bounds__(128) lbm_h1_kernel(const Lattice<real> L, real
   w_links_global(L, cell_now, x, y, p);
 #pragma unroll
   for (int q = 0; q < NQ; ++q) f[q * L.plane + k] = p[q];
+}
+
+/* What the fused kernel left unwritten (lbm_node.cuh, node_is_dead), rows [xa, xb): the re-init equilibrium of
+ * the node's previous owner, exactly as reinit_collide computes it. */
+template <typename real>
+__global__ void __launch_bounds__(128) lbm_fill_dead_kernel(const Lattice<real> L, real *A, const int *cell_prev,
+                                                            const int *cell_now, const GrainRec<real> *grains_new, int xa,
+                                                            int xb) {
+  const int y = blockIdx.x * blockDim.x + threadIdx.x;
+  const int x = xa + blockIdx.y;
+  if (y >= L.ly || x >= xb || is_ring(L, x, y)) return;
+  const size_t k = node_index(L, x, y);
+  const int cprev = cell_prev[k], cnow = cell_now[k];
+  if (!node_is_dead(L, cprev, cnow, x, y)) return;
+  real p[NQ];
+  reinit_collide(L, grains_new, cprev, cnow, x, y, p); /* both maps solid: the equilibrium alone */
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) A[q * L.plane + k] = p[q];
 }
 
 template <typename real>
@@ -320,12 +362,23 @@ cudaError_t launch_lbm_h1(const Lattice<real> &L, real *f, const int *cell_prev,
   return cudaGetLastError();
 }
 
+template <typename real>
+cudaError_t launch_lbm_fill_dead(const Lattice<real> &L, real *A, const int *cell_prev, const int *cell_now,
+                                 const GrainRec<real> *grains_new, int xa, int xb, cudaStream_t s) {
+  if (xb <= xa) return cudaSuccess;
+  dim3 grid((L.ly + 127) / 128, xb - xa);
+  lbm_fill_dead_kernel<real><<<grid, 128, 0, s>>>(L, A, cell_prev, cell_now, grains_new, xa, xb);
+  return cudaGetLastError();
+}
+
 #define INSTANTIATE_K1(real)                                                                                          \
   template cudaError_t launch_lbm_rows<real>(const CUtensorMap &, const CUtensorMap &, const CUtensorMap &,           \
                                              const FusedArgs<real> &, cudaStream_t);                                 \
   template cudaError_t launch_lbm_plain<real>(const FusedArgs<real> &, int, cudaStream_t);                            \
   template cudaError_t launch_lbm_h1<real>(const Lattice<real> &, real *, const int *, const int *,                   \
-                                           const GrainRec<real> *, int, int, cudaStream_t);
+                                           const GrainRec<real> *, int, int, cudaStream_t);                           \
+  template cudaError_t launch_lbm_fill_dead<real>(const Lattice<real> &, real *, const int *, const int *,            \
+                                                  const GrainRec<real> *, int, int, cudaStream_t);
 INSTANTIATE_K1(float)
 INSTANTIATE_K1(double)
 

@@ -46,7 +46,9 @@ namespace lbm {
 constexpr int NQ = 9;
 constexpr int CELL_FLUID = -1;          /* obst == -1 (src/main.c:999) */
 constexpr int CELL_ACT = 1 << 30;       /* act[x][y] == 1 of a solid node, folded into the map */
-constexpr int CELL_IDX = CELL_ACT - 1;
+constexpr int CELL_RIM = 1 << 29;       /* a solid node with a NON-fluid neighbour it does not share its owner with
+                                           (another grain, the wall ring): forces_fluid reads its populations */
+constexpr int CELL_IDX = CELL_RIM - 1;
 
 /* src/main.c:70-71 */
 LBM_HD int ex_of(int q) { return (q >= 1 && q <= 3) ? -1 : ((q >= 5 && q <= 7) ? 1 : 0); }
@@ -189,14 +191,23 @@ template <typename real>
 LBM_HD void equilibrium(const Lattice<real> &L, const GrainRec<real> &g, int x, int y, real *out) {
   const real ux = wall_ux(L, g, y), uy = wall_uy(L, g, x);
 #if defined(LBM_RELAXED)
-  /* default device build: one reciprocal instead of ten divisions, polynomial in `real` */
+  /* default device build: one reciprocal instead of ten divisions, polynomial in `real`, and the two populations
+   * of a direction pair (e, -e) share 1 + 4.5 (e.u)^2 - 1.5 u^2 */
   const real ic = 1 / L.c;
-  const real u_squ = (ux * ux + uy * uy) * (ic * ic);
-#pragma unroll
-  for (int q = 0; q < NQ; ++q) {
-    const real eu = (ex_of(q) * ux + ey_of(q) * uy) * ic;
-    out[q] = L.w[q] * ((real)1 + 3 * eu + (real)4.5 * eu * eu - (real)1.5 * u_squ);
-  }
+  const real X = ux * ic, Y = uy * ic;
+  const real base = (real)1 - (real)1.5 * (X * X + Y * Y);
+  const real P = X + Y, M = X - Y;
+  const real tx = base + (real)4.5 * X * X, ty = base + (real)4.5 * Y * Y;
+  const real tp = base + (real)4.5 * P * P, tm = base + (real)4.5 * M * M;
+  out[0] = L.w[0] * base;
+  out[6] = L.w[6] * (tx + 3 * X);   /* e = (+1, 0) */
+  out[2] = L.w[2] * (tx - 3 * X);   /* e = (-1, 0) */
+  out[8] = L.w[8] * (ty + 3 * Y);   /* e = (0, +1) */
+  out[4] = L.w[4] * (ty - 3 * Y);   /* e = (0, -1) */
+  out[7] = L.w[7] * (tp + 3 * P);   /* e = (+1, +1) */
+  out[3] = L.w[3] * (tp - 3 * P);   /* e = (-1, -1) */
+  out[5] = L.w[5] * (tm + 3 * M);   /* e = (+1, -1) */
+  out[1] = L.w[1] * (tm - 3 * M);   /* e = (-1, +1) */
 #else
   const real u_squ = (ux * ux + uy * uy) / (L.c * L.c);
 #pragma unroll
@@ -323,6 +334,28 @@ LBM_HD bool w_links_with_collide(const Lattice<real> &L, int x, int y) {
   return x >= 2 && y >= 2 && x <= L.lx - 3 && y <= L.ly - 3;
 }
 
+/* Dead populations.  A node that is solid under BOTH maps, carries neither CELL_ACT nor CELL_RIM and does not
+ * touch the wall ring holds the equilibrium of reinit_obst_density (a pure function of the two maps and this
+ * step's grain records), and nothing on the path reads it before it is overwritten:
+ *   - the next step's re-init overwrites the node itself (it is solid under what is then the old map);
+ *   - only a node that is fluid under this step's map uses what it pulls from a neighbour, and a solid node with
+ *     a fluid neighbour is active (the neighbour was fluid when the owner was rasterised, too);
+ *   - the ring sweep reads rows / columns 1 and lx-2 / ly-2; the bounce-back sweep reads fluid, ring and active
+ *     nodes; forces_fluid reads solid nodes with a foreign neighbour: active if that neighbour is fluid, CELL_RIM
+ *     (on both sides of the link) if it is not.
+ * The fused kernel therefore leaves such nodes unwritten (about a third of the lattice in a dense packing); the
+ * reference's values are materialised on demand -- before anything OBSERVES the populations (get_f, fields,
+ * density sum, checkpoint) -- by fill_dead (lbm_kernels.cu), from the same expression the fused kernel uses. */
+template <typename real>
+LBM_HD bool node_is_dead(const Lattice<real> &L, int cell_prev, int cell_now, int x, int y) {
+#if defined(LBMDEM_DEAD_GROUP) && LBMDEM_DEAD_GROUP == 0 /* measurement variant: write every node */
+  (void)L; (void)cell_prev; (void)cell_now; (void)x; (void)y;
+  return false;
+#else
+  return cell_prev >= 0 && cell_now >= 0 && (cell_now & (CELL_ACT | CELL_RIM)) == 0 && w_links_with_collide(L, x, y);
+#endif
+}
+
 /* ------------------------------------------------------------------------------------------
  * Sweeps 3-4 (wall ring, grain bounce-back) rewrite a SPARSE set of populations in place: ring
  * nodes and active solid nodes.  They run as separate small kernels on the stored state; after
@@ -404,18 +437,21 @@ LBM_HD bool is_active_solid(const Lattice<real> &L, const Stored<real> &S, int x
  * deferred links -- none of which a concurrent in-place pass over the other links modifies. */
 enum { SWEEP_KEEP = 0, SWEEP_WRITE = 1, SWEEP_DEFER = 2 };
 
+/* The link itself, inlined into its caller.  `g` is the record of the grain that owns (x,y).  *gap_out tells
+ * whether the link faces an active solid node across a one-node gap (the caller of the bounce-back kernel passes
+ * resolve = true and files such links in the deferred list itself); *Fn_oq_out is A[n][opp q], which the
+ * momentum exchange of the link needs as well (n is a fluid node: the sweep never writes there). */
 template <typename real>
-LBM_HD_SLOW int sweep_link(const Lattice<real> &L, const Stored<real> &S, int x, int y, int q, bool resolve, real *v,
-                           int grain = -1 /* owner of (x,y) if the caller knows it */,
-                           bool n_is_fluid = false /* the caller knows that the neighbour is fluid */) {
+LBM_HD int sweep_link_core(const Lattice<real> &L, const Stored<real> &S, const GrainRec<real> &g, int x, int y, int q,
+                           bool resolve, real *v, bool n_is_fluid, bool *gap_out, real *Fn_oq_out) {
   const int ex = ex_of(q), ey = ey_of(q), oq = opp_of(q);
   const int nx = x + ex, ny = y + ey;
   const int nnx = nx + ex, nny = ny + ey;
   const size_t ks = node_index(L, x, y), kn = node_index(L, nx, ny);
   /* the loads whose address depends on (x, y, q) alone are issued together */
   const real Fn_q = S.A[q * L.plane + kn], Fn_oq = S.A[oq * L.plane + kn];
-  if (grain < 0) grain = cell_obst(S.cell[ks]);
-  const GrainRec<real> g = S.grains[grain];
+  *Fn_oq_out = Fn_oq;
+  *gap_out = false;
   if (!n_is_fluid && !cell_is_fluid(S.cell[kn])) { /* :1161-1162 */
     *v = L.w[q];
     return SWEEP_WRITE;
@@ -423,6 +459,7 @@ LBM_HD_SLOW int sweep_link(const Lattice<real> &L, const Stored<real> &S, int x,
   /* n fluid => n is an interior node => nn lies inside the array.  An interior solid nn is active:
    * its neighbour n is fluid */
   const bool gap = !is_ring(L, nnx, nny) && !cell_is_fluid(S.cell[node_index(L, nnx, nny)]);
+  *gap_out = gap;
   if (gap && !resolve) return SWEEP_DEFER;
   const real d = link_delta(g, x, y, q);
   if (!(d > 0.)) return SWEEP_KEEP;
@@ -442,6 +479,17 @@ LBM_HD_SLOW int sweep_link(const Lattice<real> &L, const Stored<real> &S, int x,
   }
   *v = bounce_value(L, q, d, Fn_oq, Fn_q, X, eu, (real)0);
   return SWEEP_WRITE;
+}
+
+template <typename real>
+LBM_HD_SLOW int sweep_link(const Lattice<real> &L, const Stored<real> &S, int x, int y, int q, bool resolve, real *v,
+                           int grain = -1 /* owner of (x,y) if the caller knows it */,
+                           bool n_is_fluid = false /* the caller knows that the neighbour is fluid */) {
+  if (grain < 0) grain = cell_obst(S.cell[node_index(L, x, y)]);
+  const GrainRec<real> g = S.grains[grain];
+  bool gap;
+  real Fn_oq;
+  return sweep_link_core(L, S, g, x, y, q, resolve, v, n_is_fluid, &gap, &Fn_oq);
 }
 
 /* Sweep 5, the streamed value: what the two swap passes leave in f[x][y][q] (:1224-1242), from

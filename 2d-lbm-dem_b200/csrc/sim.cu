@@ -156,6 +156,8 @@ struct Sim : SimBase {
   int cur = 0, cur_cell = 0;
   bool holds_A = false;      /* f[cur] holds A of the last step (stream pending) instead of f */
   bool scratch_valid = false; /* f[1 - cur] holds the materialised f of the pending stream */
+  Lattice<real> L_fused;      /* lattice() as the last fused launch saw it */
+  bool dead_stale = false;    /* f[cur] lacks the populations the fused kernel does not write (lbm_node.cuh, node_is_dead) */
   CUtensorMap tmA[2], tmC[2], tmCh[2]; /* populations; map rows without / with the y halo */
   LinkList llist{};
   DeferList<real> defer{};
@@ -232,6 +234,8 @@ struct Sim : SimBase {
     if (P.nranks > 1) { x0 = xlo - GHOST; nxl = xhi - xlo + 2 * GHOST; } else { x0 = 0; nxl = lx; }
     pitch = (ly + 31) / 32 * 32;
     plane = (size_t)nxl * pitch;
+    /* node indices within a plane are 32-bit (list entries, the fused kernel's store offsets) */
+    if (plane >= ((size_t)1 << 31)) return fail(LBMDEM_EINVAL, "more than 2^31 nodes per GPU: use more strips");
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     if (P.nranks > 1) {
       int lo = 0, hi = 0;
@@ -483,7 +487,7 @@ struct Sim : SimBase {
       --genkey;
     }
     CK(launch_raster<real>(raster_params(), n, g, rec[cslot], R2[cslot], boxes[cslot], cell[cslot], x0, nxl, pitch, overlap, min_owner,
-                            genkey, blist, llist, stream));
+                            genkey, blist, llist, defer.count, P.strict_fp ? nullptr : facc, stream));
     act_folded[cslot] = true;
     return 0;
   }
@@ -605,16 +609,19 @@ struct Sim : SimBase {
                      : k1_fast::launch_lbm_h1<real>(L, f[cur], cell[1 - cur_cell], cell[cur_cell], rec[cur_cell], xlo, xhi, stream));
       ++all_launches;
       holds_A = true;
+      dead_stale = false;
     } else {
       if ((rc = launch_fused(0, true))) return rc;
       cur ^= 1;
+      dead_stale = true;
+      L_fused = lattice(); /* vibrating walls move the lattice origin between LBM steps: fill_dead needs this step's */
     }
     /* sweeps 3-4 in place (ring :1123-1145, grain bounce-back :1154-1222), then forces_fluid (:1285-1333) */
     const Lattice<real> L = lattice();
     const Stored<real> S = stored(cur, cur_cell);
     const bool multi = P.nranks > 1;
     long long *fa = P.strict_fp ? nullptr : facc;
-    CK(launch_bounce_begin<real>(n, defer, fa, stream));
+    /* the deferred list and the force sums were emptied by the rasteriser's first kernel */
     if (!multi) {
       CK(launch_ring_sweep<real>(L, S, f[cur], 0, lx, stream));
       CK(launch_bounce_pass<real>(L, S, f[cur], 1, lx - 1, xlo, xhi, llist, defer, fa, stream));
@@ -664,6 +671,16 @@ struct Sim : SimBase {
   int observable_f(const real **out) {
     if (!holds_A) { *out = f[cur]; return 0; }
     if (!scratch_valid) {
+      if (dead_stale) {
+        /* the stream reads every node: first materialise what the fused kernel left unwritten, on the owned rows
+         * and the row either side of them */
+        const Lattice<real> &L = L_fused;
+        const int xa = std::max(xlo - 1, 1), xb = std::min(xhi + 1, lx - 1);
+        CK(P.strict_fp ? k1_strict::launch_lbm_fill_dead<real>(L, f[cur], cell[1 - cur_cell], cell[cur_cell], rec[cur_cell], xa, xb, stream)
+                       : k1_fast::launch_lbm_fill_dead<real>(L, f[cur], cell[1 - cur_cell], cell[cur_cell], rec[cur_cell], xa, xb, stream));
+        ++all_launches;
+        dead_stale = false;
+      }
       int rc = launch_fused(1, false);
       if (rc) return rc;
       scratch_valid = true;
@@ -1059,9 +1076,12 @@ struct Sim : SimBase {
     if (!ready) return fail(LBMDEM_ESTATE, "no grains loaded");
     const size_t N = (size_t)n;
     if (!gstage) CK(cudaMalloc(&gstage, sizeof(double) * 12 * N));
+    const bool pin_in = state_in && host_is_pinned(state_in);
+    const bool pin_out = (!state_out || host_is_pinned(state_out)) && (!fhf_out || host_is_pinned(fhf_out));
     if (state_in) {
-      memcpy(hstage, state_in, sizeof(double) * 9 * N); /* hstage: 16 n doubles of pinned memory */
-      CK(cudaMemcpyAsync(gstage, hstage, sizeof(double) * 9 * N, cudaMemcpyHostToDevice, stream));
+      const double *src = state_in;
+      if (!pin_in) { memcpy(hstage, state_in, sizeof(double) * 9 * N); src = hstage; } /* hstage: 16 n doubles, pinned */
+      CK(cudaMemcpyAsync(gstage, src, sizeof(double) * 9 * N, cudaMemcpyHostToDevice, stream));
       CK(launch_grain_unpack<real>(gstage, n, 9, g.x1, stream)); /* x1 .. a3 are contiguous in the slab */
     }
     bool built = false;
@@ -1071,7 +1091,12 @@ struct Sim : SimBase {
     if (state_out || fhf_out) {
       CK(launch_grain_pack<real>(g.x1, n, 9, gstage, stream));
       CK(launch_grain_pack<real>(g.fhf1, n, 3, gstage + 9 * N, stream));
-      CK(cudaMemcpyAsync(hstage, gstage, sizeof(double) * 12 * N, cudaMemcpyDeviceToHost, stream));
+      if (pin_out) {
+        if (state_out) CK(cudaMemcpyAsync(state_out, gstage, sizeof(double) * 9 * N, cudaMemcpyDeviceToHost, stream));
+        if (fhf_out) CK(cudaMemcpyAsync(fhf_out, gstage + 9 * N, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, stream));
+      } else {
+        CK(cudaMemcpyAsync(hstage, gstage, sizeof(double) * 12 * N, cudaMemcpyDeviceToHost, stream));
+      }
     }
     if (dens) {
       const real *obs;
@@ -1080,9 +1105,16 @@ struct Sim : SimBase {
       CK(cudaMemcpyAsync(dens, dens_out, sizeof(double), cudaMemcpyDeviceToHost, stream));
     }
     if ((rc = check_flags())) return rc;
-    if (state_out) memcpy(state_out, hstage, sizeof(double) * 9 * N);
-    if (fhf_out) memcpy(fhf_out, hstage + 9 * N, sizeof(double) * 3 * N);
+    if (!pin_out) {
+      if (state_out) memcpy(state_out, hstage, sizeof(double) * 9 * N);
+      if (fhf_out) memcpy(fhf_out, hstage + 9 * N, sizeof(double) * 3 * N);
+    }
     return 0;
+  }
+  static bool host_is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
   }
 
   int attach_nccl(const void *id) override {
@@ -1219,6 +1251,12 @@ API int lbmdem_get_kernel_timer(lbmdem_ctx *ctx, double *ms, long *k1, long *all
   CTX_OR_FAIL; return ctx->sim->get_kernel_timer(ms, k1, all);
 }
 API int lbmdem_reset_kernel_timer(lbmdem_ctx *ctx, int enable) { CTX_OR_FAIL; return ctx->sim->reset_kernel_timer(enable); }
+API int lbmdem_host_alloc(size_t bytes, void **ptr) {
+  if (!ptr || !bytes) return LBMDEM_EINVAL;
+  *ptr = nullptr;
+  return cudaHostAlloc(ptr, bytes, cudaHostAllocDefault) == cudaSuccess ? 0 : LBMDEM_ECUDA;
+}
+API int lbmdem_host_free(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? 0 : LBMDEM_ECUDA; }
 API void *lbmdem_stream(lbmdem_ctx *ctx) { return (ctx && ctx->sim) ? ctx->sim->stream_ptr() : nullptr; }
 
 }  // extern "C"

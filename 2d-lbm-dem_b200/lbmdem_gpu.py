@@ -91,6 +91,8 @@ def load_library():
         "lbmdem_save_state": ([vp, C.c_char_p], C.c_int),
         "lbmdem_load_state": ([vp, C.c_char_p], C.c_int),
         "lbmdem_step_host": ([vp, vp, C.c_long, vp, vp, vp], C.c_int),
+        "lbmdem_host_alloc": ([C.c_size_t, C.POINTER(vp)], C.c_int),
+        "lbmdem_host_free": ([vp], C.c_int),
         "lbmdem_nccl_unique_id": ([vp], C.c_int),
         "lbmdem_attach_nccl": ([vp, vp], C.c_int),
         "lbmdem_get_kernel_timer": ([vp, C.POINTER(C.c_double), C.POINTER(C.c_long), C.POINTER(C.c_long)], C.c_int),
@@ -154,6 +156,8 @@ class Solver:
         return rc
 
     def close(self):
+        for p, _ in self.__dict__.pop("_pinned_bufs", {}).values():
+            self.L.lbmdem_host_free(p)
         if getattr(self, "h", None):
             self.L.lbmdem_destroy(self.h)
             self.h = None
@@ -204,11 +208,35 @@ class Solver:
         self._ck(self.L.lbmdem_step_capture(self.h, mid))
         return mid
 
+    def _pinned(self, name, shape):
+        """a float64 array in page-locked memory (lbmdem_host_alloc), kept for the life of the solver"""
+        bufs = self.__dict__.setdefault("_pinned_bufs", {})
+        if name not in bufs:
+            count = int(np.prod(shape))
+            p = C.c_void_p()
+            self._ck(self.L.lbmdem_host_alloc(8 * count, C.byref(p)))
+            arr = np.ctypeslib.as_array((C.c_double * count).from_address(p.value)).reshape(shape)
+            bufs[name] = (p, arr)
+        return bufs[name][1]
+
     def step_host(self, state_in, n_dem_steps, want_state=True, want_fhf=True, want_density=True):
-        """lbmdem_step_host: host arrays in, host arrays out (the end-to-end call)."""
-        sin = None if state_in is None else np.ascontiguousarray(state_in, dtype=np.float64)
-        sout = np.empty((self.n, 9)) if want_state else None
-        fh = np.empty((self.n, 3)) if want_fhf else None
+        """lbmdem_step_host: host arrays in, host arrays out (the end-to-end call).  The buffers are page-locked and
+        reused: the returned arrays are views that the next call overwrites; passing the returned state back in
+        costs no host copy."""
+        sout = fh = sin = None
+        if state_in is not None:
+            # two input slots, so that the state returned by the previous call can be the input of this one
+            a, b = self._pinned("in", (self.n, 9)), self._pinned("out0", (self.n, 9))
+            c = self._pinned("out1", (self.n, 9))
+            if state_in is b or state_in is c:
+                sin = state_in
+            else:
+                np.copyto(a, state_in)
+                sin = a
+        if want_state:
+            sout = self._pinned("out1", (self.n, 9)) if sin is self._pinned("out0", (self.n, 9)) else self._pinned("out0", (self.n, 9))
+        if want_fhf:
+            fh = self._pinned("fhf", (self.n, 3))
         dens = C.c_double() if want_density else None
         ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
         self._ck(self.L.lbmdem_step_host(self.h, ptr(sin), n_dem_steps, ptr(sout), ptr(fh),

@@ -281,9 +281,10 @@ def main():
     t_e2e = D.max_over_ranks(time.perf_counter() - t0)
     D.barrier()
     real_b = 4 if prec == "f32" else 8
+    # the C ABI's grain rows are doubles whatever the lattice precision: 9 up, 9 + 3 down per grain
     e2e = {"value": lx * ly * e2e_steps / t_e2e / 1e6, "unit": "MLUPS",
-           "h2d_bytes_per_step": n_grains * 9 * real_b, "d2h_bytes_per_step": n_grains * 12 * real_b + 8,
-           "call": "lbmdem_step_host: grain state up, npDEM renderScene() calls, grain state + fhf down every step, density checksum every 400 calls",
+           "h2d_bytes_per_step": n_grains * 9 * 8, "d2h_bytes_per_step": n_grains * 12 * 8 + 8,
+           "call": "lbmdem_step_host with page-locked host buffers (lbmdem_host_alloc): grain state up, npDEM renderScene() calls, grain state + fhf down every step, density checksum every 400 calls",
            "ms_per_step": 1e3 * t_e2e / e2e_steps, "density_checksum": dens}
 
     # ---- roofline of the dominant kernel (K1), measured live with CUDA events on its stream ----

@@ -19,6 +19,8 @@
 #ifndef LBMDEM_GPU_H
 #define LBMDEM_GPU_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -133,9 +135,17 @@ int lbmdem_get_fields(lbmdem_ctx *ctx, const double *grain_p_in, float *grain_pr
 
 /* End-to-end form of one coupled step with HOST buffers: upload the grain kinematic state,
  * run n_dem_steps renderScene() calls, download the new state, fhf and the density checksum.
- * Any of the output pointers may be NULL. */
+ * Any of the output pointers may be NULL.  Buffers in page-locked memory (lbmdem_host_alloc, or
+ * anything cudaHostRegister'ed) are the source / target of the PCIe copies themselves; pageable
+ * buffers go through one staging copy each way. */
 int lbmdem_step_host(lbmdem_ctx *ctx, const double *state_in /* [n][9] or NULL */, long n_dem_steps,
                      double *state_out /* [n][9] */, double *fhf_out /* [n][3] */, double *density_out);
+
+/* page-locked host memory for the buffers of lbmdem_step_host (the reference keeps its grain
+ * array in plain malloc memory, src/main.c:612; a caller that wants the copies without staging
+ * allocates it here instead) */
+int lbmdem_host_alloc(size_t bytes, void **ptr);
+int lbmdem_host_free(void *ptr);
 
 /* ---- multi-GPU (one context per GPU / process; lattice split into x strips, grains replicated) ---- */
 /* 128-byte NCCL unique id, produced on one rank and distributed by the caller */

@@ -25,6 +25,7 @@ using namespace lbm;
 namespace {
 
 int g_last_deferred = 0;
+int g_last_dead = 0;
 int g_act_folded = 1; /* 0: hand the on-demand path a bare obstacle map (what the device kernels get) */
 
 /* K2 on the host: owner = highest-index covering grain, then the act rule. */
@@ -61,7 +62,13 @@ void raster_host(int lx, int ly, int n, const RasterParams<real> &P, const real 
           const int nx = x + ex_of(q), ny = y + ey_of(q);
           if (fluid_when_grain_ran_exact(cell[(size_t)nx * ly + ny], i, n, min_owner[(size_t)nx * ly + ny])) act = true;
         }
-        if (act) cell[(size_t)x * ly + y] = i | CELL_ACT;
+        /* CELL_RIM: a NON-fluid neighbour under another owner (the boundary kernel's list criterion) */
+        bool rim = false;
+        for (int q = 1; q < NQ; ++q) {
+          const int cn = cell[(size_t)(x + ex_of(q)) * ly + y + ey_of(q)];
+          if (!cell_is_fluid(cn) && cell_obst(cn) != i) rim = true;
+        }
+        if (act || rim) cell[(size_t)x * ly + y] = i | (act ? CELL_ACT : 0) | (rim ? CELL_RIM : 0);
       }
   }
 }
@@ -119,6 +126,17 @@ int lbm_step_host(int lx, int ly, int n, const double *scal, const double *grain
       }
       for (int q = 0; q < NQ; ++q) A[q * nn + k] = p[q];
     }
+  /* the fused kernel does not write dead nodes (lbm_node.cuh, node_is_dead): poison them, so that any sweep or
+   * force link that read one would show up in the comparison with the oracle */
+  std::vector<size_t> dead;
+  for (int x = 1; x < lx - 1; ++x)
+    for (int y = 1; y < ly - 1; ++y) {
+      const size_t k = (size_t)x * ly + y;
+      if (!node_is_dead(L, cell_old[k], cell_new[k], x, y)) continue;
+      dead.push_back(k);
+      for (int q = 0; q < NQ; ++q) A[q * nn + k] = (real)NAN;
+    }
+  g_last_dead = (int)dead.size();
   Stored<real> S;
   S.A = A.data(); S.grains = rec.data();
   S.cell = g_act_folded ? cell_new.data() : cell_bare.data();
@@ -152,6 +170,15 @@ int lbm_step_host(int lx, int ly, int n, const double *scal, const double *grain
   for (auto &d : deferred) A[d.first] = d.second;
   g_last_deferred = (int)deferred.size();
 
+  /* what the path itself reads stays poisoned; the observable populations need the dead nodes materialised
+   * (the fill_dead kernel): the re-init equilibrium of the previous owner */
+  const std::vector<real> A_path(A);
+  for (size_t k : dead) {
+    const int x = (int)(k / ly), y = (int)(k % ly);
+    real p[NQ];
+    reinit_collide(L, rec.data(), cell_old[k], cell_new[k], x, y, p);
+    for (int q = 0; q < NQ; ++q) A[q * nn + k] = p[q];
+  }
   /* sweep 5: plain pull */
   for (int x = 0; x < lx; ++x)
     for (int y = 0; y < ly; ++y)
@@ -176,7 +203,7 @@ int lbm_step_host(int lx, int ly, int n, const double *scal, const double *grain
           const int ax = x + ex_of(q), ay = y + ey_of(q);
           if (cell_obst(cell_new[(size_t)ax * ly + ay]) == i) continue;
           /* f_new[s][opp q] = A[n][opp q] and f_new[n][q] = A[s][q]: read before streaming, as the device does */
-          const real fs_oq = A[opp_of(q) * nn + (size_t)ax * ly + ay], fn_q = A[q * nn + (size_t)x * ly + y];
+          const real fs_oq = A_path[opp_of(q) * nn + (size_t)ax * ly + ay], fn_q = A_path[q * nn + (size_t)x * ly + y];
           if (fs_oq != fn[opp_of(q) * nn + (size_t)x * ly + y] || fn_q != fn[q * nn + (size_t)ax * ly + ay]) return -2;
           force_link<real>(q, fs_oq, fn_q, x, y, xc, yc, &h1, &h2, &h3);
         }
@@ -429,6 +456,7 @@ extern "C" {
 #define EXPORT __attribute__((visibility("default")))
 EXPORT void hc_set_act_folded(int v) { g_act_folded = v; }
 EXPORT int hc_last_deferred(void) { return g_last_deferred; }
+EXPORT int hc_last_dead(void) { return g_last_dead; }
 /* scal: dx c Mgx Mby lid */
 EXPORT int hc_lbm_step_f64(int lx, int ly, int n, const double *scal, const double *grains, const double *f_in,
                            const int *obst_old, double *f_out, int *obst_new, int *act_new, double *fhf) {
