@@ -289,6 +289,260 @@ __global__ void __launch_bounds__(BND_WARPS * 32, LBMDEM_BND_MINB) boundary_kern
   if (nlinks) list_flush(K.entry, K.count, K.capacity, K.overflow, links, nlinks, lane);
 }
 
+/* ------------------------------------------------------------------------------------------
+ * K2, tile form (the default).  obst_construction (src/main.c:991-1065) as ONE pass over the lattice in tiles of
+ * RTX x RTY nodes: no clearing pass, no global atomic per node, no re-reading of the map through L2.
+ * ---------------------------------------------------------------------------------------- */
+/* first kernel of the step: grain records (as grain_prepare_kernel) and the grain -> tile bins */
+template <typename real>
+__global__ void grain_bin_kernel(RasterParams<real> P, int n, GrainArrays<real> g, GrainRec<real> *rec, real *R2,
+                                 GrainBox *boxes, int x0, int nxl, TileBins T, int *count_a, int *count_b, int *count_c,
+                                 long long *facc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) { *count_a = 0; *count_b = 0; *count_c = 0; }
+  if (i >= n) return;
+  GrainRec<real> r;
+  GrainBox b;
+  real R2i;
+  grain_geometry(P, g.x1[i], g.x2[i], g.r[i], g.rLB[i], &r.xc, &r.yc, &r.r2, &R2i, &b);
+  r.x1 = g.x1[i]; r.x2 = g.x2[i]; r.v1 = g.v1[i]; r.v2 = g.v2[i]; r.v3 = g.v3[i];
+  rec[i] = r;
+  R2[i] = R2i;
+  boxes[i] = b;
+  if (facc != nullptr) { facc[i] = 0; facc[n + i] = 0; facc[2 * n + i] = 0; }
+  /* every tile whose nodes or halo the bounding box touches (local rows only) */
+  const int xa = max(b.xi - 1, x0), xb = min(b.xf + 1, x0 + nxl - 1);
+  const int ya = max(b.yi - 1, 0), yb = min(b.yf + 1, P.ly - 1);
+  if (b.xf < b.xi || b.yf < b.yi || xb < xa || yb < ya) return;
+  for (int tx = (xa - x0) / RTX; tx <= (xb - x0) / RTX; ++tx)
+    for (int ty = ya / RTY; ty <= yb / RTY; ++ty) {
+      const int t = tx * T.nty + ty;
+      const int slot = atomicAdd(&T.count[t], 1);
+      if (slot < T.cap) {
+        TileEntry<real> en;
+        en.id = i; en.xi = b.xi; en.xf = b.xf; en.yi = b.yi; en.yf = b.yf;
+        en.xc = r.xc; en.yc = r.yc; en.r2 = r.r2; en.RR = R2i;
+        static_cast<TileEntry<real> *>(T.list)[(size_t)t * T.cap + slot] = en;
+      } else {
+        *(volatile int *)T.overflow = 1; /* mapped host memory */
+      }
+    }
+}
+
+constexpr int RTC0 = 4;                      /* shared-memory column of tile column 0 (16-byte aligned rows of int4) */
+constexpr int RTP = RTY + 8;                 /* shared-memory row pitch: 3 unused, left halo, RTY nodes, right halo, 3 unused */
+constexpr int RT_THREADS = 256;
+constexpr int RT_CHUNK = 64;                 /* grains staged in shared memory at a time */
+static_assert(RTY == 64 && RTX == 32 && RT_THREADS == 256, "pass 3a: a warp takes 4 rows, a lane 4 consecutive columns");
+
+template <typename real>
+__global__ void __launch_bounds__(RT_THREADS) raster_tile_kernel(int n, const GrainRec<real> *rec, const real *R2,
+                                                                 const GrainBox *boxes, int *cell, int x0, int nxl,
+                                                                 int pitch, int lx, int ly, TileBins T, BoundaryList B,
+                                                                 LinkList K) {
+  /* region = tile + one halo node all round; region row r+1 / column c+RTC0 hold tile node (r, c) */
+  __shared__ __align__(16) int own[RTX + 2][RTP]; /* owner: -1 fluid, n ring / outside the array */
+  __shared__ __align__(16) int low[RTX + 2][RTP]; /* lowest covering index where more than one disc covers the node */
+  __shared__ unsigned short cand[RTX * RTY]; /* tile nodes with a neighbour under another owner (r * RTY + c, bit 15: act) */
+  __shared__ unsigned short msk[RTX * RTY];  /* per candidate: fluid neighbours | foreign non-fluid neighbours << 8 */
+  __shared__ int s_ncand;
+  __shared__ TileEntry<real> s_en[RT_CHUNK];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int tile = blockIdx.y * T.nty + blockIdx.x;
+  const int tx0 = x0 + blockIdx.y * RTX, ty0 = blockIdx.x * RTY; /* lattice coordinates of tile node (0, 0) */
+  /* the first list entries are fetched along with the count (entries past the count are ignored) */
+  const TileEntry<real> *list = static_cast<const TileEntry<real> *>(T.list) + (size_t)tile * T.cap;
+  if (tid < min(T.cap, RT_CHUNK)) s_en[tid] = list[tid];
+  const int cnt = min(T.count[tile], T.cap);
+
+  /* ---- 1. init_obst's frame (:674-687) for the region: ring (and beyond the array) = n, interior fluid ---- */
+  if (tid == 0) s_ncand = 0;
+  if (tx0 - 1 > 0 && tx0 + RTX < lx - 1 && ty0 - 1 > 0 && ty0 + RTY < ly - 1) {
+    int4 *o4 = reinterpret_cast<int4 *>(&own[0][0]), *l4 = reinterpret_cast<int4 *>(&low[0][0]);
+    for (int idx = tid; idx < (RTX + 2) * RTP / 4; idx += RT_THREADS) {
+      o4[idx] = make_int4(-1, -1, -1, -1);
+      l4[idx] = make_int4(0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff);
+    }
+  } else {
+    for (int idx = tid; idx < (RTX + 2) * RTP; idx += RT_THREADS) {
+      const int r = idx / RTP, c = idx - r * RTP;
+      const int gx = tx0 - 1 + r, gy = ty0 - RTC0 + c;
+      own[r][c] = (gx <= 0 || gx >= lx - 1 || gy <= 0 || gy >= ly - 1) ? n : -1;
+      low[r][c] = 0x7fffffff;
+    }
+  }
+
+  /* ---- 2. the discs (:1016-1031).  The tile's grains are staged in shared memory (one round of global loads for
+   * all of them), then painted, a warp per grain: lanes along y (up to three columns each), rows in turn.
+   * Owner = highest covering index (the reference paints in index order), hence atomicMax; where a disc finds the
+   * node taken the lower of the two indices is kept: the minimum over all such meetings is the lowest covering
+   * index.  dist2 is the reference's expression (:1026), its two squares rounded separately. ---- */
+  for (int base = 0; base < cnt; base += RT_CHUNK) {
+    const int m = min(RT_CHUNK, cnt - base);
+    if (base > 0 && tid < m) s_en[tid] = list[base + tid];
+    __syncthreads();
+    /* few grains: several warps per grain, each a share of its rows */
+    const int parts = m < RT_THREADS / 32 ? (RT_THREADS / 32) / m : 1;
+    for (int k = w / parts; k < m; k += (RT_THREADS / 32) / parts) {
+      const int i = s_en[k].id;
+      const real xc = s_en[k].xc, yc = s_en[k].yc, r2 = s_en[k].r2, RR = s_en[k].RR;
+      const int ra = max(s_en[k].xi, tx0 - 1), rb = min(s_en[k].xf, tx0 + RTX);
+      const int ca = max(s_en[k].yi, ty0 - 1), cb = min(s_en[k].yf, ty0 + RTY);
+      const int y0 = ca + lane, y1 = y0 + 32, y2 = y0 + 64; /* the region is RTY + 2 = 66 nodes wide */
+      const int s0 = y0 - ty0 + RTC0, s1 = s0 + 32, s2 = s0 + 64; /* their shared-memory columns */
+      const real d0 = (y0 - yc) * (y0 - yc), d1 = (y1 - yc) * (y1 - yc), d2 = (y2 - yc) * (y2 - yc);
+      for (int x = ra + w % parts; x <= rb; x += parts) {
+        const real dx2 = (x - xc) * (x - xc);
+        int *orow = own[x - tx0 + 1], *lrow = low[x - tx0 + 1];
+        const real e0 = dx2 + d0, e1 = dx2 + d1, e2 = dx2 + d2;
+        /* the three atomics are issued together; their results are looked at afterwards */
+        int o0 = -1, o1 = -1, o2 = -1;
+        if (y0 <= cb && e0 <= RR && e0 <= r2) o0 = atomicMax(&orow[s0], i);
+        if (y1 <= cb && e1 <= RR && e1 <= r2) o1 = atomicMax(&orow[s1], i);
+        if (y2 <= cb && e2 <= RR && e2 <= r2) o2 = atomicMax(&orow[s2], i);
+        if (o0 >= 0 && o0 != i) atomicMin(&lrow[s0], min(o0, i));
+        if (o1 >= 0 && o1 != i) atomicMin(&lrow[s1], min(o1, i));
+        if (o2 >= 0 && o2 != i) atomicMin(&lrow[s2], min(o2, i));
+      }
+    }
+    __syncthreads();
+  }
+  if (cnt == 0) __syncthreads(); /* the frame of pass 1 */
+  if (tid == 0) T.count[tile] = 0; /* emptied for the next step */
+
+  /* ---- 3a. every node of the tile: the owners go to `cell` in 16-byte pieces (a lane holds four consecutive
+   * columns, a warp two rows), and the few nodes whose 3 x 3 neighbourhood is not under one owner are collected
+   * for pass 3b ---- */
+#pragma unroll 1
+  for (int it = 0; it < RTX / 16; ++it) {
+    const int r = w * (RTX / 8) + it * 2 + (lane >> 4), c0 = (lane & 15) * 4; /* tile coordinates */
+    const int x = tx0 + r;
+    const int *pm = &own[r][RTC0 + c0], *p0 = &own[r + 1][RTC0 + c0], *pp = &own[r + 2][RTC0 + c0];
+    const int4 a = *reinterpret_cast<const int4 *>(pm), v = *reinterpret_cast<const int4 *>(p0),
+               d = *reinterpret_cast<const int4 *>(pp);
+    const int aL = pm[-1], aR = pm[4], vL = p0[-1], vR = p0[4], dL = pp[-1], dR = pp[4];
+    unsigned hit = 0;
+    if (x >= x0 + 1 && x <= x0 + nxl - 2) { /* rows whose neighbours are held locally */
+      if (v.x >= 0 && v.x < n && !(aL == v.x && a.x == v.x && a.y == v.x && vL == v.x && v.y == v.x && dL == v.x && d.x == v.x && d.y == v.x)) hit |= 1u;
+      if (v.y >= 0 && v.y < n && !(a.x == v.y && a.y == v.y && a.z == v.y && v.x == v.y && v.z == v.y && d.x == v.y && d.y == v.y && d.z == v.y)) hit |= 2u;
+      if (v.z >= 0 && v.z < n && !(a.y == v.z && a.z == v.z && a.w == v.z && v.y == v.z && v.w == v.z && d.y == v.z && d.z == v.z && d.w == v.z)) hit |= 4u;
+      if (v.w >= 0 && v.w < n && !(a.z == v.w && a.w == v.w && aR == v.w && v.z == v.w && vR == v.w && d.z == v.w && d.w == v.w && dR == v.w)) hit |= 8u;
+    }
+    if (x <= x0 + nxl - 1 && ty0 + c0 + 3 < pitch) *reinterpret_cast<int4 *>(&cell[(size_t)(x - x0) * pitch + ty0 + c0]) = v;
+    if (__any_sync(0xffffffffu, hit != 0)) {
+      const int mine = __popc(hit);
+      int incl = mine;
+#pragma unroll
+      for (int dd = 1; dd < 32; dd <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, dd);
+        if (lane >= dd) incl += t;
+      }
+      int at = 0;
+      if (lane == 31) at = atomicAdd(&s_ncand, incl);
+      at = __shfl_sync(0xffffffffu, at, 31) + incl - mine;
+      while (hit) {
+        const int bit = __ffs(hit) - 1;
+        hit &= hit - 1;
+        cand[at++] = (unsigned short)(r * RTY + c0 + bit);
+      }
+    }
+  }
+  __syncthreads();
+
+  /* ---- 3b. the candidates, one per lane: act[x][y] (:1036-1052), rim bit, link masks; the two bits are added to
+   * the node's entry of `cell` (the line is still in L2).  A thread takes a contiguous share of the list ---- */
+  const int ncand = s_ncand;
+  const int share = (ncand + RT_THREADS - 1) / RT_THREADS;
+  const int e0 = min(tid * share, ncand), e1 = min(e0 + share, ncand);
+  unsigned packed = 0; /* this thread's list entries: links | nodes << 16 */
+  for (int e = e0; e < e1; ++e) {
+    const int rc = cand[e], r = rc / RTY, c = rc % RTY;
+    const int x = tx0 + r, y = ty0 + c;
+    const int i = own[r + 1][c + RTC0];
+    bool act = false;
+    unsigned foreign = 0, fluid = 0;
+#pragma unroll
+    for (int q = 1; q < NQ; ++q) {
+      const int rr = r + 1 + ex_of(q), cc = c + RTC0 + ey_of(q);
+      const int cn = own[rr][cc];
+      if (cell_is_fluid(cn)) fluid |= 1u << (q - 1);
+      if (cn != i) {
+        foreign |= 1u << (q - 1);
+        /* a neighbour owned by a LATER grain counted as fluid when grain i ran unless a grain j <= i lies
+         * under it as well (lbm_node.cuh, fluid_when_grain_ran_exact) */
+        int mo = -1;
+        if (cn > i && cn < n) { const int lo = low[rr][cc]; mo = lo == 0x7fffffff ? -1 : lo; }
+        if (fluid_when_grain_ran_exact(cn, i, n, mo)) act = true;
+      }
+    }
+    const unsigned solid_foreign = foreign & ~fluid; /* != 0: the force kernel's share (CELL_RIM) */
+    msk[e] = (unsigned short)(fluid | (solid_foreign << 8));
+    if (act) {
+      cand[e] = (unsigned short)(rc | 0x8000);
+      const bool near_ring = !(x >= 2 && y >= 2 && x <= lx - 3 && y <= ly - 3);
+      packed += (unsigned)__popc(near_ring ? 0xffu : fluid); /* bounce links; next to the ring the w-links too */
+    }
+    if (solid_foreign) packed += 1u << 16;
+    if (act || solid_foreign) cell[(size_t)(x - x0) * pitch + y] = i | (act ? CELL_ACT : 0) | (solid_foreign ? CELL_RIM : 0);
+  }
+
+  /* ---- 4. one slot range per list and WARP (no barrier: the warps finish independently) ---- */
+  unsigned incl = packed;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total == 0) return;
+  int bl = 0, bb = 0;
+  if (lane == 0 && (total & 0xffffu)) bl = atomicAdd(K.count, (int)(total & 0xffffu));
+  if (lane == 1 && (total >> 16)) bb = atomicAdd(B.count, (int)(total >> 16));
+  bl = __shfl_sync(0xffffffffu, bl, 0);
+  bb = __shfl_sync(0xffffffffu, bb, 1);
+  if (packed == 0) return;
+  const unsigned excl = incl - packed;
+  int kl = bl + (int)(excl & 0xffffu), kb = bb + (int)(excl >> 16);
+
+  /* ---- 5. the entries ---- */
+  for (int e = e0; e < e1; ++e) {
+    const unsigned m = msk[e], rc = cand[e];
+    const bool act = (rc & 0x8000u) != 0;
+    const unsigned fluid = m & 0xffu, solid_foreign = m >> 8;
+    if (!solid_foreign && !act) continue;
+    const int r = (int)(rc & 0x7fffu) / RTY, c = (int)(rc & 0x7fffu) % RTY;
+    const int x = tx0 + r, y = ty0 + c;
+    const unsigned knode = (unsigned)((x - x0) * pitch + y);
+    const unsigned i = (unsigned)own[r + 1][c + RTC0];
+    if (solid_foreign) { /* the force kernel's share: all foreign neighbours, the kernel skips the fluid ones */
+      if (kb < B.capacity) B.entry[kb] = make_uint2(knode, ((fluid | solid_foreign) << 24) | (act ? BL_ACT : 0u) | i);
+      else *(volatile int *)B.overflow = 1;
+      ++kb;
+    }
+    if (!act) continue;
+    const bool near_ring = !(x >= 2 && y >= 2 && x <= lx - 3 && y <= ly - 3);
+    unsigned links = near_ring ? 0xffu : fluid; /* bounce links (fluid neighbour); next to the ring the others as w-links */
+    while (links) {
+      const int bit = __ffs(links) - 1;
+      links &= links - 1;
+      const bool isw = !((fluid >> bit) & 1u);
+      if (kl < K.capacity) K.entry[kl] = make_uint2(knode, i | ((unsigned)(bit + 1) << 24) | (isw ? LL_W : 0u));
+      else *(volatile int *)K.overflow = 1;
+      ++kl;
+    }
+  }
+}
+
+template <typename real>
+cudaError_t launch_raster_tiles(const RasterParams<real> &P, int n, const GrainArrays<real> &g, GrainRec<real> *rec, real *R2,
+                                GrainBox *boxes, int *cell, int x0, int nxl, int pitch, const TileBins &T,
+                                const BoundaryList &B, const LinkList &K, int *defer_count, long long *facc, cudaStream_t s) {
+  grain_bin_kernel<real><<<(n + 127) / 128, 128, 0, s>>>(P, n, g, rec, R2, boxes, x0, nxl, T, B.count, K.count, defer_count, facc);
+  raster_tile_kernel<real><<<dim3(T.nty, T.ntx), RT_THREADS, 0, s>>>(n, rec, R2, boxes, cell, x0, nxl, pitch, P.lx, P.ly,
+                                                                            T, B, K);
+  return cudaGetLastError();
+}
+
 /* init_obst's frame (:674-687): ring = nbgrains, interior = -1 */
 __global__ void cell_frame_kernel(int *cell, int lx, int ly, int x0, int nxl, int pitch, int ring_value) {
   const int y = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1046,6 +1300,10 @@ cudaError_t launch_fill_rest(real *f, size_t plane, const Lattice<real> &Lw, cud
 }
 
 #define INSTANTIATE(real)                                                                                               \
+  template cudaError_t launch_raster_tiles<real>(const RasterParams<real> &, int, const GrainArrays<real> &,              \
+                                                 GrainRec<real> *, real *, GrainBox *, int *, int, int, int,              \
+                                                 const TileBins &, const BoundaryList &, const LinkList &, int *,         \
+                                                 long long *, cudaStream_t);                                              \
   template cudaError_t launch_raster<real>(const RasterParams<real> &, int, const GrainArrays<real> &, GrainRec<real> *,  \
                                            real *, GrainBox *, int *, int, int, int, int *, int *, int,                   \
                                            const BoundaryList &, const LinkList &, int *, long long *, cudaStream_t);     \

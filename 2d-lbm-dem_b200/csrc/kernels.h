@@ -132,7 +132,37 @@ struct LinkList {
 };
 constexpr unsigned LL_W = 1u << 28;
 
-/* grain records + obstacle map + act bits + boundary list of one step (K2) */
+/* Grains binned by the lattice tiles (RTX rows x RTY columns, plus one halo node all round) that their bounding
+ * box touches: filled by the first kernel of the rasteriser, consumed and emptied by the tile kernel. */
+constexpr int RTX = 32, RTY = 64;
+/* what the tile kernel needs to paint a grain: index, clamped bounding box (src/main.c:1016-1023), disc */
+template <typename real>
+struct alignas(16) TileEntry {
+  int id, xi, xf, yi, yf;
+  real xc, yc, r2, RR;   /* centre in lattice units, rLB^2, (r/dx)^2 */
+};
+struct TileBins {
+  int *count;          /* [ntx * nty] */
+  void *list;          /* [ntx * nty][cap] TileEntry<real>, any order */
+  int cap;
+  int ntx, nty;        /* tiles along x (local rows) and y */
+  int *overflow;       /* flag in mapped host memory */
+};
+
+/* K2, tile form: ONE kernel builds the whole obstacle map of the step.  A CTA paints the reduced discs of its
+ * tile's grains into shared memory (owner = highest covering index, lowest covering index kept beside it),
+ * derives act / rim bits from the shared-memory neighbourhood, writes the tile to `cell` in full rows (no
+ * clearing pass, no global atomics per node) and appends its boundary nodes and links to the two lists with
+ * one counter update per list and CTA. */
+template <typename real>
+cudaError_t launch_raster_tiles(const lbm::RasterParams<real> &P, int ngrains, const GrainArrays<real> &g,
+                                lbm::GrainRec<real> *rec, real *R2, lbm::GrainBox *boxes, int *cell, int x0, int nxl,
+                                int pitch, const TileBins &T, const BoundaryList &B, const LinkList &K,
+                                int *defer_count /* emptied as well */,
+                                long long *facc /* nullptr, or [3][n] force sums to be zeroed */, cudaStream_t s);
+
+/* grain records + obstacle map + act bits + boundary list of one step (K2), per-grain form (the first version;
+ * kept as the cross-check of the tile form, params.raster = 1) */
 template <typename real>
 cudaError_t launch_raster(const lbm::RasterParams<real> &P, int ngrains, const GrainArrays<real> &g,
                           lbm::GrainRec<real> *rec, real *R2, lbm::GrainBox *boxes, int *cell, int x0, int nxl, int pitch,

@@ -162,6 +162,7 @@ struct Sim : SimBase {
   LinkList llist{};
   DeferList<real> defer{};
   BoundaryList blist{};
+  TileBins tbins{};          /* grains binned by lattice tile, rebuilt every LBM step (kernels.h) */
   int *overlap = nullptr;
   int *min_owner = nullptr; /* [x-x0][y]: lowest covering grain of multiply covered nodes (lbm_node.cuh MINOWNER_*) */
   int genkey = 0;           /* generation key of this step's entries; counts down, the map is cleared when it wraps */
@@ -202,6 +203,7 @@ struct Sim : SimBase {
     cudaFree(defer.count); cudaFree(defer.index); cudaFree(defer.value);
     cudaFree(blist.entry); cudaFree(blist.count); cudaFree(overlap); cudaFree(llist.entry); cudaFree(llist.count);
     cudaFree(min_owner);
+    cudaFree(tbins.count); cudaFree(tbins.list);
     if (hflags) cudaFreeHost(hflags);
     if (hstage) cudaFreeHost(hstage);
     if (ev_state) cudaEventDestroy(ev_state);
@@ -279,8 +281,8 @@ struct Sim : SimBase {
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return fail(LBMDEM_ECUDA, "cuTensorMapEncodeTiled(map) failed with code " + std::to_string((int)r));
     }
-    CK(cudaHostAlloc(&hflags, 4 * sizeof(int), cudaHostAllocMapped));
-    hflags[0] = hflags[1] = hflags[2] = hflags[3] = 0;
+    CK(cudaHostAlloc(&hflags, 8 * sizeof(int), cudaHostAllocMapped));
+    for (int k = 0; k < 8; ++k) hflags[k] = 0;
     CK(cudaStreamSynchronize(stream));
     return 0;
   }
@@ -391,6 +393,23 @@ struct Sim : SimBase {
     dt = dtLB / npDEM;
     dt2 = dt * dt;
     for (int i = 0; i < n; ++i) rLB[i] = reductionR * r[i] / dx;
+    {
+      /* tile bins: a tile's region is (RTX+2) x (RTY+2) nodes; discs of radius >= R = rMin/dx whose bounding box
+       * touches it have their centre within a rectangle (RTX + 2R + 4) x (RTY + 2R + 4); a dense packing spends
+       * 2 sqrt(3) R^2 nodes per disc.  Half as much again for interpenetration, and a floor for large grains. */
+      const double R = std::max(0.5, (double)rMin / (double)dx);
+      const double est = 1.5 * (RTX + 2 * R + 4) * (RTY + 2 * R + 4) / (3.4641 * R * R) + 8;
+      cudaFree(tbins.count); cudaFree(tbins.list);
+      tbins.cap = (int)std::min(4096.0, std::max(16.0, est));
+      tbins.ntx = (nxl + RTX - 1) / RTX;
+      tbins.nty = (ly + RTY - 1) / RTY;
+      const size_t nt = (size_t)tbins.ntx * tbins.nty;
+      CK(cudaMalloc(&tbins.count, sizeof(int) * nt));
+      CK(cudaMemsetAsync(tbins.count, 0, sizeof(int) * nt, stream));
+      CK(cudaMalloc(&tbins.list, sizeof(TileEntry<real>) * nt * tbins.cap));
+      CK(cudaMemsetAsync(tbins.list, 0, sizeof(TileEntry<real>) * nt * tbins.cap, stream)); /* the tile kernel prefetches entries past the count */
+      CK(cudaHostGetDevicePointer(&tbins.overflow, hflags + 4, 0));
+    }
     /* :1329-1331 with the reference's promotions ((tau - 0.5) is double) */
     k12 = (double)(real)(rho_moy * 9 * nu * nu) / ((double)dx * ((double)tau - 0.5) * ((double)tau - 0.5));
     k3 = (double)(real)(dx * rho_moy * 9 * nu * nu) / ((double)dx * ((double)tau - 0.5) * ((double)tau - 0.5));
@@ -479,15 +498,24 @@ struct Sim : SimBase {
   }
   bool act_folded[2] = {false, false};
   int raster_into(int cslot) {
-    if (!min_owner) CK(cudaMalloc(&min_owner, sizeof(int) * plane));
-    if (genkey <= 1) { /* first use, or the key wrapped: forget every older entry */
-      CK(cudaMemsetAsync(min_owner, 0x7f, sizeof(int) * plane, stream));
-      genkey = 0x7e;
+    long long *fa = P.strict_fp ? nullptr : facc;
+    if (!(P.kernel & 2)) {
+      CK(launch_raster_tiles<real>(raster_params(), n, g, rec[cslot], R2[cslot], boxes[cslot], cell[cslot], x0, nxl, pitch, tbins,
+                                   blist, llist, defer.count, fa, stream));
+      all_launches += 2; /* grain_bin, raster_tile */
     } else {
-      --genkey;
+      /* per-grain form (cross-check): global atomicMax per node, min-owner map with generation keys */
+      if (!min_owner) CK(cudaMalloc(&min_owner, sizeof(int) * plane));
+      if (genkey <= 1) { /* first use, or the key wrapped: forget every older entry */
+        CK(cudaMemsetAsync(min_owner, 0x7f, sizeof(int) * plane, stream));
+        genkey = 0x7e;
+      } else {
+        --genkey;
+      }
+      CK(launch_raster<real>(raster_params(), n, g, rec[cslot], R2[cslot], boxes[cslot], cell[cslot], x0, nxl, pitch, overlap, min_owner,
+                              genkey, blist, llist, defer.count, fa, stream));
+      all_launches += 3; /* grain_prepare, raster, boundary (memsets not counted) */
     }
-    CK(launch_raster<real>(raster_params(), n, g, rec[cslot], R2[cslot], boxes[cslot], cell[cslot], x0, nxl, pitch, overlap, min_owner,
-                            genkey, blist, llist, defer.count, P.strict_fp ? nullptr : facc, stream));
     act_folded[cslot] = true;
     return 0;
   }
@@ -577,7 +605,7 @@ struct Sim : SimBase {
   /* sweep 5 of the stored array (+ sweeps 1-2 of the new step unless stream_only) into f[1 - cur] */
   int launch_fused(int stream_only, bool timed) {
     const FusedArgs<real> a = fused_args(1 - cur, stream_only);
-    if (P.kernel == 1) {
+    if ((P.kernel & 1)) {
       CK(P.strict_fp ? k1_strict::launch_lbm_plain<real>(a, 0, stream) : k1_fast::launch_lbm_plain<real>(a, 0, stream));
       ++all_launches;
       return 0;
@@ -600,7 +628,6 @@ struct Sim : SimBase {
     int rc;
     cur_cell ^= 1; /* the rasteriser writes the other map; the previous one stays with the stored array */
     if ((rc = raster_into(cur_cell))) return rc;
-    all_launches += 3; /* grain_prepare, raster, boundary (memsets not counted) */
     scratch_valid = false;
     if (!holds_A) {
       /* populations came from outside (init_density, set_f): sweeps 1-2 alone, in place */
@@ -707,6 +734,7 @@ struct Sim : SimBase {
     if (hflags[1]) { hflags[1] = 0; return fail(LBMDEM_ECAP, "deferred bounce-back link list is full"); }
     if (hflags[2]) { hflags[2] = 0; return fail(LBMDEM_ECAP, "boundary-node list is full"); }
     if (hflags[3]) { hflags[3] = 0; return fail(LBMDEM_ECAP, "bounce-back link list is full"); }
+    if (hflags[4]) { hflags[4] = 0; return fail(LBMDEM_ECAP, "more grains under one lattice tile than the tile bins hold"); }
     return 0;
   }
 

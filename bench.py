@@ -181,6 +181,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--strict", type=int, default=0)
+    ap.add_argument("--kernel", type=int, default=0, help="cross-check switches of lbmdem_params.kernel (0 = the product path)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--sample-gpus", type=int, default=0,
@@ -234,11 +235,13 @@ def main():
     n_grains = make_sample_file(preset, a.sample_gpus or n_gpus, rows, sample_path)
     config["grains"] = n_grains
 
-    s = D.make_strip_solver(lx, ly, scale, prec, strict_fp=a.strict)
+    s = D.make_strip_solver(lx, ly, scale, prec, strict_fp=a.strict, kernel=a.kernel)
     s.init(sample_path)
     sc = s.scalars()
     npd = sc["npDEM"]
     config.update(npDEM=npd, dx=sc["dx"], strict_fp=a.strict)
+    if a.kernel:
+        config.update(kernel=a.kernel)
     stream = torch.cuda.ExternalStream(s.stream(), device=local_rank)
 
     def timed_region(fn, k):

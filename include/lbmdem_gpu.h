@@ -58,7 +58,8 @@ typedef struct lbmdem_params {
   double lid_u;            /* moving lid, the commented-out uw terms at src/main.c:1129-1130 */
   int strict_fp;           /* 1: LBM kernel built without multiply-add contraction and forces summed in
                               the reference's serial order -> bit-identical to the reference build */
-  int kernel;              /* 0: TMA row-pipeline kernel (default); 1: plain one-thread-per-node kernel (cross-check) */
+  int kernel;              /* cross-check switches, 0 = default.  bit 0: plain one-thread-per-node LBM kernel instead of
+                              the TMA row pipeline; bit 1: per-grain rasteriser instead of the tile rasteriser */
   int neighbour_capacity;  /* per-grain Verlet capacity, default 32 */
   int vib;                 /* 1: shake the left/right walls, src/main.c:162, :1701-1706 (default 0) */
 } lbmdem_params;

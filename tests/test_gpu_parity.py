@@ -438,6 +438,50 @@ def test_overlapping_discs_and_discs_on_the_ring_strict(prec):
     assert _relerr(d.fhf(), o.fhf()) < (1e-9 if prec == "f64" else 5e-3)
 
 
+@pytest.mark.parametrize("case", ["dense", "overlap_ring"])
+def test_tile_rasteriser_equals_per_grain_rasteriser(case):
+    """The obstacle map, act bits and the two link lists come from one tile kernel (shared-memory atomics) by
+    default and from the per-grain kernels (global atomicMax, min-owner map) with kernel=2: same map, same act,
+    and -- the lists being the same sets -- the same populations and forces, bit for bit (strict build)."""
+    if case == "dense":
+        lx, ly = 200, 333
+        r, x, y = small_packing(lx, ly, 1.0, seed=5, n_target=300)
+    else:
+        lx, ly = 96, 72
+        dx = 1e-4 * lx / (lx - 1)
+        r = np.array([10, 9, 8, 7, 9, 6.5]) * dx
+        x = np.array([30, 39, 34, 3.0, 80, 95.0]) * dx
+        y = np.array([30, 31, 38, 40, 2.5, 20]) * dx
+    a = G.Solver(lx, ly, 1.0, "f64", kernel=0, strict_fp=1)
+    b = G.Solver(lx, ly, 1.0, "f64", kernel=2, strict_fp=1)
+    n = a.init_arrays(r, x, y)
+    b.init_arrays(r, x, y)
+    f0 = perturbed_f(lx, ly, 6)
+    v, w, acc = random_kinematics(n, 7)
+    st = a.grains()[:, :9].copy()
+    st[:, 3:5], st[:, 5:6] = v, w
+    for slv in (a, b):
+        slv.set_f(f0)
+        slv.set_grain_state(st)
+    for _ in range(3):
+        a.step(a.scalars()["npDEM"])
+        b.step(b.scalars()["npDEM"])
+        assert np.array_equal(a.obst(), b.obst())
+        assert np.array_equal(a.act(), b.act())
+    assert np.array_equal(a.f(), b.f())
+    assert np.array_equal(a.fhf(), b.fhf())
+    assert np.array_equal(a.grains(), b.grains())
+    # default build: the force sums are fixed point, hence independent of the order of the list entries too
+    c = G.Solver(lx, ly, 1.0, "f64", kernel=0)
+    d = G.Solver(lx, ly, 1.0, "f64", kernel=2)
+    for slv in (c, d):
+        slv.init_arrays(r, x, y)
+        slv.set_f(f0)
+        slv.set_grain_state(st)
+        slv.step(2 * slv.scalars()["npDEM"])
+    assert np.array_equal(c.f(), d.f()) and np.array_equal(c.fhf(), d.fhf())
+
+
 def test_full_size_row_kernel_equals_plain_kernel_fp64():
     """BASELINE configs[2] size (2048 x 2048, fp64, 726 grains): the TMA row pipeline and the plain
     one-thread-per-node kernel are the same map; every population identical after 3 coupled steps."""

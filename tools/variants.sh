@@ -8,6 +8,10 @@ mkdir -p $OUT
 timeout 600 python -m pytest tests -m gpu -x -q > $OUT/${RUN}_pytest.log 2>&1; echo "pytest exit $?" >> $OUT/${RUN}_pytest.log
 tail -5 $OUT/${RUN}_pytest.log
 timeout 200 python bench.py --workload $WORK --steps 300 --no-cpu-baseline > $OUT/${RUN}_default.json 2> $OUT/${RUN}_default.err
+# cross-check paths of the default library on request: KERNELS="2" -> bench.py --kernel 2 (per-grain rasteriser)
+for k in $KERNELS; do
+  timeout 200 python bench.py --workload $WORK --steps 300 --no-cpu-baseline --kernel $k > $OUT/${RUN}_kernel$k.json 2> $OUT/${RUN}_kernel$k.err
+done
 for t in "$@"; do
   LBMDEM_LIB=$PWD/2d-lbm-dem_b200/liblbmdem_gpu_$t.so timeout 200 python bench.py --workload $WORK --steps 300 --no-cpu-baseline \
       > $OUT/${RUN}_$t.json 2> $OUT/${RUN}_$t.err
@@ -25,7 +29,7 @@ done
 # optional: one full ncu capture of K1 per tag in $NCU_TAGS ("default" = the shipped library)
 for t in $NCU_TAGS; do
   L=$PWD/2d-lbm-dem_b200/liblbmdem_gpu_$t.so; [ "$t" = default ] && L=$PWD/2d-lbm-dem_b200/liblbmdem_gpu.so
-  LBMDEM_LIB=$L timeout 300 ncu --set full --clock-control none --import-source on -k regex:lbm_rows -s 4 -c 1 -f -o $OUT/${RUN}_k1_$t \
+  LBMDEM_LIB=$L timeout 300 ncu --set full --clock-control none --import-source on -k regex:${NCU_K:-lbm_rows} -s 4 -c 1 -f -o $OUT/${RUN}_k1_$t \
       python bench.py --workload $WORK --steps 3 --warmup 3 --no-cpu-baseline > $OUT/${RUN}_k1_$t.log 2>&1
 done
 python - <<PY
