@@ -382,7 +382,11 @@ __global__ void __launch_bounds__(RT_THREADS) raster_tile_kernel(int n, const Gr
     if (base > 0 && tid < m) s_en[tid] = list[base + tid];
     __syncthreads();
     /* few grains: several warps per grain, each a share of its rows */
+#if defined(LBMDEM_RT_NOSPLIT) /* measurement variant: always a warp per grain */
+    const int parts = 1;
+#else
     const int parts = m < RT_THREADS / 32 ? (RT_THREADS / 32) / m : 1;
+#endif
     for (int k = w / parts; k < m; k += (RT_THREADS / 32) / parts) {
       const int i = s_en[k].id;
       const real xc = s_en[k].xc, yc = s_en[k].yc, r2 = s_en[k].r2, RR = s_en[k].RR;

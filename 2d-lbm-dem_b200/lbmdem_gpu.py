@@ -156,6 +156,7 @@ class Solver:
         return rc
 
     def close(self):
+        self.__dict__.pop("_hostbufs", None)
         for p, _ in self.__dict__.pop("_pinned_bufs", {}).values():
             self.L.lbmdem_host_free(p)
         if getattr(self, "h", None):
@@ -223,23 +224,29 @@ class Solver:
         """lbmdem_step_host: host arrays in, host arrays out (the end-to-end call).  The buffers are page-locked and
         reused: the returned arrays are views that the next call overwrites; passing the returned state back in
         costs no host copy."""
-        sout = fh = sin = None
+        hb = self.__dict__.get("_hostbufs")
+        if hb is None:
+            # two state slots, so that the state returned by the previous call can be the input of this one
+            arrs = [self._pinned(k, (self.n, 9)) for k in ("in", "out0", "out1")] + [self._pinned("fhf", (self.n, 3))]
+            hb = self._hostbufs = [(a, a.ctypes.data_as(C.c_void_p)) for a in arrs]
+        (a_in, p_in), (a_o0, p_o0), (a_o1, p_o1), (a_fh, p_fh) = hb
+        sout = fh = None
+        psin = psout = pfh = None
+        use_o1 = False
         if state_in is not None:
-            # two input slots, so that the state returned by the previous call can be the input of this one
-            a, b = self._pinned("in", (self.n, 9)), self._pinned("out0", (self.n, 9))
-            c = self._pinned("out1", (self.n, 9))
-            if state_in is b or state_in is c:
-                sin = state_in
+            if state_in is a_o0:
+                psin, use_o1 = p_o0, True
+            elif state_in is a_o1:
+                psin = p_o1
             else:
-                np.copyto(a, state_in)
-                sin = a
+                np.copyto(a_in, state_in)
+                psin = p_in
         if want_state:
-            sout = self._pinned("out1", (self.n, 9)) if sin is self._pinned("out0", (self.n, 9)) else self._pinned("out0", (self.n, 9))
+            sout, psout = (a_o1, p_o1) if use_o1 else (a_o0, p_o0)
         if want_fhf:
-            fh = self._pinned("fhf", (self.n, 3))
+            fh, pfh = a_fh, p_fh
         dens = C.c_double() if want_density else None
-        ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
-        self._ck(self.L.lbmdem_step_host(self.h, ptr(sin), n_dem_steps, ptr(sout), ptr(fh),
+        self._ck(self.L.lbmdem_step_host(self.h, psin, n_dem_steps, psout, pfh,
                                          C.cast(C.byref(dens), C.c_void_p) if dens is not None else None))
         return sout, fh, (dens.value if dens is not None else None)
 
