@@ -1264,28 +1264,30 @@ cudaError_t launch_f_from_host_layout(real *f, int ly, int pitch, size_t plane, 
   return cudaGetLastError();
 }
 
-template <typename real>
-__global__ void grain_unpack_kernel(const double *rows, int n, int ncols, real *cols) {
+template <typename real, typename H>
+__global__ void grain_unpack_kernel(const H *rows, int n, int ncols, real *cols) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n * ncols) return;
   const int i = t / ncols, k = t - i * ncols;
   cols[(size_t)k * n + i] = (real)rows[t];
 }
-template <typename real>
-__global__ void grain_pack_kernel(const real *cols, int n, int ncols, double *rows) {
+template <typename real, typename H>
+__global__ void grain_pack_kernel(const real *cols, int n, int ncols, H *rows) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n * ncols) return;
   const int i = t / ncols, k = t - i * ncols;
-  rows[t] = (double)cols[(size_t)k * n + i];
+  rows[t] = (H)cols[(size_t)k * n + i];
 }
 template <typename real>
-cudaError_t launch_grain_unpack(const double *rows, int n, int ncols, real *cols, cudaStream_t s) {
-  grain_unpack_kernel<real><<<(n * ncols + 255) / 256, 256, 0, s>>>(rows, n, ncols, cols);
+cudaError_t launch_grain_unpack(const void *rows, bool rows_f32, int n, int ncols, real *cols, cudaStream_t s) {
+  if (rows_f32) grain_unpack_kernel<real, float><<<(n * ncols + 255) / 256, 256, 0, s>>>(static_cast<const float *>(rows), n, ncols, cols);
+  else grain_unpack_kernel<real, double><<<(n * ncols + 255) / 256, 256, 0, s>>>(static_cast<const double *>(rows), n, ncols, cols);
   return cudaGetLastError();
 }
 template <typename real>
-cudaError_t launch_grain_pack(const real *cols, int n, int ncols, double *rows, cudaStream_t s) {
-  grain_pack_kernel<real><<<(n * ncols + 255) / 256, 256, 0, s>>>(cols, n, ncols, rows);
+cudaError_t launch_grain_pack(const real *cols, int n, int ncols, void *rows, bool rows_f32, cudaStream_t s) {
+  if (rows_f32) grain_pack_kernel<real, float><<<(n * ncols + 255) / 256, 256, 0, s>>>(cols, n, ncols, static_cast<float *>(rows));
+  else grain_pack_kernel<real, double><<<(n * ncols + 255) / 256, 256, 0, s>>>(cols, n, ncols, static_cast<double *>(rows));
   return cudaGetLastError();
 }
 
@@ -1338,8 +1340,8 @@ cudaError_t launch_fill_rest(real *f, size_t plane, const Lattice<real> &Lw, cud
                                            cudaStream_t);                                                                 \
   template cudaError_t launch_f_to_host_layout<real>(const real *, int, int, size_t, int, int, double *, cudaStream_t);   \
   template cudaError_t launch_f_from_host_layout<real>(real *, int, int, size_t, int, int, const double *, cudaStream_t); \
-  template cudaError_t launch_grain_unpack<real>(const double *, int, int, real *, cudaStream_t);                         \
-  template cudaError_t launch_grain_pack<real>(const real *, int, int, double *, cudaStream_t);                           \
+  template cudaError_t launch_grain_unpack<real>(const void *, bool, int, int, real *, cudaStream_t);                     \
+  template cudaError_t launch_grain_pack<real>(const real *, int, int, void *, bool, cudaStream_t);                       \
   template cudaError_t launch_fill_rest<real>(real *, size_t, const Lattice<real> &, cudaStream_t);
 INSTANTIATE(float)
 INSTANTIATE(double)

@@ -248,11 +248,11 @@ cudaError_t launch_f_to_host_layout(const real *f, int ly, int pitch, size_t pla
 template <typename real>
 cudaError_t launch_f_from_host_layout(real *f, int ly, int pitch, size_t plane, int row0, int nrows, const double *in,
                                       cudaStream_t s);
-/* grain rows of doubles [n][ncols] (the C ABI's layout) <-> the device's arrays of `real` [ncols][n] */
+/* grain rows [n][ncols] of doubles or floats (the C ABI's layouts) <-> the device's arrays of `real` [ncols][n] */
 template <typename real>
-cudaError_t launch_grain_unpack(const double *rows, int n, int ncols, real *cols, cudaStream_t s);
+cudaError_t launch_grain_unpack(const void *rows, bool rows_f32, int n, int ncols, real *cols, cudaStream_t s);
 template <typename real>
-cudaError_t launch_grain_pack(const real *cols, int n, int ncols, double *rows, cudaStream_t s);
+cudaError_t launch_grain_pack(const real *cols, int n, int ncols, void *rows, bool rows_f32, cudaStream_t s);
 /* init_density (src/main.c:716-724) */
 template <typename real>
 cudaError_t launch_fill_rest(real *f, size_t plane, const lbm::Lattice<real> &Lw, cudaStream_t s);

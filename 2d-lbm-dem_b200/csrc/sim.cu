@@ -127,7 +127,7 @@ struct SimBase {
   virtual int save_state(const char *path) = 0;
   virtual int load_state(const char *path) = 0;
   virtual int get_fields(const double *gp, float *a, float *b, float *c, float *d, float *e) = 0;
-  virtual int step_host(const double *state_in, long n, double *state_out, double *fhf_out, double *dens) = 0;
+  virtual int step_host(const void *state_in, long n, void *state_out, void *fhf_out, double *dens, bool rows_f32) = 0;
   virtual int attach_nccl(const void *id) = 0;
   virtual int get_kernel_timer(double *ms, long *k1, long *all) = 0;
   virtual int reset_kernel_timer(int enable) = 0;
@@ -1099,31 +1099,33 @@ struct Sim : SimBase {
   /* End-to-end step with host buffers.  The rows of doubles travel as they are (one memcpy into /
    * out of pinned memory, one copy over PCIe each way); the device does the transposition and
    * the double <-> real conversion. */
-  double *gstage = nullptr; /* device: [n][9] in, then [n][9] + [n][3] out */
-  int step_host(const double *state_in, long nsteps, double *state_out, double *fhf_out, double *dens) override {
+  double *gstage = nullptr; /* device: [n][9] in, then [n][9] + [n][3] out (doubles, or floats in the same space) */
+  int step_host(const void *state_in, long nsteps, void *state_out, void *fhf_out, double *dens, bool rows_f32) override {
     if (!ready) return fail(LBMDEM_ESTATE, "no grains loaded");
-    const size_t N = (size_t)n;
+    if (rows_f32 && sizeof(real) != 4) return fail(LBMDEM_EINVAL, "float grain rows need a single-precision context");
+    const size_t N = (size_t)n, eb = rows_f32 ? sizeof(float) : sizeof(double);
     if (!gstage) CK(cudaMalloc(&gstage, sizeof(double) * 12 * N));
+    char *gs = reinterpret_cast<char *>(gstage), *hs = reinterpret_cast<char *>(hstage); /* hstage: 16 n doubles, pinned */
     const bool pin_in = state_in && host_is_pinned(state_in);
     const bool pin_out = (!state_out || host_is_pinned(state_out)) && (!fhf_out || host_is_pinned(fhf_out));
     if (state_in) {
-      const double *src = state_in;
-      if (!pin_in) { memcpy(hstage, state_in, sizeof(double) * 9 * N); src = hstage; } /* hstage: 16 n doubles, pinned */
-      CK(cudaMemcpyAsync(gstage, src, sizeof(double) * 9 * N, cudaMemcpyHostToDevice, stream));
-      CK(launch_grain_unpack<real>(gstage, n, 9, g.x1, stream)); /* x1 .. a3 are contiguous in the slab */
+      const void *src = state_in;
+      if (!pin_in) { memcpy(hs, state_in, eb * 9 * N); src = hs; }
+      CK(cudaMemcpyAsync(gs, src, eb * 9 * N, cudaMemcpyHostToDevice, stream));
+      CK(launch_grain_unpack<real>(gs, rows_f32, n, 9, g.x1, stream)); /* x1 .. a3 are contiguous in the slab */
     }
     bool built = false;
     int rc = step_async(nsteps, &built);
     if (rc) return rc;
     (void)built;
     if (state_out || fhf_out) {
-      CK(launch_grain_pack<real>(g.x1, n, 9, gstage, stream));
-      CK(launch_grain_pack<real>(g.fhf1, n, 3, gstage + 9 * N, stream));
+      CK(launch_grain_pack<real>(g.x1, n, 9, gs, rows_f32, stream));
+      CK(launch_grain_pack<real>(g.fhf1, n, 3, gs + eb * 9 * N, rows_f32, stream));
       if (pin_out) {
-        if (state_out) CK(cudaMemcpyAsync(state_out, gstage, sizeof(double) * 9 * N, cudaMemcpyDeviceToHost, stream));
-        if (fhf_out) CK(cudaMemcpyAsync(fhf_out, gstage + 9 * N, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, stream));
+        if (state_out) CK(cudaMemcpyAsync(state_out, gs, eb * 9 * N, cudaMemcpyDeviceToHost, stream));
+        if (fhf_out) CK(cudaMemcpyAsync(fhf_out, gs + eb * 9 * N, eb * 3 * N, cudaMemcpyDeviceToHost, stream));
       } else {
-        CK(cudaMemcpyAsync(hstage, gstage, sizeof(double) * 12 * N, cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemcpyAsync(hs, gs, eb * 12 * N, cudaMemcpyDeviceToHost, stream));
       }
     }
     if (dens) {
@@ -1134,8 +1136,8 @@ struct Sim : SimBase {
     }
     if ((rc = check_flags())) return rc;
     if (!pin_out) {
-      if (state_out) memcpy(state_out, hstage, sizeof(double) * 9 * N);
-      if (fhf_out) memcpy(fhf_out, hstage + 9 * N, sizeof(double) * 3 * N);
+      if (state_out) memcpy(state_out, hs, eb * 9 * N);
+      if (fhf_out) memcpy(fhf_out, hs + eb * 9 * N, eb * 3 * N);
     }
     return 0;
   }
@@ -1262,7 +1264,10 @@ API int lbmdem_get_fields(lbmdem_ctx *ctx, const double *gp, float *a, float *b,
   CTX_OR_FAIL; return ctx->sim->get_fields(gp, a, b, c, d, e);
 }
 API int lbmdem_step_host(lbmdem_ctx *ctx, const double *in, long n, double *out, double *fhf, double *dens) {
-  CTX_OR_FAIL; return ctx->sim->step_host(in, n, out, fhf, dens);
+  CTX_OR_FAIL; return ctx->sim->step_host(in, n, out, fhf, dens, false);
+}
+API int lbmdem_step_host_f32(lbmdem_ctx *ctx, const float *in, long n, float *out, float *fhf, double *dens) {
+  CTX_OR_FAIL; return ctx->sim->step_host(in, n, out, fhf, dens, true);
 }
 API int lbmdem_nccl_unique_id(void *id128) {
   std::string why;

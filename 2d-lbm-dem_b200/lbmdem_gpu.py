@@ -91,6 +91,7 @@ def load_library():
         "lbmdem_save_state": ([vp, C.c_char_p], C.c_int),
         "lbmdem_load_state": ([vp, C.c_char_p], C.c_int),
         "lbmdem_step_host": ([vp, vp, C.c_long, vp, vp, vp], C.c_int),
+        "lbmdem_step_host_f32": ([vp, vp, C.c_long, vp, vp, vp], C.c_int),
         "lbmdem_host_alloc": ([C.c_size_t, C.POINTER(vp)], C.c_int),
         "lbmdem_host_free": ([vp], C.c_int),
         "lbmdem_nccl_unique_id": ([vp], C.c_int),
@@ -157,6 +158,7 @@ class Solver:
 
     def close(self):
         self.__dict__.pop("_hostbufs", None)
+        self.__dict__.pop("_hostbufs32", None)
         for p, _ in self.__dict__.pop("_pinned_bufs", {}).values():
             self.L.lbmdem_host_free(p)
         if getattr(self, "h", None):
@@ -209,26 +211,31 @@ class Solver:
         self._ck(self.L.lbmdem_step_capture(self.h, mid))
         return mid
 
-    def _pinned(self, name, shape):
-        """a float64 array in page-locked memory (lbmdem_host_alloc), kept for the life of the solver"""
+    def _pinned(self, name, shape, f32=False):
+        """a float64 / float32 array in page-locked memory (lbmdem_host_alloc), kept for the life of the solver"""
         bufs = self.__dict__.setdefault("_pinned_bufs", {})
         if name not in bufs:
             count = int(np.prod(shape))
             p = C.c_void_p()
             self._ck(self.L.lbmdem_host_alloc(8 * count, C.byref(p)))
-            arr = np.ctypeslib.as_array((C.c_double * count).from_address(p.value)).reshape(shape)
+            ctype = C.c_float if f32 else C.c_double
+            arr = np.ctypeslib.as_array((ctype * count).from_address(p.value)).reshape(shape)
             bufs[name] = (p, arr)
         return bufs[name][1]
 
-    def step_host(self, state_in, n_dem_steps, want_state=True, want_fhf=True, want_density=True):
-        """lbmdem_step_host: host arrays in, host arrays out (the end-to-end call).  The buffers are page-locked and
-        reused: the returned arrays are views that the next call overwrites; passing the returned state back in
-        costs no host copy."""
-        hb = self.__dict__.get("_hostbufs")
+    def step_host(self, state_in, n_dem_steps, want_state=True, want_fhf=True, want_density=True, rows="f64"):
+        """lbmdem_step_host (rows="f64") / lbmdem_step_host_f32 (rows="f32", single-precision solvers): host arrays in,
+        host arrays out (the end-to-end call).  The buffers are page-locked and reused: the returned arrays are views
+        that the next call overwrites; passing the returned state back in costs no host copy."""
+        f32 = rows == "f32"
+        key = "_hostbufs32" if f32 else "_hostbufs"
+        hb = self.__dict__.get(key)
         if hb is None:
             # two state slots, so that the state returned by the previous call can be the input of this one
-            arrs = [self._pinned(k, (self.n, 9)) for k in ("in", "out0", "out1")] + [self._pinned("fhf", (self.n, 3))]
-            hb = self._hostbufs = [(a, a.ctypes.data_as(C.c_void_p)) for a in arrs]
+            sfx = "32" if f32 else ""
+            arrs = [self._pinned(k + sfx, (self.n, 9), f32) for k in ("in", "out0", "out1")] + [self._pinned("fhf" + sfx, (self.n, 3), f32)]
+            hb = [(a, a.ctypes.data_as(C.c_void_p)) for a in arrs]
+            self.__dict__[key] = hb
         (a_in, p_in), (a_o0, p_o0), (a_o1, p_o1), (a_fh, p_fh) = hb
         sout = fh = None
         psin = psout = pfh = None
@@ -246,8 +253,8 @@ class Solver:
         if want_fhf:
             fh, pfh = a_fh, p_fh
         dens = C.c_double() if want_density else None
-        self._ck(self.L.lbmdem_step_host(self.h, psin, n_dem_steps, psout, pfh,
-                                         C.cast(C.byref(dens), C.c_void_p) if dens is not None else None))
+        call = self.L.lbmdem_step_host_f32 if f32 else self.L.lbmdem_step_host
+        self._ck(call(self.h, psin, n_dem_steps, psout, pfh, C.cast(C.byref(dens), C.c_void_p) if dens is not None else None))
         return sout, fh, (dens.value if dens is not None else None)
 
     # -- scalars --------------------------------------------------------------------------

@@ -272,22 +272,25 @@ def main():
     # the reference prints its density checksum every stepConsole = 400 renderScene() calls (:1715):
     # the end-to-end loop asks for it at that cadence (it costs a stream-only pass over the lattice)
     every = max(1, 400 // npd)
+    # grain rows in the precision of the run: float for an fp32 lattice (what a -DSINGLE_PRECISION reference holds)
+    rows = "f32" if prec == "f32" else "f64"
     for _ in range(max(3, a.warmup // 2)):
-        state, fh, dens = s.step_host(state, npd)
+        state, fh, dens = s.step_host(state, npd, rows=rows)
     D.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for k in range(e2e_steps):
-        state, fh, d_ = s.step_host(state, npd, want_density=((k + 1) % every == 0 or k == e2e_steps - 1))
+        state, fh, d_ = s.step_host(state, npd, want_density=((k + 1) % every == 0 or k == e2e_steps - 1), rows=rows)
         dens = d_ if d_ is not None else dens
     torch.cuda.synchronize()
     t_e2e = D.max_over_ranks(time.perf_counter() - t0)
     D.barrier()
     real_b = 4 if prec == "f32" else 8
-    # the C ABI's grain rows are doubles whatever the lattice precision: 9 up, 9 + 3 down per grain
+    # grain rows travel in the precision of the run: 9 values up, 9 + 3 down per grain
     e2e = {"value": lx * ly * e2e_steps / t_e2e / 1e6, "unit": "MLUPS",
-           "h2d_bytes_per_step": n_grains * 9 * 8, "d2h_bytes_per_step": n_grains * 12 * 8 + 8,
-           "call": "lbmdem_step_host with page-locked host buffers (lbmdem_host_alloc): grain state up, npDEM renderScene() calls, grain state + fhf down every step, density checksum every 400 calls",
+           "h2d_bytes_per_step": n_grains * 9 * real_b, "d2h_bytes_per_step": n_grains * 12 * real_b + 8,
+           "call": ("lbmdem_step_host_f32" if rows == "f32" else "lbmdem_step_host") +
+                   " with page-locked host buffers (lbmdem_host_alloc): grain state up, npDEM renderScene() calls, grain state + fhf down every step, density checksum every 400 calls",
            "ms_per_step": 1e3 * t_e2e / e2e_steps, "density_checksum": dens}
 
     # ---- roofline of the dominant kernel (K1), measured live with CUDA events on its stream ----

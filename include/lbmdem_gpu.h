@@ -141,6 +141,10 @@ int lbmdem_get_fields(lbmdem_ctx *ctx, const double *grain_p_in, float *grain_pr
  * buffers go through one staging copy each way. */
 int lbmdem_step_host(lbmdem_ctx *ctx, const double *state_in /* [n][9] or NULL */, long n_dem_steps,
                      double *state_out /* [n][9] */, double *fhf_out /* [n][3] */, double *density_out);
+/* the same with grain rows of float: what a -DSINGLE_PRECISION build of the reference holds (`real`,
+ * src/main.c:24-40, :182-198); single-precision contexts only (LBMDEM_EINVAL otherwise) */
+int lbmdem_step_host_f32(lbmdem_ctx *ctx, const float *state_in /* [n][9] or NULL */, long n_dem_steps,
+                         float *state_out /* [n][9] */, float *fhf_out /* [n][3] */, double *density_out);
 
 /* page-locked host memory for the buffers of lbmdem_step_host (the reference keeps its grain
  * array in plain malloc memory, src/main.c:612; a caller that wants the copies without staging

@@ -258,6 +258,31 @@ def test_step_host_end_to_end_call():
     assert abs(dens - o.f().sum()) < 1e-9 * o.f().size
 
 
+def test_step_host_float_rows():
+    """lbmdem_step_host_f32: grain rows of float, what a -DSINGLE_PRECISION reference holds; the same bits as the
+    double rows rounded to float, chained over several calls through the page-locked buffers"""
+    lx, ly = 96, 80
+    r, x, y = small_packing(lx, ly, 1.0, seed=63, n_target=40)
+    a = G.Solver(lx, ly, 1.0, "f32")
+    b = G.Solver(lx, ly, 1.0, "f32")
+    n = a.init_arrays(r, x, y)
+    assert b.init_arrays(r, x, y) == n
+    npd = a.scalars()["npDEM"]
+    sa = a.grains()[:, :9].copy()
+    sb = sa.astype(np.float32)
+    for _ in range(4):
+        sa, fa, da = a.step_host(sa, npd)
+        sb, fb, db = b.step_host(sb, npd, rows="f32")
+        assert sb.dtype == np.float32 and fb.dtype == np.float32
+        assert np.array_equal(sa.astype(np.float32), sb) and np.array_equal(fa.astype(np.float32), fb)
+        assert da == db
+    d = G.Solver(lx, ly, 1.0, "f64")
+    d.init_arrays(r, x, y)
+    with pytest.raises(G.LbmdemError) as ei:
+        d.step_host(sb, npd, rows="f32")
+    assert ei.value.code == -1
+
+
 def test_errors_are_reported():
     s = G.Solver(64, 48)
     with pytest.raises(G.LbmdemError) as ei:
