@@ -73,6 +73,121 @@ void raster_host(int lx, int ly, int n, const RasterParams<real> &P, const real 
   }
 }
 
+/* K2 in its TILE form (csrc/aux_kernels.cu: grain_bin_kernel + raster_tile_kernel), restated serially: grains binned
+ * by the tiles their clamped box touches (one halo node all round), every tile painted on its own -- here in REVERSE
+ * list order, the device's order being arbitrary -- with "highest index wins, the lower of two indices that meet is
+ * kept", then act / rim bits from the tile's own copy of the neighbourhood.  Must give raster_host's map bit for bit
+ * on the rows [x0+1, x0+nxl-2] of a strip holding the local rows [x0, x0+nxl), and the link / boundary-node sets that
+ * follow from it.  Returns 0, or a negative code naming what differed. */
+constexpr int HC_RTX = 32, HC_RTY = 64; /* kernels.h: RTX, RTY */
+
+template <typename real>
+int raster_tiles_check(int lx, int ly, int n, const double *scal, const double *grains, int x0, int nxl, long *counts) {
+  std::vector<real> x1(n), x2(n), v1(n), v2(n), v3(n), r(n), rLB(n);
+  for (int i = 0; i < n; ++i) {
+    const double *g = grains + 7 * (size_t)i;
+    x1[i] = (real)g[0]; x2[i] = (real)g[1]; v1[i] = (real)g[2]; v2[i] = (real)g[3]; v3[i] = (real)g[4];
+    r[i] = (real)g[5]; rLB[i] = (real)g[6];
+  }
+  RasterParams<real> RP;
+  RP.lx = lx; RP.ly = ly; RP.dx = (real)scal[0]; RP.Mgx = (real)scal[2]; RP.Mby = (real)scal[3];
+  std::vector<int> ref;
+  std::vector<GrainRec<real>> rec;
+  std::vector<GrainBox> box;
+  std::vector<real> R2v;
+  raster_host(lx, ly, n, RP, x1.data(), x2.data(), r.data(), rLB.data(), v1.data(), v2.data(), v3.data(), ref, rec, box, R2v);
+
+  /* grain_bin_kernel */
+  const int ntx = (nxl + HC_RTX - 1) / HC_RTX, nty = (ly + HC_RTY - 1) / HC_RTY;
+  std::vector<std::vector<int>> bins((size_t)ntx * nty);
+  for (int i = 0; i < n; ++i) {
+    const GrainBox &b = box[i];
+    const int xa = std::max(b.xi - 1, x0), xb = std::min(b.xf + 1, x0 + nxl - 1);
+    const int ya = std::max(b.yi - 1, 0), yb = std::min(b.yf + 1, ly - 1);
+    if (b.xf < b.xi || b.yf < b.yi || xb < xa || yb < ya) continue;
+    for (int tx = (xa - x0) / HC_RTX; tx <= (xb - x0) / HC_RTX; ++tx)
+      for (int ty = ya / HC_RTY; ty <= yb / HC_RTY; ++ty) bins[(size_t)tx * nty + ty].push_back(i);
+  }
+  /* raster_tile_kernel */
+  const int TR = HC_RTX + 2, TC = HC_RTY + 2;
+  std::vector<int> own(TR * TC), low(TR * TC);
+  long nlinks = 0, nrim = 0, nlinks_ref = 0, nrim_ref = 0, maxbin = 0;
+  for (int tx = 0; tx < ntx; ++tx)
+    for (int ty = 0; ty < nty; ++ty) {
+      const int tx0 = x0 + tx * HC_RTX, ty0 = ty * HC_RTY;
+      for (int rr = 0; rr < TR; ++rr)
+        for (int cc = 0; cc < TC; ++cc) {
+          const int gx = tx0 - 1 + rr, gy = ty0 - 1 + cc;
+          own[rr * TC + cc] = (gx <= 0 || gx >= lx - 1 || gy <= 0 || gy >= ly - 1) ? n : -1;
+          low[rr * TC + cc] = 0x7fffffff;
+        }
+      const std::vector<int> &lst = bins[(size_t)tx * nty + ty];
+      maxbin = std::max<long>(maxbin, (long)lst.size());
+      for (size_t k = lst.size(); k-- > 0;) { /* reverse order */
+        const int i = lst[k];
+        const GrainBox &b = box[i];
+        const int ra = std::max(b.xi, tx0 - 1), rb = std::min(b.xf, tx0 + HC_RTX);
+        const int ca = std::max(b.yi, ty0 - 1), cb = std::min(b.yf, ty0 + HC_RTY);
+        for (int x = ra; x <= rb; ++x)
+          for (int y = ca; y <= cb; ++y)
+            if (disc_covers(rec[i].xc, rec[i].yc, rec[i].r2, R2v[i], x, y)) {
+              int &o = own[(x - tx0 + 1) * TC + (y - ty0 + 1)], &l = low[(x - tx0 + 1) * TC + (y - ty0 + 1)];
+              const int old = o;
+              o = std::max(o, i);
+              if (old >= 0 && old != i) l = std::min(l, std::min(old, i));
+            }
+      }
+      for (int rr = 0; rr < HC_RTX; ++rr)
+        for (int cc = 0; cc < HC_RTY; ++cc) {
+          const int x = tx0 + rr, y = ty0 + cc;
+          if (x > x0 + nxl - 1 || y >= ly) continue;
+          const int v = own[(rr + 1) * TC + cc + 1];
+          int out = v;
+          if (v >= 0 && v < n && x >= x0 + 1 && x <= x0 + nxl - 2) {
+            bool act = false;
+            unsigned foreign = 0, fluid = 0;
+            for (int q = 1; q < NQ; ++q) {
+              const int at = (rr + 1 + ex_of(q)) * TC + cc + 1 + ey_of(q);
+              const int cn = own[at];
+              if (cell_is_fluid(cn)) fluid |= 1u << (q - 1);
+              if (cn != v) {
+                foreign |= 1u << (q - 1);
+                int mo = -1;
+                if (cn > v && cn < n) mo = low[at] == 0x7fffffff ? -1 : low[at];
+                if (fluid_when_grain_ran_exact(cn, v, n, mo)) act = true;
+              }
+            }
+            const unsigned solid_foreign = foreign & ~fluid;
+            out = v | (act ? CELL_ACT : 0) | (solid_foreign ? CELL_RIM : 0);
+            if (solid_foreign) ++nrim;
+            if (act) {
+              const bool near_ring = !(x >= 2 && y >= 2 && x <= lx - 3 && y <= ly - 3);
+              for (unsigned m = near_ring ? 0xffu : fluid; m; m &= m - 1) ++nlinks;
+            }
+          }
+          const int want = ref[(size_t)x * ly + y];
+          const bool classified = x >= x0 + 1 && x <= x0 + nxl - 2;
+          if (cell_obst(out) != cell_obst(want) || (out < 0) != (want < 0)) return -1; /* owner */
+          if (classified && out != want) return (out ^ want) & CELL_ACT ? -2 : -3;     /* act / rim bit */
+        }
+    }
+  /* the sets that follow from the reference map on the classified rows */
+  for (int x = std::max(x0 + 1, 1); x <= std::min(x0 + nxl - 2, lx - 2); ++x)
+    for (int y = 1; y <= ly - 2; ++y) {
+      const int c = ref[(size_t)x * ly + y];
+      if (c < 0 || cell_obst(c) >= n) continue;
+      if (c & CELL_RIM) ++nrim_ref;
+      if (!(c & CELL_ACT)) continue;
+      const bool near_ring = !(x >= 2 && y >= 2 && x <= lx - 3 && y <= ly - 3);
+      for (int q = 1; q < NQ; ++q)
+        if (near_ring || cell_is_fluid(ref[(size_t)(x + ex_of(q)) * ly + y + ey_of(q)])) ++nlinks_ref;
+    }
+  counts[0] = nlinks; counts[1] = nrim; counts[2] = maxbin;
+  if (nlinks != nlinks_ref) return -4;
+  if (nrim != nrim_ref) return -5;
+  return 0;
+}
+
 template <typename real>
 int lbm_step_host(int lx, int ly, int n, const double *scal, const double *grains /* [n][7]: x1 x2 v1 v2 v3 r rLB */,
                   const double *f_in /* [x][y][q] */, const int *obst_old, double *f_out, int *obst_new, int *act_new,
@@ -457,6 +572,15 @@ extern "C" {
 EXPORT void hc_set_act_folded(int v) { g_act_folded = v; }
 EXPORT int hc_last_deferred(void) { return g_last_deferred; }
 EXPORT int hc_last_dead(void) { return g_last_dead; }
+/* scal: dx c Mgx Mby lid; grains [n][7]: x1 x2 v1 v2 v3 r rLB; counts[3]: links, rim nodes, largest tile bin */
+EXPORT int hc_raster_tiles_check_f64(int lx, int ly, int n, const double *scal, const double *grains, int x0, int nxl,
+                                     long *counts) {
+  return raster_tiles_check<double>(lx, ly, n, scal, grains, x0, nxl, counts);
+}
+EXPORT int hc_raster_tiles_check_f32(int lx, int ly, int n, const double *scal, const double *grains, int x0, int nxl,
+                                     long *counts) {
+  return raster_tiles_check<float>(lx, ly, n, scal, grains, x0, nxl, counts);
+}
 /* scal: dx c Mgx Mby lid */
 EXPORT int hc_lbm_step_f64(int lx, int ly, int n, const double *scal, const double *grains, const double *f_in,
                            const int *obst_old, double *f_out, int *obst_new, int *act_new, double *fhf) {

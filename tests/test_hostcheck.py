@@ -111,6 +111,44 @@ def test_lbm_step_overlapping_discs_and_discs_on_the_ring(prec):
     assert load_hostcheck().hc_last_dead() > 300
 
 
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_tile_rasteriser_formulation(prec):
+    """The tile form of K2 (grains binned by 32 x 64 tiles with a halo, shared-memory painting in arbitrary order,
+    act / rim bits from the tile's own neighbourhood) restated serially: the same map, bits and link counts as the
+    whole-lattice rasteriser -- on one GPU's lattice and on the local rows of strips (ghost rows included)."""
+    hc = load_hostcheck()
+    fn = getattr(hc, f"hc_raster_tiles_check_{prec}")
+    cases = []
+    lx, ly = 200, 333   # several tiles each way, ly not a multiple of the tile width
+    r, x, y = small_packing(lx, ly, 1.0, seed=5, n_target=300)
+    cases.append((lx, ly, r, x, y, [(0, lx), (0, 104), (96, 104), (46, 37)]))
+    lx, ly = 96, 72     # overlapping discs, discs in the wall ring, a disc partly outside the lattice
+    dx = 1e-4 * lx / (lx - 1)
+    cases.append((lx, ly, np.array([10, 9, 8, 7, 9, 6.5]) * dx, np.array([30, 39, 34, 3.0, 80, 95.0]) * dx,
+                  np.array([30, 31, 38, 40, 2.5, 20]) * dx, [(0, lx), (20, 40)]))
+    lx, ly = 160, 150   # discs larger than a tile
+    dx = 1e-4 * lx / (lx - 1)
+    cases.append((lx, ly, np.array([55.0, 30.0, 12.0]) * dx, np.array([70.0, 120.0, 20.0]) * dx, np.array([70.0, 100.0, 130.0]) * dx,
+                  [(0, lx), (60, 50)]))
+    for lx, ly, r, x, y, strips in cases:
+        o = Oracle(lx, ly, 1.0, prec)
+        n = o.init_arrays(r, x, y)
+        sc = o.scalars()
+        rng = np.random.default_rng(3)
+        for rep in range(3):
+            st = o.grains()[:, :9].copy()
+            st[:, 0:2] += rng.uniform(-0.7, 0.7, size=(n, 2)) * sc["dx"]
+            o.set_grain_state(st)
+            scal = np.array([sc["dx"], sc["c"], sc["Mgx"], sc["Mby"], 0.0])
+            for x0, nxl in strips:
+                counts = np.zeros(3, dtype=np.int64)
+                rc = fn(lx, ly, n, scal, _grain_table(o.grains()), x0, nxl, counts)
+                assert rc == 0, (lx, ly, x0, nxl, rc)
+                assert counts[0] > 0 and counts[2] >= 1
+            # the whole-lattice map of the restatement is the oracle's
+            o.lbm_step()
+
+
 def _dem_params(sc):
     keys = ["kg", "kt", "km", "ktm", "nug", "num", "numb", "nugt", "mu", "mum", "mumb", "murf", "freq", "amp", "t",
             "distVerlet"]

@@ -84,6 +84,9 @@ def load_hostcheck():
         fn = getattr(lib, f"hc_lbm_step_{sfx}")
         fn.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp, ip, dp, ip, ip, dp]
         fn.restype = C.c_int
+        fn = getattr(lib, f"hc_raster_tiles_check_{sfx}")
+        fn.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, C.c_int, C.c_int, np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")]
+        fn.restype = C.c_int
         fn = getattr(lib, f"hc_dem_step_{sfx}")
         fn.argtypes = [C.c_int, dp, C.c_int, dp, dp, dp, C.c_int, ip, ip, C.c_int, ip]
         fn.restype = C.c_int
