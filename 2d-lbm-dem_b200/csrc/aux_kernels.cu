@@ -336,10 +336,8 @@ constexpr int RT_CHUNK = 64;                 /* grains staged in shared memory a
 static_assert(RTY == 64 && RTX == 32 && RT_THREADS == 256, "pass 3a: a warp takes 4 rows, a lane 4 consecutive columns");
 
 template <typename real>
-__global__ void __launch_bounds__(RT_THREADS) raster_tile_kernel(int n, const GrainRec<real> *rec, const real *R2,
-                                                                 const GrainBox *boxes, int *cell, int x0, int nxl,
-                                                                 int pitch, int lx, int ly, TileBins T, BoundaryList B,
-                                                                 LinkList K) {
+__global__ void __launch_bounds__(RT_THREADS) raster_tile_kernel(int n, int *cell, int x0, int nxl, int pitch, int lx,
+                                                                 int ly, TileBins T, BoundaryList B, LinkList K) {
   /* region = tile + one halo node all round; region row r+1 / column c+RTC0 hold tile node (r, c) */
   __shared__ __align__(16) int own[RTX + 2][RTP]; /* owner: -1 fluid, n ring / outside the array */
   __shared__ __align__(16) int low[RTX + 2][RTP]; /* lowest covering index where more than one disc covers the node */
@@ -542,8 +540,7 @@ cudaError_t launch_raster_tiles(const RasterParams<real> &P, int n, const GrainA
                                 GrainBox *boxes, int *cell, int x0, int nxl, int pitch, const TileBins &T,
                                 const BoundaryList &B, const LinkList &K, int *defer_count, long long *facc, cudaStream_t s) {
   grain_bin_kernel<real><<<(n + 127) / 128, 128, 0, s>>>(P, n, g, rec, R2, boxes, x0, nxl, T, B.count, K.count, defer_count, facc);
-  raster_tile_kernel<real><<<dim3(T.nty, T.ntx), RT_THREADS, 0, s>>>(n, rec, R2, boxes, cell, x0, nxl, pitch, P.lx, P.ly,
-                                                                            T, B, K);
+  raster_tile_kernel<real><<<dim3(T.nty, T.ntx), RT_THREADS, 0, s>>>(n, cell, x0, nxl, pitch, P.lx, P.ly, T, B, K);
   return cudaGetLastError();
 }
 
