@@ -774,8 +774,16 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
 template <typename real>
 __global__ void __launch_bounds__(256) force_links_kernel(const __grid_constant__ Lattice<real> L,
                                                           const __grid_constant__ Stored<real> S, int xlo, int xhi,
-                                                          const BoundaryList B, long long *facc) {
+                                                          const BoundaryList B, long long *facc, real *A,
+                                                          const DeferList<real> D) {
   const int n = L.ngrains;
+  /* first the deferred bounce-back links of the sweep (defer_apply_kernel's job, one launch less).  They are links
+   * into FLUID neighbours; the force links below read populations of links into NON-fluid neighbours only (A[q][s]
+   * with s + e_q not fluid, A[opp q][n] with n + e_opp q = s solid): never the same location. */
+  if (A != nullptr) {
+    const int nd = min(*D.count, D.capacity);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nd; k += gridDim.x * blockDim.x) A[D.index[k]] = D.value[k];
+  }
   const long long items = 8ll * min(*B.count, B.capacity);
   const long long padded = (items + 31) & ~31ll; /* whole warps stay in the loop: shuffles below */
   for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < padded; u += (long long)gridDim.x * blockDim.x) {
@@ -815,8 +823,8 @@ __global__ void __launch_bounds__(256) force_links_kernel(const __grid_constant_
 }
 template <typename real>
 cudaError_t launch_force_links(const Lattice<real> &L, const Stored<real> &S, int xlo, int xhi, const BoundaryList &B,
-                               long long *facc, cudaStream_t s) {
-  force_links_kernel<real><<<148 * 4, 256, 0, s>>>(L, S, xlo, xhi, B, facc); /* adds to what the sweep kernel left */
+                               long long *facc, real *A, const DeferList<real> &D, cudaStream_t s) {
+  force_links_kernel<real><<<148 * 4, 256, 0, s>>>(L, S, xlo, xhi, B, facc, A, D); /* adds to what the sweep kernel left */
   return cudaGetLastError();
 }
 
@@ -1059,11 +1067,23 @@ __global__ void dem_kick_kernel(dem::Params<real> P, int n, GrainArrays<real> g)
   v = g.v3[i]; dem::kick(P, &v, g.a3[i]); g.v3[i] = v;
 }
 
+/* the closing kick of one sub-step (:1758-1763) and the kick-drift that opens the next (:1748-1753): the same
+ * operations on the same grain in the same order, one launch instead of two */
+template <typename real>
+__global__ void dem_kick_kick_drift_kernel(dem::Params<real> P, int n, GrainArrays<real> g) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  real x, v, a;
+  a = g.a1[i]; v = g.v1[i]; dem::kick(P, &v, a); x = g.x1[i]; dem::kick_drift(P, &x, &v, a); g.x1[i] = x; g.v1[i] = v;
+  a = g.a2[i]; v = g.v2[i]; dem::kick(P, &v, a); x = g.x2[i]; dem::kick_drift(P, &x, &v, a); g.x2[i] = x; g.v2[i] = v;
+  a = g.a3[i]; v = g.v3[i]; dem::kick(P, &v, a); x = g.x3[i]; dem::kick_drift(P, &x, &v, a); g.x3[i] = x; g.v3[i] = v;
+}
+
 template <typename real>
 cudaError_t launch_dem_step(const dem::Params<real> &P, int n, bool film, const GrainArrays<real> &g,
-                            const VerletBuffers &vb, real *mid, cudaStream_t s) {
+                            const VerletBuffers &vb, real *mid, bool drift_done, bool drift_next, cudaStream_t s) {
   const int nb = (n + 127) / 128;
-  dem_kick_drift_kernel<real><<<nb, 128, 0, s>>>(P, n, g);
+  if (!drift_done) dem_kick_drift_kernel<real><<<nb, 128, 0, s>>>(P, n, g);
   if (mid != nullptr) {
     const real *src[6] = {g.x1, g.x2, g.x3, g.v1, g.v2, g.v3};
     for (int k = 0; k < 6; ++k) {
@@ -1072,7 +1092,8 @@ cudaError_t launch_dem_step(const dem::Params<real> &P, int n, bool film, const 
     }
   }
   dem_forces_kernel<real><<<(n * 32 + 127) / 128, 128, 0, s>>>(P, n, film, g, vb);
-  dem_kick_kernel<real><<<nb, 128, 0, s>>>(P, n, g);
+  if (drift_next) dem_kick_kick_drift_kernel<real><<<nb, 128, 0, s>>>(P, n, g);
+  else dem_kick_kernel<real><<<nb, 128, 0, s>>>(P, n, g);
   return cudaGetLastError();
 }
 
@@ -1275,6 +1296,27 @@ __global__ void grain_pack_kernel(const real *cols, int n, int ncols, H *rows) {
   const int i = t / ncols, k = t - i * ncols;
   rows[t] = (H)cols[(size_t)k * n + i];
 }
+/* two groups of columns -> [n][na] followed by [n][nb] (the kinematic state and fhf of lbmdem_step_host) */
+template <typename real, typename H>
+__global__ void grain_pack2_kernel(const real *cols_a, int na, const real *cols_b, int nb, int n, H *rows) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * (na + nb)) return;
+  if (t < n * na) {
+    const int i = t / na, k = t - i * na;
+    rows[t] = (H)cols_a[(size_t)k * n + i];
+  } else {
+    const int u = t - n * na, i = u / nb, k = u - i * nb;
+    rows[t] = (H)cols_b[(size_t)k * n + i];
+  }
+}
+template <typename real>
+cudaError_t launch_grain_pack2(const real *cols_a, int na, const real *cols_b, int nb, int n, void *rows, bool rows_f32,
+                               cudaStream_t s) {
+  const int blocks = (n * (na + nb) + 255) / 256;
+  if (rows_f32) grain_pack2_kernel<real, float><<<blocks, 256, 0, s>>>(cols_a, na, cols_b, nb, n, static_cast<float *>(rows));
+  else grain_pack2_kernel<real, double><<<blocks, 256, 0, s>>>(cols_a, na, cols_b, nb, n, static_cast<double *>(rows));
+  return cudaGetLastError();
+}
 template <typename real>
 cudaError_t launch_grain_unpack(const void *rows, bool rows_f32, int n, int ncols, real *cols, cudaStream_t s) {
   if (rows_f32) grain_unpack_kernel<real, float><<<(n * ncols + 255) / 256, 256, 0, s>>>(static_cast<const float *>(rows), n, ncols, cols);
@@ -1317,7 +1359,8 @@ cudaError_t launch_fill_rest(real *f, size_t plane, const Lattice<real> &Lw, cud
                                                 const LinkList &, const DeferList<real> &, long long *, cudaStream_t);    \
   template cudaError_t launch_bounce_end<real>(real *, const DeferList<real> &, cudaStream_t);                            \
   template cudaError_t launch_force_links<real>(const Lattice<real> &, const Stored<real> &, int, int,                    \
-                                                const BoundaryList &, long long *, cudaStream_t);                         \
+                                                const BoundaryList &, long long *, real *, const DeferList<real> &,       \
+                                                cudaStream_t);                                                            \
   template cudaError_t launch_force_finish<real>(const long long *, int, double, double, real *, real *, real *,          \
                                                  cudaStream_t);                                                           \
   template cudaError_t launch_force_serial<real>(const Lattice<real> &, const Stored<real> &, int, int, double *,         \
@@ -1327,7 +1370,7 @@ cudaError_t launch_fill_rest(real *f, size_t plane, const Lattice<real> &Lw, cud
   template cudaError_t launch_verlet<real>(const dem::Params<real> &, int, const GrainArrays<real> &, real,               \
                                            const VerletBuffers &, cudaStream_t);                                         \
   template cudaError_t launch_dem_step<real>(const dem::Params<real> &, int, bool, const GrainArrays<real> &,             \
-                                             const VerletBuffers &, real *, cudaStream_t);                               \
+                                             const VerletBuffers &, real *, bool, bool, cudaStream_t);                   \
   template cudaError_t launch_dem_batch<real>(const dem::Params<real> &, int, int, const GrainArrays<real> &,             \
                                               const VerletBuffers &, cudaStream_t);                                      \
   template cudaError_t launch_density<real>(const real *, int, int, int, int, int, size_t, double *, int, double *,       \
@@ -1339,6 +1382,7 @@ cudaError_t launch_fill_rest(real *f, size_t plane, const Lattice<real> &Lw, cud
   template cudaError_t launch_f_from_host_layout<real>(real *, int, int, size_t, int, int, const double *, cudaStream_t); \
   template cudaError_t launch_grain_unpack<real>(const void *, bool, int, int, real *, cudaStream_t);                     \
   template cudaError_t launch_grain_pack<real>(const real *, int, int, void *, bool, cudaStream_t);                       \
+  template cudaError_t launch_grain_pack2<real>(const real *, int, const real *, int, int, void *, bool, cudaStream_t);   \
   template cudaError_t launch_fill_rest<real>(real *, size_t, const Lattice<real> &, cudaStream_t);
 INSTANTIATE(float)
 INSTANTIATE(double)

@@ -192,7 +192,9 @@ cudaError_t launch_bounce_end(real *A, const DeferList<real> &D, cudaStream_t s)
  * grains, the wall ring), one thread per (listed node, link); ADDS to facc[3][n] */
 template <typename real>
 cudaError_t launch_force_links(const lbm::Lattice<real> &L, const lbm::Stored<real> &S, int xlo, int xhi,
-                               const BoundaryList &B, long long *facc, cudaStream_t s);
+                               const BoundaryList &B, long long *facc,
+                               real *A /* nullptr, or the populations: the deferred links D are applied first */,
+                               const DeferList<real> &D, cudaStream_t s);
 /* fixed-point sums -> fhf (scaled, src/main.c:1329-1331) */
 template <typename real>
 cudaError_t launch_force_finish(const long long *facc, int ngrains, double k12, double k3, real *fhf1, real *fhf2,
@@ -223,7 +225,10 @@ cudaError_t launch_verlet(const dem::Params<real> &P, int n, const GrainArrays<r
 template <typename real>
 cudaError_t launch_dem_step(const dem::Params<real> &P, int n, bool film, const GrainArrays<real> &g,
                             const VerletBuffers &vb, real *mid /* nullptr, or [6][n]: x1 x2 x3 v1 v2 v3 after the
-                            kick-drift, i.e. as acceleration_grains() sees them */, cudaStream_t s);
+                            kick-drift, i.e. as acceleration_grains() sees them */,
+                            bool drift_done /* the previous sub-step's last launch did this one's kick-drift */,
+                            bool drift_next /* close with kick + the NEXT sub-step's kick-drift in one launch */,
+                            cudaStream_t s);
 
 /* nsub consecutive DEM sub-steps (normal contact law, fixed lists and fhf) in ONE launch: a single CTA, one
  * thread per grain, for small samples (n <= DEM_BATCH_MAX) where three launches per sub-step are all latency */
@@ -253,6 +258,10 @@ template <typename real>
 cudaError_t launch_grain_unpack(const void *rows, bool rows_f32, int n, int ncols, real *cols, cudaStream_t s);
 template <typename real>
 cudaError_t launch_grain_pack(const real *cols, int n, int ncols, void *rows, bool rows_f32, cudaStream_t s);
+/* two column groups in one launch: rows = [n][na] followed by [n][nb] */
+template <typename real>
+cudaError_t launch_grain_pack2(const real *cols_a, int na, const real *cols_b, int nb, int n, void *rows, bool rows_f32,
+                               cudaStream_t s);
 /* init_density (src/main.c:716-724) */
 template <typename real>
 cudaError_t launch_fill_rest(real *f, size_t plane, const lbm::Lattice<real> &Lw, cudaStream_t s);

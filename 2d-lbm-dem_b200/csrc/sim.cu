@@ -672,9 +672,10 @@ struct Sim : SimBase {
       CK(launch_bounce_pass<real>(L, S, f[cur], xhi - 3, std::min(xhi + 1, lx - 1), xlo, xhi, llist, defer, fa, stream));
       all_launches += 4;
     }
-    CK(launch_bounce_end<real>(f[cur], defer, stream));
-    all_launches += 3;
+    all_launches += 2;
     if (P.strict_fp) {
+      CK(launch_bounce_end<real>(f[cur], defer, stream));
+      ++all_launches;
       CK(launch_force_serial<real>(L, S, xlo, xhi, fpartial, stream));
       if (multi) {
         const int r = g_nccl.AllReduce(fpartial, fpartial, (size_t)3 * n, NcclApi::Float64, NcclApi::Sum, comm, stream);
@@ -682,7 +683,7 @@ struct Sim : SimBase {
       }
       CK(launch_force_scale<real>(fpartial, n, k12, k3, g.fhf1, g.fhf2, g.fhf3, stream));
     } else {
-      CK(launch_force_links<real>(L, S, xlo, xhi, blist, facc, stream));
+      CK(launch_force_links<real>(L, S, xlo, xhi, blist, facc, f[cur], defer, stream)); /* applies the deferred links first */
       if (multi) { /* integer sum: exact, identical on every rank, independent of the decomposition */
         const int r = g_nccl.AllReduce(facc, facc, (size_t)3 * n, NcclApi::Int64, NcclApi::Sum, comm, stream);
         if (r) return nccl_fail(r, "ncclAllReduce");
@@ -758,6 +759,7 @@ struct Sim : SimBase {
 
   real *mid_dev = nullptr; /* [6][n], lbmdem_step_capture */
   int step_async(long nsteps, bool *built, bool capture = false) {
+    bool drift_done = false; /* the previous call's last DEM launch already did this call's kick-drift */
     for (long k = 0; k < nsteps; ++k) {
       int rc;
       if (P.vib == 1) { /* vibrating walls (:1701-1706) */
@@ -781,8 +783,13 @@ struct Sim : SimBase {
         CK(launch_dem_batch<real>(dem_params(), n, (int)nb, g, vb, stream));
         all_launches += 1;
       } else {
-        CK(launch_dem_step<real>(dem_params(), n, film, g, vb, capture ? mid_dev : nullptr, stream));
-        all_launches += 3;
+        /* when the next call of this batch does nothing but its DEM sub-step (no LBM step, no list rebuild), this
+         * call's closing kick and the next call's kick-drift go in one launch */
+        const bool drift_next = n > DEM_BATCH_MAX && !capture && P.vib != 1 && k + 1 < nsteps &&
+                                (nbsteps + 1) % npDEM != 0 && (nbsteps + 1) % P.UpdateVerlet != 0;
+        CK(launch_dem_step<real>(dem_params(), n, film, g, vb, capture ? mid_dev : nullptr, drift_done, drift_next, stream));
+        all_launches += drift_done ? 2 : 3;
+        drift_done = drift_next;
       }
       for (long b = 0; b < nb; ++b) {
         ++nbsteps;
@@ -1119,9 +1126,10 @@ struct Sim : SimBase {
     if (rc) return rc;
     (void)built;
     if (state_out || fhf_out) {
-      CK(launch_grain_pack<real>(g.x1, n, 9, gs, rows_f32, stream));
-      CK(launch_grain_pack<real>(g.fhf1, n, 3, gs + eb * 9 * N, rows_f32, stream));
-      if (pin_out) {
+      CK(launch_grain_pack2<real>(g.x1, 9, g.fhf1, 3, n, gs, rows_f32, stream)); /* [n][9] state, then [n][3] fhf */
+      if (pin_out && state_out && fhf_out && static_cast<char *>(fhf_out) == static_cast<char *>(state_out) + eb * 9 * N) {
+        CK(cudaMemcpyAsync(state_out, gs, eb * 12 * N, cudaMemcpyDeviceToHost, stream)); /* one block on the host too */
+      } else if (pin_out) {
         if (state_out) CK(cudaMemcpyAsync(state_out, gs, eb * 9 * N, cudaMemcpyDeviceToHost, stream));
         if (fhf_out) CK(cudaMemcpyAsync(fhf_out, gs + eb * 9 * N, eb * 3 * N, cudaMemcpyDeviceToHost, stream));
       } else {

@@ -231,12 +231,18 @@ class Solver:
         key = "_hostbufs32" if f32 else "_hostbufs"
         hb = self.__dict__.get(key)
         if hb is None:
-            # two state slots, so that the state returned by the previous call can be the input of this one
+            # one input slot and two output blocks, so that the state returned by the previous call can be the input of
+            # this one; an output block holds [n][9] state followed by [n][3] fhf: one device-to-host copy
             sfx = "32" if f32 else ""
-            arrs = [self._pinned(k + sfx, (self.n, 9), f32) for k in ("in", "out0", "out1")] + [self._pinned("fhf" + sfx, (self.n, 3), f32)]
-            hb = [(a, a.ctypes.data_as(C.c_void_p)) for a in arrs]
+            n = self.n
+            a_in = self._pinned("in" + sfx, (n, 9), f32)
+            hb = [(a_in, a_in.ctypes.data_as(C.c_void_p))]
+            for k in ("blk0", "blk1"):
+                blk = self._pinned(k + sfx, (12 * n,), f32)
+                st, fhv = blk[:9 * n].reshape(n, 9), blk[9 * n:].reshape(n, 3)
+                hb.append((st, st.ctypes.data_as(C.c_void_p), fhv, fhv.ctypes.data_as(C.c_void_p)))
             self.__dict__[key] = hb
-        (a_in, p_in), (a_o0, p_o0), (a_o1, p_o1), (a_fh, p_fh) = hb
+        (a_in, p_in), (a_o0, p_o0, a_f0, p_f0), (a_o1, p_o1, a_f1, p_f1) = hb
         sout = fh = None
         psin = psout = pfh = None
         use_o1 = False
@@ -251,7 +257,7 @@ class Solver:
         if want_state:
             sout, psout = (a_o1, p_o1) if use_o1 else (a_o0, p_o0)
         if want_fhf:
-            fh, pfh = a_fh, p_fh
+            fh, pfh = (a_f1, p_f1) if use_o1 else (a_f0, p_f0)
         dens = C.c_double() if want_density else None
         call = self.L.lbmdem_step_host_f32 if f32 else self.L.lbmdem_step_host
         self._ck(call(self.h, psin, n_dem_steps, psout, pfh, C.cast(C.byref(dens), C.c_void_p) if dens is not None else None))
