@@ -194,7 +194,13 @@ __global__ void __launch_bounds__(RowCfg<real>::TY + 32, sizeof(real) == 8 ? LBM
           f[q] = As[q * C::BY + by - ey];
         }
       }
+#if defined(LBMDEM_K1_PROBE)
+      /* TIMING PROBES of the row pipeline (results are wrong by construction; build with --tag, run bench.py only):
+       * 1 = data movement alone (pull + store, no re-init / collide / w-links). */
+      if (false) {
+#else
       if (!a.stream_only) {
+#endif
         reinit_collide(L, a.grains_new, cprev, cnow, gx, gy, f);
         if (cell_is_act(cnow) && w_links_with_collide(L, gx, gy)) {
           /* active solid node: links into non-fluid neighbours take the rest value (:1161-1162) */
