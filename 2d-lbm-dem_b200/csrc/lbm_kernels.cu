@@ -71,6 +71,17 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+#if defined(LBMDEM_K1_LD_EVICT_FIRST) /* tuning variant: the populations are read once per step -> L2 evict-first */
+__device__ __forceinline__ void tma_load_3d_ef(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
+      : "memory");
+}
+#endif
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
@@ -131,7 +142,11 @@ __global__ void __launch_bounds__(RowCfg<real>::TY + 32, sizeof(real) == 8 ? LBM
         unsigned char *base = smem + (size_t)slot * C::SLOT;
         const int row = r0 - 1 + t - L.x0; /* local row */
         mbar_expect_tx(&full[slot], (uint32_t)(C::A_BYTES + C::CN_BYTES + C::CP_BYTES));
+#if defined(LBMDEM_K1_LD_EVICT_FIRST)
+        tma_load_3d_ef(base, &tmA, &full[slot], y0 - C::HY, row, 0);
+#else
         tma_load_3d(base, &tmA, &full[slot], y0 - C::HY, row, 0);
+#endif
         tma_load_2d(base + C::A_PAD, &tmCn, &full[slot], y0 - C::HC, row);
         tma_load_2d(base + C::A_PAD + C::CN_PAD, &tmCp, &full[slot], y0, row);
         if (++slot == C::NS) { slot = 0; ++round; }
@@ -215,7 +230,11 @@ __global__ void __launch_bounds__(RowCfg<real>::TY + 32, sizeof(real) == 8 ? LBM
         }
       }
 #pragma unroll
+#if defined(LBMDEM_K1_STCS) /* tuning variant: streaming stores (the output is not read again before 600 MB of other traffic) */
+      for (int q = 0; q < NQ; ++q) __stcs(&out[q * L.plane], f[q]);
+#else
       for (int q = 0; q < NQ; ++q) out[q * L.plane] = f[q];
+#endif
     }
     out += L.pitch;
     /* this warp is done with row t-1 */

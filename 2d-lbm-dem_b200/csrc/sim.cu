@@ -266,9 +266,12 @@ struct Sim : SimBase {
       const cuuint64_t strides[2] = {(cuuint64_t)pitch * sizeof(real), (cuuint64_t)plane * sizeof(real)};
       const cuuint32_t box[3] = {(cuuint32_t)C::BY, 1, (cuuint32_t)NQ};
       const cuuint32_t estr[3] = {1, 1, 1};
+#ifndef LBMDEM_K1_L2PROMO
+#define LBMDEM_K1_L2PROMO CU_TENSOR_MAP_L2_PROMOTION_L2_256B /* tuning knob: ..._NONE / _L2_64B / _L2_128B / _L2_256B */
+#endif
       CUresult r = encode(&tmA[k], sizeof(real) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
                           f[k], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          LBMDEM_K1_L2PROMO, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return fail(LBMDEM_ECUDA, "cuTensorMapEncodeTiled(f) failed with code " + std::to_string((int)r));
       const cuuint64_t cdims[2] = {(cuuint64_t)ly, (cuuint64_t)nxl};
       const cuuint64_t cstr[1] = {(cuuint64_t)pitch * sizeof(int)};
