@@ -645,6 +645,31 @@ cudaError_t launch_ring_sweep(const Lattice<real> &L, const Stored<real> &S, rea
  * Lanes that hold the same grain are summed first (exact: integers), so there is about one atomic per grain and
  * warp.  The link list is grouped by grain, so the lanes of a grain normally form one contiguous run: a segmented
  * shuffle reduction (five rounds); any other pattern takes the lane-by-lane loop. */
+#if defined(LBMDEM_SUMS_RUNS)
+/* Variant for the next tuning visit (not timed yet): one segmented reduction over every maximal run of adjacent
+ * lanes with the same grain, one atomic per run -- no lane-by-lane loop whatever the pattern.  The tile rasteriser
+ * emits links tile row by tile row, so a warp usually sees A A B B A A B B ...; profiles/README.md: the lane-by-lane
+ * loop below is then a third of this kernel's instructions. */
+__device__ __forceinline__ void grain_sums_add(long long *facc, int n, int i, long long s1, long long s2, long long s3) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int prev = __shfl_up_sync(full, i, 1);
+  const bool head = lane == 0 || prev != i;
+  const unsigned heads = __ballot_sync(full, head);
+  const unsigned above = lane == 31 ? 0u : heads >> (lane + 1);
+  const int end = above ? lane + __ffs(above) : 32; /* the next run starts there */
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const long long t1 = __shfl_down_sync(full, s1, d), t2 = __shfl_down_sync(full, s2, d), t3 = __shfl_down_sync(full, s3, d);
+    if (lane + d < end) { s1 += t1; s2 += t2; s3 += t3; }
+  }
+  if (head && i >= 0) {
+    atomicAdd((unsigned long long *)&facc[i], (unsigned long long)s1);
+    atomicAdd((unsigned long long *)&facc[n + i], (unsigned long long)s2);
+    atomicAdd((unsigned long long *)&facc[2 * n + i], (unsigned long long)s3);
+  }
+}
+#else
 __device__ __forceinline__ void grain_sums_add(long long *facc, int n, int i, long long s1, long long s2, long long s3) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -674,6 +699,7 @@ __device__ __forceinline__ void grain_sums_add(long long *facc, int n, int i, lo
     atomicAdd((unsigned long long *)&facc[2 * n + i], (unsigned long long)s3);
   }
 }
+#endif
 
 /* One thread per listed link.  Besides the sweep itself the thread holds both operands of the
  * link's momentum exchange (forces_fluid, :1313-1320: f_new[s][opp q] = A[n][opp q] and
