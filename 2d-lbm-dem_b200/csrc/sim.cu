@@ -131,6 +131,7 @@ struct SimBase {
   virtual int attach_nccl(const void *id) = 0;
   virtual int get_kernel_timer(double *ms, long *k1, long *all) = 0;
   virtual int reset_kernel_timer(int enable) = 0;
+  virtual int get_list_counts(long *c) = 0;
   virtual void *stream_ptr() = 0;
 };
 
@@ -1186,6 +1187,16 @@ struct Sim : SimBase {
     events_on = enable != 0;
     return 0;
   }
+  int get_list_counts(long *c) override {
+    if (!ready) return fail(LBMDEM_ESTATE, "no grains loaded");
+    int h[3] = {0, 0, 0};
+    CK(cudaMemcpyAsync(&h[0], llist.count, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(&h[1], blist.count, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(&h[2], defer.count, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    c[0] = h[0]; c[1] = h[1]; c[2] = h[2]; c[3] = 0;
+    return 0;
+  }
   void *stream_ptr() override { return (void *)stream; }
 };
 
@@ -1295,6 +1306,11 @@ API int lbmdem_get_kernel_timer(lbmdem_ctx *ctx, double *ms, long *k1, long *all
   CTX_OR_FAIL; return ctx->sim->get_kernel_timer(ms, k1, all);
 }
 API int lbmdem_reset_kernel_timer(lbmdem_ctx *ctx, int enable) { CTX_OR_FAIL; return ctx->sim->reset_kernel_timer(enable); }
+API int lbmdem_get_list_counts(lbmdem_ctx *ctx, long counts[4]) {
+  CTX_OR_FAIL;
+  if (!counts) return LBMDEM_EINVAL;
+  return ctx->sim->get_list_counts(counts);
+}
 API int lbmdem_host_alloc(size_t bytes, void **ptr) {
   if (!ptr || !bytes) return LBMDEM_EINVAL;
   *ptr = nullptr;

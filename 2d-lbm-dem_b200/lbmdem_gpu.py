@@ -98,6 +98,7 @@ def load_library():
         "lbmdem_attach_nccl": ([vp, vp], C.c_int),
         "lbmdem_get_kernel_timer": ([vp, C.POINTER(C.c_double), C.POINTER(C.c_long), C.POINTER(C.c_long)], C.c_int),
         "lbmdem_reset_kernel_timer": ([vp, C.c_int], C.c_int),
+        "lbmdem_get_list_counts": ([vp, C.POINTER(C.c_long)], C.c_int),
         "lbmdem_stream": ([vp], vp),
     }
     for name, (args, res) in sig.items():
@@ -372,6 +373,12 @@ class Solver:
         ms, k1, al = C.c_double(), C.c_long(), C.c_long()
         self._ck(self.L.lbmdem_get_kernel_timer(self.h, C.byref(ms), C.byref(k1), C.byref(al)))
         return ms.value, k1.value, al.value
+
+    def list_counts(self) -> dict:
+        """sizes of the sparse work lists of the last LBM step (bounce-back links, boundary nodes, deferred links)"""
+        c = (C.c_long * 4)()
+        self._ck(self.L.lbmdem_get_list_counts(self.h, c))
+        return {"links": c[0], "boundary_nodes": c[1], "deferred": c[2]}
 
     def stream(self) -> int:
         return int(self.L.lbmdem_stream(self.h) or 0)

@@ -162,6 +162,11 @@ int lbmdem_attach_nccl(lbmdem_ctx *ctx, const void *id128);
 /* CUDA-event time (ms) and launch count of the fused LBM kernel accumulated since the last reset */
 int lbmdem_get_kernel_timer(lbmdem_ctx *ctx, double *k1_ms, long *k1_launches, long *all_launches);
 int lbmdem_reset_kernel_timer(lbmdem_ctx *ctx, int enable_events);
+/* sizes of the sparse work lists of the LAST LBM step: counts[0] bounce-back links (active solid node, link into a fluid
+ * neighbour; src/main.c:1163-1185), counts[1] boundary nodes with a non-fluid foreign neighbour (forces_fluid, :1313),
+ * counts[2] links evaluated through the deferred list (the order-dependent one-node-gap case of :1176-1185),
+ * counts[3] bounce-back links whose interpolation uses the short-link branch -- reserved, 0 */
+int lbmdem_get_list_counts(lbmdem_ctx *ctx, long counts[4]);
 /* the CUDA stream all work of this context is issued on (a cudaStream_t) */
 void *lbmdem_stream(lbmdem_ctx *ctx);
 

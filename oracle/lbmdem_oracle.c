@@ -172,6 +172,13 @@ API int SFX(oracle_set_grains)(oracle *o, int n, const double *r, const double *
 
 API void SFX(oracle_set_lid)(oracle *o, double uw) { o->lid = (real)uw; }
 API void SFX(oracle_set_vib)(oracle *o, int vib) { o->vib = vib; }
+/* src/main.c:117 (read by VerletWall, :1555-1561) and :98 (main() derives xG, yG from it, :1841-1842) */
+API void SFX(oracle_set_dtt)(oracle *o, double dtt) { o->dtt = (real)dtt; }
+API void SFX(oracle_set_angleG)(oracle *o, double a) {
+  o->angleG = (real)a;
+  o->xG = -o->G * sin(o->angleG);
+  o->yG = -o->G * cos(o->angleG);
+}
 
 /* src/main.c:663-711 */
 static void init_obst(oracle *o) {

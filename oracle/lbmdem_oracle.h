@@ -36,6 +36,9 @@ typedef struct oracle oracle; /* opaque; one per precision-specific entry point 
   /* non-reference extension: moving lid, the commented-out uw terms at src/main.c:1129-1130 */\
   void oracle_set_lid_##SFX(oracle *o, double uw);                                           \
   void oracle_set_vib_##SFX(oracle *o, int vib);                                             \
+  /* dormant switches of the reference: wall-removal time (:117, :1555-1561), gravity tilt (:98, :1841) */\
+  void oracle_set_dtt_##SFX(oracle *o, double dtt);                                          \
+  void oracle_set_angleG_##SFX(oracle *o, double angleG);                                    \
   /* src/main.c:1697-1765 renderScene, n times (no file output) */                           \
   void oracle_step_##SFX(oracle *o, long n);                                                 \
   /* src/main.c:1711-1717 without the density print */                                       \

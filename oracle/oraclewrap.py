@@ -76,6 +76,12 @@ class Oracle:
     def set_vib(self, vib):
         self._fn("oracle_set_vib", [C.c_void_p, C.c_int])(self.o, int(vib))
 
+    def set_dtt(self, dtt):
+        self._fn("oracle_set_dtt", [C.c_void_p, C.c_double])(self.o, float(dtt))
+
+    def set_angleG(self, a):
+        self._fn("oracle_set_angleG", [C.c_void_p, C.c_double])(self.o, float(a))
+
     def step(self, n=1):
         self._fn("oracle_step", [C.c_void_p, C.c_long])(self.o, n)
 

@@ -53,7 +53,7 @@ static void ref_free_all(void) {
 REF_API int ref_init(const char *sample_path) {
   ref_free_all();
   /* globals that main() relies on being in their load-time state */
-  nbsteps = 0; nFile = 0; start = 0; t = 0; vib = 0;
+  nbsteps = 0; nFile = 0; start = 0; t = 0; vib = 0; dtt = 0.; angleG = 0.0;
   pf = 0.; pft = 0.; pff = 0.; ic = 0;
   TSE = 0.0; TBW = 0.0; INCE = 0.0; TSLIP = 0.0; TRW = 0.0;
   nNeighWallb = nNeighWallt = nNeighWallL = nNeighWallR = 0;
@@ -134,6 +134,14 @@ REF_API void ref_get_scalars(double *d, long *l) {
 }
 REF_API void ref_set_nbsteps(long n) { nbsteps = n; }
 REF_API void ref_set_vib(int v) { vib = v; } /* src/main.c:162 */
+/* dormant switches: the time at which VerletWall() lets the confining right / top walls go
+ * (src/main.c:117, :1555-1561) and the tilt of gravity (src/main.c:98; main() derives xG, yG from it once, :1841-1842) */
+REF_API void ref_set_dtt(double v) { dtt = (real)v; }
+REF_API void ref_set_angleG(double v) {
+  angleG = (real)v;
+  xG = -G * sin(angleG);
+  yG = -G * cos(angleG);
+}
 
 /* serial sum exactly as check_density (src/main.c:1249-1258), value returned */
 REF_API double ref_total_density(void) {

@@ -61,6 +61,14 @@ class Reference:
     def set_vib(self, vib):
         self.lib.ref_set_vib(int(vib))
 
+    def set_dtt(self, dtt):
+        self.lib.ref_set_dtt.argtypes = [C.c_double]
+        self.lib.ref_set_dtt(float(dtt))
+
+    def set_angleG(self, a):
+        self.lib.ref_set_angleG.argtypes = [C.c_double]
+        self.lib.ref_set_angleG(float(a))
+
     def step(self, n=1):
         self.lib.ref_step(n)
 

@@ -1,0 +1,138 @@
+"""BASELINE.json configs[2..4] on the reference's OWN input files at the benchmarked lattice sizes, against fixtures
+the compiled reference wrote (tools/make_golden.py --baseline; -O2 -ffp-contract=off, serial):
+
+    cfg3  bin/a08d83.data            2048 x 2048, scale 1,   fp64      10 / 100 renderScene() calls
+    cfg4  bin/a08_a4b4r18_7000.data  4096 x 4096, scale 2.7, fp32      2 / 10 / 30 calls (npDEM = 2)
+    cfg5  bin/50000.data             8192 x 8192, scale 2.6, fp64      2 / 12 calls (SURVEY 8(d) cfg 5)
+
+strict_fp = 1 must give the reference's BITS (hashes over every node and every grain).  The default build (the one
+bench.py times) is compared through the stored node samples, the 64 x 64 block sums of rho and momentum (they cover
+every node) and the grain rows: node indices bit-exact, everything else within the north_star tolerance (1e-6 fp64,
+1e-4 fp32) or -- where two CPU builds of the reference itself are further apart than that on this very run (its -O2
+and -Ofast builds, recorded as `spread` in the fixture: the fp32 DEM of a packed sample is noise-amplifying) --
+within that spread."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import lbmdem_gpu as G
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+EX = np.array([0, -1, -1, -1, 0, 1, 1, 1, 0.0])
+EY = np.array([0, 1, 0, -1, -1, -1, 0, 1, 1.0])
+
+CASES = {
+    "cfg3_a08d83_2048_f64": ("a08d83.data", 2048, 2048, 1.0, "f64"),
+    "cfg4_a08_7000_4096_f32": ("a08_a4b4r18_7000.data", 4096, 4096, 2.7, "f32"),
+    "cfg5_50000_8192_f64": ("50000.data", 8192, 8192, 2.6, "f64"),
+}
+NORTH_STAR_TOL = {"f64": 1e-6, "f32": 1e-4}
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _block_sums(a, b):
+    lx, ly = a.shape
+    return a[: lx // b * b, : ly // b * b].reshape(lx // b, b, ly // b, b).sum(axis=(1, 3))
+
+
+def _open(name, **over):
+    fixture, lx, ly, scale, prec = CASES[name]
+    gold = np.load(os.path.join(GOLD, name + ".npz"))
+    path = os.path.join(GOLD, fixture)
+    assert hashlib.sha256(open(path, "rb").read()).hexdigest() == str(gold["fixture_sha256"])
+    s = G.Solver(lx, ly, scale, prec, **over)
+    n = s.init(path)
+    sc = s.scalars()
+    for k in sc:
+        assert sc[k] == gold[f"scalar_{k}"], (name, k, sc[k], gold[f"scalar_{k}"])
+    assert _sha(s.grains()) == str(gold["init_grains_sha256"])
+    assert _sha(s.obst()) == str(gold["init_obst_sha256"])
+    return s, gold, n, prec
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_baseline_config_strict_build_gives_the_reference_bits(name):
+    s, gold, n, prec = _open(name, strict_fp=1)
+    gs = int(gold["grain_stride"])
+    done = 0
+    for m in (int(v) for v in gold["marks"]):
+        s.step(m - done)
+        done = m
+        tag = f"s{m}"
+        g, fh = s.grains()[:, :9], s.fhf()
+        assert np.array_equal(g[::gs], gold[f"{tag}_grains"]), (name, tag)
+        assert _sha(g) == str(gold[f"{tag}_grains_sha256"]), (name, tag)
+        assert _sha(fh) == str(gold[f"{tag}_fhf_sha256"]), (name, tag)
+        obst = s.obst()
+        assert _sha(obst) == str(gold[f"{tag}_obst_sha256"]), (name, tag)
+        assert int(((obst >= 0) & (obst < n)).sum()) == int(gold[f"{tag}_solid_nodes"])
+        del obst
+        assert _sha(s.act()) == str(gold[f"{tag}_act_sha256"]), (name, tag)
+        f = s.f()
+        st = int(gold["sample_stride"])
+        assert np.array_equal(f[5::st, 7::st], gold[f"{tag}_f_sample"]), (name, tag)
+        assert _sha(f) == str(gold[f"{tag}_f_sha256"]), (name, tag)
+        # every addend identical (hash above); the device reduces pairwise in fp64, numpy pairwise too
+        assert abs(s.total_density() - float(gold[f"{tag}_density_f64"])) < 1e-9 * f.shape[0] * f.shape[1]
+        del f
+    cum, half = s.verlet()
+    assert len(half) == int(gold["verlet_pairs"])
+    assert _sha(np.concatenate([cum, half])) == str(gold["verlet_sha256"])
+    wf = s.verlet_full()[2]
+    for bit, nm in enumerate("BTLR"):
+        assert np.array_equal(np.nonzero(wf & (1 << bit))[0].astype(np.int32), gold[f"wall_{nm}"]), nm
+
+
+def _rel(a, b, floor=1e-300):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), floor))
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_baseline_config_default_build_within_tolerance(name, record_property):
+    """the build bench.py times (strict_fp = 0)"""
+    s, gold, n, prec = _open(name)
+    tol = NORTH_STAR_TOL[prec]
+    gs, st, blk = int(gold["grain_stride"]), int(gold["sample_stride"]), int(gold["block"])
+    done, worst = 0, {}
+    for m in (int(v) for v in gold["marks"]):
+        s.step(m - done)
+        done = m
+        tag = f"s{m}"
+        # the bound: the north_star tolerance, or the distance between two CPU builds of the reference itself at this
+        # mark (columns: x v fhf rho jx jy obst-mismatches) where that is larger.  Horizon: SURVEY 4.3
+        sp = gold[f"{tag}_spread"] if f"{tag}_spread" in gold else np.zeros(7)
+        bound = lambda k: max(tol, float(sp[k]))
+        assert _sha(s.obst()) == str(gold[f"{tag}_obst_sha256"]), (name, tag, "node indices are bit-exact in every build")
+        g, fh = s.grains()[::gs, :9], s.fhf()[::gs]
+        go, fo = gold[f"{tag}_grains"], gold[f"{tag}_fhf"]
+        err = {"x": _rel(g[:, 0:3], go[:, 0:3]), "v": _rel(g[:, 3:6], go[:, 3:6])}
+        # fhf: relative to the largest force of the sample, floored at 1e-6 of a grain's weight (the fluid starts at
+        # rest: the first steps' forces are rounding residue of sums of O(1) populations)
+        weight = 9.81 * float(s.grains()[:, 10].max())
+        err["fhf"] = float(np.abs(fh[:, :2] - fo[:, :2]).max() / max(np.abs(fo[:, :2]).max(), 1e-6 * weight))
+        f = s.f()
+        rho, jx, jy = f.sum(-1), f @ EX, f @ EY
+        fs = gold[f"{tag}_f_sample"]
+        err["rho"] = max(_rel(rho[5::st, 7::st], fs.sum(-1)), _rel(_block_sums(rho, blk), gold[f"{tag}_rho_blocks"]))
+        # momentum: relative to the largest nodal momentum of the sample (floor 1e-3 lattice units, as the spread)
+        jref = max(np.abs(fs @ EX).max(), np.abs(fs @ EY).max(), 1e-3)
+        err["j"] = float(max(np.abs(jx[5::st, 7::st] - fs @ EX).max(), np.abs(jy[5::st, 7::st] - fs @ EY).max()) / jref)
+        err["j_blocks"] = float(max(np.abs(_block_sums(jx, blk) - gold[f"{tag}_jx_blocks"]).max(),
+                                    np.abs(_block_sums(jy, blk) - gold[f"{tag}_jy_blocks"]).max()) / (jref * blk * blk))
+        del f, rho, jx, jy
+        worst[tag] = err
+        print(name, tag, {k: f"{v:.2e}" for k, v in err.items()}, "reference -O2 vs -Ofast:", [f"{v:.1e}" for v in sp])
+        assert err["x"] < bound(0), (name, tag, err)
+        assert err["v"] < bound(1), (name, tag, err)
+        assert err["fhf"] < max(bound(2), 10 * tol), (name, tag, err)
+        assert err["rho"] < bound(3), (name, tag, err)
+        assert err["j"] < max(bound(4), bound(5)), (name, tag, err)
+        assert err["j_blocks"] < max(bound(4), bound(5)), (name, tag, err)
+    record_property("errors", repr(worst))

@@ -192,3 +192,41 @@ def test_oracle_equals_reference_with_vibrating_walls(tmp_path, monkeypatch):
         assert ref.scalars() == o.scalars()
     assert ref.scalars()["Mgx"] != 0.0
     ref.set_vib(0)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_oracle_equals_reference_top_right_walls_and_tilted_gravity(prec, tmp_path, monkeypatch):
+    """The dormant switches of SURVEY 8(f)4: with dtt large the confining right / top walls stay at the lattice
+    extent (src/main.c:117, :1555-1561), so a packing mirrored into the top-right corner drives force_WallT and
+    force_WallR (:846-887, :923-951); angleG tilts gravity (:98, :1841-1842)."""
+    from util import mirrored_state
+    monkeypatch.chdir(tmp_path)
+    ref, o, n = _both(64, 48, prec, os.path.join(GOLD, f"pack_64x48_{prec}.data"))
+    try:
+        for z in (ref, o):
+            z.set_dtt(1.0)
+            z.set_angleG(0.35)
+        sc = ref.scalars()
+        assert sc["xG"] != 0.0 and ref.scalars() == o.scalars()
+        v, w, a = random_kinematics(n, 21, vmax=0.02)
+        st = ref.grains()[:, :9].copy()
+        st[:, 3:5], st[:, 5:6] = v, w
+        st = mirrored_state(st, sc["Mdx"], sc["Mhy"])
+        r = ref.grains()[:, 9]
+        assert (st[:, 0] + r > sc["Mdx"]).any() and (st[:, 1] + r > sc["Mhy"]).any()   # grains INSIDE the two walls
+        for z in (ref, o):
+            z.set_grain_state(st)
+        for chunk in range(3):
+            ref.step(37)
+            o.step(37)
+            _assert_same(ref, o, f"dtt / angleG, after {(chunk + 1) * 37} calls:")
+            assert ref.scalars() == o.scalars()
+            wl = ref.wall_lists()
+            for a_, b_ in zip(wl, o.wall_lists()):
+                assert np.array_equal(a_, b_)
+            assert len(wl[1]) > 0 and len(wl[3]) > 0, "top / right wall lists are empty"
+        # the walls did NOT jump to 10 x the lattice extent (that is what dtt = 0 does at the first VerletWall)
+        assert ref.scalars()["Mdx"] == sc["Mdx"] and ref.scalars()["Mhy"] == sc["Mhy"]
+    finally:
+        ref.set_dtt(0.0)
+        ref.set_angleG(0.0)

@@ -91,3 +91,15 @@ def load_hostcheck():
         fn.argtypes = [C.c_int, dp, C.c_int, dp, dp, dp, C.c_int, ip, ip, C.c_int, ip]
         fn.restype = C.c_int
     return lib
+
+
+def mirrored_state(st, Mdx, Mhy):
+    """The kinematic state [n][9] point-mirrored through the centre of the box (0, Mdx) x (0, Mhy): a packing that
+    leans on the bottom / left DEM walls then leans on the TOP / RIGHT ones (force_WallT / force_WallR,
+    src/main.c:846-887, :923-951), with the same relative geometry between grains."""
+    out = np.array(st, dtype=np.float64, copy=True)
+    out[:, 0] = Mdx - out[:, 0]
+    out[:, 1] = Mhy - out[:, 1]
+    out[:, 3:5] = -out[:, 3:5]
+    out[:, 6:8] = -out[:, 6:8]
+    return out

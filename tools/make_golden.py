@@ -14,6 +14,10 @@ Cases
   pack_64x48_<p>   seeded synthetic packing + perturbed populations + random grain kinematics on
                    a 64 x 48 lattice, 30 renderScene() calls, p in f64 / f32; full state stored.
   pack_256_<p>     same on 256 x 256 with ~200 grains, 100 (f64) / 30 (f32) calls; sampled state.
+  cfg3/cfg4/cfg5   (--baseline[=name]) BASELINE.json configs[2..4] on the reference's own input files
+                   (bin/a08d83.data at 2048^2 fp64; bin/a08_a4b4r18_7000.data at 4096^2 scale 2.7 fp32;
+                   bin/50000.data at 8192^2 scale 2.6 fp64, 12 calls): hashes, node samples, 64 x 64 block sums
+                   of rho and momentum, and the drift between two builds of the reference itself.
 Large arrays are stored as a SHA-256 of their bytes (bit-exact check for the oracle and the
 strict CUDA build) plus a strided sample (tolerance check for the default CUDA build).
 """
@@ -220,10 +224,112 @@ def case_default_build():
     print("default_build_50000: density", out["density"])
 
 
+# ---- BASELINE.json configs[2..4] on the reference's OWN input files, at the benchmarked lattice sizes ----
+# name -> (input fixture, lx, ly, scale tag, precision, renderScene() call counts at which state is recorded,
+#          stride of the node sample, whether the reference's own build-to-build spread is recorded too)
+BASELINE_CASES = {
+    "cfg3_a08d83_2048_f64": ("a08d83.data", 2048, 2048, "1.", "f64", (10, 100), 16, True),
+    "cfg4_a08_7000_4096_f32": ("a08_a4b4r18_7000.data", 4096, 4096, "2.7", "f32", (2, 10, 30), 32, True),
+    "cfg5_50000_8192_f64": ("50000.data", 8192, 8192, "2.6", "f64", (2, 12), 64, False),
+}
+BLOCK = 64   # rho / momentum are also stored as sums over BLOCK x BLOCK node blocks (covers every node)
+
+
+def moments(f):
+    """rho, jx, jy per node of a [lx][ly][9] array (src/main.c:1082-1090 without the collision)."""
+    ex = np.array([0, -1, -1, -1, 0, 1, 1, 1, 0.0])
+    ey = np.array([0, 1, 0, -1, -1, -1, 0, 1, 1.0])
+    return f.sum(-1), f @ ex, f @ ey
+
+
+def block_sums(a, b=BLOCK):
+    lx, ly = a.shape
+    return a[: lx // b * b, : ly // b * b].reshape(lx // b, b, ly // b, b).sum(axis=(1, 3))
+
+
+def baseline_snapshot(ref, tag, out, stride):
+    f, obst = ref.f(), ref.obst()
+    g, fh = ref.grains()[:, :9], ref.fhf()
+    out[f"{tag}_grains_sha256"], out[f"{tag}_fhf_sha256"] = np.array(sha(g)), np.array(sha(fh))
+    gs = max(1, ref.n // 7000)   # every grain up to 7000, then a regular subset
+    out["grain_stride"] = np.int64(gs)
+    out[f"{tag}_grains"], out[f"{tag}_fhf"] = g[::gs].copy(), fh[::gs].copy()
+    out[f"{tag}_density"] = np.float64(ref.total_density())   # serial sum in `real` (saturates in fp32, App. B #17)
+    out[f"{tag}_density_f64"] = np.float64(f.sum(dtype=np.float64))
+    out[f"{tag}_f_sha256"] = np.array(sha(f))
+    out[f"{tag}_obst_sha256"] = np.array(sha(obst))
+    out[f"{tag}_act_sha256"] = np.array(sha(ref.act()))
+    out[f"{tag}_solid_nodes"] = np.int64(((obst >= 0) & (obst < ref.n)).sum())
+    out[f"{tag}_f_sample"] = np.ascontiguousarray(f[5::stride, 7::stride])
+    out[f"{tag}_obst_sample"] = np.ascontiguousarray(obst[5::stride, 7::stride])
+    rho, jx, jy = moments(f)
+    out[f"{tag}_rho_blocks"], out[f"{tag}_jx_blocks"], out[f"{tag}_jy_blocks"] = (block_sums(m) for m in (rho, jx, jy))
+    return dict(g=g, fh=fh, rho=rho, jx=jx, jy=jy, obst=obst)
+
+
+def case_baseline(name):
+    """One BASELINE config on the reference's own input: the compiled reference (-O2 -ffp-contract=off, serial)
+    from rest; optionally the same run with the reference's release flags (-Ofast ...) to record how far two
+    builds of the reference itself drift apart at each mark (the honest bound for a differently-rounded build)."""
+    fixture, lx, ly, scale, prec, marks, stride, spread = BASELINE_CASES[name]
+    src = os.path.join(GOLD, fixture)
+    if not os.path.exists(src):
+        shutil.copyfile(os.path.join("/root/reference/bin", fixture), src)
+    out = {"marks": np.array(marks, dtype=np.int64), "sample_stride": np.int64(stride), "block": np.int64(BLOCK),
+           "fixture_sha256": np.array(hashlib.sha256(open(src, "rb").read()).hexdigest())}
+    cwd = os.getcwd()
+    os.chdir(tempfile.mkdtemp(prefix="golden_"))
+    try:
+        ref = Reference(lx, ly, scale, prec)
+        n = ref.init(src)
+        scalars_of(ref, out)
+        out["init_grains_sha256"] = np.array(sha(ref.grains()))
+        out["init_obst_sha256"] = np.array(sha(ref.obst()))
+        states, done = {}, 0
+        for m in marks:
+            ref.step(m - done)
+            done = m
+            states[m] = baseline_snapshot(ref, f"s{m}", out, stride)
+            print(name, "mark", m, "density", out[f"s{m}_density_f64"], flush=True)
+        cum, half = ref.verlet()
+        out["verlet_pairs"] = np.int64(len(half))
+        out["verlet_sha256"] = np.array(sha(np.concatenate([cum, half])))
+        for nm, lst in zip("BTLR", ref.wall_lists()):
+            out[f"wall_{nm}"] = lst
+        del ref
+        if spread:
+            rel = Reference(lx, ly, scale, prec, omp=False, release=True)
+            assert rel.init(src) == n
+            done = 0
+            for m in marks:
+                rel.step(m - done)
+                done = m
+                a = states[m]
+                g, fh = rel.grains()[:, :9], rel.fhf()
+                rho, jx, jy = moments(rel.f())
+                rel_err = lambda x, y: float(np.abs(x - y).max() / max(np.abs(y).max(), 1e-300))
+                out[f"s{m}_spread"] = np.array([rel_err(g[:, 0:3], a["g"][:, 0:3]), rel_err(g[:, 3:6], a["g"][:, 3:6]),
+                                                rel_err(fh, a["fh"]), rel_err(rho, a["rho"]),
+                                                float(np.abs(jx - a["jx"]).max() / max(np.abs(a["jx"]).max(), 1e-3)),
+                                                float(np.abs(jy - a["jy"]).max() / max(np.abs(a["jy"]).max(), 1e-3)),
+                                                float((rel.obst() != a["obst"]).sum())])
+                print(name, "mark", m, "release-vs-O2 spread [x v fhf rho jx jy obst]", out[f"s{m}_spread"], flush=True)
+            del rel
+    finally:
+        os.chdir(cwd)
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(name, "n =", n, "written", os.path.getsize(os.path.join(GOLD, name + ".npz")) // 1024, "KB")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     if "--default-build" in sys.argv:
         case_default_build()
+        return
+    picked = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--baseline=")]
+    if picked or "--baseline" in sys.argv:
+        for name in (picked or BASELINE_CASES):
+            case_baseline(name)
         return
     case_outputs()
     case_a08d83()
