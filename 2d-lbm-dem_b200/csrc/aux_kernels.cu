@@ -1222,6 +1222,44 @@ cudaError_t launch_density(const real *f, int ly, int x0, int xlo, int xhi, int 
   return cudaGetLastError();
 }
 
+/* Exact, order-free fingerprint of the lattice state of the owned rows: sum mod 2^64 of
+ *   bits(f[x][y][q] widened to double) * (2 k + 1),  k = (x * ly + y) * 9 + q      -> out[0]
+ *   (obst[x][y] + 2) * (2 (x * ly + y) + 1)                                        -> out[1]
+ * with GLOBAL coordinates: integer adds commute, so the fingerprints of the strips of a decomposed run add up
+ * (mod 2^64) to the one-GPU value if and only if every population and node index is the same (up to 2^-64 odds). */
+template <typename real>
+__global__ void __launch_bounds__(256) checksum_kernel(const real *f, const int *cell, int ly, int x0, int xlo, int xhi,
+                                                       int pitch, size_t plane, unsigned long long *out) {
+  unsigned long long a = 0, b = 0;
+  const size_t nodes = (size_t)(xhi - xlo) * ly;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < nodes; t += (size_t)gridDim.x * blockDim.x) {
+    const int row = (int)(t / ly), y = (int)(t - (size_t)row * ly);
+    const size_t k = (size_t)(xlo - x0 + row) * pitch + y;
+    const unsigned long long gnode = (unsigned long long)(xlo + row) * (unsigned long long)ly + (unsigned long long)y;
+    b += (unsigned long long)(long long)(cell_obst(cell[k]) + 2) * (2ull * gnode + 1ull);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+      a += (unsigned long long)__double_as_longlong((double)f[q * plane + k]) * (2ull * (gnode * NQ + q) + 1ull);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, d);
+    b += __shfl_xor_sync(0xffffffffu, b, d);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&out[0], a);
+    atomicAdd(&out[1], b);
+  }
+}
+template <typename real>
+cudaError_t launch_checksum(const real *f, const int *cell, int ly, int x0, int xlo, int xhi, int pitch, size_t plane,
+                            unsigned long long *out, int blocks, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(out, 0, 2 * sizeof(unsigned long long), s);
+  if (e != cudaSuccess) return e;
+  checksum_kernel<real><<<blocks, 256, 0, s>>>(f, cell, ly, x0, xlo, xhi, pitch, plane, out);
+  return cudaGetLastError();
+}
+
 /* ------------------------------------------------------------------------------------------
  * K6: write_vtk's five point fields (src/main.c:284-323) for the owned rows, [y][x] order
  * ---------------------------------------------------------------------------------------- */
@@ -1401,6 +1439,8 @@ cudaError_t launch_fill_rest(real *f, size_t plane, const Lattice<real> &Lw, cud
                                               const VerletBuffers &, cudaStream_t);                                      \
   template cudaError_t launch_density<real>(const real *, int, int, int, int, int, size_t, double *, int, double *,       \
                                             cudaStream_t);                                                                \
+  template cudaError_t launch_checksum<real>(const real *, const int *, int, int, int, int, int, size_t,                  \
+                                             unsigned long long *, int, cudaStream_t);                                    \
   template cudaError_t launch_fields<real>(const real *, const int *, const GrainArrays<real> &, const real *, int, int,  \
                                            int, int, int, int, size_t, real, float *, float *, float *, float *, float *, \
                                            cudaStream_t);                                                                 \

@@ -240,6 +240,10 @@ cudaError_t launch_dem_batch(const dem::Params<real> &P, int n, int nsub, const 
 template <typename real>
 cudaError_t launch_density(const real *f, int ly, int x0, int xlo, int xhi, int pitch, size_t plane, double *partials,
                            int npartials, double *out, cudaStream_t s);
+/* exact order-free fingerprint of f[x][y][q] and obst[x][y] over the owned rows (aux_kernels.cu, checksum_kernel) */
+template <typename real>
+cudaError_t launch_checksum(const real *f, const int *cell, int ly, int x0, int xlo, int xhi, int pitch, size_t plane,
+                            unsigned long long *out /* [2], device */, int blocks, cudaStream_t s);
 /* VTK point data of the owned rows, [y][x - xlo] order, float32 (src/main.c:284-323) */
 template <typename real>
 cudaError_t launch_fields(const real *f, const int *cell, const GrainArrays<real> &g, const real *gp, int ngrains,

@@ -132,6 +132,7 @@ struct SimBase {
   virtual int get_kernel_timer(double *ms, long *k1, long *all) = 0;
   virtual int reset_kernel_timer(int enable) = 0;
   virtual int get_list_counts(long *c) = 0;
+  virtual int state_checksum(unsigned long long *c) = 0;
   virtual void *stream_ptr() = 0;
 };
 
@@ -656,24 +657,27 @@ struct Sim : SimBase {
     if (!multi) {
       CK(launch_ring_sweep<real>(L, S, f[cur], 0, lx, stream));
       CK(launch_bounce_pass<real>(L, S, f[cur], 1, lx - 1, xlo, xhi, llist, defer, fa, stream));
-    } else if (xhi - xlo < 8) {
+    } else if (xhi - xlo < 12) {
       if ((rc = halo_exchange(stream))) return rc;
       CK(launch_ring_sweep<real>(L, S, f[cur], std::max(xlo - 3, 0), std::min(xhi + 3, lx), stream));
       CK(launch_bounce_pass<real>(L, S, f[cur], std::max(xlo - 1, 1), std::min(xhi + 1, lx - 1), xlo, xhi, llist, defer, fa, stream));
     } else {
-      /* The ghost rows travel on their own stream while this one sweeps the rows that do not need them: a link
-       * of row x reads rows x-2 .. x+2, a ring node of row x reads rows x-1 .. x+1. */
+      /* The ghost rows travel on their own stream while this one sweeps the rows that do not need them.  NCCL reads
+       * the first / last GHOST owned rows while it sends them, so the interior passes WRITE nothing there: the ring
+       * sweep takes rows [xlo+4, xhi-4); a link of row x reads populations of rows x-2 .. x+2 -- ring nodes among them,
+       * which must be swept already -- so the bounce-back pass takes rows [xlo+6, xhi-6), and the ring nodes the edge
+       * passes sweep later (rows < xlo+4) read interior nodes of rows <= xlo+4, which that pass has not touched. */
       CK(cudaEventRecord(ev_state, stream));
       CK(cudaStreamWaitEvent(comm_stream, ev_state, 0));
       if ((rc = halo_exchange(comm_stream))) return rc;
       CK(cudaEventRecord(ev_halo, comm_stream));
-      CK(launch_ring_sweep<real>(L, S, f[cur], xlo + 1, xhi - 1, stream));
-      CK(launch_bounce_pass<real>(L, S, f[cur], xlo + 3, xhi - 3, xlo, xhi, llist, defer, fa, stream));
+      CK(launch_ring_sweep<real>(L, S, f[cur], xlo + GHOST, xhi - GHOST, stream));
+      CK(launch_bounce_pass<real>(L, S, f[cur], xlo + GHOST + 2, xhi - GHOST - 2, xlo, xhi, llist, defer, fa, stream));
       CK(cudaStreamWaitEvent(stream, ev_halo, 0));
-      CK(launch_ring_sweep<real>(L, S, f[cur], std::max(xlo - 3, 0), xlo + 1, stream));
-      CK(launch_ring_sweep<real>(L, S, f[cur], xhi - 1, std::min(xhi + 3, lx), stream));
-      CK(launch_bounce_pass<real>(L, S, f[cur], std::max(xlo - 1, 1), xlo + 3, xlo, xhi, llist, defer, fa, stream));
-      CK(launch_bounce_pass<real>(L, S, f[cur], xhi - 3, std::min(xhi + 1, lx - 1), xlo, xhi, llist, defer, fa, stream));
+      CK(launch_ring_sweep<real>(L, S, f[cur], std::max(xlo - 3, 0), xlo + GHOST, stream));
+      CK(launch_ring_sweep<real>(L, S, f[cur], xhi - GHOST, std::min(xhi + 3, lx), stream));
+      CK(launch_bounce_pass<real>(L, S, f[cur], std::max(xlo - 1, 1), xlo + GHOST + 2, xlo, xhi, llist, defer, fa, stream));
+      CK(launch_bounce_pass<real>(L, S, f[cur], xhi - GHOST - 2, std::min(xhi + 1, lx - 1), xlo, xhi, llist, defer, fa, stream));
       all_launches += 4;
     }
     all_launches += 2;
@@ -1187,6 +1191,17 @@ struct Sim : SimBase {
     events_on = enable != 0;
     return 0;
   }
+  int state_checksum(unsigned long long *c) override {
+    if (!ready) return fail(LBMDEM_ESTATE, "no grains loaded");
+    const real *obs;
+    int rc = observable_f(&obs);
+    if (rc) return rc;
+    unsigned long long *d = reinterpret_cast<unsigned long long *>(dens_partials); /* scratch of the density sum */
+    CK(launch_checksum<real>(obs, cell[cur_cell], ly, x0, xlo, xhi, pitch, plane, d, DENS_BLOCKS, stream));
+    CK(cudaMemcpyAsync(c, d, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    return 0;
+  }
   int get_list_counts(long *c) override {
     if (!ready) return fail(LBMDEM_ESTATE, "no grains loaded");
     int h[3] = {0, 0, 0};
@@ -1306,6 +1321,11 @@ API int lbmdem_get_kernel_timer(lbmdem_ctx *ctx, double *ms, long *k1, long *all
   CTX_OR_FAIL; return ctx->sim->get_kernel_timer(ms, k1, all);
 }
 API int lbmdem_reset_kernel_timer(lbmdem_ctx *ctx, int enable) { CTX_OR_FAIL; return ctx->sim->reset_kernel_timer(enable); }
+API int lbmdem_state_checksum(lbmdem_ctx *ctx, unsigned long long sums[2]) {
+  CTX_OR_FAIL;
+  if (!sums) return LBMDEM_EINVAL;
+  return ctx->sim->state_checksum(sums);
+}
 API int lbmdem_get_list_counts(lbmdem_ctx *ctx, long counts[4]) {
   CTX_OR_FAIL;
   if (!counts) return LBMDEM_EINVAL;

@@ -99,6 +99,7 @@ def load_library():
         "lbmdem_get_kernel_timer": ([vp, C.POINTER(C.c_double), C.POINTER(C.c_long), C.POINTER(C.c_long)], C.c_int),
         "lbmdem_reset_kernel_timer": ([vp, C.c_int], C.c_int),
         "lbmdem_get_list_counts": ([vp, C.POINTER(C.c_long)], C.c_int),
+        "lbmdem_state_checksum": ([vp, C.POINTER(C.c_ulonglong)], C.c_int),
         "lbmdem_stream": ([vp], vp),
     }
     for name, (args, res) in sig.items():
@@ -373,6 +374,12 @@ class Solver:
         ms, k1, al = C.c_double(), C.c_long(), C.c_long()
         self._ck(self.L.lbmdem_get_kernel_timer(self.h, C.byref(ms), C.byref(k1), C.byref(al)))
         return ms.value, k1.value, al.value
+
+    def state_checksum(self):
+        """(f fingerprint, obst fingerprint) of the owned rows; strips add up mod 2^64 to the one-GPU value"""
+        c = (C.c_ulonglong * 2)()
+        self._ck(self.L.lbmdem_state_checksum(self.h, c))
+        return int(c[0]), int(c[1])
 
     def list_counts(self) -> dict:
         """sizes of the sparse work lists of the last LBM step (bounce-back links, boundary nodes, deferred links)"""

@@ -158,6 +158,12 @@ int lbmdem_nccl_unique_id(void *id128);
 /* joins the communicator (collective over all ranks of the run) */
 int lbmdem_attach_nccl(lbmdem_ctx *ctx, const void *id128);
 
+/* Exact fingerprint of the lattice state over the owned rows: sums[0] = sum mod 2^64 of the bit patterns of the
+ * reference's f[x][y][q] (as double), each multiplied by 2 k + 1 with k its GLOBAL flat index (src/main.c:56);
+ * sums[1] the same over obst[x][y] + 2 (src/main.c:83).  Integer adds commute: the fingerprints of the strips of a
+ * decomposed run add up (mod 2^64) to the one-GPU value iff every population and node index is identical. */
+int lbmdem_state_checksum(lbmdem_ctx *ctx, unsigned long long sums[2]);
+
 /* ---- instrumentation ---- */
 /* CUDA-event time (ms) and launch count of the fused LBM kernel accumulated since the last reset */
 int lbmdem_get_kernel_timer(lbmdem_ctx *ctx, double *k1_ms, long *k1_launches, long *all_launches);

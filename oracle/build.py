@@ -52,7 +52,7 @@ PREBUILT = [
     (4096, 4096, "2.7", "f64", False, True),
     (2048, 2048, "1.", "f64", True, True),    # BASELINE cfg 3 / cfg 2 timed baselines (bench.py --workload)
     (1024, 1024, "1.", "f64", True, True),
-    (1024, 8192, "2.6", "f64", True, True),   # BASELINE cfg 5, one strip
+    (8192, 8192, "2.6", "f64", True, True),   # BASELINE cfg 5 as stated (bench.py --workload cfg5 --impl reference)
 ]
 
 

@@ -252,6 +252,14 @@ REF_API double ref_time_lbm(long n_lbm_steps) {
   for (long k = 0; k < n_lbm_steps; ++k) ref_lbm_step();
   return ref_now() - t0;
 }
+/* torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: the timed baseline asks for its threads explicitly */
+REF_API void ref_set_omp_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 REF_API int ref_omp_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

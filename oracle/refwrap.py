@@ -162,5 +162,8 @@ class Reference:
     def time_lbm(self, n_lbm_steps):
         return self.lib.ref_time_lbm(n_lbm_steps)
 
+    def set_omp_threads(self, n):
+        self.lib.ref_set_omp_threads(int(n))
+
     def omp_threads(self):
         return self.lib.ref_omp_threads()

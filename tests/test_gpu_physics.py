@@ -79,7 +79,8 @@ def test_top_right_walls_default_build_dem_is_bit_exact():
     st = mirrored_state(st, sc["Mdx"], sc["Mhy"])
     for z in (o, s):
         z.set_grain_state(st)
-        z.build_verlet()
+    o.phase("init_verlet")
+    s.build_verlet()
     npd = sc["npDEM"]
     o.set_nbsteps(1)
     s.set_nbsteps(1)               # nbsteps % npDEM != 0: DEM sub-steps only, fhf stays zero

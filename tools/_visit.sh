@@ -1,14 +1,17 @@
-OUT=gpurun_out; RUN=r02B; mkdir -p $OUT
-for t in ns5 ns6 stcs; do
-  LBMDEM_LIB=$PWD/2d-lbm-dem_b200/liblbmdem_gpu_$t.so timeout 200 python bench.py --workload cfg4 --steps 300 --no-cpu-baseline > $OUT/${RUN}_$t.json 2> $OUT/${RUN}_$t.err
-done
-timeout 200 python bench.py --workload cfg4 --steps 100 --no-cpu-baseline --kernel 1 > $OUT/${RUN}_kernel1.json 2> $OUT/${RUN}_kernel1.err
+OUT=gpurun_out; RUN=r02E; mkdir -p $OUT
+nvidia-smi -L | head -3
+timeout 900 python -m pytest tests -m gpu -x -q > $OUT/${RUN}_pytest.log 2>&1; tail -4 $OUT/${RUN}_pytest.log
+timeout 600 python bench.py --steps 100 --warmup 10 > $OUT/${RUN}_bench1.json 2> $OUT/${RUN}_bench1.err; echo "bench1 rc $?"
+timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > $OUT/${RUN}_ref1.json 2> $OUT/${RUN}_ref1.err; echo "ref1 rc $?"
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 100 --warmup 10 > $OUT/${RUN}_bench2.json 2> $OUT/${RUN}_bench2.err; echo "bench2 rc $?"
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus 2 --impl reference --steps 20 --warmup 5 > $OUT/${RUN}_ref2.json 2> $OUT/${RUN}_ref2.err; echo "ref2 rc $?"
+cut -c1-1500 $OUT/${RUN}_bench1.json; tail -3 $OUT/${RUN}_bench1.err
 python - <<PY
-import json,glob
-for p in sorted(glob.glob("$OUT/${RUN}_*.json")):
+import json
+for nm in ("bench1","ref1","bench2","ref2"):
     try:
-        d=json.loads(open(p).read().strip().splitlines()[-1])
-        print(p.split("${RUN}_")[1][:-5].ljust(10), "MLUPS %.0f  ms/step %.4f  K1 ms %.4f frac %.3f  e2e %.0f" % (d["value"], d["ms_per_step"], d["roofline"]["avg_launch_ms"], d["roofline"]["frac"], d["e2e"]["value"]))
+        d=json.loads(open("$OUT/${RUN}_%s.json"%nm).read().strip().splitlines()[-1])
+        print(nm, "value %.0f e2e %.0f" % (d["value"], d["e2e"]["value"]), "cores", d.get("cpu_baseline",{}).get("cores"), "check", d.get("strip_check"), "cfg5", {k:d.get("cfg5",{}).get(k) for k in ("value","ms_per_step","strip_check","failed")}, d["config"]["lattice"], d["data"])
     except Exception as e:
-        print(p, "unreadable", e)
+        print(nm, "unreadable", e)
 PY

@@ -230,7 +230,7 @@ def case_default_build():
 BASELINE_CASES = {
     "cfg3_a08d83_2048_f64": ("a08d83.data", 2048, 2048, "1.", "f64", (10, 100), 16, True),
     "cfg4_a08_7000_4096_f32": ("a08_a4b4r18_7000.data", 4096, 4096, "2.7", "f32", (2, 10, 30), 32, True),
-    "cfg5_50000_8192_f64": ("50000.data", 8192, 8192, "2.6", "f64", (2, 12), 64, False),
+    "cfg5_50000_8192_f64": ("50000.data", 8192, 8192, "2.6", "f64", (2, 12), 64, True),
 }
 BLOCK = 64   # rho / momentum are also stored as sums over BLOCK x BLOCK node blocks (covers every node)
 
