@@ -1185,6 +1185,25 @@ cudaError_t launch_dem_batch(const dem::Params<real> &P, int n, int nsub, const 
   return cudaGetLastError();
 }
 
+/* In-process strip groups (sim.cu, LocalGroup): the force sums of the ranks are added by ONE kernel per rank that reads
+ * every peer's partial sums from that peer's device memory (same device, or NVLink peer access) -- no collective
+ * library.  Integer sums are exact in any order; the fp64 sums of the strict build are added in rank order. */
+template <typename T>
+__global__ void peer_sum_kernel(PeerPtrs pp, int len, T *out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= len) return;
+  T s = 0;
+  for (int k = 0; k < pp.count; ++k) s += static_cast<const T *>(pp.p[k])[i];
+  out[i] = s;
+}
+template <typename T>
+cudaError_t launch_peer_sum(const PeerPtrs &pp, int len, T *out, cudaStream_t s) {
+  peer_sum_kernel<T><<<(len + 255) / 256, 256, 0, s>>>(pp, len, out);
+  return cudaGetLastError();
+}
+template cudaError_t launch_peer_sum<long long>(const PeerPtrs &, int, long long *, cudaStream_t);
+template cudaError_t launch_peer_sum<double>(const PeerPtrs &, int, double *, cudaStream_t);
+
 /* ------------------------------------------------------------------------------------------
  * K5: check_density / final_density (src/main.c:1249-1273), fixed-shape two-stage sum in fp64
  * ---------------------------------------------------------------------------------------- */

@@ -207,6 +207,15 @@ template <typename real>
 cudaError_t launch_force_scale(const double *partial, int ngrains, double k12, double k3, real *fhf1, real *fhf2,
                                real *fhf3, cudaStream_t s);
 
+/* partial force sums of the ranks of an in-process strip group (device pointers, peer-accessible) */
+constexpr int MAX_LOCAL_RANKS = 16;
+struct PeerPtrs {
+  const void *p[MAX_LOCAL_RANKS];
+  int count;
+};
+template <typename T>
+cudaError_t launch_peer_sum(const PeerPtrs &pp, int len, T *out, cudaStream_t s);
+
 struct VerletBuffers {
   int nbuckets;        /* power of two */
   int *bucket_count;   /* [nbuckets + 1] -> exclusive offsets after the scan */

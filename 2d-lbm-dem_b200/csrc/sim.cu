@@ -29,6 +29,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -88,6 +93,67 @@ struct NcclApi {
 };
 static NcclApi g_nccl;
 
+/* ---- in-process strip group: the ranks of a decomposed run as contexts of ONE process (one per GPU, or several on
+ * one GPU -- SURVEY 4.5's "fake multi-GPU"), each driven by its own host thread.  No collective library: a rank PULLS
+ * its ghost rows from the neighbour's device memory (cudaMemcpy2DAsync, peer copy across devices) and adds the force
+ * sums with one kernel that reads every peer's partial sums.  The host threads meet at a barrier wherever one rank's
+ * stream has to wait for an event another rank records in the same step (an event must be recorded before a
+ * cudaStreamWaitEvent on it means anything). ---- */
+struct LocalGroup {
+  struct Slot {
+    int device = 0;
+    const void *f_cur = nullptr;    /* population buffer that holds this step's state */
+    size_t plane = 0;
+    int pitch = 0, x0 = 0, xlo = 0, xhi = 0;
+    const void *partial = nullptr;  /* this step's partial force sums (long long, or double in the strict build) */
+    cudaEvent_t ev_k1 = nullptr, ev_pulled = nullptr, ev_partial = nullptr;
+    bool attached = false;
+  };
+  int P;
+  std::vector<Slot> slot;
+  std::mutex m;
+  std::condition_variable cv;
+  int arrived = 0;
+  long gen = 0;
+  bool aborted = false;
+  explicit LocalGroup(int p) : P(p), slot((size_t)p) {}
+  /* false when a member failed meanwhile: the caller gives up instead of waiting for a peer that will not come */
+  bool barrier() {
+    std::unique_lock<std::mutex> lk(m);
+    if (aborted) return false;
+    const long my = gen;
+    if (++arrived == P) {
+      arrived = 0;
+      ++gen;
+      cv.notify_all();
+      return true;
+    }
+    /* a peer that never arrives (its driver thread died, or the ranks were stepped unequally) must not hang the run */
+    if (!cv.wait_for(lk, std::chrono::seconds(300), [&] { return gen != my || aborted; })) {
+      aborted = true;
+      cv.notify_all();
+    }
+    return !aborted;
+  }
+  void abort() {
+    std::lock_guard<std::mutex> lk(m);
+    aborted = true;
+    cv.notify_all();
+  }
+};
+
+/* makes the context's device current for the duration of an API call, whatever thread calls */
+struct DeviceGuard {
+  int prev = -1, want;
+  explicit DeviceGuard(int d) : want(d) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != want) cudaSetDevice(want);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0 && prev != want) cudaSetDevice(prev);
+  }
+};
+
 typedef CUresult (*EncodeTiled_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -129,6 +195,7 @@ struct SimBase {
   virtual int get_fields(const double *gp, float *a, float *b, float *c, float *d, float *e) = 0;
   virtual int step_host(const void *state_in, long n, void *state_out, void *fhf_out, double *dens, bool rows_f32) = 0;
   virtual int attach_nccl(const void *id) = 0;
+  virtual int attach_local(LocalGroup *g) = 0;
   virtual int get_kernel_timer(double *ms, long *k1, long *all) = 0;
   virtual int reset_kernel_timer(int enable) = 0;
   virtual int get_list_counts(long *c) = 0;
@@ -175,8 +242,14 @@ struct Sim : SimBase {
   real *R2[2] = {nullptr, nullptr};
   GrainBox *boxes[2] = {nullptr, nullptr};
   EncodeTiled_t encode = nullptr;
-  long long *facc = nullptr;
-  double *fpartial = nullptr;
+  long long *facc = nullptr;      /* this step's fixed-point force sums: facc_buf[fslot] */
+  double *fpartial = nullptr;     /* strict build: this step's fp64 partial sums: fpartial_buf[fslot] */
+  long long *facc_buf[2] = {nullptr, nullptr};
+  double *fpartial_buf[2] = {nullptr, nullptr};
+  void *fsum = nullptr;           /* in-process group: the sums over all ranks (3 n long long / double) */
+  int fslot = 0;                  /* toggles every LBM step of a group run: peers may still read the previous step's sums */
+  LocalGroup *group = nullptr;
+  bool peers_ready = false;
   VerletBuffers vb{};
   double *dens_partials = nullptr, *dens_out = nullptr;
   double *stage = nullptr; /* device staging for layout conversion */
@@ -198,7 +271,8 @@ struct Sim : SimBase {
     for (int k = 0; k < 2; ++k) { cudaFree(f[k]); cudaFree(cell[k]); }
     for (real *p : grain_bufs) cudaFree(p);
     for (int k = 0; k < 2; ++k) { cudaFree(rec[k]); cudaFree(R2[k]); cudaFree(boxes[k]); }
-    cudaFree(facc); cudaFree(fpartial);
+    for (int k = 0; k < 2; ++k) { cudaFree(facc_buf[k]); cudaFree(fpartial_buf[k]); }
+    cudaFree(fsum);
     cudaFree(vb.bucket_count); cudaFree(vb.bucket_cursor); cudaFree(vb.sorted); cudaFree(vb.gcx); cudaFree(vb.gcy);
     cudaFree(vb.nbr_count); cudaFree(vb.nbr); cudaFree(vb.wflags);
     cudaFree(dens_partials); cudaFree(dens_out); cudaFree(stage); cudaFree(mid_dev); cudaFree(gstage);
@@ -293,14 +367,18 @@ struct Sim : SimBase {
   }
 
   /* ---- grains ---- */
+  /* frees and forgets: a later allocation failure must not leave a dangling pointer for the destructor */
+  template <typename T>
+  static void dfree(T *&p) {
+    cudaFree(p);
+    p = nullptr;
+  }
   int alloc_grains(int n_) {
     if (n_ <= 0) return fail(LBMDEM_EINVAL, "need at least one grain (the reference reads g[0], src/main.c:220)");
     for (real *p : grain_bufs) cudaFree(p);
     grain_bufs.clear();
-    cudaFree(mid_dev);
-    mid_dev = nullptr;
-    cudaFree(gstage);
-    gstage = nullptr;
+    dfree(mid_dev);
+    dfree(gstage);
     n = n_;
     /* one slab, so that the kinematic state (9 arrays) and state + fhf (12 arrays) move in one copy each:
      * x1 x2 x3 v1 v2 v3 a1 a2 a3 | fhf1 fhf2 fhf3 | r m It rLB */
@@ -311,18 +389,26 @@ struct Sim : SimBase {
     real **slots[] = {&g.x1, &g.x2, &g.x3, &g.v1, &g.v2, &g.v3, &g.a1, &g.a2, &g.a3, &g.fhf1, &g.fhf2, &g.fhf3,
                       &g.r, &g.m, &g.It, &g.rLB};
     for (size_t k = 0; k < 16; ++k) *slots[k] = slab + k * (size_t)n;
-    cudaFree(facc); cudaFree(fpartial);
     for (int k = 0; k < 2; ++k) {
-      cudaFree(rec[k]); cudaFree(R2[k]); cudaFree(boxes[k]);
+      dfree(rec[k]); dfree(R2[k]); dfree(boxes[k]);
       CK(cudaMalloc(&rec[k], sizeof(GrainRec<real>) * n));
       CK(cudaMalloc(&R2[k], sizeof(real) * n));
       CK(cudaMalloc(&boxes[k], sizeof(GrainBox) * n));
     }
-    CK(cudaMalloc(&facc, sizeof(long long) * 3 * n));
-    CK(cudaMemsetAsync(facc, 0, sizeof(long long) * 3 * n, stream));
-    CK(cudaMalloc(&fpartial, sizeof(double) * 3 * n));
-    cudaFree(vb.bucket_count); cudaFree(vb.bucket_cursor); cudaFree(vb.sorted); cudaFree(vb.gcx); cudaFree(vb.gcy);
-    cudaFree(vb.nbr_count); cudaFree(vb.nbr); cudaFree(vb.wflags);
+    dfree(fsum);
+    for (int k = 0; k < 2; ++k) {
+      dfree(facc_buf[k]); dfree(fpartial_buf[k]);
+      CK(cudaMalloc(&facc_buf[k], sizeof(long long) * 3 * n));
+      CK(cudaMemsetAsync(facc_buf[k], 0, sizeof(long long) * 3 * n, stream));
+      CK(cudaMalloc(&fpartial_buf[k], sizeof(double) * 3 * n));
+      CK(cudaMemsetAsync(fpartial_buf[k], 0, sizeof(double) * 3 * n, stream));
+    }
+    CK(cudaMalloc(&fsum, sizeof(double) * 3 * n));
+    fslot = 0;
+    facc = facc_buf[0];
+    fpartial = fpartial_buf[0];
+    dfree(vb.bucket_count); dfree(vb.bucket_cursor); dfree(vb.sorted); dfree(vb.gcx); dfree(vb.gcy);
+    dfree(vb.nbr_count); dfree(vb.nbr); dfree(vb.wflags);
     int nb = 1024;
     while (nb < 2 * n) nb <<= 1;
     vb.nbuckets = nb;
@@ -338,26 +424,26 @@ struct Sim : SimBase {
     CK(cudaMalloc(&vb.wflags, sizeof(int) * n));
     CK(cudaMemsetAsync(vb.wflags, 0, sizeof(int) * n, stream));
     CK(cudaHostGetDevicePointer(&vb.error, hflags, 0));
-    cudaFree(defer.count); cudaFree(defer.index); cudaFree(defer.value);
+    dfree(defer.count); dfree(defer.index); dfree(defer.value);
     defer.capacity = std::max(65536, 64 * n);
     CK(cudaMalloc(&defer.count, sizeof(int)));
     CK(cudaMalloc(&defer.index, sizeof(size_t) * defer.capacity));
     CK(cudaMalloc(&defer.value, sizeof(real) * defer.capacity));
     CK(cudaHostGetDevicePointer(&defer.overflow, hflags + 1, 0));
-    cudaFree(blist.entry); cudaFree(blist.count); cudaFree(overlap);
+    dfree(blist.entry); dfree(blist.count); dfree(overlap);
     blist.capacity = (int)std::min<size_t>(plane / 2 + 1024, (size_t)1 << 30);
     CK(cudaMalloc(&blist.entry, sizeof(uint2) * blist.capacity));
     CK(cudaMalloc(&blist.count, sizeof(int)));
     CK(cudaMemsetAsync(blist.count, 0, sizeof(int), stream));
     CK(cudaHostGetDevicePointer(&blist.overflow, hflags + 2, 0));
     CK(cudaMalloc(&overlap, sizeof(int) * n));
-    cudaFree(llist.entry); cudaFree(llist.count);
+    dfree(llist.entry); dfree(llist.count);
     llist.capacity = (int)std::min<size_t>(plane + 4096, (size_t)1 << 30);
     CK(cudaMalloc(&llist.entry, sizeof(uint2) * llist.capacity));
     CK(cudaMalloc(&llist.count, sizeof(int)));
     CK(cudaMemsetAsync(llist.count, 0, sizeof(int), stream));
     CK(cudaHostGetDevicePointer(&llist.overflow, hflags + 3, 0));
-    if (hstage) cudaFreeHost(hstage);
+    if (hstage) { cudaFreeHost(hstage); hstage = nullptr; }
     hstage_elems = (size_t)n * 16;
     CK(cudaMallocHost(&hstage, sizeof(double) * hstage_elems));
     return 0;
@@ -404,7 +490,7 @@ struct Sim : SimBase {
        * 2 sqrt(3) R^2 nodes per disc.  Half as much again for interpenetration, and a floor for large grains. */
       const double R = std::max(0.5, (double)rMin / (double)dx);
       const double est = 1.5 * (RTX + 2 * R + 4) * (RTY + 2 * R + 4) / (3.4641 * R * R) + 8;
-      cudaFree(tbins.count); cudaFree(tbins.list);
+      dfree(tbins.count); dfree(tbins.list);
       tbins.cap = (int)std::min(4096.0, std::max(16.0, est));
       tbins.ntx = (nxl + RTX - 1) / RTX;
       tbins.nty = (ly + RTY - 1) / RTY;
@@ -540,9 +626,63 @@ struct Sim : SimBase {
 
   /* GHOST rows of populations per side, as the fused kernel left them: the ring
    * and bounce-back sweeps that follow reach that far beyond the rows they write */
+  /* in-process group: every rank PULLS its ghost rows from the neighbours' device memory */
+  int halo_pull_local(cudaStream_t st) {
+    LocalGroup::Slot &me = group->slot[P.rank];
+    me.f_cur = f[cur];
+    CK(cudaEventRecord(me.ev_k1, stream)); /* the fused kernel of this step is behind this */
+    if (!group->barrier()) return fail(LBMDEM_ESTATE, "a peer of the in-process strip group failed");
+    if (!peers_ready) { /* every rank has reached its first step, so every rank is attached */
+      int rc = enable_peer_access();
+      if (rc) return rc;
+      peers_ready = true;
+    }
+    real *F = f[cur];
+    const size_t width = (size_t)GHOST * pitch * sizeof(real); /* consecutive rows are contiguous */
+    if (P.rank > 0) { /* the left neighbour's last owned rows -> the ghost rows below my first row */
+      const LocalGroup::Slot &nb = group->slot[P.rank - 1];
+      CK(cudaStreamWaitEvent(st, nb.ev_k1, 0));
+      const real *src = static_cast<const real *>(nb.f_cur) + (size_t)(nb.xhi - GHOST - nb.x0) * nb.pitch;
+      CK(cudaMemcpy2DAsync(F, plane * sizeof(real), src, nb.plane * sizeof(real), width, NQ, cudaMemcpyDefault, st));
+    }
+    if (P.rank < P.nranks - 1) { /* the right neighbour's first owned rows -> the ghost rows past my last row */
+      const LocalGroup::Slot &nb = group->slot[P.rank + 1];
+      CK(cudaStreamWaitEvent(st, nb.ev_k1, 0));
+      const real *src = static_cast<const real *>(nb.f_cur) + (size_t)(nb.xlo - nb.x0) * nb.pitch;
+      CK(cudaMemcpy2DAsync(F + (size_t)(xhi - x0) * pitch, plane * sizeof(real), src, nb.plane * sizeof(real), width, NQ,
+                           cudaMemcpyDefault, st));
+    }
+    CK(cudaEventRecord(me.ev_pulled, st));
+    if (!group->barrier()) return fail(LBMDEM_ESTATE, "a peer of the in-process strip group failed");
+    /* the passes that follow on `stream` rewrite my first / last owned rows in place: not before the neighbours
+     * have pulled them */
+    if (P.rank > 0) CK(cudaStreamWaitEvent(stream, group->slot[P.rank - 1].ev_pulled, 0));
+    if (P.rank < P.nranks - 1) CK(cudaStreamWaitEvent(stream, group->slot[P.rank + 1].ev_pulled, 0));
+    return 0;
+  }
+  /* in-process group: sums over the ranks of this step's partial force sums, into fsum */
+  template <typename T>
+  int sum_local(const T *mine, T **total) {
+    LocalGroup::Slot &me = group->slot[P.rank];
+    me.partial = mine;
+    CK(cudaEventRecord(me.ev_partial, stream));
+    if (!group->barrier()) return fail(LBMDEM_ESTATE, "a peer of the in-process strip group failed");
+    PeerPtrs pp;
+    pp.count = P.nranks;
+    for (int k = 0; k < P.nranks; ++k) {
+      pp.p[k] = group->slot[k].partial;
+      if (k != P.rank) CK(cudaStreamWaitEvent(stream, group->slot[k].ev_partial, 0));
+    }
+    *total = static_cast<T *>(fsum);
+    CK(launch_peer_sum<T>(pp, 3 * n, *total, stream));
+    ++all_launches;
+    return 0;
+  }
+
   int halo_exchange(cudaStream_t st) {
     if (P.nranks == 1) return 0;
-    if (!comm) return fail(LBMDEM_ESTATE, "nranks > 1 but no communicator attached (lbmdem_attach_nccl)");
+    if (group) return halo_pull_local(st);
+    if (!comm) return fail(LBMDEM_ESTATE, "nranks > 1 but no communicator attached (lbmdem_attach_nccl / lbmdem_attach_local)");
     const int dtype = sizeof(real) == 8 ? NcclApi::Float64 : NcclApi::Float32;
     int r = g_nccl.GroupStart();
     if (r) return nccl_fail(r, "ncclGroupStart");
@@ -631,6 +771,11 @@ struct Sim : SimBase {
   int lbm_step_async() {
     if (!ready) return fail(LBMDEM_ESTATE, "no grains loaded");
     int rc;
+    if (group) { /* peers may still be adding up the previous step's partial sums: this step fills the other buffer */
+      fslot ^= 1;
+      facc = facc_buf[fslot];
+      fpartial = fpartial_buf[fslot];
+    }
     cur_cell ^= 1; /* the rasteriser writes the other map; the previous one stays with the stored array */
     if ((rc = raster_into(cur_cell))) return rc;
     scratch_valid = false;
@@ -685,18 +830,24 @@ struct Sim : SimBase {
       CK(launch_bounce_end<real>(f[cur], defer, stream));
       ++all_launches;
       CK(launch_force_serial<real>(L, S, xlo, xhi, fpartial, stream));
-      if (multi) {
+      double *ftot = fpartial;
+      if (multi && group) {
+        if ((rc = sum_local<double>(fpartial, &ftot))) return rc;
+      } else if (multi) {
         const int r = g_nccl.AllReduce(fpartial, fpartial, (size_t)3 * n, NcclApi::Float64, NcclApi::Sum, comm, stream);
         if (r) return nccl_fail(r, "ncclAllReduce");
       }
-      CK(launch_force_scale<real>(fpartial, n, k12, k3, g.fhf1, g.fhf2, g.fhf3, stream));
+      CK(launch_force_scale<real>(ftot, n, k12, k3, g.fhf1, g.fhf2, g.fhf3, stream));
     } else {
       CK(launch_force_links<real>(L, S, xlo, xhi, blist, facc, f[cur], defer, stream)); /* applies the deferred links first */
-      if (multi) { /* integer sum: exact, identical on every rank, independent of the decomposition */
+      long long *ftot = facc;
+      if (multi && group) { /* integer sum: exact, identical on every rank, independent of the decomposition */
+        if ((rc = sum_local<long long>(facc, &ftot))) return rc;
+      } else if (multi) {
         const int r = g_nccl.AllReduce(facc, facc, (size_t)3 * n, NcclApi::Int64, NcclApi::Sum, comm, stream);
         if (r) return nccl_fail(r, "ncclAllReduce");
       }
-      CK(launch_force_finish<real>(facc, n, k12, k3, g.fhf1, g.fhf2, g.fhf3, stream));
+      CK(launch_force_finish<real>(ftot, n, k12, k3, g.fhf1, g.fhf2, g.fhf3, stream));
     }
     all_launches += 2;
     return 0;
@@ -808,13 +959,18 @@ struct Sim : SimBase {
     return 0;
   }
 
+  /* a rank of an in-process group that fails releases the peers waiting for it at the group's barrier */
+  int done(int rc) {
+    if (rc && group) group->abort();
+    return rc;
+  }
   int step(long nsteps) override {
     if (!ready) return fail(LBMDEM_ESTATE, "no grains loaded");
     bool built = false;
     int rc = step_async(nsteps, &built);
-    if (rc) return rc;
+    if (rc) return done(rc);
     (void)built;
-    return check_flags();
+    return done(check_flags());
   }
   int step_capture(double *mid) override {
     if (!ready) return fail(LBMDEM_ESTATE, "no grains loaded");
@@ -822,7 +978,7 @@ struct Sim : SimBase {
     if (!mid_dev) CK(cudaMalloc(&mid_dev, sizeof(real) * 6 * n));
     bool built = false;
     int rc = step_async(1, &built, true);
-    if (rc) return rc;
+    if (rc) return done(rc);
     std::vector<real> tmp((size_t)6 * n);
     CK(cudaMemcpyAsync(tmp.data(), mid_dev, sizeof(real) * 6 * n, cudaMemcpyDeviceToHost, stream));
     if ((rc = check_flags())) return rc;
@@ -832,15 +988,15 @@ struct Sim : SimBase {
   }
   int lbm_step() override {
     int rc = lbm_step_async();
-    if (rc) return rc;
-    return check_flags();
+    if (rc) return done(rc);
+    return done(check_flags());
   }
   int lbm_steps(long k) override {
     for (long i = 0; i < k; ++i) {
       int rc = lbm_step_async();
-      if (rc) return rc;
+      if (rc) return done(rc);
     }
-    return check_flags();
+    return done(check_flags());
   }
   int build_verlet() override {
     int rc = verlet_async();
@@ -1131,7 +1287,7 @@ struct Sim : SimBase {
     }
     bool built = false;
     int rc = step_async(nsteps, &built);
-    if (rc) return rc;
+    if (rc) return done(rc);
     (void)built;
     if (state_out || fhf_out) {
       CK(launch_grain_pack2<real>(g.x1, 9, g.fhf1, 3, n, gs, rows_f32, stream)); /* [n][9] state, then [n][3] fhf */
@@ -1171,6 +1327,38 @@ struct Sim : SimBase {
     CK(cudaSetDevice(P.device));
     const int r = g_nccl.CommInitRank(&comm, P.nranks, uid, P.rank);
     if (r) return nccl_fail(r, "ncclCommInitRank");
+    return 0;
+  }
+
+  int attach_local(LocalGroup *g) override {
+    if (!g || g->P != P.nranks) return fail(LBMDEM_EINVAL, "attach_local: the group was created for another number of ranks");
+    if (P.nranks > MAX_LOCAL_RANKS) return fail(LBMDEM_EINVAL, "attach_local: too many ranks");
+    if (comm) return fail(LBMDEM_ESTATE, "attach_local: an NCCL communicator is attached already");
+    LocalGroup::Slot &me = g->slot[P.rank];
+    if (me.attached) return fail(LBMDEM_EINVAL, "attach_local: this rank of the group is taken");
+    me.device = P.device;
+    me.plane = plane; me.pitch = pitch; me.x0 = x0; me.xlo = xlo; me.xhi = xhi;
+    CK(cudaEventCreateWithFlags(&me.ev_k1, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&me.ev_pulled, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&me.ev_partial, cudaEventDisableTiming));
+    me.attached = true;
+    group = g;
+    return 0;
+  }
+  /* peers on other devices: their partial sums are read by this rank's kernel, their rows copied directly */
+  int enable_peer_access() {
+    if (!group) return 0;
+    for (int k = 0; k < P.nranks; ++k) {
+      const int d = group->slot[k].device;
+      if (!group->slot[k].attached) return fail(LBMDEM_ESTATE, "in-process strip group: not every rank is attached");
+      if (d == P.device) continue;
+      int can = 0;
+      CK(cudaDeviceCanAccessPeer(&can, P.device, d));
+      if (!can) return fail(LBMDEM_ECUDA, "in-process strip group: no peer access between the devices of two ranks");
+      const cudaError_t e = cudaDeviceEnablePeerAccess(d, 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+      else CK(e);
+    }
     return 0;
   }
 
@@ -1249,9 +1437,11 @@ API int lbmdem_sizeof_params(void) { return (int)sizeof(lbmdem_params); }
 
 API int lbmdem_create(const lbmdem_params *p, lbmdem_ctx **out) {
   if (!p || !out) return LBMDEM_EINVAL;
-  SimBase *s = p->single_precision ? (SimBase *)new lbmdem::Sim<float>() : (SimBase *)new lbmdem::Sim<double>();
+  SimBase *s = p->single_precision ? (SimBase *)new (std::nothrow) lbmdem::Sim<float>()
+                                   : (SimBase *)new (std::nothrow) lbmdem::Sim<double>();
+  if (!s) return LBMDEM_ENOMEM;
   s->P = *p;
-  const int rc = s->init_device();
+  const int rc = s->init_device(); /* leaves the context's device current for the calling thread */
   if (rc) {
     lbmdem::g_create_error = s->err;
     delete s;
@@ -1262,7 +1452,10 @@ API int lbmdem_create(const lbmdem_params *p, lbmdem_ctx **out) {
 }
 API void lbmdem_destroy(lbmdem_ctx *ctx) {
   if (!ctx) return;
-  delete ctx->sim;
+  if (ctx->sim) {
+    lbmdem::DeviceGuard guard(ctx->sim->P.device);
+    delete ctx->sim;
+  }
   delete ctx;
 }
 API const char *lbmdem_last_error(const lbmdem_ctx *ctx) {
@@ -1270,41 +1463,55 @@ API const char *lbmdem_last_error(const lbmdem_ctx *ctx) {
 }
 
 #define CTX_OR_FAIL if (!ctx || !ctx->sim) return LBMDEM_EINVAL
-API int lbmdem_load_sample(lbmdem_ctx *ctx, const char *path) { CTX_OR_FAIL; return ctx->sim->load_sample(path); }
+/* every entry point: the context's device made current for the call (any host thread may drive a context), and no
+ * C++ exception crosses the C boundary */
+#define GUARDED(expr)                                                                                    \
+  do {                                                                                                   \
+    CTX_OR_FAIL;                                                                                         \
+    lbmdem::DeviceGuard guard__(ctx->sim->P.device);                                                     \
+    try {                                                                                                \
+      return (expr);                                                                                     \
+    } catch (const std::bad_alloc &) {                                                                   \
+      return ctx->sim->fail(LBMDEM_ENOMEM, "out of host memory");                                        \
+    } catch (const std::exception &e) {                                                                  \
+      return ctx->sim->fail(LBMDEM_EINVAL, std::string("unexpected: ") + e.what());                      \
+    }                                                                                                    \
+  } while (0)
+API int lbmdem_load_sample(lbmdem_ctx *ctx, const char *path) { GUARDED(ctx->sim->load_sample(path)); }
 API int lbmdem_set_grains(lbmdem_ctx *ctx, int n, const double *r, const double *x1, const double *x2) {
-  CTX_OR_FAIL; return ctx->sim->set_grains(n, r, x1, x2);
+  GUARDED(ctx->sim->set_grains(n, r, x1, x2));
 }
-API int lbmdem_step(lbmdem_ctx *ctx, long n) { CTX_OR_FAIL; return ctx->sim->step(n); }
-API int lbmdem_step_capture(lbmdem_ctx *ctx, double *mid) { CTX_OR_FAIL; return ctx->sim->step_capture(mid); }
-API int lbmdem_lbm_step(lbmdem_ctx *ctx) { CTX_OR_FAIL; return ctx->sim->lbm_step(); }
-API int lbmdem_lbm_steps(lbmdem_ctx *ctx, long n) { CTX_OR_FAIL; return ctx->sim->lbm_steps(n); }
-API int lbmdem_build_verlet(lbmdem_ctx *ctx) { CTX_OR_FAIL; return ctx->sim->build_verlet(); }
-API int lbmdem_get_scalars(lbmdem_ctx *ctx, double *d, long *l) { CTX_OR_FAIL; return ctx->sim->get_scalars(d, l); }
-API int lbmdem_set_nbsteps(lbmdem_ctx *ctx, long n) { CTX_OR_FAIL; return ctx->sim->set_nbsteps(n); }
-API int lbmdem_get_strip(lbmdem_ctx *ctx, int *a, int *b) { CTX_OR_FAIL; return ctx->sim->get_strip(a, b); }
-API int lbmdem_total_density(lbmdem_ctx *ctx, double *s) { CTX_OR_FAIL; return ctx->sim->total_density(s); }
-API int lbmdem_get_f(lbmdem_ctx *ctx, double *out) { CTX_OR_FAIL; return ctx->sim->get_f(out); }
-API int lbmdem_set_f(lbmdem_ctx *ctx, const double *in) { CTX_OR_FAIL; return ctx->sim->set_f(in); }
-API int lbmdem_get_obst(lbmdem_ctx *ctx, int *out) { CTX_OR_FAIL; return ctx->sim->get_obst(out); }
-API int lbmdem_set_obst(lbmdem_ctx *ctx, const int *in) { CTX_OR_FAIL; return ctx->sim->set_obst(in); }
-API int lbmdem_get_act(lbmdem_ctx *ctx, int *out) { CTX_OR_FAIL; return ctx->sim->get_act(out); }
-API int lbmdem_get_grains(lbmdem_ctx *ctx, double *out) { CTX_OR_FAIL; return ctx->sim->get_grains(out); }
-API int lbmdem_set_grain_state(lbmdem_ctx *ctx, const double *in) { CTX_OR_FAIL; return ctx->sim->set_grain_state(in); }
-API int lbmdem_get_fhf(lbmdem_ctx *ctx, double *out) { CTX_OR_FAIL; return ctx->sim->get_fhf(out); }
-API int lbmdem_set_fhf(lbmdem_ctx *ctx, const double *in) { CTX_OR_FAIL; return ctx->sim->set_fhf(in); }
+API int lbmdem_step(lbmdem_ctx *ctx, long n) { GUARDED(ctx->sim->step(n)); }
+API int lbmdem_step_capture(lbmdem_ctx *ctx, double *mid) { GUARDED(ctx->sim->step_capture(mid)); }
+API int lbmdem_lbm_step(lbmdem_ctx *ctx) { GUARDED(ctx->sim->lbm_step()); }
+API int lbmdem_lbm_steps(lbmdem_ctx *ctx, long n) { GUARDED(ctx->sim->lbm_steps(n)); }
+API int lbmdem_build_verlet(lbmdem_ctx *ctx) { GUARDED(ctx->sim->build_verlet()); }
+API int lbmdem_get_scalars(lbmdem_ctx *ctx, double *d, long *l) { GUARDED(ctx->sim->get_scalars(d, l)); }
+API int lbmdem_set_nbsteps(lbmdem_ctx *ctx, long n) { GUARDED(ctx->sim->set_nbsteps(n)); }
+API int lbmdem_get_strip(lbmdem_ctx *ctx, int *a, int *b) { GUARDED(ctx->sim->get_strip(a, b)); }
+API int lbmdem_total_density(lbmdem_ctx *ctx, double *s) { GUARDED(ctx->sim->total_density(s)); }
+API int lbmdem_get_f(lbmdem_ctx *ctx, double *out) { GUARDED(ctx->sim->get_f(out)); }
+API int lbmdem_set_f(lbmdem_ctx *ctx, const double *in) { GUARDED(ctx->sim->set_f(in)); }
+API int lbmdem_get_obst(lbmdem_ctx *ctx, int *out) { GUARDED(ctx->sim->get_obst(out)); }
+API int lbmdem_set_obst(lbmdem_ctx *ctx, const int *in) { GUARDED(ctx->sim->set_obst(in)); }
+API int lbmdem_get_act(lbmdem_ctx *ctx, int *out) { GUARDED(ctx->sim->get_act(out)); }
+API int lbmdem_get_grains(lbmdem_ctx *ctx, double *out) { GUARDED(ctx->sim->get_grains(out)); }
+API int lbmdem_set_grain_state(lbmdem_ctx *ctx, const double *in) { GUARDED(ctx->sim->set_grain_state(in)); }
+API int lbmdem_get_fhf(lbmdem_ctx *ctx, double *out) { GUARDED(ctx->sim->get_fhf(out)); }
+API int lbmdem_set_fhf(lbmdem_ctx *ctx, const double *in) { GUARDED(ctx->sim->set_fhf(in)); }
 API int lbmdem_get_verlet(lbmdem_ctx *ctx, int *count, int *nbr, int capacity, int *wf) {
-  CTX_OR_FAIL; return ctx->sim->get_verlet(count, nbr, capacity, wf);
+  GUARDED(ctx->sim->get_verlet(count, nbr, capacity, wf));
 }
-API int lbmdem_save_state(lbmdem_ctx *ctx, const char *path) { CTX_OR_FAIL; return ctx->sim->save_state(path); }
-API int lbmdem_load_state(lbmdem_ctx *ctx, const char *path) { CTX_OR_FAIL; return ctx->sim->load_state(path); }
+API int lbmdem_save_state(lbmdem_ctx *ctx, const char *path) { GUARDED(ctx->sim->save_state(path)); }
+API int lbmdem_load_state(lbmdem_ctx *ctx, const char *path) { GUARDED(ctx->sim->load_state(path)); }
 API int lbmdem_get_fields(lbmdem_ctx *ctx, const double *gp, float *a, float *b, float *c, float *d, float *e) {
-  CTX_OR_FAIL; return ctx->sim->get_fields(gp, a, b, c, d, e);
+  GUARDED(ctx->sim->get_fields(gp, a, b, c, d, e));
 }
 API int lbmdem_step_host(lbmdem_ctx *ctx, const double *in, long n, double *out, double *fhf, double *dens) {
-  CTX_OR_FAIL; return ctx->sim->step_host(in, n, out, fhf, dens, false);
+  GUARDED(ctx->sim->step_host(in, n, out, fhf, dens, false));
 }
 API int lbmdem_step_host_f32(lbmdem_ctx *ctx, const float *in, long n, float *out, float *fhf, double *dens) {
-  CTX_OR_FAIL; return ctx->sim->step_host(in, n, out, fhf, dens, true);
+  GUARDED(ctx->sim->step_host(in, n, out, fhf, dens, true));
 }
 API int lbmdem_nccl_unique_id(void *id128) {
   std::string why;
@@ -1316,20 +1523,36 @@ API int lbmdem_nccl_unique_id(void *id128) {
   memcpy(id128, &uid, sizeof uid);
   return 0;
 }
-API int lbmdem_attach_nccl(lbmdem_ctx *ctx, const void *id128) { CTX_OR_FAIL; return ctx->sim->attach_nccl(id128); }
-API int lbmdem_get_kernel_timer(lbmdem_ctx *ctx, double *ms, long *k1, long *all) {
-  CTX_OR_FAIL; return ctx->sim->get_kernel_timer(ms, k1, all);
+API int lbmdem_attach_nccl(lbmdem_ctx *ctx, const void *id128) { GUARDED(ctx->sim->attach_nccl(id128)); }
+API int lbmdem_local_group_create(int nranks, lbmdem_local_group **out) {
+  if (!out || nranks < 1 || nranks > lbmdem::MAX_LOCAL_RANKS) return LBMDEM_EINVAL;
+  *out = reinterpret_cast<lbmdem_local_group *>(new (std::nothrow) lbmdem::LocalGroup(nranks));
+  return *out ? 0 : LBMDEM_ENOMEM;
 }
-API int lbmdem_reset_kernel_timer(lbmdem_ctx *ctx, int enable) { CTX_OR_FAIL; return ctx->sim->reset_kernel_timer(enable); }
+API void lbmdem_local_group_destroy(lbmdem_local_group *group) {
+  lbmdem::LocalGroup *g = reinterpret_cast<lbmdem::LocalGroup *>(group);
+  if (!g) return;
+  for (auto &sl : g->slot) {
+    if (!sl.attached) continue;
+    lbmdem::DeviceGuard guard(sl.device);
+    cudaEventDestroy(sl.ev_k1); cudaEventDestroy(sl.ev_pulled); cudaEventDestroy(sl.ev_partial);
+  }
+  delete g;
+}
+API int lbmdem_attach_local(lbmdem_ctx *ctx, lbmdem_local_group *group) {
+  GUARDED(ctx->sim->attach_local(reinterpret_cast<lbmdem::LocalGroup *>(group)));
+}
+API int lbmdem_get_kernel_timer(lbmdem_ctx *ctx, double *ms, long *k1, long *all) {
+  GUARDED(ctx->sim->get_kernel_timer(ms, k1, all));
+}
+API int lbmdem_reset_kernel_timer(lbmdem_ctx *ctx, int enable) { GUARDED(ctx->sim->reset_kernel_timer(enable)); }
 API int lbmdem_state_checksum(lbmdem_ctx *ctx, unsigned long long sums[2]) {
-  CTX_OR_FAIL;
   if (!sums) return LBMDEM_EINVAL;
-  return ctx->sim->state_checksum(sums);
+  GUARDED(ctx->sim->state_checksum(sums));
 }
 API int lbmdem_get_list_counts(lbmdem_ctx *ctx, long counts[4]) {
-  CTX_OR_FAIL;
   if (!counts) return LBMDEM_EINVAL;
-  return ctx->sim->get_list_counts(counts);
+  GUARDED(ctx->sim->get_list_counts(counts));
 }
 API int lbmdem_host_alloc(size_t bytes, void **ptr) {
   if (!ptr || !bytes) return LBMDEM_EINVAL;

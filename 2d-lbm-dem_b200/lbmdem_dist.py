@@ -81,3 +81,96 @@ def make_strip_solver(lx, ly, scale, prec, **over):
         uid = broadcast_bytes(uid, 128, src=0)
         s.attach_nccl(uid)
     return s
+
+
+class LocalStrips:
+    """The strips of a decomposed run inside ONE process (lbmdem_local_group_*): one context per strip, each driven by
+    its own host thread, on the given devices -- all on device 0 by default, which exercises the whole strip logic
+    (ghost rows, staged sweeps, exact integer force sums) on a one-GPU machine.  Mirrors lbmdem_gpu.Solver."""
+
+    def __init__(self, lx, ly, scale, prec, nranks, devices=None, **over):
+        import ctypes as C
+        from concurrent.futures import ThreadPoolExecutor
+
+        import lbmdem_gpu as G
+        self.G, self.nranks = G, nranks
+        devices = list(devices) if devices is not None else [0] * nranks
+        assert len(devices) == nranks
+        L = G.load_library()
+        grp = C.c_void_p()
+        rc = L.lbmdem_local_group_create(nranks, C.byref(grp))
+        if rc:
+            raise G.LbmdemError(rc, "lbmdem_local_group_create")
+        self._L, self.group = L, grp
+        self.ranks = [G.Solver(lx, ly, scale, prec, device=devices[k], rank=k, nranks=nranks, **over) for k in range(nranks)]
+        for s in self.ranks:
+            s.attach_local(grp)
+        self.pool = ThreadPoolExecutor(max_workers=nranks)
+        self.lx, self.ly = lx, ly
+
+    def _all(self, fn):
+        """the same call on every rank, concurrently (the ranks meet at barriers inside the step)"""
+        futs = [self.pool.submit(fn, s) for s in self.ranks]
+        errs, out = [], []
+        for f in futs:
+            try:
+                out.append(f.result())
+            except Exception as e:  # noqa: BLE001 - collect every rank's outcome before raising
+                errs.append(e)
+        if errs:
+            raise errs[0]
+        return out
+
+    def init(self, path):
+        return self._all(lambda s: s.init(path))[0]
+
+    def init_arrays(self, r, x, y):
+        return self._all(lambda s: s.init_arrays(r, x, y))[0]
+
+    def step(self, n=1):
+        self._all(lambda s: s.step(n))
+
+    def lbm_step(self):
+        self._all(lambda s: s.lbm_step())
+
+    def set_f(self, f):
+        for s in self.ranks:
+            s.set_f(f[s.xlo:s.xhi])
+
+    def set_grain_state(self, st):
+        for s in self.ranks:
+            s.set_grain_state(st)
+
+    def f(self):
+        import numpy as np
+        return np.concatenate([s.f() for s in self.ranks], axis=0)
+
+    def obst(self):
+        import numpy as np
+        return np.concatenate([s.obst() for s in self.ranks], axis=0)
+
+    def state_checksum(self):
+        tot = [0, 0]
+        for s in self.ranks:
+            a, b = s.state_checksum()
+            tot[0] = (tot[0] + a) & ((1 << 64) - 1)
+            tot[1] = (tot[1] + b) & ((1 << 64) - 1)
+        return tuple(tot)
+
+    def total_density(self):
+        return sum(s.total_density() for s in self.ranks)
+
+    def close(self):
+        for s in self.ranks:
+            s.close()
+        self.ranks = []
+        self.pool.shutdown()
+        if self.group:
+            self._L.lbmdem_local_group_destroy(self.group)
+            self.group = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass

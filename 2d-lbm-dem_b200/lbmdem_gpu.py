@@ -99,6 +99,9 @@ def load_library():
         "lbmdem_get_kernel_timer": ([vp, C.POINTER(C.c_double), C.POINTER(C.c_long), C.POINTER(C.c_long)], C.c_int),
         "lbmdem_reset_kernel_timer": ([vp, C.c_int], C.c_int),
         "lbmdem_get_list_counts": ([vp, C.POINTER(C.c_long)], C.c_int),
+        "lbmdem_local_group_create": ([C.c_int, C.POINTER(vp)], C.c_int),
+        "lbmdem_attach_local": ([vp, vp], C.c_int),
+        "lbmdem_local_group_destroy": ([vp], None),
         "lbmdem_state_checksum": ([vp, C.POINTER(C.c_ulonglong)], C.c_int),
         "lbmdem_stream": ([vp], vp),
     }
@@ -189,6 +192,10 @@ class Solver:
     def load_state(self, path: str) -> int:
         self.n = self._ck(self.L.lbmdem_load_state(self.h, os.fsencode(path)))
         return self.n
+
+    def attach_local(self, group):
+        """joins an in-process strip group (lbmdem_local_group_create): peer copies instead of NCCL"""
+        self._ck(self.L.lbmdem_attach_local(self.h, group))
 
     def attach_nccl(self, uid: bytes):
         buf = C.create_string_buffer(uid, 128)

@@ -158,6 +158,18 @@ int lbmdem_nccl_unique_id(void *id128);
 /* joins the communicator (collective over all ranks of the run) */
 int lbmdem_attach_nccl(lbmdem_ctx *ctx, const void *id128);
 
+/* ---- in-process strip group (no collective library) ----
+ * The ranks of a decomposed run as contexts of ONE process -- one per GPU, or several on the same GPU (the strip logic
+ * exercised on a one-GPU machine) -- each driven by its own host thread.  A rank pulls its ghost rows from the
+ * neighbour's device memory (peer copies over NVLink across devices) and adds the hydrodynamic-force sums with one
+ * kernel that reads every peer's partial sums; the threads meet at a barrier inside the step, so every rank of the
+ * group must make the same stepping calls concurrently.  Create the contexts with rank / nranks set, attach each to
+ * the group, then drive them from nranks threads.  A rank that fails releases its peers (they return LBMDEM_ESTATE). */
+typedef struct lbmdem_local_group lbmdem_local_group;
+int lbmdem_local_group_create(int nranks, lbmdem_local_group **group);
+int lbmdem_attach_local(lbmdem_ctx *ctx, lbmdem_local_group *group);
+void lbmdem_local_group_destroy(lbmdem_local_group *group);   /* after the contexts are destroyed */
+
 /* Exact fingerprint of the lattice state over the owned rows: sums[0] = sum mod 2^64 of the bit patterns of the
  * reference's f[x][y][q] (as double), each multiplied by 2 k + 1 with k its GLOBAL flat index (src/main.c:56);
  * sums[1] the same over obst[x][y] + 2 (src/main.c:83).  Integer adds commute: the fingerprints of the strips of a
