@@ -16,317 +16,146 @@ using namespace lbm;
 /* ------------------------------------------------------------------------------------------
  * K2: obst_construction (src/main.c:991-1065) without the delta[] array; act[] is a bit of the map
  * ---------------------------------------------------------------------------------------- */
-/* also empties what the step's later kernels fill: the overlap flags, the three list counters and (default build)
- * the fixed-point force sums -- no memset nodes between the kernels of a step */
-template <typename real>
-__global__ void grain_prepare_kernel(RasterParams<real> P, int n, GrainArrays<real> g, GrainRec<real> *rec, real *R2,
-                                     GrainBox *boxes, int *overlap, int *count_a, int *count_b, int *count_c,
-                                     long long *facc) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) { *count_a = 0; *count_b = 0; *count_c = 0; }
-  if (i >= n) return;
-  GrainRec<real> r;
-  GrainBox b;
-  real R2i;
-  grain_geometry(P, g.x1[i], g.x2[i], g.r[i], g.rLB[i], &r.xc, &r.yc, &r.r2, &R2i, &b);
-  r.x1 = g.x1[i]; r.x2 = g.x2[i]; r.v1 = g.v1[i]; r.v2 = g.v2[i]; r.v3 = g.v3[i];
-  rec[i] = r;
-  R2[i] = R2i;
-  boxes[i] = b;
-  overlap[i] = 0;
-  if (facc != nullptr) { facc[i] = 0; facc[n + i] = 0; facc[2 * n + i] = 0; }
-}
-
 #ifndef LBMDEM_SWEEP_MINB
 #define LBMDEM_SWEEP_MINB 4
 #endif
-#ifndef LBMDEM_BSPLIT
-#define LBMDEM_BSPLIT 2
-#endif
-#ifndef LBMDEM_BND_MINB
-#define LBMDEM_BND_MINB 1
-#endif
-#ifndef LBMDEM_BND_STAGE
-#define LBMDEM_BND_STAGE 256
-#endif
-constexpr int GSPLIT = 4;              /* warps per grain in the rasteriser */
-constexpr int BSPLIT = LBMDEM_BSPLIT;  /* warps per grain in the boundary pass */
-
-/* GSPLIT warps per grain; the owner of a node is the highest-index grain covering it (:1028 run
- * in index order), hence atomicMax over the fluid value -1.  Grains whose reduced discs share a
- * node are flagged: only they can have foreign neighbours deep inside their disc. */
-template <typename real>
-__global__ void raster_kernel(int n, const GrainRec<real> *rec, const real *R2, const GrainBox *boxes, int *cell, int x0,
-                              int nxl, int pitch, int *overlap, int *min_owner, int genkey) {
-  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int i = wg / GSPLIT, part = wg % GSPLIT; /* GSPLIT warps share one grain's bounding box */
-  const int lane = threadIdx.x & 31;
-  if (i >= n) return;
-  const GrainBox b = boxes[i];
-  const real xc = rec[i].xc, yc = rec[i].yc, r2 = rec[i].r2, RR = R2[i];
-  const int xa = max(b.xi, x0), xb = min(b.xf, x0 + nxl - 1);
-  const int ny = b.yf - b.yi + 1;
-  if (ny <= 0 || xb < xa) return;
-  const int total = (xb - xa + 1) * ny;
-  const float inv_ny = 1.0f / (float)ny;
-  bool shared_node = false;
-  /* four nodes per lane and trip, so that the atomics are in flight together */
-  for (int base = part * 128; base < total; base += 128 * GSPLIT) {
-    int old[4];
-    size_t at[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      old[u] = -1;
-      at[u] = 0;
-      const int t = base + u * 32 + lane;
-      if (t < total) {
-        int row = (int)(((float)t + 0.5f) * inv_ny); /* t / ny for the small integers that occur; fixed up below */
-        int y = t - row * ny;
-        if (y < 0) { --row; y += ny; } else if (y >= ny) { ++row; y -= ny; }
-        const int x = xa + row;
-        y += b.yi;
-        if (disc_covers(xc, yc, r2, RR, x, y)) {
-          at[u] = (size_t)(x - x0) * pitch + y;
-          old[u] = atomicMax(&cell[at[u]], i);
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (old[u] >= 0 && old[u] != i) {
-        /* a node under more than one reduced disc: keep the lowest covering index as well */
-        shared_node = true;
-        overlap[old[u]] = 1;
-        atomicMin(&min_owner[at[u]], (genkey << MINOWNER_SHIFT) | min(old[u], i));
-      }
-  }
-  if (shared_node) overlap[i] = 1;
-}
-
-constexpr int BND_WARPS = 4;     /* warps (= grains) per CTA */
-constexpr int BND_CAND = LBMDEM_BND_STAGE;    /* per-warp staging: candidate nodes, node entries, link entries */
-constexpr int BND_NODES = LBMDEM_BND_STAGE;
-constexpr int BND_LINKS = 2 * LBMDEM_BND_STAGE + 256; /* a round of 32 nodes adds up to 256 links: flushed above 2 * STAGE */
-
-__device__ __forceinline__ void list_flush(uint2 *dst, int *counter, int capacity, int *overflow, const uint2 *buf, int cnt,
-                                           int lane) {
-  int slot0 = 0;
-  if (lane == 0) slot0 = atomicAdd(counter, cnt);
-  slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-  for (int k = lane; k < cnt; k += 32) {
-    if (slot0 + k < capacity) dst[slot0 + k] = buf[k];
-    else *(volatile int *)overflow = 1; /* mapped host memory */
-  }
-}
-
-/* act[x][y] (:1036-1052), the boundary-node list and the bounce-back link list, one warp per
- * grain, after ALL grains are rasterised.  A node of grain i is active iff one of its eight
- * neighbours was fluid when the reference's loop reached grain i (lbm_node.cuh,
- * fluid_when_grain_ran); the flag is folded into the map as CELL_ACT (readers of a neighbour mask
- * it off, so concurrent folding of other nodes is harmless).  Nodes of the boundary list -- a NON-fluid
- * neighbour under another owner -- get CELL_RIM: together the two bits tell the fused kernel which solid
- * nodes anything will ever read (lbm_node.cuh, node_is_dead).
- * Pass 1 works on geometry alone: nodes outside the disc cannot be owned, nodes deep inside the
- * disc of a grain that overlaps no other grain have all eight neighbours inside the same disc; what
- * remains (the rim: the two ends of every row's chord) goes into a per-warp list.  Pass 2 looks at
- * the map, one rim node per lane. */
-template <typename real>
-__global__ void __launch_bounds__(BND_WARPS * 32, LBMDEM_BND_MINB) boundary_kernel(int n, const GrainRec<real> *rec, const real *R2,
-                                                                   const GrainBox *boxes, int *cell, int x0, int nxl, int pitch,
-                                                                   int lx, int ly, const int *overlap, const int *min_owner,
-                                                                   int genkey, BoundaryList B, LinkList K) {
-  __shared__ int s_cand[BND_WARPS][BND_CAND];
-  __shared__ uint2 s_nodes[BND_WARPS][BND_NODES];
-  __shared__ uint2 s_links[BND_WARPS][BND_LINKS];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const unsigned lt = (1u << lane) - 1;
-  const int wg = blockIdx.x * BND_WARPS + w;
-  const int i = wg / BSPLIT, part = wg % BSPLIT; /* BSPLIT warps share one grain: a contiguous share of its rows each */
-  if (i >= n) return;
-  const GrainBox b = boxes[i];
-  const real xc = rec[i].xc, yc = rec[i].yc, r2 = rec[i].r2, RR = R2[i];
-  /* rows whose neighbours are held locally */
-  int xa = max(b.xi, x0 + 1), xb = min(b.xf, x0 + nxl - 2);
-  const int ny = b.yf - b.yi + 1;
-  if (ny <= 0 || xb < xa) return;
-  {
-    const int rows = xb - xa + 1, lo = rows * part / BSPLIT, hi = rows * (part + 1) / BSPLIT;
-    xb = xa + hi - 1;
-    xa = xa + lo;
-    if (xb < xa) return;
-  }
-  real inner2 = -1;
-  if (!overlap[i]) {
-    /* the eight neighbours of a node lie within sqrt(2) of it: a node at most rin from the centre has them all
-     * inside the disc (0.03 of slack for the rounding of the distance tests) */
-    const real rin = (real)(sqrt((double)r2) - 1.45);
-    if (rin > 0) inner2 = rin * rin;
-  }
-  const real rmin2 = r2 < RR ? r2 : RR;
-  int *cand = s_cand[w];
-  uint2 *nodes = s_nodes[w], *links = s_links[w];
-  int nnodes = 0, nlinks = 0;
-
-  for (int rb = xa; rb <= xb; rb += 32) {
-    /* ---- pass 1: geometry.  Lane = one row of the bounding box: the covered nodes of a row are a
-     * chord of the disc, the deep ones a shorter chord inside it; what may be rim is the two ends
-     * (bracketed with float square roots -- pass 2 repeats the exact tests) ---- */
-    const int row = rb + lane;
-    int ya1 = 0, c1 = 0, ya2 = 0, c2 = 0;
-    if (row <= xb) {
-      const real dxr = row - xc;
-      const real h2 = rmin2 - dxr * dxr;
-      if (h2 >= 0) {
-        const float h = sqrtf((float)h2);
-        /* covered nodes have |y - yc| <= h: floor / ceil of the float bounds bracket them (the float error is far
-         * below one node); deep nodes have |y - yc| < gi: the bracket stays 0.05 node inside that */
-        const int ylo = max((int)floorf((float)yc - h), b.yi), yhi = min((int)ceilf((float)yc + h), b.yf);
-        int dlo = 1, dhi = 0; /* rows of certainly deep nodes: empty unless ... */
-        if (inner2 > 0 && row >= 2 && row <= lx - 3) {
-          const real g2 = inner2 - dxr * dxr;
-          if (g2 > 0) {
-            const float gi = sqrtf((float)g2);
-            dlo = max((int)ceilf((float)yc - gi + 0.05f), 2);
-            dhi = min((int)floorf((float)yc + gi - 0.05f), ly - 3);
-          }
-        }
-        if (dlo <= dhi) {
-          ya1 = ylo; c1 = min(dlo - 1, yhi) - ylo + 1;
-          ya2 = max(dhi + 1, ylo); c2 = yhi - ya2 + 1;
-        } else {
-          ya1 = ylo; c1 = yhi - ylo + 1;
-        }
-        if (c1 < 0) c1 = 0;
-        if (c2 < 0) c2 = 0;
-      }
-    }
-    const int mine_c = c1 + c2;
-    int incl_c = mine_c;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl_c, d);
-      if (lane >= d) incl_c += v;
-    }
-    const int off = incl_c - mine_c, total = __shfl_sync(0xffffffffu, incl_c, 31);
-    for (int wbase = 0; wbase < total; wbase += BND_CAND) {
-      /* this window of the candidate sequence into the staging list */
-      const int j0 = max(0, wbase - off), j1 = min(mine_c, wbase + BND_CAND - off);
-      for (int j = j0; j < j1; ++j) {
-        const int y = (j < c1) ? ya1 + j : ya2 + (j - c1);
-        cand[off + j - wbase] = ((row - xa) << 16) | (y - b.yi);
-      }
-      const int ncand = min(BND_CAND, total - wbase);
-      __syncwarp();
-    /* ---- pass 2: the map, one rim node per lane ---- */
-    for (int c0 = 0; c0 < ncand; c0 += 32) {
-      bool emit = false;
-      uint2 e = make_uint2(0u, 0u);
-      unsigned bounce = 0, wl = 0, knode = 0; /* links for the sweep list */
-      if (c0 + lane < ncand) {
-        const int xy = cand[c0 + lane];
-        const int x = xa + (xy >> 16), y = b.yi + (xy & 0xffff);
-        const size_t k = (size_t)(x - x0) * pitch + y;
-        knode = (unsigned)k;
-        /* the exact tests: covered by the disc (src/main.c:1026-1029) and not deep inside it */
-        const real dist2 = (x - xc) * (x - xc) + (y - yc) * (y - yc);
-        const bool deep = dist2 < inner2 && x >= 2 && y >= 2 && x <= lx - 3 && y <= ly - 3;
-        if (!deep && dist2 <= RR && dist2 <= r2 && cell_obst(cell[k]) == i) {
-          bool act = false;
-          unsigned foreign = 0, fluid = 0;
-#pragma unroll
-          for (int q = 1; q < NQ; ++q) {
-            const int nx = x + ex_of(q), nyy = y + ey_of(q);
-            const size_t kq = (size_t)(nx - x0) * pitch + nyy;
-            const int cn = cell[kq];
-            if (cell_is_fluid(cn)) fluid |= 1u << (q - 1);
-            const int kown = cell_obst(cn);
-            if (kown != i) {
-              foreign |= 1u << (q - 1);
-              /* a neighbour owned by a LATER grain counted as fluid when grain i ran unless a grain
-               * j <= i lies under it as well: only then is the min-owner map consulted */
-              const int mo = (kown > i && kown < n) ? min_owner_decode(min_owner[kq], genkey) : -1;
-              if (fluid_when_grain_ran_exact(cn, i, n, mo)) act = true;
-            }
-          }
-          const bool rim = (foreign & ~fluid) != 0;
-          if (act || rim) atomicOr(&cell[k], (act ? CELL_ACT : 0) | (rim ? CELL_RIM : 0));
-          if (act) {
-            bounce = fluid;
-            if (!(x >= 2 && y >= 2 && x <= lx - 3 && y <= ly - 3)) wl = ~fluid & 0xffu; /* next to the ring */
-          }
-          if (rim) { /* the force kernel's share: foreign neighbours that are not fluid */
-            emit = true;
-            e = make_uint2((unsigned)k, (foreign << 24) | (act ? BL_ACT : 0u) | (unsigned)i);
-          }
-        }
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, emit);
-      if (emit) nodes[nnodes + __popc(m & lt)] = e;
-      nnodes += __popc(m);
-      /* links: one round per direction, the lanes that own such a link take consecutive slots */
-#pragma unroll
-      for (int q = 1; q < NQ; ++q) {
-        const bool isb = (bounce >> (q - 1)) & 1u, isw = (wl >> (q - 1)) & 1u;
-        const unsigned mq = __ballot_sync(0xffffffffu, isb || isw);
-        if (isb || isw)
-          links[nlinks + __popc(mq & lt)] = make_uint2(knode, (unsigned)i | ((unsigned)q << 24) | (isw ? LL_W : 0u));
-        nlinks += __popc(mq);
-      }
-      __syncwarp();
-      if (nnodes > BND_NODES - 32) {
-        list_flush(B.entry, B.count, B.capacity, B.overflow, nodes, nnodes, lane);
-        nnodes = 0;
-      }
-      if (nlinks > BND_LINKS - 256) {
-        list_flush(K.entry, K.count, K.capacity, K.overflow, links, nlinks, lane);
-        nlinks = 0;
-      }
-      __syncwarp();
-    }
-    }
-  }
-  if (nnodes) list_flush(B.entry, B.count, B.capacity, B.overflow, nodes, nnodes, lane);
-  if (nlinks) list_flush(K.entry, K.count, K.capacity, K.overflow, links, nlinks, lane);
-}
 
 /* ------------------------------------------------------------------------------------------
  * K2, tile form (the default).  obst_construction (src/main.c:991-1065) as ONE pass over the lattice in tiles of
  * RTX x RTY nodes: no clearing pass, no global atomic per node, no re-reading of the map through L2.
  * ---------------------------------------------------------------------------------------- */
-/* first kernel of the step: grain records (as grain_prepare_kernel) and the grain -> tile bins */
+/* a tile's part of the map depends on the owners of its nodes AND of the halo node all round: a node whose covering
+ * set changed stamps the tiles of its 3 x 3 neighbourhood; a tile stamped for the first time at this step joins the
+ * step's list of tiles to rebuild */
+__device__ __forceinline__ void stamp_tile(const TileBins &T, int t, int step) {
+  if (atomicMax(&T.stamp[t], step) < step) T.dirty[(step & 1) * T.ntx * T.nty + atomicAdd(&T.ndirty[step & 1], 1)] = t;
+}
+__device__ __forceinline__ void stamp_around(const TileBins &T, int x, int y, int x0, int nxl, int ly, int step) {
+  const int ra = max(x - 1, x0) - x0, rb = min(x + 1, x0 + nxl - 1) - x0, ya = max(y - 1, 0), yb = min(y + 1, ly - 1);
+  if (rb < ra || yb < ya) return;
+  const int ta = ra / RTX, tb = rb / RTX, ua = ya / RTY, ub = yb / RTY;
+  stamp_tile(T, ta * T.nty + ua, step);
+  if (ub != ua) stamp_tile(T, ta * T.nty + ub, step);
+  if (tb != ta) {
+    stamp_tile(T, tb * T.nty + ua, step);
+    if (ub != ua) stamp_tile(T, tb * T.nty + ub, step);
+  }
+}
+
+/* Which nodes of lattice row `row` does a grain's reduced disc (src/main.c:1026-1029) cover under placement b but not
+ * under placement a, or the other way round?  The covered nodes of a row are an interval around yc (the reference's
+ * expression is monotone in |y - yc|, roundings included), so the two placements can only disagree between the ends
+ * of the two intervals; while the centre moves by less than half a node and the interval ends by less than a node
+ * (the caller checks the first and treats near-tangent rows -- where an end can run -- conservatively), those are the
+ * integers next to the four ends.  They are tested under both placements with the exact expression; every node that
+ * differs stamps its tiles.  Returns true if the row needs the conservative treatment instead. */
 template <typename real>
-__global__ void grain_bin_kernel(RasterParams<real> P, int n, GrainArrays<real> g, GrainRec<real> *rec, real *R2,
-                                 GrainBox *boxes, int x0, int nxl, TileBins T, int *count_a, int *count_b, int *count_c,
-                                 long long *facc) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) { *count_a = 0; *count_b = 0; *count_c = 0; }
+__device__ __forceinline__ bool row_cover_diff(const TileBins &T, int x0, int nxl, int ly, int step, int row, real xa, real ya,
+                                               real r2a, real RRa, const GrainBox &ba, real xb, real yb, real r2b, real RRb,
+                                               const GrainBox &bb) {
+  const real rma = r2a < RRa ? r2a : RRa, rmb = r2b < RRb ? r2b : RRb;
+  const real da = row - xa, db = row - xb;
+  const real h2a = rma - da * da, h2b = rmb - db * db;
+  if (!(h2a >= 0) && !(h2b >= 0)) return false; /* neither placement covers a node of this row */
+  /* near the top / bottom of the disc the chord is short and its ends move fast: every node of both chords (a few) */
+  if (!(h2a >= 4) || !(h2b >= 4)) {
+    const float ha = h2a > 0 ? sqrtf((float)h2a) : 0.f, hb = h2b > 0 ? sqrtf((float)h2b) : 0.f;
+    const int lo = (int)floorf(fminf((float)ya - ha, (float)yb - hb)) - 1, hi = (int)ceilf(fmaxf((float)ya + ha, (float)yb + hb)) + 1;
+    if (hi - lo > 24) return true;
+    for (int y = lo; y <= hi; ++y) {
+      const bool ca = box_has(ba, row, y) && disc_covers(xa, ya, r2a, RRa, row, y);
+      const bool cb = box_has(bb, row, y) && disc_covers(xb, yb, r2b, RRb, row, y);
+      if (ca != cb) stamp_around(T, row, y, x0, nxl, ly, step);
+    }
+    return false;
+  }
+  const float ha = sqrtf((float)h2a), hb = sqrtf((float)h2b);
+  if (fabsf(ha - hb) > 0.75f) return true; /* cannot happen for |centre shift| < 1/2 and h >= 2; kept as a guard */
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    /* the two placements' ends of this side lie within 1.25 nodes of each other: one window covers both */
+    const float ea = (float)ya + (e ? ha : -ha), eb = (float)yb + (e ? hb : -hb);
+    const int lo = (int)floorf(fminf(ea, eb)) - 1, hi = (int)floorf(fmaxf(ea, eb)) + 2;
+    for (int y = lo; y <= hi; ++y) {
+      const bool ca = box_has(ba, row, y) && disc_covers(xa, ya, r2a, RRa, row, y);
+      const bool cb = box_has(bb, row, y) && disc_covers(xb, yb, r2b, RRb, row, y);
+      if (ca != cb) stamp_around(T, row, y, x0, nxl, ly, step);
+    }
+  }
+  return false;
+}
+
+/* First kernel of the step, one WARP per grain: the grain's record for this step, its tile bins, and -- the point of
+ * it -- which lattice tiles hold a node that the grain covers now but did not cover in the previous step's map, or
+ * the other way round.  A grain moves by 1e-3 .. 1e-2 node per LBM step, so nearly every tile of the map (and of the
+ * two link lists) is the previous step's: the tile kernel rebuilds the stamped tiles alone.  Stamping errs on the safe
+ * side: a grain that moved by half a node or more, or whose radius changed, stamps every tile it touches, before and
+ * after.  first_run: no previous map (set-up). */
+template <typename real>
+__global__ void __launch_bounds__(128) grain_bin_kernel(RasterParams<real> P, int n, GrainArrays<real> g, GrainRec<real> *rec,
+                                                        real *R2, GrainBox *boxes, const GrainRec<real> *rec_old,
+                                                        const real *R2_old, const GrainBox *boxes_old, int x0, int nxl,
+                                                        TileBins T, int step, int first_run, int *defer_count,
+                                                        long long *facc) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *defer_count = 0;
   if (i >= n) return;
   GrainRec<real> r;
   GrainBox b;
   real R2i;
   grain_geometry(P, g.x1[i], g.x2[i], g.r[i], g.rLB[i], &r.xc, &r.yc, &r.r2, &R2i, &b);
-  r.x1 = g.x1[i]; r.x2 = g.x2[i]; r.v1 = g.v1[i]; r.v2 = g.v2[i]; r.v3 = g.v3[i];
-  rec[i] = r;
-  R2[i] = R2i;
-  boxes[i] = b;
-  if (facc != nullptr) { facc[i] = 0; facc[n + i] = 0; facc[2 * n + i] = 0; }
-  /* every tile whose nodes or halo the bounding box touches (local rows only) */
-  const int xa = max(b.xi - 1, x0), xb = min(b.xf + 1, x0 + nxl - 1);
-  const int ya = max(b.yi - 1, 0), yb = min(b.yf + 1, P.ly - 1);
-  if (b.xf < b.xi || b.yf < b.yi || xb < xa || yb < ya) return;
-  for (int tx = (xa - x0) / RTX; tx <= (xb - x0) / RTX; ++tx)
-    for (int ty = ya / RTY; ty <= yb / RTY; ++ty) {
-      const int t = tx * T.nty + ty;
-      const int slot = atomicAdd(&T.count[t], 1);
-      if (slot < T.cap) {
-        TileEntry<real> en;
-        en.id = i; en.xi = b.xi; en.xf = b.xf; en.yi = b.yi; en.yf = b.yf;
-        en.xc = r.xc; en.yc = r.yc; en.r2 = r.r2; en.RR = R2i;
-        static_cast<TileEntry<real> *>(T.list)[(size_t)t * T.cap + slot] = en;
-      } else {
-        *(volatile int *)T.overflow = 1; /* mapped host memory */
-      }
+  bool all_tiles = first_run != 0;
+  GrainBox ob = b;
+  if (!all_tiles) {
+    const GrainRec<real> o = rec_old[i];
+    const real RRo = R2_old[i];
+    ob = boxes_old[i];
+    if (!(fabs((double)(r.xc - o.xc)) < 0.5 && fabs((double)(r.yc - o.yc)) < 0.5) || o.r2 != r.r2 || RRo != R2i) {
+      all_tiles = true;
+    } else {
+      const int ra = min(b.xi, ob.xi), rb = max(b.xf, ob.xf);
+      bool d = false;
+      for (int row = ra + lane; row <= rb; row += 32)
+        d |= row_cover_diff<real>(T, x0, nxl, P.ly, step, row, o.xc, o.yc, o.r2, RRo, ob, r.xc, r.yc, r.r2, R2i, b);
+      all_tiles = __any_sync(0xffffffffu, d);
     }
+  }
+  if (lane == 0) {
+    r.x1 = g.x1[i]; r.x2 = g.x2[i]; r.v1 = g.v1[i]; r.v2 = g.v2[i]; r.v3 = g.v3[i];
+    rec[i] = r;
+    R2[i] = R2i;
+    boxes[i] = b;
+  }
+  if (facc != nullptr && lane < 3) facc[lane * n + i] = 0;
+  if (lane != 0) return;
+  /* every tile whose nodes or halo the bounding box touches (local rows only) */
+  {
+    const int xa = max(b.xi - 1, x0), xb = min(b.xf + 1, x0 + nxl - 1);
+    const int ya = max(b.yi - 1, 0), yb = min(b.yf + 1, P.ly - 1);
+    if (!(b.xf < b.xi || b.yf < b.yi || xb < xa || yb < ya))
+      for (int tx = (xa - x0) / RTX; tx <= (xb - x0) / RTX; ++tx)
+        for (int ty = ya / RTY; ty <= yb / RTY; ++ty) {
+          const int t = tx * T.nty + ty;
+          const int slot = atomicAdd(&T.count[t], 1);
+          if (slot < T.cap) {
+            TileEntry<real> en;
+            en.id = i; en.xi = b.xi; en.xf = b.xf; en.yi = b.yi; en.yf = b.yf;
+            en.xc = r.xc; en.yc = r.yc; en.r2 = r.r2; en.RR = R2i;
+            static_cast<TileEntry<real> *>(T.list)[(size_t)t * T.cap + slot] = en;
+          } else {
+            *(volatile int *)T.overflow = 1; /* mapped host memory */
+          }
+          if (all_tiles) stamp_tile(T, t, step);
+        }
+  }
+  /* ... and the tiles the previous placement touched */
+  if (all_tiles && !first_run) {
+    const int xa = max(ob.xi - 1, x0), xb = min(ob.xf + 1, x0 + nxl - 1);
+    const int ya = max(ob.yi - 1, 0), yb = min(ob.yf + 1, P.ly - 1);
+    if (!(ob.xf < ob.xi || ob.yf < ob.yi || xb < xa || yb < ya))
+      for (int tx = (xa - x0) / RTX; tx <= (xb - x0) / RTX; ++tx)
+        for (int ty = ya / RTY; ty <= yb / RTY; ++ty) stamp_tile(T, tx * T.nty + ty, step);
+  }
 }
 
 constexpr int RTC0 = 4;                      /* shared-memory column of tile column 0 (16-byte aligned rows of int4) */
@@ -336,25 +165,57 @@ constexpr int RT_CHUNK = 64;                 /* grains staged in shared memory a
 static_assert(RTY == 64 && RTX == 32 && RT_THREADS == 256, "pass 3a: a warp takes 4 rows, a lane 4 consecutive columns");
 
 template <typename real>
-__global__ void __launch_bounds__(RT_THREADS) raster_tile_kernel(int n, int *cell, int x0, int nxl, int pitch, int lx,
-                                                                 int ly, TileBins T, BoundaryList B, LinkList K) {
+__global__ void __launch_bounds__(RT_THREADS) raster_tile_kernel(int n, int *cell, const int *cell_other, int x0, int nxl,
+                                                                 int pitch, int lx, int ly, TileBins T, BoundaryList B,
+                                                                 LinkList K, int step, int force_full) {
   /* region = tile + one halo node all round; region row r+1 / column c+RTC0 hold tile node (r, c) */
   __shared__ __align__(16) int own[RTX + 2][RTP]; /* owner: -1 fluid, n ring / outside the array */
   __shared__ __align__(16) int low[RTX + 2][RTP]; /* lowest covering index where more than one disc covers the node */
   __shared__ unsigned short cand[RTX * RTY]; /* tile nodes with a neighbour under another owner (r * RTY + c, bit 15: act) */
   __shared__ unsigned short msk[RTX * RTY];  /* per candidate: fluid neighbours | foreign non-fluid neighbours << 8 */
-  __shared__ int s_ncand;
+  __shared__ int s_ncand, s_nlinks, s_nnodes, s_last;
   __shared__ TileEntry<real> s_en[RT_CHUNK];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int tile = blockIdx.y * T.nty + blockIdx.x;
-  const int tx0 = x0 + blockIdx.y * RTX, ty0 = blockIdx.x * RTY; /* lattice coordinates of tile node (0, 0) */
+  const int ntiles = T.ntx * T.nty;
+  /* Work items.  Tiles stamped at this step (some covered node changed in them or in their halo) are REBUILT.
+   * Tiles stamped at the previous step only are COPIED from the other copy of the map: `cell` was last written two
+   * steps ago, and their list segments -- rebuilt last step -- are still right.  Every other tile is right in both
+   * copies already.  force_full: every tile is rebuilt. */
+  const int nd_cur = force_full ? ntiles : T.ndirty[step & 1];
+  const int nd_all = force_full ? ntiles : nd_cur + T.ndirty[(step - 1) & 1];
+  for (int item = blockIdx.x; item < nd_all; item += gridDim.x) {
+  int tile = item;
+  bool copy_only = false;
+  if (!force_full) {
+    if (item < nd_cur) {
+      tile = T.dirty[(step & 1) * ntiles + item];
+    } else {
+      tile = T.dirty[((step - 1) & 1) * ntiles + item - nd_cur];
+      if (T.stamp[tile] == step) continue; /* rebuilt at this step as well: it is in the first list */
+      copy_only = true;
+    }
+  }
+  const int tile_x = tile / T.nty, tile_y = tile - tile_x * T.nty;
+  const int tx0 = x0 + tile_x * RTX, ty0 = tile_y * RTY; /* lattice coordinates of tile node (0, 0) */
+  if (copy_only) {
+#pragma unroll
+    for (int it = 0; it < RTX / 16; ++it) {
+      const int r = w * (RTX / 8) + it * 2 + (lane >> 4), c0 = (lane & 15) * 4;
+      const int x = tx0 + r;
+      if (x <= x0 + nxl - 1 && ty0 + c0 + 3 < pitch) {
+        const size_t k = (size_t)(x - x0) * pitch + ty0 + c0;
+        *reinterpret_cast<int4 *>(&cell[k]) = *reinterpret_cast<const int4 *>(&cell_other[k]);
+      }
+    }
+    continue;
+  }
   /* the first list entries are fetched along with the count (entries past the count are ignored) */
   const TileEntry<real> *list = static_cast<const TileEntry<real> *>(T.list) + (size_t)tile * T.cap;
   if (tid < min(T.cap, RT_CHUNK)) s_en[tid] = list[tid];
   const int cnt = min(T.count[tile], T.cap);
 
   /* ---- 1. init_obst's frame (:674-687) for the region: ring (and beyond the array) = n, interior fluid ---- */
-  if (tid == 0) s_ncand = 0;
+  if (tid == 0) { s_ncand = 0; s_nlinks = 0; s_nnodes = 0; }
   if (tx0 - 1 > 0 && tx0 + RTX < lx - 1 && ty0 - 1 > 0 && ty0 + RTY < ly - 1) {
     int4 *o4 = reinterpret_cast<int4 *>(&own[0][0]), *l4 = reinterpret_cast<int4 *>(&low[0][0]);
     for (int idx = tid; idx < (RTX + 2) * RTP / 4; idx += RT_THREADS) {
@@ -410,7 +271,6 @@ __global__ void __launch_bounds__(RT_THREADS) raster_tile_kernel(int n, int *cel
     __syncthreads();
   }
   if (cnt == 0) __syncthreads(); /* the frame of pass 1 */
-  if (tid == 0) T.count[tile] = 0; /* emptied for the next step */
 
   /* ---- 3a. every node of the tile: the owners go to `cell` in 16-byte pieces (a lane holds four consecutive
    * columns, a warp two rows), and the few nodes whose 3 x 3 neighbourhood is not under one owner are collected
@@ -488,7 +348,7 @@ __global__ void __launch_bounds__(RT_THREADS) raster_tile_kernel(int n, int *cel
     if (act || solid_foreign) cell[(size_t)(x - x0) * pitch + y] = i | (act ? CELL_ACT : 0) | (solid_foreign ? CELL_RIM : 0);
   }
 
-  /* ---- 4. one slot range per list and WARP (no barrier: the warps finish independently) ---- */
+  /* ---- 4. one slot range per list and WARP inside the tile's own segments of the two lists ---- */
   unsigned incl = packed;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -496,15 +356,14 @@ __global__ void __launch_bounds__(RT_THREADS) raster_tile_kernel(int n, int *cel
     if (lane >= d) incl += t;
   }
   const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-  if (total == 0) return;
   int bl = 0, bb = 0;
-  if (lane == 0 && (total & 0xffffu)) bl = atomicAdd(K.count, (int)(total & 0xffffu));
-  if (lane == 1 && (total >> 16)) bb = atomicAdd(B.count, (int)(total >> 16));
+  if (lane == 0 && (total & 0xffffu)) bl = atomicAdd(&s_nlinks, (int)(total & 0xffffu));
+  if (lane == 1 && (total >> 16)) bb = atomicAdd(&s_nnodes, (int)(total >> 16));
   bl = __shfl_sync(0xffffffffu, bl, 0);
   bb = __shfl_sync(0xffffffffu, bb, 1);
-  if (packed == 0) return;
   const unsigned excl = incl - packed;
   int kl = bl + (int)(excl & 0xffffu), kb = bb + (int)(excl >> 16);
+  uint2 *Kseg = K.entry + (size_t)tile * K.cap, *Bseg = B.entry + (size_t)tile * B.cap;
 
   /* ---- 5. the entries ---- */
   for (int e = e0; e < e1; ++e) {
@@ -517,7 +376,7 @@ __global__ void __launch_bounds__(RT_THREADS) raster_tile_kernel(int n, int *cel
     const unsigned knode = (unsigned)((x - x0) * pitch + y);
     const unsigned i = (unsigned)own[r + 1][c + RTC0];
     if (solid_foreign) { /* the force kernel's share: all foreign neighbours, the kernel skips the fluid ones */
-      if (kb < B.capacity) B.entry[kb] = make_uint2(knode, ((fluid | solid_foreign) << 24) | (act ? BL_ACT : 0u) | i);
+      if (kb < B.cap) Bseg[kb] = make_uint2(knode, ((fluid | solid_foreign) << 24) | (act ? BL_ACT : 0u) | i);
       else *(volatile int *)B.overflow = 1;
       ++kb;
     }
@@ -528,19 +387,45 @@ __global__ void __launch_bounds__(RT_THREADS) raster_tile_kernel(int n, int *cel
       const int bit = __ffs(links) - 1;
       links &= links - 1;
       const bool isw = !((fluid >> bit) & 1u);
-      if (kl < K.capacity) K.entry[kl] = make_uint2(knode, i | ((unsigned)(bit + 1) << 24) | (isw ? LL_W : 0u));
+      if (kl < K.cap) Kseg[kl] = make_uint2(knode, i | ((unsigned)(bit + 1) << 24) | (isw ? LL_W : 0u));
       else *(volatile int *)K.overflow = 1;
       ++kl;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    K.tcount[tile] = min(s_nlinks, K.cap);
+    B.tcount[tile] = min(s_nnodes, B.cap);
+  }
+  __syncthreads(); /* the next tile re-uses the shared arrays */
+  } /* work items */
+  /* the last CTA to finish empties the bins of every tile and the dirty list the next step will fill */
+  if (tid == 0) {
+    __threadfence();
+    s_last = atomicAdd(T.ticket, 1) == (int)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last) {
+    for (int t = tid; t < ntiles; t += RT_THREADS) T.count[t] = 0;
+    if (tid == 0) {
+      T.ndirty[(step + 1) & 1] = 0;
+      *T.ticket = 0;
     }
   }
 }
 
 template <typename real>
 cudaError_t launch_raster_tiles(const RasterParams<real> &P, int n, const GrainArrays<real> &g, GrainRec<real> *rec, real *R2,
-                                GrainBox *boxes, int *cell, int x0, int nxl, int pitch, const TileBins &T,
-                                const BoundaryList &B, const LinkList &K, int *defer_count, long long *facc, cudaStream_t s) {
-  grain_bin_kernel<real><<<(n + 127) / 128, 128, 0, s>>>(P, n, g, rec, R2, boxes, x0, nxl, T, B.count, K.count, defer_count, facc);
-  raster_tile_kernel<real><<<dim3(T.nty, T.ntx), RT_THREADS, 0, s>>>(n, cell, x0, nxl, pitch, P.lx, P.ly, T, B, K);
+                                GrainBox *boxes, const GrainRec<real> *rec_old, const real *R2_old, const GrainBox *boxes_old,
+                                int *cell, const int *cell_other, int x0, int nxl, int pitch, const TileBins &T,
+                                const BoundaryList &B, const LinkList &K, int *defer_count, long long *facc, int step,
+                                int first_run, int force_full, cudaStream_t s) {
+  grain_bin_kernel<real><<<(n + 3) / 4, 128, 0, s>>>(P, n, g, rec, R2, boxes, rec_old, R2_old, boxes_old, x0, nxl, T, step,
+                                                     first_run, defer_count, facc);
+  const int ntiles = T.ntx * T.nty;
+  const int ctas = force_full ? ntiles : min(ntiles, T.resident_ctas);
+  raster_tile_kernel<real><<<ctas, RT_THREADS, 0, s>>>(n, cell, cell_other, x0, nxl, pitch, P.lx, P.ly, T, B, K, step,
+                                                       force_full);
   return cudaGetLastError();
 }
 
@@ -553,25 +438,6 @@ __global__ void cell_frame_kernel(int *cell, int lx, int ly, int x0, int nxl, in
   int v = -1;
   if (x <= 0 || x >= lx - 1 || y <= 0 || y >= ly - 1) v = ring_value;
   cell[(size_t)row * pitch + y] = v;
-}
-
-template <typename real>
-cudaError_t launch_raster(const RasterParams<real> &P, int n, const GrainArrays<real> &g, GrainRec<real> *rec, real *R2,
-                          GrainBox *boxes, int *cell, int x0, int nxl, int pitch, int *overlap, int *min_owner, int genkey,
-                          const BoundaryList &B, const LinkList &K, int *defer_count, long long *facc, cudaStream_t s) {
-  grain_prepare_kernel<real><<<(n + 127) / 128, 128, 0, s>>>(P, n, g, rec, R2, boxes, overlap, B.count, K.count, defer_count, facc);
-  /* clear the interior: rows with global x in [1, lx-2], columns [1, ly-2] (:997-1005) */
-  const int ra = max(1 - x0, 0), rb = min(P.lx - 2 - x0, nxl - 1);
-  cudaError_t e;
-  if (rb >= ra) {
-    e = cudaMemset2DAsync(cell + (size_t)ra * pitch + 1, sizeof(int) * pitch, 0xFF, sizeof(int) * (P.ly - 2), rb - ra + 1, s);
-    if (e != cudaSuccess) return e;
-  }
-  raster_kernel<real><<<(n * GSPLIT * 32 + 255) / 256, 256, 0, s>>>(n, rec, R2, boxes, cell, x0, nxl, pitch, overlap,
-                                                                 min_owner, genkey);
-  boundary_kernel<real><<<(n * BSPLIT + BND_WARPS - 1) / BND_WARPS, BND_WARPS * 32, 0, s>>>(n, rec, R2, boxes, cell, x0, nxl, pitch,
-                                                                                    P.lx, P.ly, overlap, min_owner, genkey, B, K);
-  return cudaGetLastError();
 }
 
 cudaError_t launch_cell_frame(int *cell, int lx, int ly, int x0, int nxl, int pitch, int ring_value, cudaStream_t s) {
@@ -645,8 +511,8 @@ cudaError_t launch_ring_sweep(const Lattice<real> &L, const Stored<real> &S, rea
  * Lanes that hold the same grain are summed first (exact: integers), so there is about one atomic per grain and
  * warp.  The link list is grouped by grain, so the lanes of a grain normally form one contiguous run: a segmented
  * shuffle reduction (five rounds); any other pattern takes the lane-by-lane loop. */
-#if defined(LBMDEM_SUMS_RUNS)
-/* Variant for the next tuning visit (not timed yet): one segmented reduction over every maximal run of adjacent
+#if !defined(LBMDEM_SUMS_MATCH)
+/* One segmented reduction over every maximal run of adjacent
  * lanes with the same grain, one atomic per run -- no lane-by-lane loop whatever the pattern.  The tile rasteriser
  * emits links tile row by tile row, so a warp usually sees A A B B A A B B ...; profiles/README.md: the lane-by-lane
  * loop below is then a third of this kernel's instructions. */
@@ -709,14 +575,18 @@ template <typename real>
 __global__ void __launch_bounds__(256, LBMDEM_SWEEP_MINB) bounce_sweep_kernel(const __grid_constant__ Lattice<real> L,
                                                            const __grid_constant__ Stored<real> S, real *A, int xa, int xb,
                                                            int xlo, int xhi, const LinkList K, const DeferList<real> D,
-                                                           long long *facc) {
-  const int items = min(*K.count, K.capacity);
+                                                           long long *facc, int tx_first, int nty) {
+  /* one CTA per lattice tile (tile rows tx_first ..): the tile's own segment of the link list */
+  const int tile = (tx_first + blockIdx.y) * nty + blockIdx.x;
+  const int items = K.tcount[tile];
+  if (items == 0) return;
+  const uint2 *seg = K.entry + (size_t)tile * K.cap;
   const int padded = (items + 31) & ~31; /* whole warps stay in the loop: grain_sums_add shuffles */
-  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < padded; u += gridDim.x * blockDim.x) {
+  for (int u = threadIdx.x; u < padded; u += blockDim.x) {
     int fi = -1;
     long long s1 = 0, s2 = 0, s3 = 0;
     if (u < items) {
-      const uint2 en = K.entry[u];
+      const uint2 en = seg[u];
       const int q = (int)((en.y >> 24) & 15u);
       const int row = (int)(en.x / (unsigned)L.pitch);
       const int x = L.x0 + row, y = (int)(en.x - (unsigned)row * (unsigned)L.pitch);
@@ -773,7 +643,10 @@ template <typename real>
 cudaError_t launch_bounce_pass(const Lattice<real> &L, const Stored<real> &S, real *A, int xa, int xb, int xlo, int xhi,
                                const LinkList &K, const DeferList<real> &D, long long *facc, cudaStream_t s) {
   if (xb <= xa || L.ngrains <= 0) return cudaSuccess;
-  bounce_sweep_kernel<real><<<148 * 16, 256, 0, s>>>(L, S, A, xa, xb, xlo, xhi, K, D, facc);
+  /* the tile rows that hold lattice rows [xa, xb) */
+  const int t0 = max(xa - L.x0, 0) / RTX, t1 = min((xb - 1 - L.x0) / RTX, K.ntx - 1);
+  if (t1 < t0) return cudaSuccess;
+  bounce_sweep_kernel<real><<<dim3(K.nty, t1 - t0 + 1), 256, 0, s>>>(L, S, A, xa, xb, xlo, xhi, K, D, facc, t0, K.nty);
   return cudaGetLastError();
 }
 template <typename real>
@@ -806,17 +679,21 @@ __global__ void __launch_bounds__(256) force_links_kernel(const __grid_constant_
   /* first the deferred bounce-back links of the sweep (defer_apply_kernel's job, one launch less).  They are links
    * into FLUID neighbours; the force links below read populations of links into NON-fluid neighbours only (A[q][s]
    * with s + e_q not fluid, A[opp q][n] with n + e_opp q = s solid): never the same location. */
+  const int cta = blockIdx.y * gridDim.x + blockIdx.x, nctas = gridDim.x * gridDim.y;
   if (A != nullptr) {
     const int nd = min(*D.count, D.capacity);
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nd; k += gridDim.x * blockDim.x) A[D.index[k]] = D.value[k];
+    for (int k = cta * blockDim.x + threadIdx.x; k < nd; k += nctas * blockDim.x) A[D.index[k]] = D.value[k];
   }
-  const long long items = 8ll * min(*B.count, B.capacity);
-  const long long padded = (items + 31) & ~31ll; /* whole warps stay in the loop: shuffles below */
-  for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < padded; u += (long long)gridDim.x * blockDim.x) {
+  /* one CTA per lattice tile: the tile's own segment of the boundary-node list, eight lanes per node */
+  const int items = 8 * B.tcount[cta];
+  if (items == 0) return;
+  const uint2 *seg = B.entry + (size_t)cta * B.cap;
+  const int padded = (items + 31) & ~31; /* whole warps stay in the loop: shuffles below */
+  for (int u = threadIdx.x; u < padded; u += blockDim.x) {
     long long s1 = 0, s2 = 0, s3 = 0;
     int i = -1;
     if (u < items) {
-      const uint2 en = B.entry[u >> 3];
+      const uint2 en = seg[u >> 3];
       const int q = 1 + (int)(u & 7);
       const int row = (int)(en.x / (unsigned)L.pitch);
       const int x = L.x0 + row, y = (int)(en.x - (unsigned)row * (unsigned)L.pitch);
@@ -850,7 +727,7 @@ __global__ void __launch_bounds__(256) force_links_kernel(const __grid_constant_
 template <typename real>
 cudaError_t launch_force_links(const Lattice<real> &L, const Stored<real> &S, int xlo, int xhi, const BoundaryList &B,
                                long long *facc, real *A, const DeferList<real> &D, cudaStream_t s) {
-  force_links_kernel<real><<<148 * 4, 256, 0, s>>>(L, S, xlo, xhi, B, facc, A, D); /* adds to what the sweep kernel left */
+  force_links_kernel<real><<<dim3(B.nty, B.ntx), 256, 0, s>>>(L, S, xlo, xhi, B, facc, A, D); /* adds to what the sweep kernel left */
   return cudaGetLastError();
 }
 
@@ -1429,12 +1306,10 @@ cudaError_t launch_fill_rest(real *f, size_t plane, const Lattice<real> &Lw, cud
 
 #define INSTANTIATE(real)                                                                                               \
   template cudaError_t launch_raster_tiles<real>(const RasterParams<real> &, int, const GrainArrays<real> &,              \
-                                                 GrainRec<real> *, real *, GrainBox *, int *, int, int, int,              \
+                                                 GrainRec<real> *, real *, GrainBox *, const GrainRec<real> *,            \
+                                                 const real *, const GrainBox *, int *, const int *, int, int, int,       \
                                                  const TileBins &, const BoundaryList &, const LinkList &, int *,         \
-                                                 long long *, cudaStream_t);                                              \
-  template cudaError_t launch_raster<real>(const RasterParams<real> &, int, const GrainArrays<real> &, GrainRec<real> *,  \
-                                           real *, GrainBox *, int *, int, int, int, int *, int *, int,                   \
-                                           const BoundaryList &, const LinkList &, int *, long long *, cudaStream_t);     \
+                                                 long long *, int, int, int, cudaStream_t);                               \
   template cudaError_t launch_act_map<real>(const Lattice<real> &, const Stored<real> &, int, int, int *, cudaStream_t);  \
   template cudaError_t launch_ring_sweep<real>(const Lattice<real> &, const Stored<real> &, real *, int, int,             \
                                                cudaStream_t);                                                             \

@@ -110,13 +110,18 @@ LBMDEM_DECLARE_K1(k1_fast)
 LBMDEM_DECLARE_K1(k1_strict)
 
 /* ---- everything below lives in the contraction-free translation unit (aux_kernels.cu) ---- */
-/* Boundary nodes of one step's obstacle map: solid nodes with at least one neighbour that is not
- * owned by the same grain and not fluid.  entry.x = local node index (row * pitch + y), entry.y = grain index
- * | BL_ACT if act[x][y] == 1 | mask << 24 where bit q-1 of mask marks link q as leaving the grain. */
+/* The two sparse work lists of a step are kept PER LATTICE TILE (RTX rows x RTY columns): tile t owns the segment
+ * entry[t * cap .. t * cap + tcount[t]).  The tile kernel rewrites a tile's segments only when the tile's part of the
+ * obstacle map changed (see grain_bin_kernel); the sweep kernels run one CTA per tile.
+ *
+ * Boundary nodes: solid nodes with at least one neighbour that is not owned by the same grain and not fluid.
+ * entry.x = local node index (row * pitch + y), entry.y = grain index | BL_ACT if act[x][y] == 1 | mask << 24 where
+ * bit q-1 of mask marks link q as leaving the grain. */
 struct BoundaryList {
   uint2 *entry;
-  int *count;          /* device counter */
-  int capacity;
+  int *tcount;         /* [ntx * nty] entries per tile */
+  int cap;             /* entries per tile segment */
+  int ntx, nty;
   int *overflow;       /* flag in mapped host memory */
 };
 constexpr unsigned BL_ACT = 1u << 23;
@@ -126,8 +131,9 @@ constexpr unsigned BL_GRAIN = BL_ACT - 1;
  * the rest value (a w-link next to the wall ring, lbm_node.cuh w_links_with_collide). */
 struct LinkList {
   uint2 *entry;
-  int *count;
-  int capacity;
+  int *tcount;
+  int cap;
+  int ntx, nty;
   int *overflow;       /* flag in mapped host memory */
 };
 constexpr unsigned LL_W = 1u << 28;
@@ -146,29 +152,31 @@ struct TileBins {
   void *list;          /* [ntx * nty][cap] TileEntry<real>, any order */
   int cap;
   int ntx, nty;        /* tiles along x (local rows) and y */
+  int *stamp;          /* [ntx * nty] rasteriser step at which some covered node of the tile (halo included) last changed */
+  int *dirty;          /* [2][ntx * nty] tiles stamped at even / odd rasteriser steps, in the order they were stamped */
+  int *ndirty;         /* [2] their numbers */
+  int *ticket;         /* the tile kernel's CTAs count themselves out: the last one empties the bins */
+  int resident_ctas;   /* CTAs of the tile kernel one wave holds on this device */
   int *overflow;       /* flag in mapped host memory */
 };
 
-/* K2, tile form: ONE kernel builds the whole obstacle map of the step.  A CTA paints the reduced discs of its
- * tile's grains into shared memory (owner = highest covering index, lowest covering index kept beside it),
- * derives act / rim bits from the shared-memory neighbourhood, writes the tile to `cell` in full rows (no
- * clearing pass, no global atomics per node) and appends its boundary nodes and links to the two lists with
- * one counter update per list and CTA. */
+/* K2: the obstacle map of the step (obst_construction, src/main.c:991-1065) with act / rim bits, and the two sparse
+ * lists.  grain_bin_kernel: records, tile bins, and which tiles hold a node whose owner may have changed since the
+ * previous step (rec_old ...: the previous step's records).  raster_tile_kernel, one CTA per tile, for the tiles
+ * stamped at this step or the previous one (all of them when force_full): paints the reduced discs of the tile's
+ * grains into shared memory (owner = highest covering index, lowest covering index kept beside it), derives act /
+ * rim bits from the shared-memory neighbourhood, writes the tile to `cell` in full rows and rewrites the tile's
+ * segments of the two lists.  Also empties the deferred list and zeroes the force sums. */
 template <typename real>
 cudaError_t launch_raster_tiles(const lbm::RasterParams<real> &P, int ngrains, const GrainArrays<real> &g,
-                                lbm::GrainRec<real> *rec, real *R2, lbm::GrainBox *boxes, int *cell, int x0, int nxl,
-                                int pitch, const TileBins &T, const BoundaryList &B, const LinkList &K,
+                                lbm::GrainRec<real> *rec, real *R2, lbm::GrainBox *boxes,
+                                const lbm::GrainRec<real> *rec_old, const real *R2_old, const lbm::GrainBox *boxes_old,
+                                int *cell, const int *cell_other /* the previous step's map */, int x0, int nxl, int pitch,
+                                const TileBins &T, const BoundaryList &B, const LinkList &K,
                                 int *defer_count /* emptied as well */,
-                                long long *facc /* nullptr, or [3][n] force sums to be zeroed */, cudaStream_t s);
-
-/* grain records + obstacle map + act bits + boundary list of one step (K2), per-grain form (the first version;
- * kept as the cross-check of the tile form, params.raster = 1) */
-template <typename real>
-cudaError_t launch_raster(const lbm::RasterParams<real> &P, int ngrains, const GrainArrays<real> &g,
-                          lbm::GrainRec<real> *rec, real *R2, lbm::GrainBox *boxes, int *cell, int x0, int nxl, int pitch,
-                          int *overlap, int *min_owner /* [x-x0][y], lbm_node.cuh MINOWNER_* */, int genkey,
-                          const BoundaryList &B, const LinkList &K, int *defer_count /* emptied as well */,
-                          long long *facc /* nullptr, or [3][n] force sums to be zeroed */, cudaStream_t s);
+                                long long *facc /* nullptr, or [3][n] force sums to be zeroed */, int step,
+                                int first_run /* no previous records */, int force_full /* rebuild every tile */,
+                                cudaStream_t s);
 cudaError_t launch_cell_frame(int *cell, int lx, int ly, int x0, int nxl, int pitch, int ring_value, cudaStream_t s);
 /* act[x][y] as the reference would hold it (tests / diagnostics) */
 template <typename real>

@@ -232,9 +232,9 @@ struct Sim : SimBase {
   DeferList<real> defer{};
   BoundaryList blist{};
   TileBins tbins{};          /* grains binned by lattice tile, rebuilt every LBM step (kernels.h) */
-  int *overlap = nullptr;
-  int *min_owner = nullptr; /* [x-x0][y]: lowest covering grain of multiply covered nodes (lbm_node.cuh MINOWNER_*) */
-  int genkey = 0;           /* generation key of this step's entries; counts down, the map is cleared when it wraps */
+  int sm_count = 148;        /* cudaDevAttrMultiProcessorCount of the context's device: sizes the persistent grids */
+  int raster_step = 1;       /* counts rasteriser runs: tile stamps are compared with it (kernels.h TileBins::stamp) */
+  int raster_full_until = 0; /* runs up to this one rebuild every tile (set-up, state or map set from outside) */
   int *hflags = nullptr;      /* mapped host memory: [0] Verlet capacity exceeded, [1] deferred-link list full, [2] boundary list full */
   std::vector<real *> grain_bufs;
   GrainArrays<real> g{};
@@ -277,9 +277,8 @@ struct Sim : SimBase {
     cudaFree(vb.nbr_count); cudaFree(vb.nbr); cudaFree(vb.wflags);
     cudaFree(dens_partials); cudaFree(dens_out); cudaFree(stage); cudaFree(mid_dev); cudaFree(gstage);
     cudaFree(defer.count); cudaFree(defer.index); cudaFree(defer.value);
-    cudaFree(blist.entry); cudaFree(blist.count); cudaFree(overlap); cudaFree(llist.entry); cudaFree(llist.count);
-    cudaFree(min_owner);
-    cudaFree(tbins.count); cudaFree(tbins.list);
+    cudaFree(blist.entry); cudaFree(blist.tcount); cudaFree(llist.entry); cudaFree(llist.tcount);
+    cudaFree(tbins.count); cudaFree(tbins.list); cudaFree(tbins.stamp);
     if (hflags) cudaFreeHost(hflags);
     if (hstage) cudaFreeHost(hstage);
     if (ev_state) cudaEventDestroy(ev_state);
@@ -288,7 +287,7 @@ struct Sim : SimBase {
     if (stream) cudaStreamDestroy(stream);
   }
 
-  static constexpr int DENS_BLOCKS = 1184; /* 8 x 148 SMs */
+  int DENS_BLOCKS = 1184;                  /* 8 x the device's SM count (init_device) */
   static constexpr int GHOST = 4;          /* extra rows per side of a strip */
 
   int init_device() override {
@@ -299,6 +298,8 @@ struct Sim : SimBase {
     CK(cudaSetDevice(P.device));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, P.device));
+    sm_count = prop.multiProcessorCount;
+    DENS_BLOCKS = 8 * sm_count;
     if (prop.major < 10)
       return fail(LBMDEM_ECUDA, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
                                     "; the kernels are built for sm_100a only");
@@ -430,19 +431,6 @@ struct Sim : SimBase {
     CK(cudaMalloc(&defer.index, sizeof(size_t) * defer.capacity));
     CK(cudaMalloc(&defer.value, sizeof(real) * defer.capacity));
     CK(cudaHostGetDevicePointer(&defer.overflow, hflags + 1, 0));
-    dfree(blist.entry); dfree(blist.count); dfree(overlap);
-    blist.capacity = (int)std::min<size_t>(plane / 2 + 1024, (size_t)1 << 30);
-    CK(cudaMalloc(&blist.entry, sizeof(uint2) * blist.capacity));
-    CK(cudaMalloc(&blist.count, sizeof(int)));
-    CK(cudaMemsetAsync(blist.count, 0, sizeof(int), stream));
-    CK(cudaHostGetDevicePointer(&blist.overflow, hflags + 2, 0));
-    CK(cudaMalloc(&overlap, sizeof(int) * n));
-    dfree(llist.entry); dfree(llist.count);
-    llist.capacity = (int)std::min<size_t>(plane + 4096, (size_t)1 << 30);
-    CK(cudaMalloc(&llist.entry, sizeof(uint2) * llist.capacity));
-    CK(cudaMalloc(&llist.count, sizeof(int)));
-    CK(cudaMemsetAsync(llist.count, 0, sizeof(int), stream));
-    CK(cudaHostGetDevicePointer(&llist.overflow, hflags + 3, 0));
     if (hstage) { cudaFreeHost(hstage); hstage = nullptr; }
     hstage_elems = (size_t)n * 16;
     CK(cudaMallocHost(&hstage, sizeof(double) * hstage_elems));
@@ -490,16 +478,43 @@ struct Sim : SimBase {
        * 2 sqrt(3) R^2 nodes per disc.  Half as much again for interpenetration, and a floor for large grains. */
       const double R = std::max(0.5, (double)rMin / (double)dx);
       const double est = 1.5 * (RTX + 2 * R + 4) * (RTY + 2 * R + 4) / (3.4641 * R * R) + 8;
-      dfree(tbins.count); dfree(tbins.list);
+      dfree(tbins.count); dfree(tbins.list); dfree(tbins.stamp);
       tbins.cap = (int)std::min(4096.0, std::max(16.0, est));
       tbins.ntx = (nxl + RTX - 1) / RTX;
       tbins.nty = (ly + RTY - 1) / RTY;
       const size_t nt = (size_t)tbins.ntx * tbins.nty;
       CK(cudaMalloc(&tbins.count, sizeof(int) * nt));
       CK(cudaMemsetAsync(tbins.count, 0, sizeof(int) * nt, stream));
+      /* one block: stamps, the two dirty lists, their counts, the tile kernel's exit ticket */
+      CK(cudaMalloc(&tbins.stamp, sizeof(int) * (3 * nt + 3)));
+      CK(cudaMemsetAsync(tbins.stamp, 0, sizeof(int) * (3 * nt + 3), stream));
+      tbins.dirty = tbins.stamp + nt;
+      tbins.ndirty = tbins.stamp + 3 * nt;
+      tbins.ticket = tbins.stamp + 3 * nt + 2;
+      tbins.resident_ctas = sm_count * 7;
+      raster_step = 1;
       CK(cudaMalloc(&tbins.list, sizeof(TileEntry<real>) * nt * tbins.cap));
       CK(cudaMemsetAsync(tbins.list, 0, sizeof(TileEntry<real>) * nt * tbins.cap, stream)); /* the tile kernel prefetches entries past the count */
       CK(cudaHostGetDevicePointer(&tbins.overflow, hflags + 4, 0));
+      /* the two sparse lists, one segment per tile.  A tile of RTX x RTY nodes holds about RTX RTY / (2 sqrt(3) R^2)
+       * discs of a dense packing, each with a rim of 2 pi 0.85 R nodes, about 3.5 fluid links per rim node; twice
+       * that for interpenetration and polydispersity, and never less than the rim of one straight wall through the tile
+       * (next to the lattice ring every link of a rim node is listed: 8 per node). */
+      const double rim = (double)RTX * RTY / (3.4641 * R * R) * 6.2832 * 0.85 * R;
+      dfree(llist.entry); dfree(llist.tcount); dfree(blist.entry); dfree(blist.tcount);
+      llist.cap = (int)std::min((double)(8 * RTX * RTY), std::max(8.0 * (RTX + RTY), 2 * 3.5 * rim));
+      blist.cap = (int)std::min((double)(RTX * RTY), std::max(2.0 * (RTX + RTY), 2 * rim));
+      llist.ntx = blist.ntx = tbins.ntx;
+      llist.nty = blist.nty = tbins.nty;
+      CK(cudaMalloc(&llist.entry, sizeof(uint2) * nt * llist.cap));
+      CK(cudaMalloc(&llist.tcount, sizeof(int) * nt));
+      CK(cudaMemsetAsync(llist.tcount, 0, sizeof(int) * nt, stream));
+      CK(cudaMalloc(&blist.entry, sizeof(uint2) * nt * blist.cap));
+      CK(cudaMalloc(&blist.tcount, sizeof(int) * nt));
+      CK(cudaMemsetAsync(blist.tcount, 0, sizeof(int) * nt, stream));
+      CK(cudaHostGetDevicePointer(&blist.overflow, hflags + 2, 0));
+      CK(cudaHostGetDevicePointer(&llist.overflow, hflags + 3, 0));
+      raster_full_until = raster_step + 2; /* both copies of the map and every list segment are built from scratch */
     }
     /* :1329-1331 with the reference's promotions ((tau - 0.5) is double) */
     k12 = (double)(real)(rho_moy * 9 * nu * nu) / ((double)dx * ((double)tau - 0.5) * ((double)tau - 0.5));
@@ -590,26 +605,18 @@ struct Sim : SimBase {
   bool act_folded[2] = {false, false};
   int raster_into(int cslot) {
     long long *fa = P.strict_fp ? nullptr : facc;
-    if (!(P.kernel & 2)) {
-      CK(launch_raster_tiles<real>(raster_params(), n, g, rec[cslot], R2[cslot], boxes[cslot], cell[cslot], x0, nxl, pitch, tbins,
-                                   blist, llist, defer.count, fa, stream));
-      all_launches += 2; /* grain_bin, raster_tile */
-    } else {
-      /* per-grain form (cross-check): global atomicMax per node, min-owner map with generation keys */
-      if (!min_owner) CK(cudaMalloc(&min_owner, sizeof(int) * plane));
-      if (genkey <= 1) { /* first use, or the key wrapped: forget every older entry */
-        CK(cudaMemsetAsync(min_owner, 0x7f, sizeof(int) * plane, stream));
-        genkey = 0x7e;
-      } else {
-        --genkey;
-      }
-      CK(launch_raster<real>(raster_params(), n, g, rec[cslot], R2[cslot], boxes[cslot], cell[cslot], x0, nxl, pitch, overlap, min_owner,
-                              genkey, blist, llist, defer.count, fa, stream));
-      all_launches += 3; /* grain_prepare, raster, boundary (memsets not counted) */
-    }
+    /* params.kernel bit 1: every tile rebuilt every step (the cross-check of the incremental rasteriser) */
+    const int full = (raster_step <= raster_full_until || (P.kernel & 2)) ? 1 : 0;
+    CK(launch_raster_tiles<real>(raster_params(), n, g, rec[cslot], R2[cslot], boxes[cslot], rec[1 - cslot], R2[1 - cslot],
+                                 boxes[1 - cslot], cell[cslot], cell[1 - cslot], x0, nxl, pitch, tbins, blist, llist,
+                                 defer.count, fa, raster_step, raster_step == 1 ? 1 : 0, full, stream));
+    ++raster_step;
+    all_launches += 2; /* grain_bin, raster_tile */
     act_folded[cslot] = true;
     return 0;
   }
+  /* the grain state or the map came from outside: the next two rasteriser runs rebuild everything */
+  void raster_invalidate() { raster_full_until = raster_step + 2; }
   dem::Params<real> dem_params() const {
     dem::Params<real> D;
     D.kg = (real)P.kg; D.kt = (real)P.kt; D.km = (real)P.km; D.ktm = (real)P.ktm; D.nug = (real)P.nug;
@@ -1074,6 +1081,7 @@ struct Sim : SimBase {
     int rc = settle(); /* a pending stream belongs to the map that is about to be replaced */
     if (rc) return rc;
     act_folded[cur_cell] = false;
+    raster_invalidate(); /* this map is not what the grain records would give */
     CK(cudaMemcpy2DAsync(cell[cur_cell] + (size_t)(xlo - x0) * pitch, sizeof(int) * pitch, in, sizeof(int) * ly,
                          sizeof(int) * ly, xhi - xlo, cudaMemcpyHostToDevice, stream));
     CK(cudaStreamSynchronize(stream));
@@ -1392,12 +1400,22 @@ struct Sim : SimBase {
   }
   int get_list_counts(long *c) override {
     if (!ready) return fail(LBMDEM_ESTATE, "no grains loaded");
-    int h[3] = {0, 0, 0};
-    CK(cudaMemcpyAsync(&h[0], llist.count, sizeof(int), cudaMemcpyDeviceToHost, stream));
-    CK(cudaMemcpyAsync(&h[1], blist.count, sizeof(int), cudaMemcpyDeviceToHost, stream));
-    CK(cudaMemcpyAsync(&h[2], defer.count, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    const size_t nt = (size_t)tbins.ntx * tbins.nty;
+    std::vector<int> kc(nt), bc(nt);
+    int nd = 0;
+    CK(cudaMemcpyAsync(kc.data(), llist.tcount, sizeof(int) * nt, cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(bc.data(), blist.tcount, sizeof(int) * nt, cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(&nd, defer.count, sizeof(int), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
-    c[0] = h[0]; c[1] = h[1]; c[2] = h[2]; c[3] = 0;
+    c[0] = c[1] = 0;
+    for (size_t t = 0; t < nt; ++t) { c[0] += kc[t]; c[1] += bc[t]; }
+    c[2] = nd;
+    /* tiles the rasteriser rebuilt at its last run (stamped at that run or the one before) */
+    std::vector<int> st(nt);
+    CK(cudaMemcpy(st.data(), tbins.stamp, sizeof(int) * nt, cudaMemcpyDeviceToHost));
+    c[3] = 0;
+    for (size_t t = 0; t < nt; ++t) c[3] += st[t] == raster_step - 1;
+    if ((P.kernel & 2) || raster_step - 1 <= raster_full_until) c[3] = (long)nt; /* that run rebuilt every tile */
     return 0;
   }
   void *stream_ptr() override { return (void *)stream; }

@@ -392,7 +392,7 @@ class Solver:
         """sizes of the sparse work lists of the last LBM step (bounce-back links, boundary nodes, deferred links)"""
         c = (C.c_long * 4)()
         self._ck(self.L.lbmdem_get_list_counts(self.h, c))
-        return {"links": c[0], "boundary_nodes": c[1], "deferred": c[2]}
+        return {"links": c[0], "boundary_nodes": c[1], "deferred": c[2], "tiles_rebuilt": c[3]}
 
     def stream(self) -> int:
         return int(self.L.lbmdem_stream(self.h) or 0)

@@ -296,6 +296,9 @@ def measure(workload, a, rank, local_rank, world, tmpdir, with_check, with_e2e=T
     ms_total = timed_region(lambda k: s.step(npd * k), steps)
     k1_ms, k1_n, launches = s.kernel_timer()
     clk = clocks.stop()
+    lc = s.list_counts()
+    config["sparse_work_last_step"] = {"bounce_links": lc["links"], "boundary_nodes": lc["boundary_nodes"],
+                                       "tiles_rebuilt": lc["tiles_rebuilt"], "tiles": ((s.nx + (8 if world > 1 else 0) + 31) // 32) * ((ly + 63) // 64)}
     s.reset_kernel_timer(False)
     mlups = lx * ly * steps / (ms_total * 1e-3) / 1e6
     real_b = 4 if prec == "f32" else 8

@@ -183,7 +183,8 @@ int lbmdem_reset_kernel_timer(lbmdem_ctx *ctx, int enable_events);
 /* sizes of the sparse work lists of the LAST LBM step: counts[0] bounce-back links (active solid node, link into a fluid
  * neighbour; src/main.c:1163-1185), counts[1] boundary nodes with a non-fluid foreign neighbour (forces_fluid, :1313),
  * counts[2] links evaluated through the deferred list (the order-dependent one-node-gap case of :1176-1185),
- * counts[3] bounce-back links whose interpolation uses the short-link branch -- reserved, 0 */
+ * counts[3] lattice tiles (32 x 64 nodes) whose part of the obstacle map and lists the last rasteriser run rebuilt: the
+ * others were carried over unchanged from the previous step (no covered node changed in them) */
 int lbmdem_get_list_counts(lbmdem_ctx *ctx, long counts[4]);
 /* the CUDA stream all work of this context is issued on (a cudaStream_t) */
 void *lbmdem_stream(lbmdem_ctx *ctx);

@@ -464,10 +464,11 @@ def test_overlapping_discs_and_discs_on_the_ring_strict(prec):
 
 
 @pytest.mark.parametrize("case", ["dense", "overlap_ring"])
-def test_tile_rasteriser_equals_per_grain_rasteriser(case):
-    """The obstacle map, act bits and the two link lists come from one tile kernel (shared-memory atomics) by
-    default and from the per-grain kernels (global atomicMax, min-owner map) with kernel=2: same map, same act,
-    and -- the lists being the same sets -- the same populations and forces, bit for bit (strict build)."""
+def test_incremental_rasteriser_equals_full_rebuild(case):
+    """By default the rasteriser rebuilds only the lattice tiles in which some covered node changed since the previous
+    step (grains move by a small fraction of a node per LBM step) and carries the rest of the map and of the two link
+    lists over; with kernel=2 every tile is rebuilt every step.  Same map, same act, same populations and forces, bit
+    for bit -- and the default run must really have skipped tiles."""
     if case == "dense":
         lx, ly = 200, 333
         r, x, y = small_packing(lx, ly, 1.0, seed=5, n_target=300)
@@ -482,17 +483,26 @@ def test_tile_rasteriser_equals_per_grain_rasteriser(case):
     n = a.init_arrays(r, x, y)
     b.init_arrays(r, x, y)
     f0 = perturbed_f(lx, ly, 6)
-    v, w, acc = random_kinematics(n, 7)
+    v, w, acc = random_kinematics(n, 7, vmax=0.3)      # fast enough for nodes to change owner every few LBM steps
     st = a.grains()[:, :9].copy()
     st[:, 3:5], st[:, 5:6] = v, w
     for slv in (a, b):
         slv.set_f(f0)
         slv.set_grain_state(st)
-    for _ in range(3):
-        a.step(a.scalars()["npDEM"])
-        b.step(b.scalars()["npDEM"])
+    ntiles = ((lx + 31) // 32) * ((ly + 63) // 64)
+    rebuilt, obst0 = [], a.obst()
+    npd = a.scalars()["npDEM"]
+    for _ in range(12):
+        a.step(npd)
+        b.step(npd)
         assert np.array_equal(a.obst(), b.obst())
         assert np.array_equal(a.act(), b.act())
+        ca, cb = a.list_counts(), b.list_counts()
+        assert (ca["links"], ca["boundary_nodes"], ca["deferred"]) == (cb["links"], cb["boundary_nodes"], cb["deferred"])
+        assert cb["tiles_rebuilt"] == ntiles
+        rebuilt.append(ca["tiles_rebuilt"])
+    assert not np.array_equal(a.obst(), obst0), "no node changed owner: the test does not exercise the incremental path"
+    assert min(rebuilt[3:]) < ntiles, rebuilt
     assert np.array_equal(a.f(), b.f())
     assert np.array_equal(a.fhf(), b.fhf())
     assert np.array_equal(a.grains(), b.grains())
@@ -503,8 +513,26 @@ def test_tile_rasteriser_equals_per_grain_rasteriser(case):
         slv.init_arrays(r, x, y)
         slv.set_f(f0)
         slv.set_grain_state(st)
-        slv.step(2 * slv.scalars()["npDEM"])
+        slv.step(8 * npd)
     assert np.array_equal(c.f(), d.f()) and np.array_equal(c.fhf(), d.fhf())
+
+
+def test_grains_at_rest_leave_every_tile_alone():
+    """LBM steps without DEM sub-steps: after the two rebuilds that follow set-up no tile is touched again"""
+    lx, ly = 200, 160
+    r, x, y = small_packing(lx, ly, 1.0, seed=15, n_target=120)
+    o = Oracle(lx, ly, 1.0, "f64")
+    s = G.Solver(lx, ly, 1.0, "f64", strict_fp=1)
+    n = o.init_arrays(r, x, y)
+    assert s.init_arrays(r, x, y) == n
+    f0 = perturbed_f(lx, ly, 16)
+    for z in (o, s):
+        z.set_f(f0)
+    for k in range(5):
+        o.lbm_step()
+        s.lbm_step()
+    assert s.list_counts()["tiles_rebuilt"] == 0
+    assert np.array_equal(o.f(), s.f()) and np.array_equal(o.obst(), s.obst()) and np.array_equal(o.fhf(), s.fhf())
 
 
 def test_full_size_row_kernel_equals_plain_kernel_fp64():
