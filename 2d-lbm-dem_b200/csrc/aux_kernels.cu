@@ -7,7 +7,11 @@
  * do (gather form over a sorted full neighbour list == the reference's scatter order, see
  * dem_forces_kernel).
  */
+#include <cooperative_groups.h>
+
 #include "kernels.h"
+
+namespace cg = cooperative_groups;
 
 namespace lbmdem {
 
@@ -572,12 +576,10 @@ __device__ __forceinline__ void grain_sums_add(long long *facc, int n, int i, lo
  * f_new[n][q] = the value it just produced), so links into FLUID neighbours are added to the
  * grain's force sums here (facc != nullptr, owned rows only); force_links_kernel adds the rest. */
 template <typename real>
-__global__ void __launch_bounds__(256, LBMDEM_SWEEP_MINB) bounce_sweep_kernel(const __grid_constant__ Lattice<real> L,
-                                                           const __grid_constant__ Stored<real> S, real *A, int xa, int xb,
-                                                           int xlo, int xhi, const LinkList K, const DeferList<real> D,
-                                                           long long *facc, int tx_first, int nty) {
-  /* one CTA per lattice tile (tile rows tx_first ..): the tile's own segment of the link list */
-  const int tile = (tx_first + blockIdx.y) * nty + blockIdx.x;
+__device__ __forceinline__ void bounce_tile_links(const Lattice<real> &L, const Stored<real> &S, real *A, int xa, int xb,
+                                                  int xlo, int xhi, const LinkList &K, const DeferList<real> &D,
+                                                  long long *facc, int tile) {
+  /* the tile's own segment of the link list */
   const int items = K.tcount[tile];
   if (items == 0) return;
   const uint2 *seg = K.entry + (size_t)tile * K.cap;
@@ -632,6 +634,14 @@ __global__ void __launch_bounds__(256, LBMDEM_SWEEP_MINB) bounce_sweep_kernel(co
   }
 }
 template <typename real>
+__global__ void __launch_bounds__(256, LBMDEM_SWEEP_MINB) bounce_sweep_kernel(const __grid_constant__ Lattice<real> L,
+                                                           const __grid_constant__ Stored<real> S, real *A, int xa, int xb,
+                                                           int xlo, int xhi, const LinkList K, const DeferList<real> D,
+                                                           long long *facc, int tx_first, int nty) {
+  /* one CTA per lattice tile (tile rows tx_first ..) */
+  bounce_tile_links<real>(L, S, A, xa, xb, xlo, xhi, K, D, facc, (tx_first + blockIdx.y) * nty + blockIdx.x);
+}
+template <typename real>
 __global__ void defer_apply_kernel(real *A, const DeferList<real> D) {
   const int n = min(*D.count, D.capacity);
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) A[D.index[k]] = D.value[k];
@@ -670,24 +680,16 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
  * the wall ring); every link is rounded to 64-bit fixed point before it is
  * added, so the result is independent of the order of the adds and of the strip decomposition.
  * The eight lanes of a node are summed with shuffles, then one lane adds to the grain's sums. */
+/* the tile's own segment of the boundary-node list, eight lanes per node: links into NON-fluid foreign neighbours
+ * (other grains, the wall ring); every link is rounded to 64-bit fixed point before it is added, so the result is
+ * independent of the order of the adds and of the strip decomposition */
 template <typename real>
-__global__ void __launch_bounds__(256) force_links_kernel(const __grid_constant__ Lattice<real> L,
-                                                          const __grid_constant__ Stored<real> S, int xlo, int xhi,
-                                                          const BoundaryList B, long long *facc, real *A,
-                                                          const DeferList<real> D) {
+__device__ __forceinline__ void force_tile_nodes(const Lattice<real> &L, const Stored<real> &S, int xlo, int xhi,
+                                                 const BoundaryList &B, long long *facc, int tile) {
   const int n = L.ngrains;
-  /* first the deferred bounce-back links of the sweep (defer_apply_kernel's job, one launch less).  They are links
-   * into FLUID neighbours; the force links below read populations of links into NON-fluid neighbours only (A[q][s]
-   * with s + e_q not fluid, A[opp q][n] with n + e_opp q = s solid): never the same location. */
-  const int cta = blockIdx.y * gridDim.x + blockIdx.x, nctas = gridDim.x * gridDim.y;
-  if (A != nullptr) {
-    const int nd = min(*D.count, D.capacity);
-    for (int k = cta * blockDim.x + threadIdx.x; k < nd; k += nctas * blockDim.x) A[D.index[k]] = D.value[k];
-  }
-  /* one CTA per lattice tile: the tile's own segment of the boundary-node list, eight lanes per node */
-  const int items = 8 * B.tcount[cta];
+  const int items = 8 * B.tcount[tile];
   if (items == 0) return;
-  const uint2 *seg = B.entry + (size_t)cta * B.cap;
+  const uint2 *seg = B.entry + (size_t)tile * B.cap;
   const int padded = (items + 31) & ~31; /* whole warps stay in the loop: shuffles below */
   for (int u = threadIdx.x; u < padded; u += blockDim.x) {
     long long s1 = 0, s2 = 0, s3 = 0;
@@ -701,10 +703,17 @@ __global__ void __launch_bounds__(256) force_links_kernel(const __grid_constant_
         i = (int)(en.y & BL_GRAIN);
         const size_t kn = node_index(L, x + ex_of(q), y + ey_of(q));
         /* links into fluid neighbours were added by the sweep kernel */
-        if (((en.y >> 24) & (1u << (q - 1))) && !cell_is_fluid(S.cell[kn])) {
+        const int cn = S.cell[kn];
+        if (((en.y >> 24) & (1u << (q - 1))) && !cell_is_fluid(cn)) {
+          /* Both populations belong to links into NON-fluid neighbours.  Next to the wall ring the sweep gives such a
+           * link of an active node the rest value (a listed w-link, possibly of another tile and still to be written
+           * when this runs inside rim_kernel): take that value directly.  Everywhere else nothing in this launch
+           * writes them (the fused kernel has put the rest value there already). */
+          const int nx = x + ex_of(q), ny = y + ey_of(q), oq = opp_of(q);
+          const real fn = (cell_is_act(cn) && !is_ring(L, nx, ny) && !w_links_with_collide(L, nx, ny)) ? L.w[oq] : S.A[oq * L.plane + kn];
+          const real fs = ((en.y & BL_ACT) && !w_links_with_collide(L, x, y)) ? L.w[q] : S.A[q * L.plane + en.x];
           real h1 = 0, h2 = 0, h3 = 0;
-          force_link<real>(q, S.A[opp_of(q) * L.plane + kn], S.A[q * L.plane + en.x], x, y, S.grains[i].xc, S.grains[i].yc,
-                           &h1, &h2, &h3);
+          force_link<real>(q, fn, fs, x, y, S.grains[i].xc, S.grains[i].yc, &h1, &h2, &h3);
           s1 = __double2ll_rn((double)h1 * FORCE_FIX);
           s2 = __double2ll_rn((double)h2 * FORCE_FIX);
           s3 = __double2ll_rn((double)h3 * TORQUE_FIX);
@@ -724,6 +733,56 @@ __global__ void __launch_bounds__(256) force_links_kernel(const __grid_constant_
     }
   }
 }
+
+template <typename real>
+__global__ void __launch_bounds__(256) force_links_kernel(const __grid_constant__ Lattice<real> L,
+                                                          const __grid_constant__ Stored<real> S, int xlo, int xhi,
+                                                          const BoundaryList B, long long *facc, real *A,
+                                                          const DeferList<real> D) {
+  /* first the deferred bounce-back links of the sweep (defer_apply_kernel's job, one launch less).  They are links
+   * into FLUID neighbours; the force links below read populations of links into NON-fluid neighbours only (A[q][s]
+   * with s + e_q not fluid, A[opp q][n] with n + e_opp q = s solid): never the same location. */
+  const int cta = blockIdx.y * gridDim.x + blockIdx.x, nctas = gridDim.x * gridDim.y;
+  if (A != nullptr) {
+    const int nd = min(*D.count, D.capacity);
+    for (int k = cta * blockDim.x + threadIdx.x; k < nd; k += nctas * blockDim.x) A[D.index[k]] = D.value[k];
+  }
+  force_tile_nodes<real>(L, S, xlo, xhi, B, facc, cta); /* one CTA per lattice tile */
+}
+
+/* Single-GPU form of sweep 4 + forces_fluid: ONE launch, one CTA per lattice tile -- the tile's bounce-back links
+ * (with their momentum exchange), then its boundary nodes; the CTAs count themselves out and the last one applies
+ * the deferred links (they read pre-sweep values: only after EVERY link has been evaluated). */
+template <typename real>
+__global__ void __launch_bounds__(256, LBMDEM_SWEEP_MINB) rim_kernel(const __grid_constant__ Lattice<real> L,
+                                                                    const __grid_constant__ Stored<real> S, real *A, int xa,
+                                                                    int xb, int xlo, int xhi, const LinkList K,
+                                                                    const BoundaryList B, const DeferList<real> D,
+                                                                    long long *facc, int *ticket) {
+  __shared__ int s_last;
+  const int tile = blockIdx.y * gridDim.x + blockIdx.x, nctas = gridDim.x * gridDim.y;
+  bounce_tile_links<real>(L, S, A, xa, xb, xlo, xhi, K, D, facc, tile);
+  if (facc != nullptr) force_tile_nodes<real>(L, S, xlo, xhi, B, facc, tile);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(ticket, 1) == nctas - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int nd = min(*(volatile int *)D.count, D.capacity);
+  for (int k = threadIdx.x; k < nd; k += blockDim.x) A[__ldcg(&D.index[k])] = __ldcg(&D.value[k]);
+  if (threadIdx.x == 0) *ticket = 0;
+}
+template <typename real>
+cudaError_t launch_rim(const Lattice<real> &L, const Stored<real> &S, real *A, int xa, int xb, int xlo, int xhi,
+                       const LinkList &K, const BoundaryList &B, const DeferList<real> &D, long long *facc, int *ticket,
+                       cudaStream_t s) {
+  rim_kernel<real><<<dim3(K.nty, K.ntx), 256, 0, s>>>(L, S, A, xa, xb, xlo, xhi, K, B, D, facc, ticket);
+  return cudaGetLastError();
+}
+
 template <typename real>
 cudaError_t launch_force_links(const Lattice<real> &L, const Stored<real> &S, int xlo, int xhi, const BoundaryList &B,
                                long long *facc, real *A, const DeferList<real> &D, cudaStream_t s) {
@@ -731,22 +790,35 @@ cudaError_t launch_force_links(const Lattice<real> &L, const Stored<real> &S, in
   return cudaGetLastError();
 }
 
+/* fhf of one grain from the fixed-point sums (default build) or the fp64 sums in the reference's order (strict
+ * build), scaled as src/main.c:1329-1331 */
 template <typename real>
-__global__ void force_finish_kernel(const long long *facc, int n, double k12, double k3, real *fhf1, real *fhf2,
-                                    real *fhf3) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const real h1 = (real)((double)facc[i] / FORCE_FIX);
-  const real h2 = (real)((double)facc[n + i] / FORCE_FIX);
-  const real h3 = (real)((double)facc[2 * n + i] / TORQUE_FIX);
-  fhf1[i] = (real)((double)h1 * k12);
-  fhf2[i] = (real)((double)h2 * k12);
-  fhf3[i] = (real)((double)h3 * k3);
+__device__ __forceinline__ void force_finish_one(const ForceFinish &fin, int n, int i, real *f1, real *f2, real *f3) {
+  real h1, h2, h3;
+  if (fin.fixed_point) {
+    const long long *facc = static_cast<const long long *>(fin.sums);
+    h1 = (real)((double)facc[i] / FORCE_FIX);
+    h2 = (real)((double)facc[n + i] / FORCE_FIX);
+    h3 = (real)((double)facc[2 * n + i] / TORQUE_FIX);
+  } else {
+    const double *partial = static_cast<const double *>(fin.sums);
+    h1 = (real)partial[i]; h2 = (real)partial[n + i]; h3 = (real)partial[2 * n + i];
+  }
+  *f1 = (real)((double)h1 * fin.k12);
+  *f2 = (real)((double)h2 * fin.k12);
+  *f3 = (real)((double)h3 * fin.k3);
 }
 template <typename real>
-cudaError_t launch_force_finish(const long long *facc, int n, double k12, double k3, real *fhf1, real *fhf2, real *fhf3,
-                                cudaStream_t s) {
-  force_finish_kernel<real><<<(n + 127) / 128, 128, 0, s>>>(facc, n, k12, k3, fhf1, fhf2, fhf3);
+__global__ void force_finish_kernel(ForceFinish fin, int n, real *fhf1, real *fhf2, real *fhf3) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  real f1, f2, f3;
+  force_finish_one<real>(fin, n, i, &f1, &f2, &f3);
+  fhf1[i] = f1; fhf2[i] = f2; fhf3[i] = f3;
+}
+template <typename real>
+cudaError_t launch_force_finish(const ForceFinish &fin, int n, real *fhf1, real *fhf2, real *fhf3, cudaStream_t s) {
+  force_finish_kernel<real><<<(n + 127) / 128, 128, 0, s>>>(fin, n, fhf1, fhf2, fhf3);
   return cudaGetLastError();
 }
 
@@ -779,21 +851,6 @@ cudaError_t launch_force_serial(const Lattice<real> &L, const Stored<real> &S, i
   force_serial_kernel<real><<<(L.ngrains + 63) / 64, 64, 0, s>>>(L, S, xlo, xhi, partial);
   return cudaGetLastError();
 }
-template <typename real>
-__global__ void force_scale_kernel(const double *partial, int n, double k12, double k3, real *fhf1, real *fhf2, real *fhf3) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  fhf1[i] = (real)((double)(real)partial[i] * k12);
-  fhf2[i] = (real)((double)(real)partial[n + i] * k12);
-  fhf3[i] = (real)((double)(real)partial[2 * n + i] * k3);
-}
-template <typename real>
-cudaError_t launch_force_scale(const double *partial, int n, double k12, double k3, real *fhf1, real *fhf2, real *fhf3,
-                               cudaStream_t s) {
-  force_scale_kernel<real><<<(n + 127) / 128, 128, 0, s>>>(partial, n, k12, k3, fhf1, fhf2, fhf3);
-  return cudaGetLastError();
-}
-
 /* ------------------------------------------------------------------------------------------
  * K3: Verlet lists from a hashed uniform cell list.  The reference builds a half list with an
  * O(N^2) double loop (initVerlet, :1519-1543); here every grain gets its FULL list (both
@@ -1004,7 +1061,7 @@ cudaError_t launch_dem_step(const dem::Params<real> &P, int n, bool film, const 
  * neighbours are added in list order, like the warp kernel's shuffle loop and the reference's scatter loop. */
 template <typename real>
 __global__ void __launch_bounds__(DEM_BATCH_MAX) dem_batch_kernel(dem::Params<real> P, int n, int nsub, GrainArrays<real> g,
-                                                                  VerletBuffers vb) {
+                                                                  VerletBuffers vb, ForceFinish fin) {
   const int i = threadIdx.x;
   const bool on = i < n;
   real x1 = 0, x2 = 0, x3 = 0, v1 = 0, v2 = 0, v3 = 0, a1 = 0, a2 = 0, a3 = 0, ri = 0, mi = 1, Iti = 1, f1 = 0, f2 = 0, f3 = 0;
@@ -1012,7 +1069,12 @@ __global__ void __launch_bounds__(DEM_BATCH_MAX) dem_batch_kernel(dem::Params<re
   if (on) {
     x1 = g.x1[i]; x2 = g.x2[i]; x3 = g.x3[i]; v1 = g.v1[i]; v2 = g.v2[i]; v3 = g.v3[i];
     a1 = g.a1[i]; a2 = g.a2[i]; a3 = g.a3[i]; ri = g.r[i]; mi = g.m[i]; Iti = g.It[i];
-    f1 = g.fhf1[i]; f2 = g.fhf2[i]; f3 = g.fhf3[i];
+    if (fin.sums != nullptr) { /* the launch follows an LBM step: force_finish_kernel's job first */
+      force_finish_one<real>(fin, n, i, &f1, &f2, &f3);
+      g.fhf1[i] = f1; g.fhf2[i] = f2; g.fhf3[i] = f3;
+    } else {
+      f1 = g.fhf1[i]; f2 = g.fhf2[i]; f3 = g.fhf3[i];
+    }
     cnt = vb.nbr_count[i]; wfl = vb.wflags[i];
   }
   for (int s = 0; s < nsub; ++s) {
@@ -1055,11 +1117,96 @@ __global__ void __launch_bounds__(DEM_BATCH_MAX) dem_batch_kernel(dem::Params<re
 }
 template <typename real>
 cudaError_t launch_dem_batch(const dem::Params<real> &P, int n, int nsub, const GrainArrays<real> &g, const VerletBuffers &vb,
-                             cudaStream_t s) {
+                             const ForceFinish &fin, cudaStream_t s) {
   if (n > DEM_BATCH_MAX) return cudaErrorInvalidValue;
   const int threads = (n + 31) / 32 * 32;
-  dem_batch_kernel<real><<<1, threads, 0, s>>>(P, n, nsub, g, vb);
+  dem_batch_kernel<real><<<1, threads, 0, s>>>(P, n, nsub, g, vb, fin);
   return cudaGetLastError();
+}
+
+/* Mid-size and large samples: the sub-steps between two LBM steps in ONE cooperative launch, thread i = grain i, the
+ * CTAs meeting at a grid barrier where dem_batch_kernel's single CTA meets at __syncthreads().  Same arithmetic in the
+ * same order (neighbour contributions added in list order), hence the same bits as the three-launch form.
+ * fin.sums != nullptr: the launch follows an LBM step and first turns the fixed-point force sums into fhf
+ * (force_finish_kernel's job).  film_first: the first sub-step is a film step (alternate contact law, :1342-1426). */
+template <typename real>
+__global__ void __launch_bounds__(DEM_COOP_THREADS) dem_coop_kernel(dem::Params<real> P, int n, int nsub, bool film_first,
+                                                                    GrainArrays<real> g, VerletBuffers vb, ForceFinish fin) {
+  cg::grid_group grid = cg::this_grid();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool on = i < n;
+  real x1 = 0, x2 = 0, x3 = 0, v1 = 0, v2 = 0, v3 = 0, a1 = 0, a2 = 0, a3 = 0, ri = 0, mi = 1, Iti = 1, f1 = 0, f2 = 0, f3 = 0;
+  int cnt = 0, wfl = 0;
+  if (on) {
+    x1 = g.x1[i]; x2 = g.x2[i]; x3 = g.x3[i]; v1 = g.v1[i]; v2 = g.v2[i]; v3 = g.v3[i];
+    a1 = g.a1[i]; a2 = g.a2[i]; a3 = g.a3[i]; ri = g.r[i]; mi = g.m[i]; Iti = g.It[i];
+    if (fin.sums != nullptr) {
+      force_finish_one<real>(fin, n, i, &f1, &f2, &f3);
+      g.fhf1[i] = f1; g.fhf2[i] = f2; g.fhf3[i] = f3;
+    } else {
+      f1 = g.fhf1[i]; f2 = g.fhf2[i]; f3 = g.fhf3[i];
+    }
+    cnt = vb.nbr_count[i]; wfl = vb.wflags[i];
+  }
+  for (int s = 0; s < nsub; ++s) {
+    const bool film = film_first && s == 0;
+    if (on) {
+      dem::kick_drift(P, &x1, &v1, a1);
+      dem::kick_drift(P, &x2, &v2, a2);
+      dem::kick_drift(P, &x3, &v3, a3);
+      g.x1[i] = x1; g.x2[i] = x2; g.v1[i] = v1; g.v2[i] = v2; g.v3[i] = v3; /* what the neighbours read */
+    }
+    grid.sync();
+    if (on) {
+      a1 = f1; a2 = f2; a3 = f3;
+      for (int k = 0; k < cnt; ++k) {
+        const int j = vb.nbr[(size_t)i * vb.cap + k];
+        const real xj1 = g.x1[j], xj2 = g.x2[j], vj1 = g.v1[j], vj2 = g.v2[j], vj3 = g.v3[j], rj = g.r[j];
+        dem::Force<real> F;
+        if (i < j) {
+          if (dem::pair_force(P, film, x1, x2, v1, v2, v3, ri, xj1, xj2, vj1, vj2, vj3, rj, &F)) {
+            a1 = a1 + F.f1; a2 = a2 + F.f2; a3 = a3 + F.f3;
+          }
+        } else {
+          if (dem::pair_force(P, film, xj1, xj2, vj1, vj2, vj3, rj, x1, x2, v1, v2, v3, ri, &F)) {
+            a1 = a1 + (-F.f1); a2 = a2 + (-F.f2); a3 = a3 + F.f3;
+          }
+        }
+      }
+      dem::add_wall_forces(P, wfl, x1, x2, v1, v2, v3, ri, &a1, &a2, &a3);
+      dem::finish_acceleration(P, mi, Iti, &a1, &a2, &a3);
+    }
+    grid.sync(); /* everybody has read the mid-step velocities before they move on */
+    if (on) {
+      dem::kick(P, &v1, a1);
+      dem::kick(P, &v2, a2);
+      dem::kick(P, &v3, a3);
+    }
+  }
+  if (on) {
+    g.x3[i] = x3; g.v1[i] = v1; g.v2[i] = v2; g.v3[i] = v3; g.a1[i] = a1; g.a2[i] = a2; g.a3[i] = a3;
+  }
+}
+template <typename real>
+cudaError_t launch_dem_coop(const dem::Params<real> &P, int n, int nsub, bool film_first, const GrainArrays<real> &g,
+                            const VerletBuffers &vb, const ForceFinish &fin, cudaStream_t s) {
+  dem::Params<real> Pc = P;
+  GrainArrays<real> gc = g;
+  VerletBuffers vc = vb;
+  ForceFinish fc = fin;
+  void *args[] = {&Pc, &n, &nsub, &film_first, &gc, &vc, &fc};
+  const dim3 grid((n + DEM_COOP_THREADS - 1) / DEM_COOP_THREADS), block(DEM_COOP_THREADS);
+  return cudaLaunchCooperativeKernel((const void *)dem_coop_kernel<real>, grid, block, args, 0, s);
+}
+template <typename real>
+cudaError_t dem_coop_capacity(int *max_grains) {
+  int dev = 0, sms = 0, per_sm = 0;
+  cudaError_t e;
+  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+  if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dem_coop_kernel<real>, DEM_COOP_THREADS, 0)) != cudaSuccess) return e;
+  *max_grains = sms * per_sm * DEM_COOP_THREADS;
+  return cudaSuccess;
 }
 
 /* In-process strip groups (sim.cu, LocalGroup): the force sums of the ranks are added by ONE kernel per rank that reads
@@ -1315,22 +1462,26 @@ cudaError_t launch_fill_rest(real *f, size_t plane, const Lattice<real> &Lw, cud
                                                cudaStream_t);                                                             \
   template cudaError_t launch_bounce_pass<real>(const Lattice<real> &, const Stored<real> &, real *, int, int, int, int,  \
                                                 const LinkList &, const DeferList<real> &, long long *, cudaStream_t);    \
+  template cudaError_t launch_rim<real>(const Lattice<real> &, const Stored<real> &, real *, int, int, int, int,          \
+                                        const LinkList &, const BoundaryList &, const DeferList<real> &, long long *,     \
+                                        int *, cudaStream_t);                                                             \
   template cudaError_t launch_bounce_end<real>(real *, const DeferList<real> &, cudaStream_t);                            \
   template cudaError_t launch_force_links<real>(const Lattice<real> &, const Stored<real> &, int, int,                    \
                                                 const BoundaryList &, long long *, real *, const DeferList<real> &,       \
                                                 cudaStream_t);                                                            \
-  template cudaError_t launch_force_finish<real>(const long long *, int, double, double, real *, real *, real *,          \
+  template cudaError_t launch_force_finish<real>(const ForceFinish &, int, real *, real *, real *,                        \
                                                  cudaStream_t);                                                           \
   template cudaError_t launch_force_serial<real>(const Lattice<real> &, const Stored<real> &, int, int, double *,         \
                                                  cudaStream_t);                                                           \
-  template cudaError_t launch_force_scale<real>(const double *, int, double, double, real *, real *, real *,              \
-                                                cudaStream_t);                                                            \
   template cudaError_t launch_verlet<real>(const dem::Params<real> &, int, const GrainArrays<real> &, real,               \
                                            const VerletBuffers &, cudaStream_t);                                         \
   template cudaError_t launch_dem_step<real>(const dem::Params<real> &, int, bool, const GrainArrays<real> &,             \
                                              const VerletBuffers &, real *, bool, bool, cudaStream_t);                   \
   template cudaError_t launch_dem_batch<real>(const dem::Params<real> &, int, int, const GrainArrays<real> &,             \
-                                              const VerletBuffers &, cudaStream_t);                                      \
+                                              const VerletBuffers &, const ForceFinish &, cudaStream_t);                 \
+  template cudaError_t launch_dem_coop<real>(const dem::Params<real> &, int, int, bool, const GrainArrays<real> &,        \
+                                             const VerletBuffers &, const ForceFinish &, cudaStream_t);                  \
+  template cudaError_t dem_coop_capacity<real>(int *);                                                                    \
   template cudaError_t launch_density<real>(const real *, int, int, int, int, int, size_t, double *, int, double *,       \
                                             cudaStream_t);                                                                \
   template cudaError_t launch_checksum<real>(const real *, const int *, int, int, int, int, int, size_t,                  \

@@ -203,17 +203,25 @@ cudaError_t launch_force_links(const lbm::Lattice<real> &L, const lbm::Stored<re
                                const BoundaryList &B, long long *facc,
                                real *A /* nullptr, or the populations: the deferred links D are applied first */,
                                const DeferList<real> &D, cudaStream_t s);
-/* fixed-point sums -> fhf (scaled, src/main.c:1329-1331) */
+/* sums -> fhf, scaled as src/main.c:1329-1331: from the fixed-point sums (default build) or the fp64 sums the strict
+ * build adds in the reference's order.  Passed to the first DEM launch after an LBM step (it does the conversion for
+ * its own grain), or to launch_force_finish when something else wants fhf first. */
+struct ForceFinish {
+  const void *sums;    /* nullptr: fhf is up to date */
+  int fixed_point;     /* 1: long long [3][n] scaled by FORCE_FIX / TORQUE_FIX; 0: double [3][n] */
+  double k12, k3;
+};
 template <typename real>
-cudaError_t launch_force_finish(const long long *facc, int ngrains, double k12, double k3, real *fhf1, real *fhf2,
-                                real *fhf3, cudaStream_t s);
+cudaError_t launch_force_finish(const ForceFinish &fin, int ngrains, real *fhf1, real *fhf2, real *fhf3, cudaStream_t s);
 /* forces_fluid in the reference's own summation order, one thread per grain (strict mode) */
 template <typename real>
 cudaError_t launch_force_serial(const lbm::Lattice<real> &L, const lbm::Stored<real> &S, int xlo, int xhi,
                                 double *partial /* [3][n] unscaled */, cudaStream_t s);
+/* single-GPU form of the bounce-back sweep + the rest of forces_fluid in ONE launch (aux_kernels.cu, rim_kernel) */
 template <typename real>
-cudaError_t launch_force_scale(const double *partial, int ngrains, double k12, double k3, real *fhf1, real *fhf2,
-                               real *fhf3, cudaStream_t s);
+cudaError_t launch_rim(const lbm::Lattice<real> &L, const lbm::Stored<real> &S, real *A, int xa, int xb, int xlo, int xhi,
+                       const LinkList &K, const BoundaryList &B, const DeferList<real> &D, long long *facc, int *ticket,
+                       cudaStream_t s);
 
 /* partial force sums of the ranks of an in-process strip group (device pointers, peer-accessible) */
 constexpr int MAX_LOCAL_RANKS = 16;
@@ -252,7 +260,15 @@ cudaError_t launch_dem_step(const dem::Params<real> &P, int n, bool film, const 
 constexpr int DEM_BATCH_MAX = 1024;
 template <typename real>
 cudaError_t launch_dem_batch(const dem::Params<real> &P, int n, int nsub, const GrainArrays<real> &g, const VerletBuffers &vb,
-                             cudaStream_t s);
+                             const ForceFinish &fin, cudaStream_t s);
+/* the same for any sample that fits one co-resident grid (dem_coop_capacity): a cooperative launch, grid barriers
+ * where the single-CTA kernel has CTA barriers */
+constexpr int DEM_COOP_THREADS = 256;
+template <typename real>
+cudaError_t launch_dem_coop(const dem::Params<real> &P, int n, int nsub, bool film_first, const GrainArrays<real> &g,
+                            const VerletBuffers &vb, const ForceFinish &fin, cudaStream_t s);
+template <typename real>
+cudaError_t dem_coop_capacity(int *max_grains);
 
 template <typename real>
 cudaError_t launch_density(const real *f, int ly, int x0, int xlo, int xhi, int pitch, size_t plane, double *partials,

@@ -232,6 +232,8 @@ struct Sim : SimBase {
   DeferList<real> defer{};
   BoundaryList blist{};
   TileBins tbins{};          /* grains binned by lattice tile, rebuilt every LBM step (kernels.h) */
+  ForceFinish fin_pending{nullptr, 1, 0, 0}; /* fhf1..3 still have to be derived from these sums (kernels.h ForceFinish) */
+  int coop_cap = 0;          /* grains the cooperative DEM kernel can take (one co-resident grid) */
   int sm_count = 148;        /* cudaDevAttrMultiProcessorCount of the context's device: sizes the persistent grids */
   int raster_step = 1;       /* counts rasteriser runs: tile stamps are compared with it (kernels.h TileBins::stamp) */
   int raster_full_until = 0; /* runs up to this one rebuild every tile (set-up, state or map set from outside) */
@@ -300,6 +302,7 @@ struct Sim : SimBase {
     CK(cudaGetDeviceProperties(&prop, P.device));
     sm_count = prop.multiProcessorCount;
     DENS_BLOCKS = 8 * sm_count;
+    if (prop.cooperativeLaunch) CK(dem_coop_capacity<real>(&coop_cap));
     if (prop.major < 10)
       return fail(LBMDEM_ECUDA, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
                                     "; the kernels are built for sm_100a only");
@@ -447,6 +450,7 @@ struct Sim : SimBase {
   int finish_setup(const std::vector<real> &r, const std::vector<real> &x1, const std::vector<real> &x2) {
     int rc = alloc_grains((int)r.size());
     if (rc) return rc;
+    fin_pending.sums = nullptr;
     const double pi = 3.14159265358979; /* src/main.c:42 */
     const real tau = (real)P.tau, nu = (real)P.nu, rho_moy = (real)P.rho_moy, reductionR = (real)P.reductionR;
     const real G = (real)P.G, angleG = (real)P.angleG, kg = (real)P.kg, iterDEM = (real)P.iterDEM;
@@ -808,7 +812,8 @@ struct Sim : SimBase {
     /* the deferred list and the force sums were emptied by the rasteriser's first kernel */
     if (!multi) {
       CK(launch_ring_sweep<real>(L, S, f[cur], 0, lx, stream));
-      CK(launch_bounce_pass<real>(L, S, f[cur], 1, lx - 1, xlo, xhi, llist, defer, fa, stream));
+      if (P.strict_fp) CK(launch_bounce_pass<real>(L, S, f[cur], 1, lx - 1, xlo, xhi, llist, defer, fa, stream));
+      else CK(launch_rim<real>(L, S, f[cur], 1, lx - 1, xlo, xhi, llist, blist, defer, fa, tbins.ticket, stream));
     } else if (xhi - xlo < 12) {
       if ((rc = halo_exchange(stream))) return rc;
       CK(launch_ring_sweep<real>(L, S, f[cur], std::max(xlo - 3, 0), std::min(xhi + 3, lx), stream));
@@ -837,6 +842,7 @@ struct Sim : SimBase {
       CK(launch_bounce_end<real>(f[cur], defer, stream));
       ++all_launches;
       CK(launch_force_serial<real>(L, S, xlo, xhi, fpartial, stream));
+      ++all_launches;
       double *ftot = fpartial;
       if (multi && group) {
         if ((rc = sum_local<double>(fpartial, &ftot))) return rc;
@@ -844,19 +850,33 @@ struct Sim : SimBase {
         const int r = g_nccl.AllReduce(fpartial, fpartial, (size_t)3 * n, NcclApi::Float64, NcclApi::Sum, comm, stream);
         if (r) return nccl_fail(r, "ncclAllReduce");
       }
-      CK(launch_force_scale<real>(ftot, n, k12, k3, g.fhf1, g.fhf2, g.fhf3, stream));
+      fin_pending = ForceFinish{ftot, 0, k12, k3};
     } else {
-      CK(launch_force_links<real>(L, S, xlo, xhi, blist, facc, f[cur], defer, stream)); /* applies the deferred links first */
       long long *ftot = facc;
-      if (multi && group) { /* integer sum: exact, identical on every rank, independent of the decomposition */
-        if ((rc = sum_local<long long>(facc, &ftot))) return rc;
-      } else if (multi) {
-        const int r = g_nccl.AllReduce(facc, facc, (size_t)3 * n, NcclApi::Int64, NcclApi::Sum, comm, stream);
-        if (r) return nccl_fail(r, "ncclAllReduce");
+      if (multi) {
+        CK(launch_force_links<real>(L, S, xlo, xhi, blist, facc, f[cur], defer, stream)); /* applies the deferred links first */
+        ++all_launches;
+        if (group) { /* integer sum: exact, identical on every rank, independent of the decomposition */
+          if ((rc = sum_local<long long>(facc, &ftot))) return rc;
+        } else {
+          const int r = g_nccl.AllReduce(facc, facc, (size_t)3 * n, NcclApi::Int64, NcclApi::Sum, comm, stream);
+          if (r) return nccl_fail(r, "ncclAllReduce");
+        }
       }
-      CK(launch_force_finish<real>(ftot, n, k12, k3, g.fhf1, g.fhf2, g.fhf3, stream));
+      fin_pending = ForceFinish{ftot, 1, k12, k3};
     }
-    all_launches += 2;
+    /* the sums become fhf1..3 in the first DEM launch that follows (or in materialise_fhf) */
+    return 0;
+  }
+  ForceFinish take_pending() {
+    const ForceFinish f = fin_pending;
+    fin_pending.sums = nullptr;
+    return f;
+  }
+  int materialise_fhf() {
+    if (!fin_pending.sums) return 0;
+    CK(launch_force_finish<real>(take_pending(), n, g.fhf1, g.fhf2, g.fhf3, stream));
+    ++all_launches;
     return 0;
   }
 
@@ -940,15 +960,21 @@ struct Sim : SimBase {
         *built = true;
       }
       const bool film = (nbsteps % P.stepFilm == 0);
-      /* small samples: this call's sub-step and those of the following calls that do nothing else go in one launch */
+      /* this call's sub-step and those of the following calls that do nothing else go in ONE launch: a single CTA for
+       * small samples, a cooperative grid for anything that fits one wave; the launch also turns the force sums of
+       * the LBM step into fhf */
       long nb = 1;
-      if (n <= DEM_BATCH_MAX && !film && !capture && P.vib != 1) {
+      const bool one_cta = n <= DEM_BATCH_MAX && !film, coop = n > DEM_BATCH_MAX && n <= coop_cap;
+      if ((one_cta || coop) && !capture && P.vib != 1 && !(P.kernel & 4)) {
         while (k + nb < nsteps && (nbsteps + nb) % npDEM != 0 && (nbsteps + nb) % P.UpdateVerlet != 0 &&
                (nbsteps + nb) % P.stepFilm != 0)
           ++nb;
-        CK(launch_dem_batch<real>(dem_params(), n, (int)nb, g, vb, stream));
+        if (one_cta) CK(launch_dem_batch<real>(dem_params(), n, (int)nb, g, vb, take_pending(), stream));
+        else CK(launch_dem_coop<real>(dem_params(), n, (int)nb, film, g, vb, take_pending(), stream));
         all_launches += 1;
+        drift_done = false;
       } else {
+        if ((rc = materialise_fhf())) return rc;
         /* when the next call of this batch does nothing but its DEM sub-step (no LBM step, no list rebuild), this
          * call's closing kick and the next call's kick-drift go in one launch */
         const bool drift_next = n > DEM_BATCH_MAX && !capture && P.vib != 1 && k + 1 < nsteps &&
@@ -995,12 +1021,14 @@ struct Sim : SimBase {
   }
   int lbm_step() override {
     int rc = lbm_step_async();
+    if (!rc) rc = materialise_fhf();
     if (rc) return done(rc);
     return done(check_flags());
   }
   int lbm_steps(long k) override {
     for (long i = 0; i < k; ++i) {
       int rc = lbm_step_async();
+      if (!rc) rc = materialise_fhf();
       if (rc) return done(rc);
     }
     return done(check_flags());
@@ -1130,11 +1158,14 @@ struct Sim : SimBase {
   }
   int get_fhf(double *out) override {
     if (!ready) return fail(LBMDEM_ESTATE, "no grains loaded");
+    int rc = materialise_fhf();
+    if (rc) return rc;
     real *cols[3] = {g.fhf1, g.fhf2, g.fhf3};
     return download_cols(cols, 3, out, 3, 0);
   }
   int set_fhf(const double *in) override {
     if (!ready) return fail(LBMDEM_ESTATE, "no grains loaded");
+    fin_pending.sums = nullptr; /* whatever the last LBM step left is superseded */
     real *cols[3] = {g.fhf1, g.fhf2, g.fhf3};
     return upload_cols(cols, 3, in, 3, 0);
   }
@@ -1177,7 +1208,8 @@ struct Sim : SimBase {
     h.version = 1; h.lx = lx; h.ly = ly; h.single = sizeof(real) == 4; h.n = n; h.nranks = P.nranks; h.rank = P.rank;
     h.cap = vb.cap; h.scale = P.scale; h.nbsteps = nbsteps; h.nFile = nFile;
     h.t = t; h.Mgx = Mgx; h.Mdx = Mdx; h.Mby = Mby; h.Mhy = Mhy;
-    int rc = 0;
+    int rc = materialise_fhf();
+    if (rc) { fclose(fp); return rc; }
     const size_t rows = (size_t)(xhi - xlo);
     std::vector<real> slab((size_t)16 * n);
     std::vector<int> cnt(n), nbr((size_t)n * vb.cap), wf(n), ob(rows * ly);
@@ -1297,6 +1329,7 @@ struct Sim : SimBase {
     int rc = step_async(nsteps, &built);
     if (rc) return done(rc);
     (void)built;
+    if ((rc = materialise_fhf())) return rc;
     if (state_out || fhf_out) {
       CK(launch_grain_pack2<real>(g.x1, 9, g.fhf1, 3, n, gs, rows_f32, stream)); /* [n][9] state, then [n][3] fhf */
       if (pin_out && state_out && fhf_out && static_cast<char *>(fhf_out) == static_cast<char *>(state_out) + eb * 9 * N) {

@@ -59,7 +59,9 @@ typedef struct lbmdem_params {
   int strict_fp;           /* 1: LBM kernel built without multiply-add contraction and forces summed in
                               the reference's serial order -> bit-identical to the reference build */
   int kernel;              /* cross-check switches, 0 = default.  bit 0: plain one-thread-per-node LBM kernel instead of
-                              the TMA row pipeline; bit 1: per-grain rasteriser instead of the tile rasteriser */
+                              the TMA row pipeline; bit 1: the rasteriser rebuilds every lattice tile every step instead
+                              of the tiles in which a covered node changed; bit 2: three launches per DEM sub-step
+                              instead of one launch for all the sub-steps between two LBM steps */
   int neighbour_capacity;  /* per-grain Verlet capacity, default 32 */
   int vib;                 /* 1: shake the left/right walls, src/main.c:162, :1701-1706 (default 0) */
 } lbmdem_params;

@@ -651,3 +651,42 @@ def test_reference_default_build_size_strict(tmp_path):
     # the reference adds 1.6e8 terms serially; the device reduces pairwise: the SUMS differ in the 9th digit
     # although every addend is identical (f hash above)
     assert abs(s.total_density() - float(gold["density"])) < 1e-8 * 7826 * 2325
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_one_launch_dem_equals_three_launch_dem(prec):
+    """The DEM sub-steps between two LBM steps run as ONE launch (a single CTA up to 1024 grains, a cooperative grid
+    above: grid barriers where the reference's loops end) by default and as three launches per sub-step with
+    kernel=4.  Same arithmetic in the same order: same bits, and the oracle's bits in the strict build -- here with
+    more than 1024 grains, across a Verlet rebuild, and across the film step (alternate contact law)."""
+    lx, ly = 400, 300
+    r, x, y = small_packing(lx, ly, 1.0, seed=31, n_target=1500)
+    o = Oracle(lx, ly, 1.0, prec)
+    a = G.Solver(lx, ly, 1.0, prec, strict_fp=1)
+    b = G.Solver(lx, ly, 1.0, prec, strict_fp=1, kernel=4)
+    n = o.init_arrays(r, x, y)
+    assert n > 1024 and a.init_arrays(r, x, y) == n and b.init_arrays(r, x, y) == n
+    v, w, acc = random_kinematics(n, 32, vmax=0.02)
+    st = o.grains()[:, :9].copy()
+    st[:, 3:5], st[:, 5:6] = v, w
+    f0 = perturbed_f(lx, ly, 33)
+    for z in (o, a, b):
+        z.set_f(f0)
+        z.set_grain_state(st)
+        z.set_nbsteps(7950)                 # the film step (8000) and a Verlet rebuild fall inside the run
+    for chunk in range(3):
+        for z in (o, a, b):
+            z.step(37)
+        assert np.array_equal(a.grains(), b.grains()) and np.array_equal(a.fhf(), b.fhf())
+        assert np.array_equal(o.grains()[:, :9], a.grains()[:, :9]), chunk
+        assert np.array_equal(o.fhf(), a.fhf())
+    assert np.array_equal(o.f(), a.f()) and np.array_equal(a.f(), b.f())
+    # default build: fixed-point sums turned into fhf inside the DEM launch
+    c = G.Solver(lx, ly, 1.0, prec)
+    d = G.Solver(lx, ly, 1.0, prec, kernel=4)
+    for z in (c, d):
+        z.init_arrays(r, x, y)
+        z.set_f(f0)
+        z.set_grain_state(st)
+        z.step(45)
+    assert np.array_equal(c.grains(), d.grains()) and np.array_equal(c.fhf(), d.fhf()) and np.array_equal(c.f(), d.f())

@@ -1,5 +1,5 @@
-OUT=gpurun_out; RUN=r02I; mkdir -p $OUT
-timeout 900 python -m pytest tests -m gpu -x -q > $OUT/${RUN}_pytest.log 2>&1; tail -12 $OUT/${RUN}_pytest.log
+OUT=gpurun_out; RUN=r02K; mkdir -p $OUT
+timeout 900 python -m pytest tests -m gpu -q > $OUT/${RUN}_pytest.log 2>&1; tail -12 $OUT/${RUN}_pytest.log
 timeout 300 python bench.py --steps 300 --no-cpu-baseline --no-cfg5 > $OUT/${RUN}_bench.json 2> $OUT/${RUN}_bench.err; echo "rc $?"
 timeout 300 python bench.py --steps 300 --no-cpu-baseline --no-cfg5 --kernel 2 > $OUT/${RUN}_bench_full.json 2> $OUT/${RUN}_bench_full.err; echo "rc $?"
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${RUN}_launches.csv python bench.py --steps 3 --warmup 8 --no-cpu-baseline --no-cfg5 > $OUT/${RUN}_launches.log 2>&1
