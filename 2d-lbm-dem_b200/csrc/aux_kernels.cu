@@ -110,10 +110,23 @@ __global__ void __launch_bounds__(128) grain_bin_kernel(RasterParams<real> P, in
   grain_geometry(P, g.x1[i], g.x2[i], g.r[i], g.rLB[i], &r.xc, &r.yc, &r.r2, &R2i, &b);
   bool all_tiles = first_run != 0;
   GrainBox ob = b;
+  if (!first_run) ob = boxes_old[i];
+  /* strip-decomposed runs replicate the grains: most of them are nowhere near this rank's rows, now or a step ago */
+  const bool far_now = b.xf + 1 < x0 || b.xi - 1 > x0 + nxl - 1 || b.xf < b.xi || b.yf < b.yi;
+  const bool far_old = ob.xf + 1 < x0 || ob.xi - 1 > x0 + nxl - 1 || ob.xf < ob.xi || ob.yf < ob.yi;
+  if (far_now && far_old) {
+    if (lane == 0) {
+      r.x1 = g.x1[i]; r.x2 = g.x2[i]; r.v1 = g.v1[i]; r.v2 = g.v2[i]; r.v3 = g.v3[i];
+      rec[i] = r;
+      R2[i] = R2i;
+      boxes[i] = b;
+    }
+    if (facc != nullptr && lane < 3) facc[lane * n + i] = 0;
+    return;
+  }
   if (!all_tiles) {
     const GrainRec<real> o = rec_old[i];
     const real RRo = R2_old[i];
-    ob = boxes_old[i];
     if (!(fabs((double)(r.xc - o.xc)) < 0.5 && fabs((double)(r.yc - o.yc)) < 0.5) || o.r2 != r.r2 || RRo != R2i) {
       all_tiles = true;
     } else {
@@ -623,6 +636,8 @@ __device__ __forceinline__ void bounce_tile_links(const Lattice<real> &L, const 
             real h1 = 0, h2 = 0, h3 = 0;
             force_link<real>(q, Fn_oq, v, x, y, g.xc, g.yc, &h1, &h2, &h3);
             fi = owner;
+            if (!(fabs((double)h1) < 1024. && fabs((double)h2) < 1024. && fabs((double)h3) < 16384.))
+              *(volatile int *)D.range_flag = 1; /* NaN or diverged populations: the sums would wrap */
             s1 = __double2ll_rn((double)h1 * FORCE_FIX);
             s2 = __double2ll_rn((double)h2 * FORCE_FIX);
             s3 = __double2ll_rn((double)h3 * TORQUE_FIX);
@@ -685,7 +700,7 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
  * independent of the order of the adds and of the strip decomposition */
 template <typename real>
 __device__ __forceinline__ void force_tile_nodes(const Lattice<real> &L, const Stored<real> &S, int xlo, int xhi,
-                                                 const BoundaryList &B, long long *facc, int tile) {
+                                                 const BoundaryList &B, long long *facc, int tile, int *range_flag) {
   const int n = L.ngrains;
   const int items = 8 * B.tcount[tile];
   if (items == 0) return;
@@ -714,6 +729,7 @@ __device__ __forceinline__ void force_tile_nodes(const Lattice<real> &L, const S
           const real fs = ((en.y & BL_ACT) && !w_links_with_collide(L, x, y)) ? L.w[q] : S.A[q * L.plane + en.x];
           real h1 = 0, h2 = 0, h3 = 0;
           force_link<real>(q, fn, fs, x, y, S.grains[i].xc, S.grains[i].yc, &h1, &h2, &h3);
+          if (!(fabs((double)h1) < 1024. && fabs((double)h2) < 1024. && fabs((double)h3) < 16384.)) *(volatile int *)range_flag = 1;
           s1 = __double2ll_rn((double)h1 * FORCE_FIX);
           s2 = __double2ll_rn((double)h2 * FORCE_FIX);
           s3 = __double2ll_rn((double)h3 * TORQUE_FIX);
@@ -747,7 +763,7 @@ __global__ void __launch_bounds__(256) force_links_kernel(const __grid_constant_
     const int nd = min(*D.count, D.capacity);
     for (int k = cta * blockDim.x + threadIdx.x; k < nd; k += nctas * blockDim.x) A[D.index[k]] = D.value[k];
   }
-  force_tile_nodes<real>(L, S, xlo, xhi, B, facc, cta); /* one CTA per lattice tile */
+  force_tile_nodes<real>(L, S, xlo, xhi, B, facc, cta, D.range_flag); /* one CTA per lattice tile */
 }
 
 /* Single-GPU form of sweep 4 + forces_fluid: ONE launch, one CTA per lattice tile -- the tile's bounce-back links
@@ -762,7 +778,7 @@ __global__ void __launch_bounds__(256, LBMDEM_SWEEP_MINB) rim_kernel(const __gri
   __shared__ int s_last;
   const int tile = blockIdx.y * gridDim.x + blockIdx.x, nctas = gridDim.x * gridDim.y;
   bounce_tile_links<real>(L, S, A, xa, xb, xlo, xhi, K, D, facc, tile);
-  if (facc != nullptr) force_tile_nodes<real>(L, S, xlo, xhi, B, facc, tile);
+  if (facc != nullptr) force_tile_nodes<real>(L, S, xlo, xhi, B, facc, tile, D.range_flag);
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -797,6 +813,12 @@ __device__ __forceinline__ void force_finish_one(const ForceFinish &fin, int n, 
   real h1, h2, h3;
   if (fin.fixed_point) {
     const long long *facc = static_cast<const long long *>(fin.sums);
+    /* the 64-bit sums hold |fhf1|, |fhf2| < 2^11 and |fhf3| < 2^15 (lattice units): a sum in the top quarter of the
+     * range has wrapped or is about to -- populations that diverged, or NaN (which converts to the most negative
+     * value).  Reported instead of carried on silently. */
+    const long long lim = 1ll << 61;
+    if (fin.range_flag != nullptr && (llabs(facc[i]) >= lim || llabs(facc[n + i]) >= lim || llabs(facc[2 * n + i]) >= lim))
+      *(volatile int *)fin.range_flag = 1; /* mapped host memory */
     h1 = (real)((double)facc[i] / FORCE_FIX);
     h2 = (real)((double)facc[n + i] / FORCE_FIX);
     h3 = (real)((double)facc[2 * n + i] / TORQUE_FIX);

@@ -77,7 +77,8 @@ struct DeferList {
   size_t *index;       /* flat element index into the population buffer */
   real *value;
   int capacity;
-  int *overflow;       /* device flag */
+  int *overflow;       /* flag in mapped host memory */
+  int *range_flag;     /* flag in mapped host memory: a link's momentum exchange does not fit the fixed-point sums */
 };
 
 template <typename real>
@@ -210,6 +211,7 @@ struct ForceFinish {
   const void *sums;    /* nullptr: fhf is up to date */
   int fixed_point;     /* 1: long long [3][n] scaled by FORCE_FIX / TORQUE_FIX; 0: double [3][n] */
   double k12, k3;
+  int *range_flag;     /* mapped host memory: raised when a fixed-point sum is about to leave its range */
 };
 template <typename real>
 cudaError_t launch_force_finish(const ForceFinish &fin, int ngrains, real *fhf1, real *fhf2, real *fhf3, cudaStream_t s);

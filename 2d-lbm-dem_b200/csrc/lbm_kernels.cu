@@ -33,6 +33,9 @@
 #ifndef K1_NS
 #error "compile with -DK1_NS=k1_fast or -DK1_NS=k1_strict"
 #endif
+#ifndef LBMDEM_K1_SMEM_PAD
+#define LBMDEM_K1_SMEM_PAD 0 /* tuning knob: unused dynamic shared memory per CTA, i.e. fewer resident CTAs */
+#endif
 #ifndef LBMDEM_DEAD_GROUP
 #define LBMDEM_DEAD_GROUP 8   /* lanes per skip decision of the row kernel: 8 floats = one 32-byte sector (0: never skip) */
 #endif
@@ -94,7 +97,15 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-/* TY consumer threads (one node of the row each) + one producer warp that owns the TMA queue */
+/* TY consumer threads (one node of the row each) + one producer warp that owns the TMA queue -- or, with
+ * LBMDEM_K1_NOPROD, no producer warp: the first consumer lane issues the loads of row t+2 at the top of iteration t
+ * (the same moment the producer could: when every warp has released row t-2), and the 1920 registers of the idle
+ * producer lanes buy two more resident CTAs per SM */
+#if defined(LBMDEM_K1_NOPROD)
+#define K1_THREADS(C) (C::TY)
+#else
+#define K1_THREADS(C) (C::TY + 32)
+#endif
 #ifndef LBMDEM_K1_MINB_F32
 #define LBMDEM_K1_MINB_F32 1
 #endif
@@ -102,7 +113,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 #define LBMDEM_K1_MINB_F64 4   /* caps the fp64 build at 102 registers: 4 CTAs per SM (profiles/r01_k1_tuning.txt) */
 #endif
 template <typename real>
-__global__ void __launch_bounds__(RowCfg<real>::TY + 32, sizeof(real) == 8 ? LBMDEM_K1_MINB_F64 : LBMDEM_K1_MINB_F32)
+__global__ void __launch_bounds__(K1_THREADS(RowCfg<real>), sizeof(real) == 8 ? LBMDEM_K1_MINB_F64 : LBMDEM_K1_MINB_F32)
     lbm_rows_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                          const __grid_constant__ CUtensorMap tmCp,
                                                                          const __grid_constant__ CUtensorMap tmCn,
@@ -132,6 +143,28 @@ __global__ void __launch_bounds__(RowCfg<real>::TY + 32, sizeof(real) == 8 ? LBM
   }
   __syncthreads();
 
+  auto issue_row = [&](int t, int slot) { /* loaded row t is global row r0 - 1 + t */
+    unsigned char *base = smem + (size_t)slot * C::SLOT;
+    const int row = r0 - 1 + t - L.x0; /* local row */
+#if defined(LBMDEM_K1_PROBE) && LBMDEM_K1_PROBE == 3 /* 3 = writes alone: only the two map rows are loaded */
+    mbar_expect_tx(&full[slot], (uint32_t)(C::CN_BYTES + C::CP_BYTES));
+    tma_load_2d(base + C::A_PAD, &tmCn, &full[slot], y0 - C::HC, row);
+    tma_load_2d(base + C::A_PAD + C::CN_PAD, &tmCp, &full[slot], y0, row);
+    return;
+#endif
+    mbar_expect_tx(&full[slot], (uint32_t)(C::A_BYTES + C::CN_BYTES + C::CP_BYTES));
+#if defined(LBMDEM_K1_LD_EVICT_FIRST)
+    tma_load_3d_ef(base, &tmA, &full[slot], y0 - C::HY, row, 0);
+#else
+    tma_load_3d(base, &tmA, &full[slot], y0 - C::HY, row, 0);
+#endif
+    tma_load_2d(base + C::A_PAD, &tmCn, &full[slot], y0 - C::HC, row);
+    tma_load_2d(base + C::A_PAD + C::CN_PAD, &tmCp, &full[slot], y0, row);
+  };
+#if defined(LBMDEM_K1_NOPROD)
+  if (threadIdx.x == 0) /* fill the ring */
+    for (int t = 0; t < min(nload, C::NS); ++t) issue_row(t, t);
+#else
   if (threadIdx.x >= C::TY) {
     /* ---- producer warp: one lane keeps the ring full ---- */
     if (threadIdx.x == C::TY) {
@@ -139,21 +172,13 @@ __global__ void __launch_bounds__(RowCfg<real>::TY + 32, sizeof(real) == 8 ? LBM
       uint32_t round = 0; /* how many times the ring has wrapped */
       for (int t = 0; t < nload; ++t) {
         if (round > 0) mbar_wait(&empty[slot], (round - 1) & 1); /* all consumer warps are done with row t - NS */
-        unsigned char *base = smem + (size_t)slot * C::SLOT;
-        const int row = r0 - 1 + t - L.x0; /* local row */
-        mbar_expect_tx(&full[slot], (uint32_t)(C::A_BYTES + C::CN_BYTES + C::CP_BYTES));
-#if defined(LBMDEM_K1_LD_EVICT_FIRST)
-        tma_load_3d_ef(base, &tmA, &full[slot], y0 - C::HY, row, 0);
-#else
-        tma_load_3d(base, &tmA, &full[slot], y0 - C::HY, row, 0);
-#endif
-        tma_load_2d(base + C::A_PAD, &tmCn, &full[slot], y0 - C::HC, row);
-        tma_load_2d(base + C::A_PAD + C::CN_PAD, &tmCp, &full[slot], y0, row);
+        issue_row(t, slot);
         if (++slot == C::NS) { slot = 0; ++round; }
       }
     }
     return;
   }
+#endif
 
   /* ---- consumer warps ---- */
   const int jy = threadIdx.x;
@@ -166,11 +191,23 @@ __global__ void __launch_bounds__(RowCfg<real>::TY + 32, sizeof(real) == 8 ? LBM
   mbar_wait(&full[0], 0);
   mbar_wait(&full[1], 0);
 
+#if defined(LBMDEM_K1_PROBE)
+  real probe_acc = 0;
+#endif
   int slot_m = 0, slot_0 = 1; /* slots of rows t-1 and t */
   uint32_t round_p = 0;       /* ring round of row t+1 */
   for (int t = 1; t <= nload - 2; ++t) {
     int slot_p = slot_0 + 1;
     if (slot_p == C::NS) { slot_p = 0; ++round_p; }
+#if defined(LBMDEM_K1_NOPROD)
+    /* row t-2 was released by every warp at the end of iteration t-1 (or is about to be): its slot takes row
+     * t-2+NS.  Loaded rows 0 .. NS-1 went in before the loop. */
+    if (threadIdx.x == 0 && t >= 2 && t - 2 + C::NS < nload) {
+      const int tl = t - 2 + C::NS, sl = (t - 2) % C::NS;
+      mbar_wait(&empty[sl], ((t - 2) / C::NS) & 1);
+      issue_row(tl, sl);
+    }
+#endif
     mbar_wait(&full[slot_p], round_p & 1);
     const int *Cn0 = reinterpret_cast<const int *>(smem + (size_t)slot_0 * C::SLOT + C::A_PAD);
     const int gx = r0 - 1 + t;
@@ -229,8 +266,17 @@ __global__ void __launch_bounds__(RowCfg<real>::TY + 32, sizeof(real) == 8 ? LBM
           }
         }
       }
+#if defined(LBMDEM_K1_PROBE) && LBMDEM_K1_PROBE == 2 /* 2 = reads alone: the row's values are folded into one register */
+      {
+        real acc = 0;
 #pragma unroll
-#if defined(LBMDEM_K1_STCS) /* tuning variant: streaming stores (the output is not read again before 600 MB of other traffic) */
+        for (int q = 0; q < NQ; ++q) acc += f[q];
+        probe_acc += acc;
+      }
+      if (false)
+#endif
+#pragma unroll
+#if !defined(LBMDEM_K1_NO_STCS) /* streaming stores: the output is not read again before 600 MB of other traffic (measured: -2.5 %) */
       for (int q = 0; q < NQ; ++q) __stcs(&out[q * L.plane], f[q]);
 #else
       for (int q = 0; q < NQ; ++q) out[q * L.plane] = f[q];
@@ -243,6 +289,9 @@ __global__ void __launch_bounds__(RowCfg<real>::TY + 32, sizeof(real) == 8 ? LBM
     slot_m = slot_0;
     slot_0 = slot_p;
   }
+#if defined(LBMDEM_K1_PROBE)
+  if (probe_acc == (real)12345.678) a.out[0] = probe_acc; /* keeps the loads of probe 2 alive */
+#endif
 }
 
 /* the w-links of an active solid node (see lbm_rows_kernel), map read from global memory */
@@ -338,14 +387,21 @@ cudaError_t launch_lbm_rows(const CUtensorMap &tmA, const CUtensorMap &tmCp, con
   using C = RowCfg<real>;
   static int resident = 0;
   if (!resident) {
-    cudaError_t e = cudaFuncSetAttribute(lbm_rows_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(lbm_rows_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM + LBMDEM_K1_SMEM_PAD);
+    if (e != cudaSuccess) return e;
+    /* the whole 228 KB as shared memory: the kernel reads through TMA and barely uses L1, and with the driver's
+     * default carve-out (164 KB, ncu: launch__occupancy_limit_shared_mem) a deeper ring costs resident CTAs */
+    e = cudaFuncSetAttribute(lbm_rows_kernel<real>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 0, per_sm = 0;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbm_rows_kernel<real>, C::TY + 32, C::SMEM)) != cudaSuccess)
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lbm_rows_kernel<real>, K1_THREADS(C), C::SMEM + LBMDEM_K1_SMEM_PAD)) != cudaSuccess)
       return e;
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+#if defined(LBMDEM_K1_CTAS)
+    per_sm = LBMDEM_K1_CTAS; /* tuning knob: trust the carve-out request instead of the occupancy calculator */
+#endif
     resident = sms * per_sm;
   }
   const int R0 = a.xlo > 1 ? a.xlo : 1, R1 = a.xhi < a.L.lx - 1 ? a.xhi : a.L.lx - 1;
@@ -356,7 +412,7 @@ cudaError_t launch_lbm_rows(const CUtensorMap &tmA, const CUtensorMap &tmCp, con
   if (chunks < 1) chunks = 1;
   if (chunks > R1 - R0) chunks = R1 - R0;
   dim3 grid(strips, chunks);
-  lbm_rows_kernel<real><<<grid, C::TY + 32, C::SMEM, s>>>(tmA, tmCp, tmCn, a);
+  lbm_rows_kernel<real><<<grid, K1_THREADS(C), C::SMEM + LBMDEM_K1_SMEM_PAD, s>>>(tmA, tmCp, tmCn, a);
   return cudaGetLastError();
 }
 

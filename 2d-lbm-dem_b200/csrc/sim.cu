@@ -232,7 +232,8 @@ struct Sim : SimBase {
   DeferList<real> defer{};
   BoundaryList blist{};
   TileBins tbins{};          /* grains binned by lattice tile, rebuilt every LBM step (kernels.h) */
-  ForceFinish fin_pending{nullptr, 1, 0, 0}; /* fhf1..3 still have to be derived from these sums (kernels.h ForceFinish) */
+  ForceFinish fin_pending{nullptr, 1, 0, 0, nullptr};
+  int *range_flag_dev = nullptr; /* device view of hflags[5] */ /* fhf1..3 still have to be derived from these sums (kernels.h ForceFinish) */
   int coop_cap = 0;          /* grains the cooperative DEM kernel can take (one co-resident grid) */
   int sm_count = 148;        /* cudaDevAttrMultiProcessorCount of the context's device: sizes the persistent grids */
   int raster_step = 1;       /* counts rasteriser runs: tile stamps are compared with it (kernels.h TileBins::stamp) */
@@ -315,7 +316,10 @@ struct Sim : SimBase {
     if (P.nranks > 1 && xhi - xlo < 4) return fail(LBMDEM_EINVAL, "strips must be at least 4 rows wide");
     if (P.nranks > 1) { x0 = xlo - GHOST; nxl = xhi - xlo + 2 * GHOST; } else { x0 = 0; nxl = lx; }
     pitch = (ly + 31) / 32 * 32;
-    plane = (size_t)nxl * pitch;
+#ifndef LBMDEM_PLANE_PAD
+#define LBMDEM_PLANE_PAD 0 /* tuning knob: extra elements between the population planes (de-aliases power-of-two strides) */
+#endif
+    plane = (size_t)nxl * pitch + LBMDEM_PLANE_PAD;
     /* node indices within a plane are 32-bit (list entries, the fused kernel's store offsets) */
     if (plane >= ((size_t)1 << 31)) return fail(LBMDEM_EINVAL, "more than 2^31 nodes per GPU: use more strips");
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -366,6 +370,7 @@ struct Sim : SimBase {
     }
     CK(cudaHostAlloc(&hflags, 8 * sizeof(int), cudaHostAllocMapped));
     for (int k = 0; k < 8; ++k) hflags[k] = 0;
+    CK(cudaHostGetDevicePointer(&range_flag_dev, hflags + 5, 0));
     CK(cudaStreamSynchronize(stream));
     return 0;
   }
@@ -434,6 +439,7 @@ struct Sim : SimBase {
     CK(cudaMalloc(&defer.index, sizeof(size_t) * defer.capacity));
     CK(cudaMalloc(&defer.value, sizeof(real) * defer.capacity));
     CK(cudaHostGetDevicePointer(&defer.overflow, hflags + 1, 0));
+    defer.range_flag = range_flag_dev;
     if (hstage) { cudaFreeHost(hstage); hstage = nullptr; }
     hstage_elems = (size_t)n * 16;
     CK(cudaMallocHost(&hstage, sizeof(double) * hstage_elems));
@@ -850,7 +856,7 @@ struct Sim : SimBase {
         const int r = g_nccl.AllReduce(fpartial, fpartial, (size_t)3 * n, NcclApi::Float64, NcclApi::Sum, comm, stream);
         if (r) return nccl_fail(r, "ncclAllReduce");
       }
-      fin_pending = ForceFinish{ftot, 0, k12, k3};
+      fin_pending = ForceFinish{ftot, 0, k12, k3, nullptr};
     } else {
       long long *ftot = facc;
       if (multi) {
@@ -863,7 +869,7 @@ struct Sim : SimBase {
           if (r) return nccl_fail(r, "ncclAllReduce");
         }
       }
-      fin_pending = ForceFinish{ftot, 1, k12, k3};
+      fin_pending = ForceFinish{ftot, 1, k12, k3, range_flag_dev};
     }
     /* the sums become fhf1..3 in the first DEM launch that follows (or in materialise_fhf) */
     return 0;
@@ -922,6 +928,7 @@ struct Sim : SimBase {
     if (hflags[2]) { hflags[2] = 0; return fail(LBMDEM_ECAP, "boundary-node list is full"); }
     if (hflags[3]) { hflags[3] = 0; return fail(LBMDEM_ECAP, "bounce-back link list is full"); }
     if (hflags[4]) { hflags[4] = 0; return fail(LBMDEM_ECAP, "more grains under one lattice tile than the tile bins hold"); }
+    if (hflags[5]) { hflags[5] = 0; return fail(LBMDEM_ERANGE, "a hydrodynamic-force sum left the range of the 64-bit fixed-point accumulators (diverged populations?)"); }
     return 0;
   }
 

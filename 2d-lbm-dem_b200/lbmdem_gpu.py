@@ -22,7 +22,7 @@ _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 _fp = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 _ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
-ERRORS = {-1: "EINVAL", -2: "ECUDA", -3: "ENOMEM", -4: "ESTATE", -5: "EIO", -6: "ECAP", -7: "ENCCL"}
+ERRORS = {-1: "EINVAL", -2: "ECUDA", -3: "ENOMEM", -4: "ESTATE", -5: "EIO", -6: "ECAP", -7: "ENCCL", -8: "ERANGE"}
 
 
 class LbmdemError(RuntimeError):

@@ -35,7 +35,8 @@ enum {
   LBMDEM_ESTATE = -4,   /* call out of order (e.g. step before set_grains) */
   LBMDEM_EIO = -5,      /* sample file could not be read */
   LBMDEM_ECAP = -6,     /* neighbour-list capacity exceeded (the reference only prints, :1535) */
-  LBMDEM_ENCCL = -7
+  LBMDEM_ENCCL = -7,
+  LBMDEM_ERANGE = -8    /* a hydrodynamic-force sum left the range of the fixed-point accumulators (diverged run) */
 };
 
 /* What the reference fixes at compile time (-Dlx -Dly -Dscale -DSINGLE_PRECISION,

@@ -158,3 +158,15 @@ def test_one_node_gap_links_default_build():
     assert np.array_equal(o.obst(), s.obst())
     assert np.abs(o.f() - s.f()).max() < 1e-12
     assert _relerr(s.fhf(), o.fhf()) < 1e-9
+
+
+def test_diverged_populations_raise_the_range_flag():
+    """the 64-bit fixed-point force sums assume |sum| < 2^11: populations of 1e6 next to a grain must not wrap silently"""
+    lx, ly = 96, 72
+    r, x, y = small_packing(lx, ly, 1.0, 5, n_target=30)
+    s = G.Solver(lx, ly, 1.0, "f64")
+    s.init_arrays(r, x, y)
+    s.set_f(perturbed_f(lx, ly, 6) * 1e6)
+    with pytest.raises(G.LbmdemError) as ei:
+        s.step(3)
+    assert ei.value.code == -8
