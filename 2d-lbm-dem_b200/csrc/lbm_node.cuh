@@ -291,26 +291,64 @@ LBM_HD void mrt_collide(const Lattice<real> &L, real *p) {
 #endif
 }
 
+/* ---- arithmetic of the grain bounce-back links, immune to multiply-add contraction ----
+ * Every product and sum of the link arithmetic is an explicitly rounded operation on the device, so that it gives the
+ * same bits whichever translation unit it is compiled in (the sparse sweep kernels are built with -fmad=false, the
+ * fused LBM kernel with contraction in the default build); the host build of tests/hostcheck uses -ffp-contract=off. */
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ float x_mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float x_add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float x_sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float x_div(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double x_mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double x_add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double x_sub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double x_div(double a, double b) { return __ddiv_rn(a, b); }
+#else
+inline float x_mul(float a, float b) { return a * b; }
+inline float x_add(float a, float b) { return a + b; }
+inline float x_sub(float a, float b) { return a - b; }
+inline float x_div(float a, float b) { return a / b; }
+inline double x_mul(double a, double b) { return a * b; }
+inline double x_add(double a, double b) { return a + b; }
+inline double x_sub(double a, double b) { return a - b; }
+inline double x_div(double a, double b) { return a / b; }
+#endif
+
+/* e_q . u_wall at solid node (x,y) of grain g: `ex * wall_ux + ey * wall_uy` with the sub-expressions of :974-980 */
+template <typename real>
+LBM_HD real link_eu(const Lattice<real> &L, const GrainRec<real> &g, int x, int y, int q) {
+  const real ux = x_sub(g.v1, x_mul(x_sub(x_add(x_mul((real)y, L.dx), L.Mby), g.x2), g.v3));
+  const real uy = x_add(g.v2, x_mul(x_sub(x_add(x_mul((real)x, L.dx), L.Mgx), g.x1), g.v3));
+  return x_add(x_mul((real)ex_of(q), ux), x_mul((real)ey_of(q), uy));
+}
+
 /* src/main.c:1053-1058: link fraction for the link from solid node (x,y) along q to its fluid
  * neighbour, measured from the fluid node.  C semantics: fabs/sqrt are the double functions. */
 template <typename real>
 LBM_HD real link_delta(const GrainRec<real> &g, int x, int y, int q) {
   const int ex = ex_of(q), ey = ey_of(q);
   const real aa = fabs((double)ex) + fabs((double)ey);
-  const real bb = (x + ex - g.xc) * ex + (y + ey - g.yc) * ey;
-  const real cc = (x + ex - g.xc) * (x + ex - g.xc) + (y + ey - g.yc) * (y + ey - g.yc) - g.r2;
-  return (bb - sqrt(fabs((double)(bb * bb - aa * cc)))) / aa;
+  const real dxn = x_sub((real)(x + ex), g.xc), dyn = x_sub((real)(y + ey), g.yc);
+  const real bb = x_add(x_mul(dxn, (real)ex), x_mul(dyn, (real)ey));
+  const real cc = x_sub(x_add(x_mul(dxn, dxn), x_mul(dyn, dyn)), g.r2);
+  const real disc = x_sub(x_mul(bb, bb), x_mul(aa, cc));
+  return (real)x_div(x_sub((double)bb, sqrt(fabs((double)disc))), (double)aa);
 }
 
 /* src/main.c:1166-1185 (and :1198-1217): the two interpolated bounce-back formulas.
  * Fn_oq = F[n][opp q], Fn_q = F[n][q], Xnn_oq = f[nn][opp q] as seen by the reference's sweep,
- * eu = ex*u_wall_x + ey*u_wall_y at the SOLID node.  `keep` is returned when delta <= 0. */
+ * eu = ex*u_wall_x + ey*u_wall_y at the SOLID node.  `keep` is returned when delta <= 0.
+ * (`2 * d`, `3 * (w / c)` ...: int literals, evaluated in `real`; the comparisons with 0.5 in double.) */
 template <typename real>
 LBM_HD real bounce_value(const Lattice<real> &L, int q, real d, real Fn_oq, real Fn_q, real Xnn_oq, real eu,
                          real keep) {
   real v = keep;
-  if (d >= 0.5) v = Fn_oq / (2 * d) + (2 * d - 1) * Fn_q / (2 * d) + 3 * (L.w[q] / L.c) * eu / d;
-  if (d > 0. && d < 0.5) v = 2 * d * Fn_oq + (1 - 2 * d) * Xnn_oq + 6 * (L.w[q] / L.c) * eu;
+  const real d2 = x_mul((real)2, d), wc = x_div(L.w[q], L.c);
+  if (d >= 0.5)
+    v = x_add(x_add(x_div(Fn_oq, d2), x_div(x_mul(x_sub(d2, (real)1), Fn_q), d2)), x_div(x_mul(x_mul((real)3, wc), eu), d));
+  if (d > 0. && d < 0.5)
+    v = x_add(x_add(x_mul(d2, Fn_oq), x_mul(x_sub((real)1, d2), Xnn_oq)), x_mul(x_mul((real)6, wc), eu));
   return v;
 }
 
@@ -437,10 +475,35 @@ LBM_HD bool is_active_solid(const Lattice<real> &L, const Stored<real> &S, int x
  * deferred links -- none of which a concurrent in-place pass over the other links modifies. */
 enum { SWEEP_KEEP = 0, SWEEP_WRITE = 1, SWEEP_DEFER = 2 };
 
-/* The link itself, inlined into its caller.  `g` is the record of the grain that owns (x,y).  *gap_out tells
- * whether the link faces an active solid node across a one-node gap (the caller of the bounce-back kernel passes
- * resolve = true and files such links in the deferred list itself); *Fn_oq_out is A[n][opp q], which the
- * momentum exchange of the link needs as well (n is a fluid node: the sweep never writes there). */
+/* One bounce-back link from its operands alone.  g: the grain that owns the solid node s = (x,y); Fn_oq, Fn_q: the
+ * two populations of the fluid neighbour n = s + e_q; X: f[nn][opp q], nn = n + e_q, BEFORE the sweep; gap: nn is an
+ * active solid node (of grain gp) across a one-node gap -- then the reference, sweeping x-outer y-inner, has already
+ * rewritten X if nn comes before s, and that new value is recomputed here from the pre-sweep operands of the partner
+ * link (nn, opp q): its fluid neighbour is n as well, its second fluid-side node is s itself, hence Fs_q = f[s][q]
+ * before the sweep.  Returns SWEEP_KEEP (delta <= 0: f[s][q] stays) or SWEEP_WRITE (*v is the new f[s][q]). */
+template <typename real>
+LBM_HD int link_value(const Lattice<real> &L, const GrainRec<real> &g, int x, int y, int q, real Fn_oq, real Fn_q, real X,
+                      bool gap, const GrainRec<real> *gp, real Fs_q, real *v) {
+  const real d = link_delta(g, x, y, q);
+  if (!(d > 0.)) return SWEEP_KEEP;
+  const real eu = link_eu(L, g, x, y, q);
+  if (d < 0.5 && gap) {
+    const int oq = opp_of(q), nnx = x + 2 * ex_of(q), nny = y + 2 * ey_of(q);
+    if (nnx < x || (nnx == x && nny < y)) {
+      const real dp = link_delta(*gp, nnx, nny, oq);
+      const real eup = link_eu(L, *gp, nnx, nny, oq);
+      X = bounce_value(L, oq, dp, Fn_q, Fn_oq, Fs_q, eup, X);
+    }
+  }
+  *v = bounce_value(L, q, d, Fn_oq, Fn_q, X, eu, (real)0);
+  return SWEEP_WRITE;
+}
+
+/* The link with its operands read from the stored array (the sparse sweep kernels, tests/hostcheck).  `g` is the
+ * record of the grain that owns (x,y).  *gap_out tells whether the link faces an active solid node across a one-node
+ * gap (the caller of the bounce-back kernel passes resolve = true and files such links in the deferred list itself);
+ * *Fn_oq_out is A[n][opp q], which the momentum exchange of the link needs as well (n is a fluid node: the sweep
+ * never writes there). */
 template <typename real>
 LBM_HD int sweep_link_core(const Lattice<real> &L, const Stored<real> &S, const GrainRec<real> &g, int x, int y, int q,
                            bool resolve, real *v, bool n_is_fluid, bool *gap_out, real *Fn_oq_out) {
@@ -458,27 +521,19 @@ LBM_HD int sweep_link_core(const Lattice<real> &L, const Stored<real> &S, const 
   }
   /* n fluid => n is an interior node => nn lies inside the array.  An interior solid nn is active:
    * its neighbour n is fluid */
-  const bool gap = !is_ring(L, nnx, nny) && !cell_is_fluid(S.cell[node_index(L, nnx, nny)]);
+  const size_t knn = node_index(L, nnx, nny);
+  const int cnn = S.cell[knn];
+  const bool gap = !is_ring(L, nnx, nny) && !cell_is_fluid(cnn);
   *gap_out = gap;
   if (gap && !resolve) return SWEEP_DEFER;
-  const real d = link_delta(g, x, y, q);
-  if (!(d > 0.)) return SWEEP_KEEP;
-  const real eu = ex * wall_ux(L, g, y) + ey * wall_uy(L, g, x);
-  real X = 0;
-  if (d < 0.5) {
-    const size_t knn = node_index(L, nnx, nny);
-    X = S.A[oq * L.plane + knn];
-    if (gap && (nnx < x || (nnx == x && nny < y))) {
-      /* the partner link (nn, opp q) was swept earlier: its new value, from the pre-sweep state.
-       * Its fluid neighbour is n, its second fluid-side node is s itself. */
-      const GrainRec<real> gp = S.grains[cell_obst(S.cell[knn])];
-      const real dp = link_delta(gp, nnx, nny, oq);
-      const real eup = ex_of(oq) * wall_ux(L, gp, nny) + ey_of(oq) * wall_uy(L, gp, nnx);
-      X = bounce_value(L, oq, dp, Fn_q, Fn_oq, S.A[q * L.plane + ks], eup, X);
-    }
+  const real X = S.A[oq * L.plane + knn];
+  real Fs_q = 0;
+  GrainRec<real> gp = g;
+  if (gap) {
+    Fs_q = S.A[q * L.plane + ks];
+    gp = S.grains[cell_obst(cnn)];
   }
-  *v = bounce_value(L, q, d, Fn_oq, Fn_q, X, eu, (real)0);
-  return SWEEP_WRITE;
+  return link_value(L, g, x, y, q, Fn_oq, Fn_q, X, gap, &gp, Fs_q, v);
 }
 
 template <typename real>
