@@ -182,9 +182,10 @@ constexpr int RT_CHUNK = 64;                 /* grains staged in shared memory a
 static_assert(RTY == 64 && RTX == 32 && RT_THREADS == 256, "pass 3a: a warp takes 4 rows, a lane 4 consecutive columns");
 
 template <typename real>
-__global__ void __launch_bounds__(RT_THREADS) raster_tile_kernel(int n, int *cell, const int *cell_other, int x0, int nxl,
-                                                                 int pitch, int lx, int ly, TileBins T, BoundaryList B,
-                                                                 LinkList K, int step, int force_full) {
+__global__ void __launch_bounds__(RT_THREADS) raster_tile_kernel(int n, int *cell, const int *cell_other, unsigned char *cls,
+                                                                 const unsigned char *cls_other, int x0, int nxl, int pitch,
+                                                                 int lx, int ly, TileBins T, BoundaryList B, LinkList K,
+                                                                 int step, int force_full) {
   /* region = tile + one halo node all round; region row r+1 / column c+RTC0 hold tile node (r, c) */
   __shared__ __align__(16) int own[RTX + 2][RTP]; /* owner: -1 fluid, n ring / outside the array */
   __shared__ __align__(16) int low[RTX + 2][RTP]; /* lowest covering index where more than one disc covers the node */
@@ -222,6 +223,7 @@ __global__ void __launch_bounds__(RT_THREADS) raster_tile_kernel(int n, int *cel
       if (x <= x0 + nxl - 1 && ty0 + c0 + 3 < pitch) {
         const size_t k = (size_t)(x - x0) * pitch + ty0 + c0;
         *reinterpret_cast<int4 *>(&cell[k]) = *reinterpret_cast<const int4 *>(&cell_other[k]);
+        *reinterpret_cast<uchar4 *>(&cls[k]) = *reinterpret_cast<const uchar4 *>(&cls_other[k]);
       }
     }
     continue;
@@ -307,7 +309,11 @@ __global__ void __launch_bounds__(RT_THREADS) raster_tile_kernel(int n, int *cel
       if (v.z >= 0 && v.z < n && !(a.y == v.z && a.z == v.z && a.w == v.z && v.y == v.z && v.w == v.z && d.y == v.z && d.z == v.z && d.w == v.z)) hit |= 4u;
       if (v.w >= 0 && v.w < n && !(a.z == v.w && a.w == v.w && aR == v.w && v.z == v.w && vR == v.w && d.z == v.w && d.w == v.w && dR == v.w)) hit |= 8u;
     }
-    if (x <= x0 + nxl - 1 && ty0 + c0 + 3 < pitch) *reinterpret_cast<int4 *>(&cell[(size_t)(x - x0) * pitch + ty0 + c0]) = v;
+    if (x <= x0 + nxl - 1 && ty0 + c0 + 3 < pitch) {
+      const size_t k = (size_t)(x - x0) * pitch + ty0 + c0;
+      *reinterpret_cast<int4 *>(&cell[k]) = v;
+      *reinterpret_cast<uchar4 *>(&cls[k]) = make_uchar4(cell_class(v.x, n), cell_class(v.y, n), cell_class(v.z, n), cell_class(v.w, n));
+    }
     if (__any_sync(0xffffffffu, hit != 0)) {
       const int mine = __popc(hit);
       int incl = mine;
@@ -362,7 +368,10 @@ __global__ void __launch_bounds__(RT_THREADS) raster_tile_kernel(int n, int *cel
       packed += (unsigned)__popc(near_ring ? 0xffu : fluid); /* bounce links; next to the ring the w-links too */
     }
     if (solid_foreign) packed += 1u << 16;
-    if (act || solid_foreign) cell[(size_t)(x - x0) * pitch + y] = i | (act ? CELL_ACT : 0) | (solid_foreign ? CELL_RIM : 0);
+    if (act || solid_foreign) {
+      cell[(size_t)(x - x0) * pitch + y] = i | (act ? CELL_ACT : 0) | (solid_foreign ? CELL_RIM : 0);
+      cls[(size_t)(x - x0) * pitch + y] = (unsigned char)(CLS_SOLID | (act ? CLS_ACT : 0) | (solid_foreign ? CLS_RIM : 0));
+    }
   }
 
   /* ---- 4. one slot range per list and WARP inside the tile's own segments of the two lists ---- */
@@ -434,20 +443,20 @@ __global__ void __launch_bounds__(RT_THREADS) raster_tile_kernel(int n, int *cel
 template <typename real>
 cudaError_t launch_raster_tiles(const RasterParams<real> &P, int n, const GrainArrays<real> &g, GrainRec<real> *rec, real *R2,
                                 GrainBox *boxes, const GrainRec<real> *rec_old, const real *R2_old, const GrainBox *boxes_old,
-                                int *cell, const int *cell_other, int x0, int nxl, int pitch, const TileBins &T,
-                                const BoundaryList &B, const LinkList &K, int *defer_count, long long *facc, int step,
-                                int first_run, int force_full, cudaStream_t s) {
+                                int *cell, const int *cell_other, unsigned char *cls, const unsigned char *cls_other, int x0,
+                                int nxl, int pitch, const TileBins &T, const BoundaryList &B, const LinkList &K,
+                                int *defer_count, long long *facc, int step, int first_run, int force_full, cudaStream_t s) {
   grain_bin_kernel<real><<<(n + 3) / 4, 128, 0, s>>>(P, n, g, rec, R2, boxes, rec_old, R2_old, boxes_old, x0, nxl, T, step,
                                                      first_run, defer_count, facc);
   const int ntiles = T.ntx * T.nty;
   const int ctas = force_full ? ntiles : min(ntiles, T.resident_ctas);
-  raster_tile_kernel<real><<<ctas, RT_THREADS, 0, s>>>(n, cell, cell_other, x0, nxl, pitch, P.lx, P.ly, T, B, K, step,
-                                                       force_full);
+  raster_tile_kernel<real><<<ctas, RT_THREADS, 0, s>>>(n, cell, cell_other, cls, cls_other, x0, nxl, pitch, P.lx, P.ly, T, B, K,
+                                                       step, force_full);
   return cudaGetLastError();
 }
 
 /* init_obst's frame (:674-687): ring = nbgrains, interior = -1 */
-__global__ void cell_frame_kernel(int *cell, int lx, int ly, int x0, int nxl, int pitch, int ring_value) {
+__global__ void cell_frame_kernel(int *cell, unsigned char *cls, int lx, int ly, int x0, int nxl, int pitch, int ring_value) {
   const int y = blockIdx.x * blockDim.x + threadIdx.x;
   const int row = blockIdx.y;
   if (y >= pitch || row >= nxl) return;
@@ -455,11 +464,23 @@ __global__ void cell_frame_kernel(int *cell, int lx, int ly, int x0, int nxl, in
   int v = -1;
   if (x <= 0 || x >= lx - 1 || y <= 0 || y >= ly - 1) v = ring_value;
   cell[(size_t)row * pitch + y] = v;
+  cls[(size_t)row * pitch + y] = cell_class(v, ring_value);
 }
 
-cudaError_t launch_cell_frame(int *cell, int lx, int ly, int x0, int nxl, int pitch, int ring_value, cudaStream_t s) {
+cudaError_t launch_cell_frame(int *cell, unsigned char *cls, int lx, int ly, int x0, int nxl, int pitch, int ring_value,
+                              cudaStream_t s) {
   dim3 grid((pitch + 255) / 256, nxl);
-  cell_frame_kernel<<<grid, 256, 0, s>>>(cell, lx, ly, x0, nxl, pitch, ring_value);
+  cell_frame_kernel<<<grid, 256, 0, s>>>(cell, cls, lx, ly, x0, nxl, pitch, ring_value);
+  return cudaGetLastError();
+}
+
+__global__ void cls_from_cell_kernel(const int *cell, unsigned char *cls, size_t count, int ngrains) {
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < count) cls[k] = cell_class(cell[k], ngrains);
+}
+cudaError_t launch_cls_from_cell(const int *cell, unsigned char *cls, int nxl, int pitch, int ngrains, cudaStream_t s) {
+  const size_t count = (size_t)nxl * pitch;
+  cls_from_cell_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(cell, cls, count, ngrains);
   return cudaGetLastError();
 }
 
@@ -1476,7 +1497,8 @@ cudaError_t launch_fill_rest(real *f, size_t plane, const Lattice<real> &Lw, cud
 #define INSTANTIATE(real)                                                                                               \
   template cudaError_t launch_raster_tiles<real>(const RasterParams<real> &, int, const GrainArrays<real> &,              \
                                                  GrainRec<real> *, real *, GrainBox *, const GrainRec<real> *,            \
-                                                 const real *, const GrainBox *, int *, const int *, int, int, int,       \
+                                                 const real *, const GrainBox *, int *, const int *, unsigned char *,     \
+                                                 const unsigned char *, int, int, int,                                    \
                                                  const TileBins &, const BoundaryList &, const LinkList &, int *,         \
                                                  long long *, int, int, int, cudaStream_t);                               \
   template cudaError_t launch_act_map<real>(const Lattice<real> &, const Stored<real> &, int, int, int *, cudaStream_t);  \

@@ -28,7 +28,9 @@ namespace lbmdem {
 /* Row pipeline of the fused LBM kernel.  A CTA owns TY consecutive y-columns and marches along
  * x; each TMA transaction brings ONE lattice row of the strip into a ring of NS shared-memory
  * slots: the nine population planes (TY nodes plus a halo of HY nodes per side), the matching row
- * of this step's obstacle map (halo HC) and of the stored step's map (no halo).
+ * of this step's obstacle map (halo HC) -- its class bytes only, lbm_node.cuh cell_class -- and of the
+ * stored step's map (no halo; int32: the re-initialised nodes need their owner, and fetching it from
+ * global memory inside the loop put two dependent loads in front of the equilibrium: measured 27 % slower).
  * The TMA unit wants the byte offset of the box origin along the contiguous dimension to be a
  * multiple of 16 (measured on B200: any other inner coordinate raises "illegal instruction",
  * tools/tma_probe.cu), so the y halo is 16 / sizeof(real) nodes wide instead of one; a box is at
@@ -42,10 +44,10 @@ struct RowCfg {
 #endif
   static constexpr int NS = LBMDEM_K1_NS;   /* ring slots */
   static constexpr int BY = TY + 2 * HY;
-  static constexpr int HC = 4;
+  static constexpr int HC = 16;             /* y halo of the class-byte row of this step's map (one byte per node) */
   static constexpr int BC = TY + 2 * HC;
   static constexpr int A_BYTES = lbm::NQ * BY * (int)sizeof(real);
-  static constexpr int CN_BYTES = BC * 4, CP_BYTES = TY * 4;
+  static constexpr int CN_BYTES = BC, CP_BYTES = TY * 4;
   static constexpr int A_PAD = (A_BYTES + 127) / 128 * 128;
   static constexpr int CN_PAD = (CN_BYTES + 127) / 128 * 128;
   static constexpr int CP_PAD = (CP_BYTES + 127) / 128 * 128;
@@ -62,8 +64,8 @@ template <typename real>
 struct FusedArgs {
   lbm::Lattice<real> L;
   const real *A;                           /* stored populations, sweeps 1-4 applied, [q][x-x0][y] */
-  const int *cell_prev;                    /* obstacle map of the stored step */
-  const int *cell_new;                     /* obstacle map of this step */
+  const int *cell_prev;                    /* obstacle map of the stored step (the row kernel reads owners from it) */
+  const int *cell_new;                     /* obstacle map of this step (plain / ring kernel) */
   const lbm::GrainRec<real> *grains_new;   /* grain records of this step */
   real *out;                               /* [q][x-x0][y] */
   int xlo, xhi;                            /* owned global rows [xlo, xhi) */
@@ -172,13 +174,18 @@ template <typename real>
 cudaError_t launch_raster_tiles(const lbm::RasterParams<real> &P, int ngrains, const GrainArrays<real> &g,
                                 lbm::GrainRec<real> *rec, real *R2, lbm::GrainBox *boxes,
                                 const lbm::GrainRec<real> *rec_old, const real *R2_old, const lbm::GrainBox *boxes_old,
-                                int *cell, const int *cell_other /* the previous step's map */, int x0, int nxl, int pitch,
+                                int *cell, const int *cell_other /* the previous step's map */,
+                                unsigned char *cls, const unsigned char *cls_other /* their class bytes */, int x0, int nxl,
+                                int pitch,
                                 const TileBins &T, const BoundaryList &B, const LinkList &K,
                                 int *defer_count /* emptied as well */,
                                 long long *facc /* nullptr, or [3][n] force sums to be zeroed */, int step,
                                 int first_run /* no previous records */, int force_full /* rebuild every tile */,
                                 cudaStream_t s);
-cudaError_t launch_cell_frame(int *cell, int lx, int ly, int x0, int nxl, int pitch, int ring_value, cudaStream_t s);
+cudaError_t launch_cell_frame(int *cell, unsigned char *cls, int lx, int ly, int x0, int nxl, int pitch, int ring_value,
+                              cudaStream_t s);
+/* class bytes of a map that came from outside (lbmdem_set_obst): fluid / solid / ring only */
+cudaError_t launch_cls_from_cell(const int *cell, unsigned char *cls, int nxl, int pitch, int ngrains, cudaStream_t s);
 /* act[x][y] as the reference would hold it (tests / diagnostics) */
 template <typename real>
 cudaError_t launch_act_map(const lbm::Lattice<real> &L, const lbm::Stored<real> &S, int xlo, int xhi, int *act_out,

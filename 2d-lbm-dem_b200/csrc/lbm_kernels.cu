@@ -107,7 +107,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 #define K1_THREADS(C) (C::TY + 32)
 #endif
 #ifndef LBMDEM_K1_MINB_F32
-#define LBMDEM_K1_MINB_F32 1
+#define LBMDEM_K1_MINB_F32 7   /* 56 registers: 7 CTAs per SM (r02W: 0.2294 ms against 0.2351 ms with 64 registers) */
 #endif
 #ifndef LBMDEM_K1_MINB_F64
 #define LBMDEM_K1_MINB_F64 4   /* caps the fp64 build at 102 registers: 4 CTAs per SM (profiles/r01_k1_tuning.txt) */
@@ -209,19 +209,26 @@ __global__ void __launch_bounds__(K1_THREADS(RowCfg<real>), sizeof(real) == 8 ? 
     }
 #endif
     mbar_wait(&full[slot_p], round_p & 1);
-    const int *Cn0 = reinterpret_cast<const int *>(smem + (size_t)slot_0 * C::SLOT + C::A_PAD);
+    /* class bytes (lbm_node.cuh cell_class) of this step's map, row t with its y halo; behind them the stored step's map */
+    const unsigned char *Kn0 = smem + (size_t)slot_0 * C::SLOT + C::A_PAD;
     const int gx = r0 - 1 + t;
-    int cnow = 0, cprev = 0;
+    unsigned know = 0;
+    int cprev = 0;
     bool work = active;
     if (active) {
-      cnow = Cn0[jy + C::HC];
-      cprev = Cn0[C::CN_PAD / 4 + jy];
+      know = Kn0[jy + C::HC];
+      cprev = reinterpret_cast<const int *>(Kn0 + C::CN_PAD)[jy];
     }
     {
       /* deep inside a grain under both maps: nothing reads what the re-init sweep would leave here (lbm_node.cuh,
        * node_is_dead; the fill_dead kernel materialises it when the populations are observed).  Skipped in whole
        * aligned groups of DEAD_GROUP lanes only, so that no 32-byte sector of the output is written in part. */
-      bool skip = !active || (!a.stream_only && node_is_dead(L, cprev, cnow, gx, gy));
+#if defined(LBMDEM_DEAD_GROUP) && LBMDEM_DEAD_GROUP == 0
+      const bool dead = false;
+#else
+      const bool dead = cprev >= 0 && (know & CLS_SOLID) && !(know & (CLS_ACT | CLS_RIM)) && w_links_with_collide(L, gx, gy);
+#endif
+      bool skip = !active || (!a.stream_only && dead);
 #if LBMDEM_DEAD_GROUP > 1
       const unsigned all = __ballot_sync(0xffffffffu, skip);
       const unsigned grp = (LBMDEM_DEAD_GROUP >= 32 ? 0xffffffffu : ((1u << (LBMDEM_DEAD_GROUP & 31)) - 1u))
@@ -253,16 +260,18 @@ __global__ void __launch_bounds__(K1_THREADS(RowCfg<real>), sizeof(real) == 8 ? 
 #else
       if (!a.stream_only) {
 #endif
-        reinit_collide(L, a.grains_new, cprev, cnow, gx, gy, f);
-        if (cell_is_act(cnow) && w_links_with_collide(L, gx, gy)) {
+        /* sweeps 1-2 (lbm_node.cuh reinit_collide) */
+        if (!cell_is_fluid(cprev)) equilibrium(L, a.grains_new[cell_obst(cprev)], gx, gy, f);
+        if (know == 0) mrt_collide(L, f);
+        if ((know & CLS_ACT) && w_links_with_collide(L, gx, gy)) {
           /* active solid node: links into non-fluid neighbours take the rest value (:1161-1162) */
-          const int *Cnm = reinterpret_cast<const int *>(smem + (size_t)slot_m * C::SLOT + C::A_PAD);
-          const int *Cnp = reinterpret_cast<const int *>(smem + (size_t)slot_p * C::SLOT + C::A_PAD);
+          const unsigned char *Knm = smem + (size_t)slot_m * C::SLOT + C::A_PAD;
+          const unsigned char *Knp = smem + (size_t)slot_p * C::SLOT + C::A_PAD;
 #pragma unroll
           for (int q = 1; q < NQ; ++q) {
             const int ex = ex_of(q), ey = ey_of(q);
-            const int *Cs = ex > 0 ? Cnp : (ex < 0 ? Cnm : Cn0); /* neighbour row x + ex */
-            if (!cell_is_fluid(Cs[jy + C::HC + ey])) f[q] = L.w[q];
+            const unsigned char *Ks = ex > 0 ? Knp : (ex < 0 ? Knm : Kn0); /* neighbour row x + ex */
+            if (Ks[jy + C::HC + ey] != 0) f[q] = L.w[q];
           }
         }
       }

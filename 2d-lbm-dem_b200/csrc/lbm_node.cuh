@@ -59,6 +59,19 @@ LBM_HD bool cell_is_fluid(int c) { return c < 0; }
 LBM_HD int cell_obst(int c) { return c < 0 ? -1 : (c & CELL_IDX); }
 LBM_HD bool cell_is_act(int c) { return c >= 0 && (c & CELL_ACT) != 0; }
 
+/* One byte per node beside the map: all the fused LBM kernel needs of a node's map entry -- except the owner index,
+ * which it fetches from the int map for the few nodes that are re-initialised (solid under the stored step's map and
+ * not dead).  0 = fluid. */
+constexpr unsigned char CLS_SOLID = 1;  /* not fluid: a grain node or the wall ring */
+constexpr unsigned char CLS_ACT = 2;    /* CELL_ACT */
+constexpr unsigned char CLS_RIM = 4;    /* CELL_RIM */
+constexpr unsigned char CLS_RING = 8;   /* the wall ring (obst == nbgrains): no grain record behind it */
+LBM_HD unsigned char cell_class(int c, int ngrains) {
+  if (c < 0) return 0;
+  return (unsigned char)(CLS_SOLID | ((c & CELL_ACT) ? CLS_ACT : 0) | ((c & CELL_RIM) ? CLS_RIM : 0) |
+                         ((c & CELL_IDX) >= ngrains ? CLS_RING : 0));
+}
+
 /* what the LBM kernels need to know about one grain (filled by the rasteriser, K2) */
 template <typename real>
 struct GrainRec {

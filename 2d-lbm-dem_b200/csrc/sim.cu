@@ -222,6 +222,7 @@ struct Sim : SimBase {
   cudaEvent_t ev_state = nullptr, ev_halo = nullptr;
   real *f[2] = {nullptr, nullptr};
   int *cell[2] = {nullptr, nullptr};
+  unsigned char *cls[2] = {nullptr, nullptr}; /* class byte per node of cell[k] (lbm_node.cuh cell_class): what the row kernel streams */
   int cur = 0, cur_cell = 0;
   bool holds_A = false;      /* f[cur] holds A of the last step (stream pending) instead of f */
   bool scratch_valid = false; /* f[1 - cur] holds the materialised f of the pending stream */
@@ -271,7 +272,7 @@ struct Sim : SimBase {
   ~Sim() override {
     if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
     for (auto &e : ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
-    for (int k = 0; k < 2; ++k) { cudaFree(f[k]); cudaFree(cell[k]); }
+    for (int k = 0; k < 2; ++k) { cudaFree(f[k]); cudaFree(cell[k]); cudaFree(cls[k]); }
     for (real *p : grain_bufs) cudaFree(p);
     for (int k = 0; k < 2; ++k) { cudaFree(rec[k]); cudaFree(R2[k]); cudaFree(boxes[k]); }
     for (int k = 0; k < 2; ++k) { cudaFree(facc_buf[k]); cudaFree(fpartial_buf[k]); }
@@ -334,6 +335,7 @@ struct Sim : SimBase {
       CK(cudaMalloc(&f[k], sizeof(real) * plane * NQ));
       CK(cudaMemsetAsync(f[k], 0, sizeof(real) * plane * NQ, stream));
       CK(cudaMalloc(&cell[k], sizeof(int) * plane));
+      CK(cudaMalloc(&cls[k], plane));
     }
     CK(cudaMalloc(&dens_partials, sizeof(double) * DENS_BLOCKS));
     CK(cudaMalloc(&dens_out, sizeof(double)));
@@ -357,14 +359,16 @@ struct Sim : SimBase {
                           f[k], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                           LBMDEM_K1_L2PROMO, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return fail(LBMDEM_ECUDA, "cuTensorMapEncodeTiled(f) failed with code " + std::to_string((int)r));
+      /* the stored step's map (int32, no halo) and the class bytes of this step's (one byte per node, y halo) */
       const cuuint64_t cdims[2] = {(cuuint64_t)ly, (cuuint64_t)nxl};
       const cuuint64_t cstr[1] = {(cuuint64_t)pitch * sizeof(int)};
       const cuuint32_t cbox[2] = {(cuuint32_t)C::TY, 1};
       r = encode(&tmC[k], CU_TENSOR_MAP_DATA_TYPE_INT32, 2, cell[k], cdims, cstr, cbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      const cuuint64_t bstr[1] = {(cuuint64_t)pitch};
       const cuuint32_t cboxh[2] = {(cuuint32_t)C::BC, 1};
       if (r == CUDA_SUCCESS)
-        r = encode(&tmCh[k], CU_TENSOR_MAP_DATA_TYPE_INT32, 2, cell[k], cdims, cstr, cboxh, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        r = encode(&tmCh[k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, cls[k], cdims, bstr, cboxh, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return fail(LBMDEM_ECUDA, "cuTensorMapEncodeTiled(map) failed with code " + std::to_string((int)r));
     }
@@ -536,7 +540,7 @@ struct Sim : SimBase {
     const Lattice<real> L = lattice();
     CK(launch_fill_rest<real>(f[0], plane, L, stream));
     CK(launch_fill_rest<real>(f[1], plane, L, stream));
-    for (int k = 0; k < 2; ++k) CK(launch_cell_frame(cell[k], lx, ly, x0, nxl, pitch, n, stream));
+    for (int k = 0; k < 2; ++k) CK(launch_cell_frame(cell[k], cls[k], lx, ly, x0, nxl, pitch, n, stream));
     cur = 0;
     cur_cell = 0;
     holds_A = false;
@@ -618,7 +622,8 @@ struct Sim : SimBase {
     /* params.kernel bit 1: every tile rebuilt every step (the cross-check of the incremental rasteriser) */
     const int full = (raster_step <= raster_full_until || (P.kernel & 2)) ? 1 : 0;
     CK(launch_raster_tiles<real>(raster_params(), n, g, rec[cslot], R2[cslot], boxes[cslot], rec[1 - cslot], R2[1 - cslot],
-                                 boxes[1 - cslot], cell[cslot], cell[1 - cslot], x0, nxl, pitch, tbins, blist, llist,
+                                 boxes[1 - cslot], cell[cslot], cell[1 - cslot], cls[cslot], cls[1 - cslot], x0, nxl, pitch, tbins,
+                                 blist, llist,
                                  defer.count, fa, raster_step, raster_step == 1 ? 1 : 0, full, stream));
     ++raster_step;
     all_launches += 2; /* grain_bin, raster_tile */
@@ -1119,6 +1124,7 @@ struct Sim : SimBase {
     raster_invalidate(); /* this map is not what the grain records would give */
     CK(cudaMemcpy2DAsync(cell[cur_cell] + (size_t)(xlo - x0) * pitch, sizeof(int) * pitch, in, sizeof(int) * ly,
                          sizeof(int) * ly, xhi - xlo, cudaMemcpyHostToDevice, stream));
+    CK(launch_cls_from_cell(cell[cur_cell], cls[cur_cell], nxl, pitch, n, stream));
     CK(cudaStreamSynchronize(stream));
     return 0;
   }
