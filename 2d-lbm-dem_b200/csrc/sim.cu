@@ -62,6 +62,7 @@ struct NcclApi {
   typedef int (*Recv_t)(void *, size_t, int, int, void *, cudaStream_t);
   typedef int (*Group_t)(void);
   typedef int (*AllReduce_t)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+  typedef int (*Broadcast_t)(const void *, void *, size_t, int, int, void *, cudaStream_t);
   typedef const char *(*ErrStr_t)(int);
   void *handle = nullptr;
   GetUniqueId_t GetUniqueId = nullptr;
@@ -71,6 +72,7 @@ struct NcclApi {
   Recv_t Recv = nullptr;
   Group_t GroupStart = nullptr, GroupEnd = nullptr;
   AllReduce_t AllReduce = nullptr;
+  Broadcast_t Broadcast = nullptr;
   ErrStr_t GetErrorString = nullptr;
   enum { Int64 = 4, Float32 = 7, Float64 = 8, Sum = 0 };
   bool load(std::string *why) {
@@ -86,7 +88,7 @@ struct NcclApi {
   if (!field) { *why = std::string("dlsym ") + name; return false; }
     SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
     SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd")
-    SYM(AllReduce, "ncclAllReduce") SYM(GetErrorString, "ncclGetErrorString")
+    SYM(AllReduce, "ncclAllReduce") SYM(Broadcast, "ncclBroadcast") SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
     return true;
   }
@@ -193,7 +195,9 @@ struct SimBase {
   virtual int save_state(const char *path) = 0;
   virtual int load_state(const char *path) = 0;
   virtual int get_fields(const double *gp, float *a, float *b, float *c, float *d, float *e) = 0;
-  virtual int step_host(const void *state_in, long n, void *state_out, void *fhf_out, double *dens, bool rows_f32) = 0;
+  virtual int step_host(const void *state_in, long n, void *state_out, void *fhf_out, double *dens, bool rows_f32,
+                        bool share) = 0;
+  virtual int get_share(int *i0, int *i1) = 0;
   virtual int attach_nccl(const void *id) = 0;
   virtual int attach_local(LocalGroup *g) = 0;
   virtual int get_kernel_timer(double *ms, long *k1, long *all) = 0;
@@ -1324,18 +1328,48 @@ struct Sim : SimBase {
    * out of pinned memory, one copy over PCIe each way); the device does the transposition and
    * the double <-> real conversion. */
   double *gstage = nullptr; /* device: [n][9] in, then [n][9] + [n][3] out (doubles, or floats in the same space) */
-  int step_host(const void *state_in, long nsteps, void *state_out, void *fhf_out, double *dens, bool rows_f32) override {
+  /* the grains this rank moves across the host boundary in the `share` form of the end-to-end call: a balanced
+   * contiguous index range per rank (all of them on one GPU) */
+  void share_range(int rank, int *i0, int *i1) const {
+    const int base = n / P.nranks, rem = n % P.nranks;
+    *i0 = rank * base + std::min(rank, rem);
+    *i1 = *i0 + base + (rank < rem ? 1 : 0);
+  }
+  int get_share(int *i0, int *i1) override {
+    if (!ready) return fail(LBMDEM_ESTATE, "no grains loaded");
+    share_range(P.rank, i0, i1);
+    return 0;
+  }
+  int step_host(const void *state_in, long nsteps, void *state_out, void *fhf_out, double *dens, bool rows_f32,
+                bool share) override {
     if (!ready) return fail(LBMDEM_ESTATE, "no grains loaded");
     if (rows_f32 && sizeof(real) != 4) return fail(LBMDEM_EINVAL, "float grain rows need a single-precision context");
+    if (share && P.nranks > 1 && !comm) return fail(LBMDEM_ESTATE, "the share form of lbmdem_step_host needs the NCCL communicator");
     const size_t N = (size_t)n, eb = rows_f32 ? sizeof(float) : sizeof(double);
+    int i0 = 0, i1 = n;
+    if (share) share_range(P.rank, &i0, &i1);
+    const size_t M = (size_t)(i1 - i0); /* rows that cross the host boundary */
     if (!gstage) CK(cudaMalloc(&gstage, sizeof(double) * 12 * N));
     char *gs = reinterpret_cast<char *>(gstage), *hs = reinterpret_cast<char *>(hstage); /* hstage: 16 n doubles, pinned */
     const bool pin_in = state_in && host_is_pinned(state_in);
     const bool pin_out = (!state_out || host_is_pinned(state_out)) && (!fhf_out || host_is_pinned(fhf_out));
     if (state_in) {
       const void *src = state_in;
-      if (!pin_in) { memcpy(hs, state_in, eb * 9 * N); src = hs; }
-      CK(cudaMemcpyAsync(gs, src, eb * 9 * N, cudaMemcpyHostToDevice, stream));
+      if (!pin_in) { memcpy(hs, state_in, eb * 9 * M); src = hs; }
+      CK(cudaMemcpyAsync(gs + eb * 9 * (size_t)i0, src, eb * 9 * M, cudaMemcpyHostToDevice, stream));
+      if (share && P.nranks > 1) {
+        /* every rank's rows to every rank, over NVLink instead of PCIe: one broadcast per rank, in place, one group */
+        int r = g_nccl.GroupStart();
+        for (int k = 0; k < P.nranks && !r; ++k) {
+          int a, b;
+          share_range(k, &a, &b);
+          char *at = gs + eb * 9 * (size_t)a;
+          r = g_nccl.Broadcast(at, at, (size_t)9 * (b - a), rows_f32 ? NcclApi::Float32 : NcclApi::Float64, k, comm, stream);
+        }
+        const int r2 = g_nccl.GroupEnd();
+        if (r) return nccl_fail(r, "ncclBroadcast");
+        if (r2) return nccl_fail(r2, "ncclGroupEnd");
+      }
       CK(launch_grain_unpack<real>(gs, rows_f32, n, 9, g.x1, stream)); /* x1 .. a3 are contiguous in the slab */
     }
     bool built = false;
@@ -1345,13 +1379,15 @@ struct Sim : SimBase {
     if ((rc = materialise_fhf())) return rc;
     if (state_out || fhf_out) {
       CK(launch_grain_pack2<real>(g.x1, 9, g.fhf1, 3, n, gs, rows_f32, stream)); /* [n][9] state, then [n][3] fhf */
-      if (pin_out && state_out && fhf_out && static_cast<char *>(fhf_out) == static_cast<char *>(state_out) + eb * 9 * N) {
+      const char *st = gs + eb * 9 * (size_t)i0, *fh = gs + eb * 9 * N + eb * 3 * (size_t)i0;
+      if (pin_out && !share && state_out && fhf_out && static_cast<char *>(fhf_out) == static_cast<char *>(state_out) + eb * 9 * N) {
         CK(cudaMemcpyAsync(state_out, gs, eb * 12 * N, cudaMemcpyDeviceToHost, stream)); /* one block on the host too */
       } else if (pin_out) {
-        if (state_out) CK(cudaMemcpyAsync(state_out, gs, eb * 9 * N, cudaMemcpyDeviceToHost, stream));
-        if (fhf_out) CK(cudaMemcpyAsync(fhf_out, gs + eb * 9 * N, eb * 3 * N, cudaMemcpyDeviceToHost, stream));
+        if (state_out) CK(cudaMemcpyAsync(state_out, st, eb * 9 * M, cudaMemcpyDeviceToHost, stream));
+        if (fhf_out) CK(cudaMemcpyAsync(fhf_out, fh, eb * 3 * M, cudaMemcpyDeviceToHost, stream));
       } else {
-        CK(cudaMemcpyAsync(hs, gs, eb * 12 * N, cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemcpyAsync(hs, st, eb * 9 * M, cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemcpyAsync(hs + eb * 9 * M, fh, eb * 3 * M, cudaMemcpyDeviceToHost, stream));
       }
     }
     if (dens) {
@@ -1362,8 +1398,8 @@ struct Sim : SimBase {
     }
     if ((rc = check_flags())) return rc;
     if (!pin_out) {
-      if (state_out) memcpy(state_out, hs, eb * 9 * N);
-      if (fhf_out) memcpy(fhf_out, hs + eb * 9 * N, eb * 3 * N);
+      if (state_out) memcpy(state_out, hs, eb * 9 * M);
+      if (fhf_out) memcpy(fhf_out, hs + eb * 9 * M, eb * 3 * M);
     }
     return 0;
   }
@@ -1572,10 +1608,20 @@ API int lbmdem_get_fields(lbmdem_ctx *ctx, const double *gp, float *a, float *b,
   GUARDED(ctx->sim->get_fields(gp, a, b, c, d, e));
 }
 API int lbmdem_step_host(lbmdem_ctx *ctx, const double *in, long n, double *out, double *fhf, double *dens) {
-  GUARDED(ctx->sim->step_host(in, n, out, fhf, dens, false));
+  GUARDED(ctx->sim->step_host(in, n, out, fhf, dens, false, false));
 }
 API int lbmdem_step_host_f32(lbmdem_ctx *ctx, const float *in, long n, float *out, float *fhf, double *dens) {
-  GUARDED(ctx->sim->step_host(in, n, out, fhf, dens, true));
+  GUARDED(ctx->sim->step_host(in, n, out, fhf, dens, true, false));
+}
+API int lbmdem_get_share(lbmdem_ctx *ctx, int *i0, int *i1) {
+  if (!i0 || !i1) return LBMDEM_EINVAL;
+  GUARDED(ctx->sim->get_share(i0, i1));
+}
+API int lbmdem_step_host_share(lbmdem_ctx *ctx, const double *in, long n, double *out, double *fhf, double *dens) {
+  GUARDED(ctx->sim->step_host(in, n, out, fhf, dens, false, true));
+}
+API int lbmdem_step_host_share_f32(lbmdem_ctx *ctx, const float *in, long n, float *out, float *fhf, double *dens) {
+  GUARDED(ctx->sim->step_host(in, n, out, fhf, dens, true, true));
 }
 API int lbmdem_nccl_unique_id(void *id128) {
   std::string why;

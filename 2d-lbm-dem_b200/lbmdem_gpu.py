@@ -99,6 +99,9 @@ def load_library():
         "lbmdem_get_kernel_timer": ([vp, C.POINTER(C.c_double), C.POINTER(C.c_long), C.POINTER(C.c_long)], C.c_int),
         "lbmdem_reset_kernel_timer": ([vp, C.c_int], C.c_int),
         "lbmdem_get_list_counts": ([vp, C.POINTER(C.c_long)], C.c_int),
+        "lbmdem_get_share": ([vp, C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
+        "lbmdem_step_host_share": ([vp, vp, C.c_long, vp, vp, vp], C.c_int),
+        "lbmdem_step_host_share_f32": ([vp, vp, C.c_long, vp, vp, vp], C.c_int),
         "lbmdem_local_group_create": ([C.c_int, C.POINTER(vp)], C.c_int),
         "lbmdem_attach_local": ([vp, vp], C.c_int),
         "lbmdem_local_group_destroy": ([vp], None),
@@ -162,8 +165,8 @@ class Solver:
         return rc
 
     def close(self):
-        self.__dict__.pop("_hostbufs", None)
-        self.__dict__.pop("_hostbufs32", None)
+        for k in [k for k in self.__dict__ if k.startswith("_hostbufs")]:
+            self.__dict__.pop(k, None)
         for p, _ in self.__dict__.pop("_pinned_bufs", {}).values():
             self.L.lbmdem_host_free(p)
         if getattr(self, "h", None):
@@ -232,18 +235,26 @@ class Solver:
             bufs[name] = (p, arr)
         return bufs[name][1]
 
-    def step_host(self, state_in, n_dem_steps, want_state=True, want_fhf=True, want_density=True, rows="f64"):
+    def share(self):
+        """[i0, i1): the grain rows this rank moves across the host boundary in step_host(..., share=True)"""
+        a, b = C.c_int(), C.c_int()
+        self._ck(self.L.lbmdem_get_share(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def step_host(self, state_in, n_dem_steps, want_state=True, want_fhf=True, want_density=True, rows="f64", share=False):
         """lbmdem_step_host (rows="f64") / lbmdem_step_host_f32 (rows="f32", single-precision solvers): host arrays in,
-        host arrays out (the end-to-end call).  The buffers are page-locked and reused: the returned arrays are views
-        that the next call overwrites; passing the returned state back in costs no host copy."""
+        host arrays out (the end-to-end call).  share=True: the *_share forms -- this rank's rows [i0, i1) of the grains
+        only (see share()).  The buffers are page-locked and reused: the returned arrays are views that the next call
+        overwrites; passing the returned state back in costs no host copy."""
         f32 = rows == "f32"
-        key = "_hostbufs32" if f32 else "_hostbufs"
+        key = "_hostbufs" + ("32" if f32 else "") + ("s" if share else "")
         hb = self.__dict__.get(key)
         if hb is None:
             # one input slot and two output blocks, so that the state returned by the previous call can be the input of
             # this one; an output block holds [n][9] state followed by [n][3] fhf: one device-to-host copy
-            sfx = "32" if f32 else ""
-            n = self.n
+            sfx = key[9:]
+            i0, i1 = self.share() if share else (0, self.n)
+            n = i1 - i0
             a_in = self._pinned("in" + sfx, (n, 9), f32)
             hb = [(a_in, a_in.ctypes.data_as(C.c_void_p))]
             for k in ("blk0", "blk1"):
@@ -268,7 +279,10 @@ class Solver:
         if want_fhf:
             fh, pfh = (a_f1, p_f1) if use_o1 else (a_f0, p_f0)
         dens = C.c_double() if want_density else None
-        call = self.L.lbmdem_step_host_f32 if f32 else self.L.lbmdem_step_host
+        if share:
+            call = self.L.lbmdem_step_host_share_f32 if f32 else self.L.lbmdem_step_host_share
+        else:
+            call = self.L.lbmdem_step_host_f32 if f32 else self.L.lbmdem_step_host
         self._ck(call(self.h, psin, n_dem_steps, psout, pfh, C.cast(C.byref(dens), C.c_void_p) if dens is not None else None))
         return sout, fh, (dens.value if dens is not None else None)
 

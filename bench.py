@@ -306,7 +306,11 @@ def measure(workload, a, rank, local_rank, world, tmpdir, with_check, with_e2e=T
     e2e = None
     if with_e2e:
         # ---- end-to-end arm: host buffers in, host buffers out, every step ----
-        state = s.grains()[:, :9].copy()
+        # with N > 1 GPUs every rank moves ITS share of the (replicated) grain rows across the host boundary and the
+        # ranks pass them on over NVLink (lbmdem_step_host_share); with one GPU that is lbmdem_step_host
+        share = world > 1
+        i0, i1 = s.share() if share else (0, n_grains)
+        state = s.grains()[i0:i1, :9].copy()
         # the reference prints its density checksum every stepConsole = 400 renderScene() calls (:1715):
         # the end-to-end loop asks for it at that cadence (it costs a stream-only pass over the lattice)
         every = max(1, 400 // npd)
@@ -314,21 +318,22 @@ def measure(workload, a, rank, local_rank, world, tmpdir, with_check, with_e2e=T
         grain_rows = "f32" if prec == "f32" else "f64"
         dens = None
         for _ in range(max(3, warmup // 2)):
-            state, fh, dens = s.step_host(state, npd, rows=grain_rows)
+            state, fh, dens = s.step_host(state, npd, rows=grain_rows, share=share)
         D.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for k in range(steps):
-            state, fh, d_ = s.step_host(state, npd, want_density=((k + 1) % every == 0 or k == steps - 1), rows=grain_rows)
+            state, fh, d_ = s.step_host(state, npd, want_density=((k + 1) % every == 0 or k == steps - 1), rows=grain_rows, share=share)
             dens = d_ if d_ is not None else dens
         torch.cuda.synchronize()
         t_e2e = D.max_over_ranks(time.perf_counter() - t0)
         D.barrier()
         # grain rows travel in the precision of the run: 9 values up, 9 + 3 down per grain
         e2e = {"value": lx * ly * steps / t_e2e / 1e6, "unit": "MLUPS",
-               "h2d_bytes_per_step": n_grains * 9 * real_b, "d2h_bytes_per_step": n_grains * 12 * real_b + 8,
-               "call": ("lbmdem_step_host_f32" if grain_rows == "f32" else "lbmdem_step_host") +
-                       " with page-locked host buffers (lbmdem_host_alloc): grain state up, npDEM renderScene() calls, grain state + fhf down every step, density checksum every 400 calls",
+               "h2d_bytes_per_step": n_grains * 9 * real_b, "d2h_bytes_per_step": n_grains * 12 * real_b + 8 * world,
+               "call": ("lbmdem_step_host" + ("_share" if share else "") + ("_f32" if grain_rows == "f32" else "")) +
+                       " with page-locked host buffers (lbmdem_host_alloc): grain state up, npDEM renderScene() calls, grain state + fhf down every step, density checksum every 400 calls" +
+                       ("; every rank moves its share of the grain rows, the bytes are the sum over the ranks" if share else ""),
                "ms_per_step": 1e3 * t_e2e / steps, "density_checksum": dens}
 
     # ---- roofline of the dominant kernel (K1), measured live with CUDA events on its stream ----

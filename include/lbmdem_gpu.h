@@ -149,6 +149,17 @@ int lbmdem_step_host(lbmdem_ctx *ctx, const double *state_in /* [n][9] or NULL *
 int lbmdem_step_host_f32(lbmdem_ctx *ctx, const float *state_in /* [n][9] or NULL */, long n_dem_steps,
                          float *state_out /* [n][9] */, float *fhf_out /* [n][3] */, double *density_out);
 
+/* Strip-decomposed runs replicate the grains on every GPU, but only one copy has to cross the host boundary: in the
+ * `share` form every rank uploads and downloads the rows of ITS share of the grains -- the contiguous index range
+ * [i0, i1) of lbmdem_get_share, a balanced split over the ranks -- and the ranks pass the uploaded rows on to each other
+ * over NVLink (one ncclBroadcast per rank) before the step.  state_in / state_out: [i1-i0][9], fhf_out: [i1-i0][3].
+ * With one rank it is lbmdem_step_host. */
+int lbmdem_get_share(lbmdem_ctx *ctx, int *i0, int *i1);
+int lbmdem_step_host_share(lbmdem_ctx *ctx, const double *state_in, long n_dem_steps, double *state_out, double *fhf_out,
+                           double *density_out);
+int lbmdem_step_host_share_f32(lbmdem_ctx *ctx, const float *state_in, long n_dem_steps, float *state_out, float *fhf_out,
+                               double *density_out);
+
 /* page-locked host memory for the buffers of lbmdem_step_host (the reference keeps its grain
  * array in plain malloc memory, src/main.c:612; a caller that wants the copies without staging
  * allocates it here instead) */

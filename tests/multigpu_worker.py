@@ -58,6 +58,19 @@ def main():
         part = torch.tensor([strip.total_density()], dtype=torch.float64, device="cuda")
         torch.distributed.all_reduce(part)
         assert abs(part.item() - one.total_density()) < 1e-9 * lx * ly
+        # end-to-end call in its share form: every rank uploads / downloads its share of the grain rows, the ranks pass
+        # them on over NCCL; same result as the one-GPU call with all rows
+        npd = one.scalars()["npDEM"]
+        i0, i1 = strip.share()
+        assert (i0, i1) == D.strip_bounds(n, rank, world)
+        rows = "f32" if prec == "f32" else "f64"
+        full = one.grains()[:, :9].copy()
+        for _ in range(2):
+            so, fo, _d = one.step_host(full, npd, rows=rows)
+            ss, fs, _d = strip.step_host(full[i0:i1], npd, rows=rows, share=True)
+            assert np.array_equal(ss, so[i0:i1]) and np.array_equal(fs, fo[i0:i1]), f"{prec} rank {rank}: share form differs"
+            full = np.array(so, dtype=np.float64)
+        assert np.array_equal(strip.grains(), one.grains())
         # checkpoint / restart of a decomposed run: one file per rank, bit-exact continuation
         import tempfile
         ck = os.path.join(tempfile.gettempdir(), f"lbmdem_ck_{prec}_{os.environ.get('MASTER_PORT', '0')}")

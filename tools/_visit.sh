@@ -1,15 +1,15 @@
-OUT=gpurun_out; RUN=r02W; mkdir -p $OUT
-for t in mb7; do
-  LBMDEM_LIB=$PWD/2d-lbm-dem_b200/liblbmdem_gpu_$t.so timeout 200 python bench.py --steps 300 --no-cpu-baseline --no-cfg5 > $OUT/${RUN}_$t.json 2> $OUT/${RUN}_$t.err
+OUT=gpurun_out; RUN=r02X; mkdir -p $OUT
+timeout 900 python -m pytest tests -m gpu -q -x > $OUT/${RUN}_pytest.log 2>&1; tail -8 $OUT/${RUN}_pytest.log
+for n in 2 4; do
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2955$n bench.py --gpus $n --steps 100 --warmup 10 > $OUT/${RUN}_bench$n.json 2> $OUT/${RUN}_bench$n.err; echo "bench$n rc $?"
 done
-timeout 200 python bench.py --steps 300 --no-cpu-baseline --no-cfg5 > $OUT/${RUN}_default.json 2> $OUT/${RUN}_default.err
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:lbm_rows -s 6 -c 1 -f -o $OUT/${RUN}_k1 python bench.py --steps 3 --warmup 8 --no-cpu-baseline --no-cfg5 > $OUT/${RUN}_k1.log 2>&1
+timeout 300 python bench.py --steps 100 --warmup 10 --no-cpu-baseline > $OUT/${RUN}_bench1.json 2> $OUT/${RUN}_bench1.err
 python - <<PY
-import json,glob
-for p in sorted(glob.glob("$OUT/${RUN}_*.json")):
+import json
+for nm in ("bench1","bench2","bench4"):
     try:
-        d=json.loads(open(p).read().strip().splitlines()[-1])
-        print(p.split("${RUN}_")[1][:-5].ljust(14), "MLUPS %.0f  ms/step %.4f  K1 ms %.4f frac %.3f  e2e %.0f" % (d["value"], d["ms_per_step"], d["roofline"]["avg_launch_ms"], d["roofline"]["frac"], d["e2e"]["value"]))
+        d=json.loads(open("$OUT/${RUN}_%s.json"%nm).read().strip().splitlines()[-1])
+        print(nm, "value %.0f ms %.4f e2e %.0f K1 %.4f" % (d["value"], d["ms_per_step"], d["e2e"]["value"], d["roofline"]["avg_launch_ms"]), "check", d.get("strip_check",{}).get("ok"), "cfg5 %.0f ms %.4f e2e %.0f check %s" % (d["cfg5"]["value"], d["cfg5"]["ms_per_step"], d["cfg5"]["e2e"]["value"], d["cfg5"].get("strip_check",{}).get("ok")))
     except Exception as e:
-        print(p, "unreadable", e)
+        print(nm, "unreadable", e)
 PY
