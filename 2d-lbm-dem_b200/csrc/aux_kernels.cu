@@ -796,21 +796,26 @@ __global__ void __launch_bounds__(256, LBMDEM_SWEEP_MINB) rim_kernel(const __gri
                                                                     int xb, int xlo, int xhi, const LinkList K,
                                                                     const BoundaryList B, const DeferList<real> D,
                                                                     long long *facc, int *ticket) {
-  __shared__ int s_last;
+  __shared__ int s_done;
   const int tile = blockIdx.y * gridDim.x + blockIdx.x, nctas = gridDim.x * gridDim.y;
+  if (threadIdx.x == 0) s_done = 0;
+  __syncthreads();
   bounce_tile_links<real>(L, S, A, xa, xb, xlo, xhi, K, D, facc, tile);
   if (facc != nullptr) force_tile_nodes<real>(L, S, xlo, xhi, B, facc, tile, D.range_flag);
-  __syncthreads();
-  if (threadIdx.x == 0) {
+  /* no CTA barrier at the end (a quarter of the warp samples sat at one): the warps count themselves out in shared
+   * memory, the CTA's last warp counts the CTA out, and the last warp of the grid applies the deferred links */
+  __syncwarp();
+  int last = 0;
+  if ((threadIdx.x & 31) == 0) {
     __threadfence();
-    s_last = atomicAdd(ticket, 1) == nctas - 1;
+    if (atomicAdd(&s_done, 1) == (int)(blockDim.x >> 5) - 1) last = atomicAdd(ticket, 1) == nctas - 1;
   }
-  __syncthreads();
-  if (!s_last) return;
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (!last) return;
   __threadfence();
   const int nd = min(*(volatile int *)D.count, D.capacity);
-  for (int k = threadIdx.x; k < nd; k += blockDim.x) A[__ldcg(&D.index[k])] = __ldcg(&D.value[k]);
-  if (threadIdx.x == 0) *ticket = 0;
+  for (int k = threadIdx.x & 31; k < nd; k += 32) A[__ldcg(&D.index[k])] = __ldcg(&D.value[k]);
+  if ((threadIdx.x & 31) == 0) *ticket = 0;
 }
 template <typename real>
 cudaError_t launch_rim(const Lattice<real> &L, const Stored<real> &S, real *A, int xa, int xb, int xlo, int xhi,

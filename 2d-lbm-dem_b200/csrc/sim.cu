@@ -1209,7 +1209,19 @@ struct Sim : SimBase {
     double scale;
     long nbsteps, nFile;
     double t, Mgx, Mdx, Mby, Mhy;
+    unsigned long long physics; /* fingerprint of the physical parameters the run was made with (version 2) */
   };
+  /* FNV-1a over the parameters that decide the continuation: a restart with other physics must fail, not drift */
+  unsigned long long physics_hash() const {
+    const double v[] = {P.tau, P.nu, P.rho_moy, P.reductionR, P.s2, P.s3, P.s5, P.s7, P.s8, P.s9, P.G, P.angleG, P.kg, P.kt,
+                        P.km, P.ktm, P.nug, P.num, P.numb, P.nugt, P.mu, P.mum, P.mumb, P.murf, P.rscale, P.distVerlet, P.dtt,
+                        P.iterDEM, P.freq, P.amp, P.rhoS, (double)P.UpdateVerlet, (double)P.stepFilm, P.lid_u,
+                        (double)P.strict_fp, (double)P.vib};
+    unsigned long long h = 1469598103934665603ull;
+    const unsigned char *b = reinterpret_cast<const unsigned char *>(v);
+    for (size_t k = 0; k < sizeof v; ++k) h = (h ^ b[k]) * 1099511628211ull;
+    return h;
+  }
   std::string rank_path(const char *path) const { /* one file per rank of a strip-decomposed run */
     return P.nranks > 1 ? std::string(path) + ".rank" + std::to_string(P.rank) : std::string(path);
   }
@@ -1222,7 +1234,7 @@ struct Sim : SimBase {
     CkHeader h;
     memset(&h, 0, sizeof h);
     memcpy(h.magic, "LBMDEMCK", 8);
-    h.version = 1; h.lx = lx; h.ly = ly; h.single = sizeof(real) == 4; h.n = n; h.nranks = P.nranks; h.rank = P.rank;
+    h.version = 2; h.physics = physics_hash(); h.lx = lx; h.ly = ly; h.single = sizeof(real) == 4; h.n = n; h.nranks = P.nranks; h.rank = P.rank;
     h.cap = vb.cap; h.scale = P.scale; h.nbsteps = nbsteps; h.nFile = nFile;
     h.t = t; h.Mgx = Mgx; h.Mdx = Mdx; h.Mby = Mby; h.Mhy = Mhy;
     int rc = materialise_fhf();
@@ -1253,9 +1265,29 @@ struct Sim : SimBase {
     FILE *fp = fopen(path, "rb");
     if (!fp) return fail(LBMDEM_EIO, std::string("cannot open ") + path);
     CkHeader h;
-    if (fread(&h, sizeof h, 1, fp) != 1 || memcmp(h.magic, "LBMDEMCK", 8) || h.version != 1) {
+    if (fread(&h, sizeof h, 1, fp) != 1 || memcmp(h.magic, "LBMDEMCK", 8) || h.version != 2) {
       fclose(fp);
-      return fail(LBMDEM_EIO, std::string("not a checkpoint: ") + path);
+      return fail(LBMDEM_EIO, std::string("not a checkpoint (of this version): ") + path);
+    }
+    if (h.physics != physics_hash()) {
+      fclose(fp);
+      return fail(LBMDEM_EINVAL, "checkpoint was written with other physical parameters (tau, nu, contact constants, strict_fp ...)");
+    }
+    {
+      /* the header is not trusted: sizes that disagree with the file itself are rejected before anything is allocated */
+      const long at = ftell(fp);
+      fseek(fp, 0, SEEK_END);
+      const long size = ftell(fp);
+      fseek(fp, at, SEEK_SET);
+      const size_t rows_ = (size_t)(xhi - xlo), rb = sizeof(real);
+      const bool sane = h.n > 0 && h.cap > 0 && h.cap <= 4096;
+      const size_t want = sane ? sizeof h + rb * 16 * (size_t)h.n + sizeof(int) * ((size_t)h.n * (2 + (size_t)h.cap)) +
+                                     sizeof(int) * rows_ * ly + sizeof(double) * rows_ * ly * NQ
+                               : 0;
+      if (!sane || size < 0 || (size_t)size != want) {
+        fclose(fp);
+        return fail(LBMDEM_EIO, std::string("corrupt or truncated checkpoint: ") + path);
+      }
     }
     if (h.lx != lx || h.ly != ly || h.single != (int)(sizeof(real) == 4) || h.nranks != P.nranks || h.rank != P.rank ||
         h.scale != P.scale || h.n <= 0) {

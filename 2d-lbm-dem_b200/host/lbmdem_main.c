@@ -21,6 +21,7 @@
  * (The PostScript contact plot DEM%06d.ps of write_forces() is not produced.)
  */
 #include <math.h>
+#include <signal.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -45,6 +46,7 @@ typedef struct {
   char nccl_id[128];
   volatile int arrived, sense;    /* sense-reversing barrier */
   volatile int failed;            /* some rank died: everybody leaves */
+  volatile int pids[64];          /* the ranks' process ids: a rank that fails takes down peers that may sit in a collective */
   double partial[64];             /* per-rank contribution to a sum (density checksum) */
 } shared_t;
 static shared_t *sh;
@@ -75,10 +77,20 @@ static double rank_sum(double v) {
   return s;
 }
 
+/* Any fatal path of a multi-rank run: tell the peers (those waiting at the barrier leave by themselves) and, after a
+ * moment, terminate the ones that are blocked inside an NCCL collective waiting for this rank -- by process id, never
+ * by group or pattern. */
+static void fail_run(void) {
+  if (!sh) exit(EXIT_FAILURE);
+  sh->failed = 1;
+  usleep(200000);
+  for (int r = 0; r < nranks; ++r)
+    if (r != rank && sh->pids[r] > 0) kill((pid_t)sh->pids[r], SIGTERM);
+  exit(EXIT_FAILURE);
+}
 static void die(const char *what) {
   fprintf(stderr, "lbmdem: rank %d: %s: %s\n", rank, what, lbmdem_last_error(ctx));
-  if (sh) sh->failed = 1;
-  exit(EXIT_FAILURE);
+  fail_run();
 }
 #define CK(call) do { if ((call) < 0) die(#call); } while (0)
 
@@ -149,6 +161,7 @@ int main(int argc, char **argv) {
       if (pid < 0) { fprintf(stderr, "lbmdem: fork failed\n"); return EXIT_FAILURE; }
       if (pid == 0) { rank = r; break; }
     }
+    sh->pids[rank] = (int)getpid();
     p.rank = rank; p.nranks = nranks; p.device += rank;
     if (rank != 0) { /* only rank 0 talks */
       if (!freopen("/dev/null", "w", stdout)) return EXIT_FAILURE;
@@ -157,16 +170,15 @@ int main(int argc, char **argv) {
 
   if (lbmdem_create(&p, &ctx)) {
     fprintf(stderr, "lbmdem: rank %d: %s\n", rank, lbmdem_last_error(NULL));
-    if (sh) sh->failed = 1;
-    return EXIT_FAILURE;
+    fail_run();
   }
   if (nranks > 1) {
     if (rank == 0) {
-      if (lbmdem_nccl_unique_id(sh->nccl_id)) { fprintf(stderr, "lbmdem: %s\n", lbmdem_last_error(NULL)); sh->failed = 1; return EXIT_FAILURE; }
+      if (lbmdem_nccl_unique_id(sh->nccl_id)) { fprintf(stderr, "lbmdem: %s\n", lbmdem_last_error(NULL)); fail_run(); }
       __atomic_store_n(&sh->id_ready, 1, __ATOMIC_RELEASE);
     } else {
       while (!__atomic_load_n(&sh->id_ready, __ATOMIC_ACQUIRE)) {
-        if (sh->failed) return EXIT_FAILURE;
+        if (sh->failed) exit(EXIT_FAILURE);
         usleep(100);
       }
     }
@@ -183,7 +195,7 @@ int main(int argc, char **argv) {
     int cnt = 0;
     if (!fp || !fgets(com, sizeof com, fp) || fscanf(fp, "%d\n", &cnt) != 1) {
       fprintf(stderr, "lbmdem: cannot read %s\n", argv[1]);
-      return EXIT_FAILURE;
+      fail_run();
     }
     fclose(fp);
     printf("%s\n", com);
@@ -204,7 +216,7 @@ int main(int argc, char **argv) {
   double *gp = malloc(sizeof(double) * (size_t)n);
   const int cap = p.neighbour_capacity;
   int *cnt = malloc(sizeof(int) * (size_t)n), *nbr = malloc(sizeof(int) * (size_t)n * cap), *wfl = malloc(sizeof(int) * (size_t)n);
-  if (!grains || !fhf || !mid || !diag || !gp || !cnt || !nbr || !wfl) return EXIT_FAILURE;
+  if (!grains || !fhf || !mid || !diag || !gp || !cnt || !nbr || !wfl) fail_run();
   CK(lbmdem_get_grains(ctx, grains));
   check_sample(n, grains, p.rhoS);
   printf("no space %le\n", dx);
@@ -217,7 +229,7 @@ int main(int argc, char **argv) {
   }
   time(&now);
   printf("Current local time and date: %s", asctime(localtime(&now)));
-  if (rank == 0 && !restart && lbmdem_write_stats_header(outdir)) { fprintf(stderr, "lbmdem: cannot write stats.data\n"); return EXIT_FAILURE; }
+  if (rank == 0 && !restart && lbmdem_write_stats_header(outdir)) { fprintf(stderr, "lbmdem: cannot write stats.data\n"); fail_run(); }
   lbmdem_diag *dg = lbmdem_diag_create(n, &p);
 
   const size_t nn = (size_t)(xhi - xlo) * p.ly; /* nodes of this rank's strip */
@@ -265,7 +277,7 @@ int main(int argc, char **argv) {
     if (nbsteps % STEP_FILM == 0) { /* write_vtk, nFile++ (:1767-1772) */
       if (!f_gp) {
         f_gp = malloc(4 * nn); f_gv = malloc(12 * nn); f_ga = malloc(12 * nn); f_fp = malloc(4 * nn); f_fv = malloc(12 * nn);
-        if (!f_gp || !f_gv || !f_ga || !f_fp || !f_fv) return EXIT_FAILURE;
+        if (!f_gp || !f_gv || !f_ga || !f_fp || !f_fv) fail_run();
       }
       lbmdem_diag_get(dg, diag);
       for (int i = 0; i < n; ++i) gp[i] = diag[17 * (size_t)i];
@@ -285,8 +297,7 @@ int main(int argc, char **argv) {
       }
       if (rank == 0 && lbmdem_write_vtk_frame(outdir, nFile, p.lx, p.ly, w_gp, w_gv, w_ga, w_fp, w_fv)) {
         fprintf(stderr, "lbmdem: cannot write the VTK frame\n");
-        if (sh) sh->failed = 1;
-        return EXIT_FAILURE;
+        fail_run();
       }
       barrier(); /* the shared arrays are free again */
       nFile++;
@@ -295,7 +306,7 @@ int main(int argc, char **argv) {
       CK(lbmdem_get_fhf(ctx, fhf));
       if (rank == 0 && lbmdem_write_dem(dg, outdir, nFile, nbsteps, grains, fhf, d11, summary)) {
         fprintf(stderr, "lbmdem: cannot write DEM%06d.dat\n", nFile);
-        return EXIT_FAILURE;
+        fail_run();
       }
     }
     if (nbsteps % p.UpdateVerlet == 0) {

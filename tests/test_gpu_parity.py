@@ -690,3 +690,33 @@ def test_one_launch_dem_equals_three_launch_dem(prec):
         z.set_grain_state(st)
         z.step(45)
     assert np.array_equal(c.grains(), d.grains()) and np.array_equal(c.fhf(), d.fhf()) and np.array_equal(c.f(), d.f())
+
+
+def test_checkpoint_is_validated(tmp_path):
+    """a checkpoint continued with other physics, or a truncated / doctored file, is refused (no silent drift, no
+    allocation sized by an untrusted header)"""
+    lx, ly = 96, 72
+    r, x, y = small_packing(lx, ly, 1.0, seed=11, n_target=30)
+    a = G.Solver(lx, ly, 1.0, "f64")
+    a.init_arrays(r, x, y)
+    a.step(25)
+    ck = str(tmp_path / "s.ck")
+    a.save_state(ck)
+    with pytest.raises(G.LbmdemError) as ei:
+        G.Solver(lx, ly, 1.0, "f64", tau=0.51).load_state(ck)
+    assert ei.value.code == -1 and "physical parameters" in str(ei.value)
+    raw = open(ck, "rb").read()
+    open(ck, "wb").write(raw[:-1000])
+    with pytest.raises(G.LbmdemError) as ei:
+        G.Solver(lx, ly, 1.0, "f64").load_state(ck)
+    assert ei.value.code == -5
+    import struct
+    bad = bytearray(raw)
+    struct.pack_into("<i", bad, 8 + 7 * 4, 1 << 30)      # the neighbour capacity field of the header
+    open(ck, "wb").write(bytes(bad))
+    with pytest.raises(G.LbmdemError) as ei:
+        G.Solver(lx, ly, 1.0, "f64").load_state(ck)
+    assert ei.value.code == -5
+    open(ck, "wb").write(raw)
+    b = G.Solver(lx, ly, 1.0, "f64")
+    assert b.load_state(ck) == a.n

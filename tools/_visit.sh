@@ -1,15 +1,17 @@
-OUT=gpurun_out; RUN=r02X; mkdir -p $OUT
-timeout 900 python -m pytest tests -m gpu -q -x > $OUT/${RUN}_pytest.log 2>&1; tail -8 $OUT/${RUN}_pytest.log
-for n in 2 4; do
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2955$n bench.py --gpus $n --steps 100 --warmup 10 > $OUT/${RUN}_bench$n.json 2> $OUT/${RUN}_bench$n.err; echo "bench$n rc $?"
+OUT=gpurun_out; RUN=r02Y; mkdir -p $OUT
+timeout 900 python -m pytest tests -m gpu -q -x > $OUT/${RUN}_pytest.log 2>&1; tail -5 $OUT/${RUN}_pytest.log
+timeout 200 python bench.py --steps 300 --no-cpu-baseline --no-cfg5 > $OUT/${RUN}_default.json 2> $OUT/${RUN}_default.err
+for t in sw5 sw6; do
+  LBMDEM_LIB=$PWD/2d-lbm-dem_b200/liblbmdem_gpu_$t.so timeout 200 python bench.py --steps 300 --no-cpu-baseline --no-cfg5 > $OUT/${RUN}_$t.json 2> $OUT/${RUN}_$t.err
 done
-timeout 300 python bench.py --steps 100 --warmup 10 --no-cpu-baseline > $OUT/${RUN}_bench1.json 2> $OUT/${RUN}_bench1.err
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $OUT/${RUN}_launches.csv python bench.py --steps 3 --warmup 8 --no-cpu-baseline --no-cfg5 > $OUT/${RUN}_launches.log 2>&1
 python - <<PY
-import json
-for nm in ("bench1","bench2","bench4"):
+import json,glob
+for p in sorted(glob.glob("$OUT/${RUN}_*.json")):
     try:
-        d=json.loads(open("$OUT/${RUN}_%s.json"%nm).read().strip().splitlines()[-1])
-        print(nm, "value %.0f ms %.4f e2e %.0f K1 %.4f" % (d["value"], d["ms_per_step"], d["e2e"]["value"], d["roofline"]["avg_launch_ms"]), "check", d.get("strip_check",{}).get("ok"), "cfg5 %.0f ms %.4f e2e %.0f check %s" % (d["cfg5"]["value"], d["cfg5"]["ms_per_step"], d["cfg5"]["e2e"]["value"], d["cfg5"].get("strip_check",{}).get("ok")))
+        d=json.loads(open(p).read().strip().splitlines()[-1])
+        print(p.split("${RUN}_")[1][:-5].ljust(14), "MLUPS %.0f  ms/step %.4f  K1 ms %.4f frac %.3f  e2e %.0f" % (d["value"], d["ms_per_step"], d["roofline"]["avg_launch_ms"], d["roofline"]["frac"], d["e2e"]["value"]))
     except Exception as e:
-        print(nm, "unreadable", e)
+        print(p, "unreadable", e)
 PY
+python tools/ncu_summary.py launches $OUT/${RUN}_launches.csv | cut -c1-120 | sed -n 3,10p
