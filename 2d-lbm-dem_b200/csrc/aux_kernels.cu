@@ -870,33 +870,69 @@ cudaError_t launch_force_finish(const ForceFinish &fin, int n, real *fhf1, real 
   return cudaGetLastError();
 }
 
-/* forces_fluid exactly as written (:1295-1325): one thread per grain, x outer, y inner, q inner */
+/* forces_fluid exactly as written (:1295-1325): the three sums of a grain are accumulated in the reference's order --
+ * x outer, y inner, q inner -- which is what makes the strict build bit-identical.  One WARP per grain: the lanes load
+ * the populations of 32 consecutive y of a row in parallel (the expensive part), then every lane replays the additions
+ * in order, taking each term from the lane that holds it. */
 template <typename real>
-__global__ void force_serial_kernel(const __grid_constant__ Lattice<real> L, const __grid_constant__ Stored<real> S,
-                                    int xlo, int xhi, double *partial) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) force_serial_kernel(const __grid_constant__ Lattice<real> L,
+                                                           const __grid_constant__ Stored<real> S, int xlo, int xhi,
+                                                           double *partial) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int n = L.ngrains;
   if (i >= n) return;
   const GrainBox b = S.boxes[i];
   const real xc = S.grains[i].xc, yc = S.grains[i].yc;
   real h1 = 0, h2 = 0, h3 = 0;
   for (int x = max(b.xi, xlo); x <= min(b.xf, xhi - 1); ++x)
-    for (int y = b.yi; y <= b.yf; ++y) {
-      const size_t k = node_index(L, x, y);
-      if (cell_obst(S.cell[k]) != i) continue;
-#pragma unroll 1
-      for (int q = 1; q < NQ; ++q) {
-        const size_t kn = node_index(L, x + ex_of(q), y + ey_of(q));
-        if (cell_obst(S.cell[kn]) == i) continue;
-        force_link<real>(q, S.A[opp_of(q) * L.plane + kn], S.A[q * L.plane + k], x, y, xc, yc, &h1, &h2, &h3);
+    for (int yb = b.yi; yb <= b.yf; yb += 32) {
+      const int y = yb + lane;
+      unsigned mask = 0; /* bit q-1: link q of node (x, y) leaves the grain */
+      real t[NQ];        /* f_new[s][opp q] + f_new[n][q] of those links */
+#pragma unroll
+      for (int q = 1; q < NQ; ++q) t[q] = 0;
+      if (y <= b.yf) {
+        const size_t k = node_index(L, x, y);
+        const int c = S.cell[k];
+        /* a node with a neighbour outside the grain carries the act bit (fluid neighbour) or the rim bit (another
+         * grain, the wall ring): the others have no link to add and their neighbours are not looked at */
+        if (cell_obst(c) == i && (!S.act_folded || (c & (CELL_ACT | CELL_RIM)))) {
+#pragma unroll
+          for (int q = 1; q < NQ; ++q) {
+            const size_t kn = node_index(L, x + ex_of(q), y + ey_of(q));
+            if (cell_obst(S.cell[kn]) != i) {
+              mask |= 1u << (q - 1);
+              t[q] = S.A[opp_of(q) * L.plane + kn] + S.A[q * L.plane + k];
+            }
+          }
+        }
+      }
+      unsigned nodes = __ballot_sync(0xffffffffu, mask != 0);
+      while (nodes) {
+        const int src = __ffs(nodes) - 1;
+        nodes &= nodes - 1;
+        const unsigned m = __shfl_sync(0xffffffffu, mask, src);
+        const int ys = yb + src;
+#pragma unroll
+        for (int q = 1; q < NQ; ++q) {
+          const real v = __shfl_sync(0xffffffffu, t[q], src);
+          if ((m >> (q - 1)) & 1u) { /* force_link (lbm_node.cuh) with the sum of the two populations already formed */
+            const int oq = opp_of(q);
+            const real fnx = v * ex_of(oq);
+            const real fny = v * ey_of(oq);
+            h1 = h1 + fnx;
+            h2 = h2 + fny;
+            h3 = h3 - fnx * (ys - yc) + fny * (x - xc);
+          }
+        }
       }
     }
-  partial[i] = h1; partial[n + i] = h2; partial[2 * n + i] = h3;
+  if (lane == 0) { partial[i] = h1; partial[n + i] = h2; partial[2 * n + i] = h3; }
 }
 template <typename real>
 cudaError_t launch_force_serial(const Lattice<real> &L, const Stored<real> &S, int xlo, int xhi, double *partial,
                                 cudaStream_t s) {
-  force_serial_kernel<real><<<(L.ngrains + 63) / 64, 64, 0, s>>>(L, S, xlo, xhi, partial);
+  force_serial_kernel<real><<<(L.ngrains + 3) / 4, 128, 0, s>>>(L, S, xlo, xhi, partial);
   return cudaGetLastError();
 }
 /* ------------------------------------------------------------------------------------------

@@ -60,9 +60,18 @@ def main():
             d[f"{work}_bytes_per_launch"] = sum(tot) / len(tot)
             d[f"{work}_source"] = f"{rnd}_{work}_k1_ncu.txt: dram__bytes_read.sum + dram__bytes_write.sum, mean of {len(tot)} launches"
             json.dump(d, open(path, "w"), indent=1)
-    for name in ("bench.json", "smi.txt", "host.txt", "pytest.log"):
+    if os.path.exists(g("strips_launches.csv")):
+        open(os.path.join(dst, f"{rnd}_strips_launches.txt"), "w").write(
+            "# python tools/strip_launches.py 2 6: two strips of the benchmarked sample in ONE process (in-process strip group)\n"
+            + capture(ncu_summary.launches, g("strips_launches.csv")))
+    for name in ("bench.json", "smi.txt", "host.txt", "pytest.log", "smoke.log"):
         if os.path.exists(g(name)):
             shutil.copyfile(g(name), os.path.join(dst, f"{rnd}_{work}_{name}"))
+    for name, out in (("cfg2.json", "cfg2_bench.json"), ("cfg3.json", "cfg3_bench.json"), ("cfg5.json", "cfg5_bench.json"),
+                      ("strict.json", "cfg4_bench_strict_build.json"), ("ref.json", "cfg4_bench_reference_arm.json"),
+                      ("memcheck.log", "sanitizer_memcheck_smoke.log"), ("racecheck.log", "sanitizer_racecheck_smoke.log")):
+        if os.path.exists(g(name)):
+            shutil.copyfile(g(name), os.path.join(dst, f"{rnd}_{out}"))
 
 
 if __name__ == "__main__":
