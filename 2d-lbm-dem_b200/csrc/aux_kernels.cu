@@ -697,7 +697,7 @@ cudaError_t launch_bounce_pass(const Lattice<real> &L, const Stored<real> &S, re
 }
 template <typename real>
 cudaError_t launch_bounce_end(real *A, const DeferList<real> &D, cudaStream_t s) {
-  defer_apply_kernel<real><<<8, 256, 0, s>>>(A, D);
+  defer_apply_kernel<real><<<296, 256, 0, s>>>(A, D);
   return cudaGetLastError();
 }
 
@@ -795,7 +795,7 @@ __global__ void __launch_bounds__(256, LBMDEM_SWEEP_MINB) rim_kernel(const __gri
                                                                     const __grid_constant__ Stored<real> S, real *A, int xa,
                                                                     int xb, int xlo, int xhi, const LinkList K,
                                                                     const BoundaryList B, const DeferList<real> D,
-                                                                    long long *facc, int *ticket) {
+                                                                    long long *facc, int *ticket, int apply_here) {
   __shared__ int s_done;
   const int tile = blockIdx.y * gridDim.x + blockIdx.x, nctas = gridDim.x * gridDim.y;
   if (threadIdx.x == 0) s_done = 0;
@@ -814,14 +814,22 @@ __global__ void __launch_bounds__(256, LBMDEM_SWEEP_MINB) rim_kernel(const __gri
   if (!last) return;
   __threadfence();
   const int nd = min(*(volatile int *)D.count, D.capacity);
-  for (int k = threadIdx.x & 31; k < nd; k += 32) A[__ldcg(&D.index[k])] = __ldcg(&D.value[k]);
-  if ((threadIdx.x & 31) == 0) *ticket = 0;
+  /* a handful of deferred links (the usual case: grains of 15+ nodes radius) are applied here; a packing of small
+   * grains has them by the hundred thousand (one-node gaps everywhere), and the host -- told the count through
+   * mapped memory -- then follows this launch with defer_apply_kernel (apply_here == 0) */
+  if (apply_here)
+    for (int k = threadIdx.x & 31; k < nd; k += 32) A[__ldcg(&D.index[k])] = __ldcg(&D.value[k]);
+  if ((threadIdx.x & 31) == 0) {
+    *ticket = 0;
+    *(volatile int *)D.seen = nd;
+  }
 }
 template <typename real>
 cudaError_t launch_rim(const Lattice<real> &L, const Stored<real> &S, real *A, int xa, int xb, int xlo, int xhi,
                        const LinkList &K, const BoundaryList &B, const DeferList<real> &D, long long *facc, int *ticket,
-                       cudaStream_t s) {
-  rim_kernel<real><<<dim3(K.nty, K.ntx), 256, 0, s>>>(L, S, A, xa, xb, xlo, xhi, K, B, D, facc, ticket);
+                       int apply_here, cudaStream_t s) {
+  rim_kernel<real><<<dim3(K.nty, K.ntx), 256, 0, s>>>(L, S, A, xa, xb, xlo, xhi, K, B, D, facc, ticket, apply_here);
+  if (!apply_here) defer_apply_kernel<real><<<296, 256, 0, s>>>(A, D);
   return cudaGetLastError();
 }
 
@@ -1549,7 +1557,7 @@ cudaError_t launch_fill_rest(real *f, size_t plane, const Lattice<real> &Lw, cud
                                                 const LinkList &, const DeferList<real> &, long long *, cudaStream_t);    \
   template cudaError_t launch_rim<real>(const Lattice<real> &, const Stored<real> &, real *, int, int, int, int,          \
                                         const LinkList &, const BoundaryList &, const DeferList<real> &, long long *,     \
-                                        int *, cudaStream_t);                                                             \
+                                        int *, int, cudaStream_t);                                                        \
   template cudaError_t launch_bounce_end<real>(real *, const DeferList<real> &, cudaStream_t);                            \
   template cudaError_t launch_force_links<real>(const Lattice<real> &, const Stored<real> &, int, int,                    \
                                                 const BoundaryList &, long long *, real *, const DeferList<real> &,       \

@@ -81,6 +81,7 @@ struct DeferList {
   int capacity;
   int *overflow;       /* flag in mapped host memory */
   int *range_flag;     /* flag in mapped host memory: a link's momentum exchange does not fit the fixed-point sums */
+  int *seen;           /* mapped host memory: how many links the last sweep deferred (the host sizes the next launch by it) */
 };
 
 template <typename real>
@@ -230,7 +231,7 @@ cudaError_t launch_force_serial(const lbm::Lattice<real> &L, const lbm::Stored<r
 template <typename real>
 cudaError_t launch_rim(const lbm::Lattice<real> &L, const lbm::Stored<real> &S, real *A, int xa, int xb, int xlo, int xhi,
                        const LinkList &K, const BoundaryList &B, const DeferList<real> &D, long long *facc, int *ticket,
-                       cudaStream_t s);
+                       int apply_here /* 0: a defer_apply launch follows (many deferred links) */, cudaStream_t s);
 
 /* partial force sums of the ranks of an in-process strip group (device pointers, peer-accessible) */
 constexpr int MAX_LOCAL_RANKS = 16;

@@ -448,6 +448,7 @@ struct Sim : SimBase {
     CK(cudaMalloc(&defer.value, sizeof(real) * defer.capacity));
     CK(cudaHostGetDevicePointer(&defer.overflow, hflags + 1, 0));
     defer.range_flag = range_flag_dev;
+    CK(cudaHostGetDevicePointer(&defer.seen, hflags + 6, 0));
     if (hstage) { cudaFreeHost(hstage); hstage = nullptr; }
     hstage_elems = (size_t)n * 16;
     CK(cudaMallocHost(&hstage, sizeof(double) * hstage_elems));
@@ -828,7 +829,12 @@ struct Sim : SimBase {
     if (!multi) {
       CK(launch_ring_sweep<real>(L, S, f[cur], 0, lx, stream));
       if (P.strict_fp) CK(launch_bounce_pass<real>(L, S, f[cur], 1, lx - 1, xlo, xhi, llist, defer, fa, stream));
-      else CK(launch_rim<real>(L, S, f[cur], 1, lx - 1, xlo, xhi, llist, blist, defer, fa, tbins.ticket, stream));
+      else {
+        /* hflags[6]: the number of links the previous sweep deferred; beyond a few hundred a launch of its own applies them */
+        const int apply_here = *(volatile int *)(hflags + 6) <= 512 ? 1 : 0;
+        CK(launch_rim<real>(L, S, f[cur], 1, lx - 1, xlo, xhi, llist, blist, defer, fa, tbins.ticket, apply_here, stream));
+        if (!apply_here) ++all_launches;
+      }
     } else if (xhi - xlo < 12) {
       if ((rc = halo_exchange(stream))) return rc;
       CK(launch_ring_sweep<real>(L, S, f[cur], std::max(xlo - 3, 0), std::min(xhi + 3, lx), stream));

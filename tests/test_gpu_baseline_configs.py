@@ -1,6 +1,7 @@
 """BASELINE.json configs[2..4] on the reference's OWN input files at the benchmarked lattice sizes, against fixtures
 the compiled reference wrote (tools/make_golden.py --baseline; -O2 -ffp-contract=off, serial):
 
+    cfg1  bin/50000-test.data        7826 x 2325 (the reference's DEFAULT build), fp64      13 / 37 calls
     cfg3  bin/a08d83.data            2048 x 2048, scale 1,   fp64      10 / 100 renderScene() calls
     cfg4  bin/a08_a4b4r18_7000.data  4096 x 4096, scale 2.7, fp32      2 / 10 / 30 calls (npDEM = 2)
     cfg5  bin/50000.data             8192 x 8192, scale 2.6, fp64      2 / 12 calls (SURVEY 8(d) cfg 5)
@@ -33,6 +34,7 @@ EX = np.array([0, -1, -1, -1, 0, 1, 1, 1, 0.0])
 EY = np.array([0, 1, 0, -1, -1, -1, 0, 1, 1.0])
 
 CASES = {
+    "cfg1_50000test_default_f64": ("50000-test.data", 7826, 2325, 1.0, "f64"),
     "cfg3_a08d83_2048_f64": ("a08d83.data", 2048, 2048, 1.0, "f64"),
     "cfg4_a08_7000_4096_f32": ("a08_a4b4r18_7000.data", 4096, 4096, 2.7, "f32"),
     "cfg5_50000_8192_f64": ("50000.data", 8192, 8192, 2.6, "f64"),

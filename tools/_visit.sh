@@ -1,10 +1,11 @@
-OUT=gpurun_out; RUN=r02b; mkdir -p $OUT
-timeout 900 python -m pytest tests -m gpu -q -x > $OUT/${RUN}_pytest.log 2>&1; tail -5 $OUT/${RUN}_pytest.log
-timeout 300 python bench.py --steps 300 --no-cpu-baseline --no-cfg5 --strict 1 > $OUT/${RUN}_strict.json 2> $OUT/${RUN}_strict.err
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $OUT/${RUN}_launches.csv python bench.py --steps 3 --warmup 8 --no-cpu-baseline --no-cfg5 --strict 1 > $OUT/${RUN}_launches.log 2>&1
+OUT=gpurun_out; RUN=r02e; mkdir -p $OUT
+python tools/_prof_default.py
+timeout 900 python -m pytest tests -m gpu -q -x > $OUT/${RUN}_pytest.log 2>&1; tail -4 $OUT/${RUN}_pytest.log
+rm -f $OUT/default_build_run.log
+timeout 600 bash tools/run_default_build.sh
+timeout 300 python bench.py --steps 300 --no-cpu-baseline --no-cfg5 > $OUT/${RUN}_bench.json 2> $OUT/${RUN}_bench.err
 python - <<PY
 import json
-d=json.loads(open("$OUT/${RUN}_strict.json").read().strip().splitlines()[-1])
-print("strict MLUPS %.0f ms/step %.4f K1 %.4f frac %.3f e2e %.0f" % (d["value"], d["ms_per_step"], d["roofline"]["avg_launch_ms"], d["roofline"]["frac"], d["e2e"]["value"]))
+d=json.loads(open("$OUT/${RUN}_bench.json").read().strip().splitlines()[-1])
+print("MLUPS %.0f ms/step %.4f K1 %.4f frac %.3f e2e %.0f launches %d" % (d["value"], d["ms_per_step"], d["roofline"]["avg_launch_ms"], d["roofline"]["frac"], d["e2e"]["value"], d["gpu_launches"]))
 PY
-python tools/ncu_summary.py launches $OUT/${RUN}_launches.csv | cut -c1-120 | sed -n 3,12p

@@ -228,6 +228,9 @@ def case_default_build():
 # name -> (input fixture, lx, ly, scale tag, precision, renderScene() call counts at which state is recorded,
 #          stride of the node sample, whether the reference's own build-to-build spread is recorded too)
 BASELINE_CASES = {
+    # BASELINE configs[0]: the reference's DEFAULT build on its own 47 980-grain sample (grains above y = 232 mm lie outside
+    # the lattice: legal, the loops clamp); 37 calls = 4 LBM steps and the O(N^2) Verlet build
+    "cfg1_50000test_default_f64": ("50000-test.data", 7826, 2325, "1.", "f64", (13, 37), 64, False),
     "cfg3_a08d83_2048_f64": ("a08d83.data", 2048, 2048, "1.", "f64", (10, 100), 16, True),
     "cfg4_a08_7000_4096_f32": ("a08_a4b4r18_7000.data", 4096, 4096, "2.7", "f32", (2, 10, 30), 32, True),
     "cfg5_50000_8192_f64": ("50000.data", 8192, 8192, "2.6", "f64", (2, 12), 64, True),
