@@ -46,45 +46,48 @@ __device__ __forceinline__ void stamp_around(const TileBins &T, int x, int y, in
   }
 }
 
-/* Which nodes of lattice row `row` does a grain's reduced disc (src/main.c:1026-1029) cover under placement b but not
- * under placement a, or the other way round?  The covered nodes of a row are an interval around yc (the reference's
- * expression is monotone in |y - yc|, roundings included), so the two placements can only disagree between the ends
- * of the two intervals; while the centre moves by less than half a node and the interval ends by less than a node
- * (the caller checks the first and treats near-tangent rows -- where an end can run -- conservatively), those are the
- * integers next to the four ends.  They are tested under both placements with the exact expression; every node that
- * differs stamps its tiles.  Returns true if the row needs the conservative treatment instead. */
+/* The nodes of lattice row `row` that a grain's reduced disc covers (src/main.c:1016-1029: inside the clamped bounding
+ * box and dist2 <= r2, dist2 <= R2) are an interval of y -- the reference's expression is monotone in |y - yc|,
+ * roundings included.  Its ends [*lo, *hi] (empty: *lo > *hi), EXACTLY: a float square root puts each end within a
+ * node, the reference's own expression settles it. */
+template <typename real>
+__device__ __forceinline__ void row_cover_interval(int row, real xc, real yc, real r2, real RR, const GrainBox &b, int *lo,
+                                                   int *hi) {
+  *lo = 1;
+  *hi = 0;
+  if (row < b.xi || row > b.xf || b.yf < b.yi) return;
+  const real rm = r2 < RR ? r2 : RR;
+  const real dxr = row - xc;
+  const real h2 = rm - dxr * dxr;
+  if (!(h2 >= 0)) return; /* not even the node nearest to the centre line: see grain_bin_kernel's note on monotony */
+  const float h = sqrtf((float)h2);
+  int l = max((int)ceilf((float)yc - h), b.yi), u = min((int)floorf((float)yc + h), b.yf);
+  /* at most one node off, either way */
+  if (l - 1 >= b.yi && disc_covers(xc, yc, r2, RR, row, l - 1)) --l;
+  else if (l <= b.yf && !disc_covers(xc, yc, r2, RR, row, l)) ++l;
+  if (u + 1 <= b.yf && disc_covers(xc, yc, r2, RR, row, u + 1)) ++u;
+  else if (u >= b.yi && !disc_covers(xc, yc, r2, RR, row, u)) --u;
+  *lo = l;
+  *hi = u;
+}
+
+/* Which nodes of row `row` does the disc cover under one placement and not under the other?  The symmetric difference
+ * of the two intervals; every such node stamps its tiles.  Returns true if there are implausibly many (the caller then
+ * stamps every tile the grain touches instead). */
 template <typename real>
 __device__ __forceinline__ bool row_cover_diff(const TileBins &T, int x0, int nxl, int ly, int step, int row, real xa, real ya,
                                                real r2a, real RRa, const GrainBox &ba, real xb, real yb, real r2b, real RRb,
                                                const GrainBox &bb) {
-  const real rma = r2a < RRa ? r2a : RRa, rmb = r2b < RRb ? r2b : RRb;
-  const real da = row - xa, db = row - xb;
-  const real h2a = rma - da * da, h2b = rmb - db * db;
-  if (!(h2a >= 0) && !(h2b >= 0)) return false; /* neither placement covers a node of this row */
-  /* near the top / bottom of the disc the chord is short and its ends move fast: every node of both chords (a few) */
-  if (!(h2a >= 4) || !(h2b >= 4)) {
-    const float ha = h2a > 0 ? sqrtf((float)h2a) : 0.f, hb = h2b > 0 ? sqrtf((float)h2b) : 0.f;
-    const int lo = (int)floorf(fminf((float)ya - ha, (float)yb - hb)) - 1, hi = (int)ceilf(fmaxf((float)ya + ha, (float)yb + hb)) + 1;
-    if (hi - lo > 24) return true;
-    for (int y = lo; y <= hi; ++y) {
-      const bool ca = box_has(ba, row, y) && disc_covers(xa, ya, r2a, RRa, row, y);
-      const bool cb = box_has(bb, row, y) && disc_covers(xb, yb, r2b, RRb, row, y);
-      if (ca != cb) stamp_around(T, row, y, x0, nxl, ly, step);
-    }
-    return false;
-  }
-  const float ha = sqrtf((float)h2a), hb = sqrtf((float)h2b);
-  if (fabsf(ha - hb) > 0.75f) return true; /* cannot happen for |centre shift| < 1/2 and h >= 2; kept as a guard */
-#pragma unroll
-  for (int e = 0; e < 2; ++e) {
-    /* the two placements' ends of this side lie within 1.25 nodes of each other: one window covers both */
-    const float ea = (float)ya + (e ? ha : -ha), eb = (float)yb + (e ? hb : -hb);
-    const int lo = (int)floorf(fminf(ea, eb)) - 1, hi = (int)floorf(fmaxf(ea, eb)) + 2;
-    for (int y = lo; y <= hi; ++y) {
-      const bool ca = box_has(ba, row, y) && disc_covers(xa, ya, r2a, RRa, row, y);
-      const bool cb = box_has(bb, row, y) && disc_covers(xb, yb, r2b, RRb, row, y);
-      if (ca != cb) stamp_around(T, row, y, x0, nxl, ly, step);
-    }
+  int la, ha, lb, hb;
+  row_cover_interval<real>(row, xa, ya, r2a, RRa, ba, &la, &ha);
+  row_cover_interval<real>(row, xb, yb, r2b, RRb, bb, &lb, &hb);
+  if (la == lb && ha == hb) return false;
+  if (la > ha && lb > hb) return false; /* both empty */
+  const int ymin = min(la > ha ? lb : la, lb > hb ? la : lb), ymax = max(la > ha ? hb : ha, lb > hb ? ha : hb);
+  if (ymax - ymin > 64) return true;
+  for (int y = ymin; y <= ymax; ++y) {
+    const bool ca = y >= la && y <= ha, cb = y >= lb && y <= hb;
+    if (ca != cb) stamp_around(T, row, y, x0, nxl, ly, step);
   }
   return false;
 }
@@ -144,34 +147,35 @@ __global__ void __launch_bounds__(128) grain_bin_kernel(RasterParams<real> P, in
     boxes[i] = b;
   }
   if (facc != nullptr && lane < 3) facc[lane * n + i] = 0;
-  if (lane != 0) return;
-  /* every tile whose nodes or halo the bounding box touches (local rows only) */
+  /* every tile whose nodes or halo the bounding box touches (local rows only): a lane per tile */
   {
     const int xa = max(b.xi - 1, x0), xb = min(b.xf + 1, x0 + nxl - 1);
     const int ya = max(b.yi - 1, 0), yb = min(b.yf + 1, P.ly - 1);
-    if (!(b.xf < b.xi || b.yf < b.yi || xb < xa || yb < ya))
-      for (int tx = (xa - x0) / RTX; tx <= (xb - x0) / RTX; ++tx)
-        for (int ty = ya / RTY; ty <= yb / RTY; ++ty) {
-          const int t = tx * T.nty + ty;
-          const int slot = atomicAdd(&T.count[t], 1);
-          if (slot < T.cap) {
-            TileEntry<real> en;
-            en.id = i; en.xi = b.xi; en.xf = b.xf; en.yi = b.yi; en.yf = b.yf;
-            en.xc = r.xc; en.yc = r.yc; en.r2 = r.r2; en.RR = R2i;
-            static_cast<TileEntry<real> *>(T.list)[(size_t)t * T.cap + slot] = en;
-          } else {
-            *(volatile int *)T.overflow = 1; /* mapped host memory */
-          }
-          if (all_tiles) stamp_tile(T, t, step);
+    if (!(b.xf < b.xi || b.yf < b.yi || xb < xa || yb < ya)) {
+      const int tx0 = (xa - x0) / RTX, ntx = (xb - x0) / RTX - tx0 + 1, ty0 = ya / RTY, nty = yb / RTY - ty0 + 1;
+      for (int k = lane; k < ntx * nty; k += 32) {
+        const int t = (tx0 + k / nty) * T.nty + ty0 + k % nty;
+        const int slot = atomicAdd(&T.count[t], 1);
+        if (slot < T.cap) {
+          TileEntry<real> en;
+          en.id = i; en.xi = b.xi; en.xf = b.xf; en.yi = b.yi; en.yf = b.yf;
+          en.xc = r.xc; en.yc = r.yc; en.r2 = r.r2; en.RR = R2i;
+          static_cast<TileEntry<real> *>(T.list)[(size_t)t * T.cap + slot] = en;
+        } else {
+          *(volatile int *)T.overflow = 1; /* mapped host memory */
         }
+        if (all_tiles) stamp_tile(T, t, step);
+      }
+    }
   }
   /* ... and the tiles the previous placement touched */
   if (all_tiles && !first_run) {
     const int xa = max(ob.xi - 1, x0), xb = min(ob.xf + 1, x0 + nxl - 1);
     const int ya = max(ob.yi - 1, 0), yb = min(ob.yf + 1, P.ly - 1);
-    if (!(ob.xf < ob.xi || ob.yf < ob.yi || xb < xa || yb < ya))
-      for (int tx = (xa - x0) / RTX; tx <= (xb - x0) / RTX; ++tx)
-        for (int ty = ya / RTY; ty <= yb / RTY; ++ty) stamp_tile(T, tx * T.nty + ty, step);
+    if (!(ob.xf < ob.xi || ob.yf < ob.yi || xb < xa || yb < ya)) {
+      const int tx0 = (xa - x0) / RTX, ntx = (xb - x0) / RTX - tx0 + 1, ty0 = ya / RTY, nty = yb / RTY - ty0 + 1;
+      for (int k = lane; k < ntx * nty; k += 32) stamp_tile(T, (tx0 + k / nty) * T.nty + ty0 + k % nty, step);
+    }
   }
 }
 
@@ -1154,6 +1158,9 @@ cudaError_t launch_dem_step(const dem::Params<real> &P, int n, bool film, const 
 template <typename real>
 __global__ void __launch_bounds__(DEM_BATCH_MAX) dem_batch_kernel(dem::Params<real> P, int n, int nsub, GrainArrays<real> g,
                                                                   VerletBuffers vb, ForceFinish fin) {
+  /* what a grain's neighbours read of it stays in shared memory for all the sub-steps (40 KB in fp64): a sub-step is a
+   * few shared-memory gathers between two CTA barriers instead of a chain of L2 round trips */
+  __shared__ real s_x1[DEM_BATCH_MAX], s_x2[DEM_BATCH_MAX], s_v1[DEM_BATCH_MAX], s_v2[DEM_BATCH_MAX], s_v3[DEM_BATCH_MAX];
   const int i = threadIdx.x;
   const bool on = i < n;
   real x1 = 0, x2 = 0, x3 = 0, v1 = 0, v2 = 0, v3 = 0, a1 = 0, a2 = 0, a3 = 0, ri = 0, mi = 1, Iti = 1, f1 = 0, f2 = 0, f3 = 0;
@@ -1174,14 +1181,14 @@ __global__ void __launch_bounds__(DEM_BATCH_MAX) dem_batch_kernel(dem::Params<re
       dem::kick_drift(P, &x1, &v1, a1);
       dem::kick_drift(P, &x2, &v2, a2);
       dem::kick_drift(P, &x3, &v3, a3);
-      g.x1[i] = x1; g.x2[i] = x2; g.v1[i] = v1; g.v2[i] = v2; g.v3[i] = v3; /* what the neighbours read */
+      s_x1[i] = x1; s_x2[i] = x2; s_v1[i] = v1; s_v2[i] = v2; s_v3[i] = v3; /* what the neighbours read */
     }
     __syncthreads();
     if (on) {
       a1 = f1; a2 = f2; a3 = f3;
       for (int k = 0; k < cnt; ++k) {
         const int j = vb.nbr[(size_t)i * vb.cap + k];
-        const real xj1 = g.x1[j], xj2 = g.x2[j], vj1 = g.v1[j], vj2 = g.v2[j], vj3 = g.v3[j], rj = g.r[j];
+        const real xj1 = s_x1[j], xj2 = s_x2[j], vj1 = s_v1[j], vj2 = s_v2[j], vj3 = s_v3[j], rj = g.r[j];
         dem::Force<real> F;
         if (i < j) {
           if (dem::pair_force(P, false, x1, x2, v1, v2, v3, ri, xj1, xj2, vj1, vj2, vj3, rj, &F)) {
@@ -1204,7 +1211,7 @@ __global__ void __launch_bounds__(DEM_BATCH_MAX) dem_batch_kernel(dem::Params<re
     }
   }
   if (on) {
-    g.x3[i] = x3; g.v1[i] = v1; g.v2[i] = v2; g.v3[i] = v3; g.a1[i] = a1; g.a2[i] = a2; g.a3[i] = a3;
+    g.x1[i] = x1; g.x2[i] = x2; g.x3[i] = x3; g.v1[i] = v1; g.v2[i] = v2; g.v3[i] = v3; g.a1[i] = a1; g.a2[i] = a2; g.a3[i] = a3;
   }
 }
 template <typename real>
