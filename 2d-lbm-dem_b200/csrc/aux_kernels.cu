@@ -1153,85 +1153,21 @@ cudaError_t launch_dem_step(const dem::Params<real> &P, int n, bool film, const 
   return cudaGetLastError();
 }
 
-/* Small samples: the same sub-step, nsub times, by one CTA (thread i = grain i).  The contributions of the
- * neighbours are added in list order, like the warp kernel's shuffle loop and the reference's scatter loop. */
-template <typename real>
-__global__ void __launch_bounds__(DEM_BATCH_MAX) dem_batch_kernel(dem::Params<real> P, int n, int nsub, GrainArrays<real> g,
-                                                                  VerletBuffers vb, ForceFinish fin) {
-  /* what a grain's neighbours read of it stays in shared memory for all the sub-steps (40 KB in fp64): a sub-step is a
-   * few shared-memory gathers between two CTA barriers instead of a chain of L2 round trips */
-  __shared__ real s_x1[DEM_BATCH_MAX], s_x2[DEM_BATCH_MAX], s_v1[DEM_BATCH_MAX], s_v2[DEM_BATCH_MAX], s_v3[DEM_BATCH_MAX];
-  const int i = threadIdx.x;
-  const bool on = i < n;
-  real x1 = 0, x2 = 0, x3 = 0, v1 = 0, v2 = 0, v3 = 0, a1 = 0, a2 = 0, a3 = 0, ri = 0, mi = 1, Iti = 1, f1 = 0, f2 = 0, f3 = 0;
-  int cnt = 0, wfl = 0;
-  if (on) {
-    x1 = g.x1[i]; x2 = g.x2[i]; x3 = g.x3[i]; v1 = g.v1[i]; v2 = g.v2[i]; v3 = g.v3[i];
-    a1 = g.a1[i]; a2 = g.a2[i]; a3 = g.a3[i]; ri = g.r[i]; mi = g.m[i]; Iti = g.It[i];
-    if (fin.sums != nullptr) { /* the launch follows an LBM step: force_finish_kernel's job first */
-      force_finish_one<real>(fin, n, i, &f1, &f2, &f3);
-      g.fhf1[i] = f1; g.fhf2[i] = f2; g.fhf3[i] = f3;
-    } else {
-      f1 = g.fhf1[i]; f2 = g.fhf2[i]; f3 = g.fhf3[i];
-    }
-    cnt = vb.nbr_count[i]; wfl = vb.wflags[i];
-  }
-  for (int s = 0; s < nsub; ++s) {
-    if (on) {
-      dem::kick_drift(P, &x1, &v1, a1);
-      dem::kick_drift(P, &x2, &v2, a2);
-      dem::kick_drift(P, &x3, &v3, a3);
-      s_x1[i] = x1; s_x2[i] = x2; s_v1[i] = v1; s_v2[i] = v2; s_v3[i] = v3; /* what the neighbours read */
-    }
-    __syncthreads();
-    if (on) {
-      a1 = f1; a2 = f2; a3 = f3;
-      for (int k = 0; k < cnt; ++k) {
-        const int j = vb.nbr[(size_t)i * vb.cap + k];
-        const real xj1 = s_x1[j], xj2 = s_x2[j], vj1 = s_v1[j], vj2 = s_v2[j], vj3 = s_v3[j], rj = g.r[j];
-        dem::Force<real> F;
-        if (i < j) {
-          if (dem::pair_force(P, false, x1, x2, v1, v2, v3, ri, xj1, xj2, vj1, vj2, vj3, rj, &F)) {
-            a1 = a1 + F.f1; a2 = a2 + F.f2; a3 = a3 + F.f3;
-          }
-        } else {
-          if (dem::pair_force(P, false, xj1, xj2, vj1, vj2, vj3, rj, x1, x2, v1, v2, v3, ri, &F)) {
-            a1 = a1 + (-F.f1); a2 = a2 + (-F.f2); a3 = a3 + F.f3;
-          }
-        }
-      }
-      dem::add_wall_forces(P, wfl, x1, x2, v1, v2, v3, ri, &a1, &a2, &a3);
-      dem::finish_acceleration(P, mi, Iti, &a1, &a2, &a3);
-    }
-    __syncthreads(); /* everybody has read the mid-step velocities before they move on */
-    if (on) {
-      dem::kick(P, &v1, a1);
-      dem::kick(P, &v2, a2);
-      dem::kick(P, &v3, a3);
-    }
-  }
-  if (on) {
-    g.x1[i] = x1; g.x2[i] = x2; g.x3[i] = x3; g.v1[i] = v1; g.v2[i] = v2; g.v3[i] = v3; g.a1[i] = a1; g.a2[i] = a2; g.a3[i] = a3;
-  }
-}
-template <typename real>
-cudaError_t launch_dem_batch(const dem::Params<real> &P, int n, int nsub, const GrainArrays<real> &g, const VerletBuffers &vb,
-                             const ForceFinish &fin, cudaStream_t s) {
-  if (n > DEM_BATCH_MAX) return cudaErrorInvalidValue;
-  const int threads = (n + 31) / 32 * 32;
-  dem_batch_kernel<real><<<1, threads, 0, s>>>(P, n, nsub, g, vb, fin);
-  return cudaGetLastError();
-}
-
-/* Mid-size and large samples: the sub-steps between two LBM steps in ONE cooperative launch, thread i = grain i, the
- * CTAs meeting at a grid barrier where dem_batch_kernel's single CTA meets at __syncthreads().  Same arithmetic in the
- * same order (neighbour contributions added in list order), hence the same bits as the three-launch form.
+/* The DEM sub-steps between two LBM steps in ONE launch, thread i = grain i: kick-drift, barrier, forces (gather over the
+ * sorted full list), barrier, kick -- the barriers standing where the reference's loops end.  Up to 1024 grains: one
+ * thread-block CLUSTER of 8 CTAs of 128 threads (8 SMs share the fp64 contact arithmetic -- a single CTA spent 8 us per
+ * sub-step on one SM's fp64 pipe -- and meet at the hardware cluster barrier); above: a cooperative grid with grid
+ * barriers.  Same arithmetic in the same order (neighbour contributions added in list order), hence the same bits as
+ * the three-launch form.
  * fin.sums != nullptr: the launch follows an LBM step and first turns the fixed-point force sums into fhf
  * (force_finish_kernel's job).  film_first: the first sub-step is a film step (alternate contact law, :1342-1426). */
-template <typename real>
+template <typename real, bool CLUSTER>
 __global__ void __launch_bounds__(DEM_COOP_THREADS) dem_coop_kernel(dem::Params<real> P, int n, int nsub, bool film_first,
                                                                     GrainArrays<real> g, VerletBuffers vb, ForceFinish fin) {
-  cg::grid_group grid = cg::this_grid();
+  auto everybody = [] {
+    if constexpr (CLUSTER) cg::this_cluster().sync();
+    else cg::this_grid().sync();
+  };
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool on = i < n;
   real x1 = 0, x2 = 0, x3 = 0, v1 = 0, v2 = 0, v3 = 0, a1 = 0, a2 = 0, a3 = 0, ri = 0, mi = 1, Iti = 1, f1 = 0, f2 = 0, f3 = 0;
@@ -1255,7 +1191,7 @@ __global__ void __launch_bounds__(DEM_COOP_THREADS) dem_coop_kernel(dem::Params<
       dem::kick_drift(P, &x3, &v3, a3);
       g.x1[i] = x1; g.x2[i] = x2; g.v1[i] = v1; g.v2[i] = v2; g.v3[i] = v3; /* what the neighbours read */
     }
-    grid.sync();
+    everybody();
     if (on) {
       a1 = f1; a2 = f2; a3 = f3;
       for (int k = 0; k < cnt; ++k) {
@@ -1275,7 +1211,7 @@ __global__ void __launch_bounds__(DEM_COOP_THREADS) dem_coop_kernel(dem::Params<
       dem::add_wall_forces(P, wfl, x1, x2, v1, v2, v3, ri, &a1, &a2, &a3);
       dem::finish_acceleration(P, mi, Iti, &a1, &a2, &a3);
     }
-    grid.sync(); /* everybody has read the mid-step velocities before they move on */
+    everybody(); /* everybody has read the mid-step velocities before they move on */
     if (on) {
       dem::kick(P, &v1, a1);
       dem::kick(P, &v2, a2);
@@ -1289,13 +1225,27 @@ __global__ void __launch_bounds__(DEM_COOP_THREADS) dem_coop_kernel(dem::Params<
 template <typename real>
 cudaError_t launch_dem_coop(const dem::Params<real> &P, int n, int nsub, bool film_first, const GrainArrays<real> &g,
                             const VerletBuffers &vb, const ForceFinish &fin, cudaStream_t s) {
+  if (n <= DEM_CLUSTER_MAX) { /* one cluster of 8 CTAs */
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(DEM_CLUSTER_MAX / DEM_COOP_THREADS);
+    cfg.blockDim = dim3(DEM_COOP_THREADS);
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = DEM_CLUSTER_MAX / DEM_COOP_THREADS;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, dem_coop_kernel<real, true>, P, n, nsub, film_first, g, vb, fin);
+  }
   dem::Params<real> Pc = P;
   GrainArrays<real> gc = g;
   VerletBuffers vc = vb;
   ForceFinish fc = fin;
   void *args[] = {&Pc, &n, &nsub, &film_first, &gc, &vc, &fc};
   const dim3 grid((n + DEM_COOP_THREADS - 1) / DEM_COOP_THREADS), block(DEM_COOP_THREADS);
-  return cudaLaunchCooperativeKernel((const void *)dem_coop_kernel<real>, grid, block, args, 0, s);
+  return cudaLaunchCooperativeKernel((const void *)dem_coop_kernel<real, false>, grid, block, args, 0, s);
 }
 template <typename real>
 cudaError_t dem_coop_capacity(int *max_grains) {
@@ -1303,7 +1253,7 @@ cudaError_t dem_coop_capacity(int *max_grains) {
   cudaError_t e;
   if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
   if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dem_coop_kernel<real>, DEM_COOP_THREADS, 0)) != cudaSuccess) return e;
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dem_coop_kernel<real, false>, DEM_COOP_THREADS, 0)) != cudaSuccess) return e;
   *max_grains = sms * per_sm * DEM_COOP_THREADS;
   return cudaSuccess;
 }
@@ -1577,8 +1527,6 @@ cudaError_t launch_fill_rest(real *f, size_t plane, const Lattice<real> &Lw, cud
                                            const VerletBuffers &, cudaStream_t);                                         \
   template cudaError_t launch_dem_step<real>(const dem::Params<real> &, int, bool, const GrainArrays<real> &,             \
                                              const VerletBuffers &, real *, bool, bool, cudaStream_t);                   \
-  template cudaError_t launch_dem_batch<real>(const dem::Params<real> &, int, int, const GrainArrays<real> &,             \
-                                              const VerletBuffers &, const ForceFinish &, cudaStream_t);                 \
   template cudaError_t launch_dem_coop<real>(const dem::Params<real> &, int, int, bool, const GrainArrays<real> &,        \
                                              const VerletBuffers &, const ForceFinish &, cudaStream_t);                  \
   template cudaError_t dem_coop_capacity<real>(int *);                                                                    \

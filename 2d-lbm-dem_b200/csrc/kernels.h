@@ -265,15 +265,11 @@ cudaError_t launch_dem_step(const dem::Params<real> &P, int n, bool film, const 
                             bool drift_next /* close with kick + the NEXT sub-step's kick-drift in one launch */,
                             cudaStream_t s);
 
-/* nsub consecutive DEM sub-steps (normal contact law, fixed lists and fhf) in ONE launch: a single CTA, one
- * thread per grain, for small samples (n <= DEM_BATCH_MAX) where three launches per sub-step are all latency */
-constexpr int DEM_BATCH_MAX = 1024;
-template <typename real>
-cudaError_t launch_dem_batch(const dem::Params<real> &P, int n, int nsub, const GrainArrays<real> &g, const VerletBuffers &vb,
-                             const ForceFinish &fin, cudaStream_t s);
-/* the same for any sample that fits one co-resident grid (dem_coop_capacity): a cooperative launch, grid barriers
- * where the single-CTA kernel has CTA barriers */
-constexpr int DEM_COOP_THREADS = 256;
+/* nsub consecutive DEM sub-steps (fixed lists and fhf) in ONE launch, a thread per grain: one thread-block cluster of
+ * 8 CTAs up to DEM_CLUSTER_MAX grains, a cooperative grid for anything that fits one co-resident wave
+ * (dem_coop_capacity); the launch that follows an LBM step also turns the force sums into fhf (fin) */
+constexpr int DEM_COOP_THREADS = 128;
+constexpr int DEM_CLUSTER_MAX = 1024;
 template <typename real>
 cudaError_t launch_dem_coop(const dem::Params<real> &P, int n, int nsub, bool film_first, const GrainArrays<real> &g,
                             const VerletBuffers &vb, const ForceFinish &fin, cudaStream_t s);

@@ -982,24 +982,23 @@ struct Sim : SimBase {
         *built = true;
       }
       const bool film = (nbsteps % P.stepFilm == 0);
-      /* this call's sub-step and those of the following calls that do nothing else go in ONE launch: a single CTA for
-       * small samples, a cooperative grid for anything that fits one wave; the launch also turns the force sums of
-       * the LBM step into fhf */
+      /* this call's sub-step and those of the following calls that do nothing else go in ONE launch: a thread-block
+       * cluster for small samples, a cooperative grid for anything that fits one wave; the launch also turns the force
+       * sums of the LBM step into fhf */
       long nb = 1;
-      const bool one_cta = n <= DEM_BATCH_MAX && !film, coop = n > DEM_BATCH_MAX && n <= coop_cap;
-      if ((one_cta || coop) && !capture && P.vib != 1 && !(P.kernel & 4)) {
+      const bool coop = n <= DEM_CLUSTER_MAX || n <= coop_cap;
+      if (coop && !capture && P.vib != 1 && !(P.kernel & 4)) {
         while (k + nb < nsteps && (nbsteps + nb) % npDEM != 0 && (nbsteps + nb) % P.UpdateVerlet != 0 &&
                (nbsteps + nb) % P.stepFilm != 0)
           ++nb;
-        if (one_cta) CK(launch_dem_batch<real>(dem_params(), n, (int)nb, g, vb, take_pending(), stream));
-        else CK(launch_dem_coop<real>(dem_params(), n, (int)nb, film, g, vb, take_pending(), stream));
+        CK(launch_dem_coop<real>(dem_params(), n, (int)nb, film, g, vb, take_pending(), stream));
         all_launches += 1;
         drift_done = false;
       } else {
         if ((rc = materialise_fhf())) return rc;
         /* when the next call of this batch does nothing but its DEM sub-step (no LBM step, no list rebuild), this
          * call's closing kick and the next call's kick-drift go in one launch */
-        const bool drift_next = n > DEM_BATCH_MAX && !capture && P.vib != 1 && k + 1 < nsteps &&
+        const bool drift_next = !capture && P.vib != 1 && k + 1 < nsteps &&
                                 (nbsteps + 1) % npDEM != 0 && (nbsteps + 1) % P.UpdateVerlet != 0;
         CK(launch_dem_step<real>(dem_params(), n, film, g, vb, capture ? mid_dev : nullptr, drift_done, drift_next, stream));
         all_launches += drift_done ? 2 : 3;

@@ -655,7 +655,7 @@ def test_reference_default_build_size_strict(tmp_path):
 
 @pytest.mark.parametrize("prec", ["f64", "f32"])
 def test_one_launch_dem_equals_three_launch_dem(prec):
-    """The DEM sub-steps between two LBM steps run as ONE launch (a single CTA up to 1024 grains, a cooperative grid
+    """The DEM sub-steps between two LBM steps run as ONE launch (a thread-block cluster up to 1024 grains, a cooperative grid
     above: grid barriers where the reference's loops end) by default and as three launches per sub-step with
     kernel=4.  Same arithmetic in the same order: same bits, and the oracle's bits in the strict build -- here with
     more than 1024 grains, across a Verlet rebuild, and across the film step (alternate contact law)."""
