@@ -187,7 +187,8 @@ static_assert(RTY == 64 && RTX == 32 && RT_THREADS == 256, "pass 3a: a warp take
 
 template <typename real>
 __global__ void __launch_bounds__(RT_THREADS) raster_tile_kernel(int n, int *cell, const int *cell_other, unsigned char *cls,
-                                                                 const unsigned char *cls_other, int x0, int nxl, int pitch,
+                                                                 const unsigned char *cls_other, unsigned short *own16,
+                                                                 const unsigned short *own16_other, int x0, int nxl, int pitch,
                                                                  int lx, int ly, TileBins T, BoundaryList B, LinkList K,
                                                                  int step, int force_full) {
   /* region = tile + one halo node all round; region row r+1 / column c+RTC0 hold tile node (r, c) */
@@ -228,6 +229,7 @@ __global__ void __launch_bounds__(RT_THREADS) raster_tile_kernel(int n, int *cel
         const size_t k = (size_t)(x - x0) * pitch + ty0 + c0;
         *reinterpret_cast<int4 *>(&cell[k]) = *reinterpret_cast<const int4 *>(&cell_other[k]);
         *reinterpret_cast<uchar4 *>(&cls[k]) = *reinterpret_cast<const uchar4 *>(&cls_other[k]);
+        *reinterpret_cast<ushort4 *>(&own16[k]) = *reinterpret_cast<const ushort4 *>(&own16_other[k]);
       }
     }
     continue;
@@ -317,6 +319,7 @@ __global__ void __launch_bounds__(RT_THREADS) raster_tile_kernel(int n, int *cel
       const size_t k = (size_t)(x - x0) * pitch + ty0 + c0;
       *reinterpret_cast<int4 *>(&cell[k]) = v;
       *reinterpret_cast<uchar4 *>(&cls[k]) = make_uchar4(cell_class(v.x, n), cell_class(v.y, n), cell_class(v.z, n), cell_class(v.w, n));
+      *reinterpret_cast<ushort4 *>(&own16[k]) = make_ushort4(cell_own16(v.x), cell_own16(v.y), cell_own16(v.z), cell_own16(v.w));
     }
     if (__any_sync(0xffffffffu, hit != 0)) {
       const int mine = __popc(hit);
@@ -447,20 +450,22 @@ __global__ void __launch_bounds__(RT_THREADS) raster_tile_kernel(int n, int *cel
 template <typename real>
 cudaError_t launch_raster_tiles(const RasterParams<real> &P, int n, const GrainArrays<real> &g, GrainRec<real> *rec, real *R2,
                                 GrainBox *boxes, const GrainRec<real> *rec_old, const real *R2_old, const GrainBox *boxes_old,
-                                int *cell, const int *cell_other, unsigned char *cls, const unsigned char *cls_other, int x0,
-                                int nxl, int pitch, const TileBins &T, const BoundaryList &B, const LinkList &K,
+                                int *cell, const int *cell_other, unsigned char *cls, const unsigned char *cls_other,
+                                unsigned short *own16, const unsigned short *own16_other, int x0, int nxl, int pitch,
+                                const TileBins &T, const BoundaryList &B, const LinkList &K,
                                 int *defer_count, long long *facc, int step, int first_run, int force_full, cudaStream_t s) {
   grain_bin_kernel<real><<<(n + 3) / 4, 128, 0, s>>>(P, n, g, rec, R2, boxes, rec_old, R2_old, boxes_old, x0, nxl, T, step,
                                                      first_run, defer_count, facc);
   const int ntiles = T.ntx * T.nty;
   const int ctas = force_full ? ntiles : min(ntiles, T.resident_ctas);
-  raster_tile_kernel<real><<<ctas, RT_THREADS, 0, s>>>(n, cell, cell_other, cls, cls_other, x0, nxl, pitch, P.lx, P.ly, T, B, K,
-                                                       step, force_full);
+  raster_tile_kernel<real><<<ctas, RT_THREADS, 0, s>>>(n, cell, cell_other, cls, cls_other, own16, own16_other, x0, nxl, pitch,
+                                                       P.lx, P.ly, T, B, K, step, force_full);
   return cudaGetLastError();
 }
 
 /* init_obst's frame (:674-687): ring = nbgrains, interior = -1 */
-__global__ void cell_frame_kernel(int *cell, unsigned char *cls, int lx, int ly, int x0, int nxl, int pitch, int ring_value) {
+__global__ void cell_frame_kernel(int *cell, unsigned char *cls, unsigned short *own16, int lx, int ly, int x0, int nxl,
+                                  int pitch, int ring_value) {
   const int y = blockIdx.x * blockDim.x + threadIdx.x;
   const int row = blockIdx.y;
   if (y >= pitch || row >= nxl) return;
@@ -469,22 +474,27 @@ __global__ void cell_frame_kernel(int *cell, unsigned char *cls, int lx, int ly,
   if (x <= 0 || x >= lx - 1 || y <= 0 || y >= ly - 1) v = ring_value;
   cell[(size_t)row * pitch + y] = v;
   cls[(size_t)row * pitch + y] = cell_class(v, ring_value);
+  own16[(size_t)row * pitch + y] = cell_own16(v);
 }
 
-cudaError_t launch_cell_frame(int *cell, unsigned char *cls, int lx, int ly, int x0, int nxl, int pitch, int ring_value,
-                              cudaStream_t s) {
+cudaError_t launch_cell_frame(int *cell, unsigned char *cls, unsigned short *own16, int lx, int ly, int x0, int nxl, int pitch,
+                              int ring_value, cudaStream_t s) {
   dim3 grid((pitch + 255) / 256, nxl);
-  cell_frame_kernel<<<grid, 256, 0, s>>>(cell, cls, lx, ly, x0, nxl, pitch, ring_value);
+  cell_frame_kernel<<<grid, 256, 0, s>>>(cell, cls, own16, lx, ly, x0, nxl, pitch, ring_value);
   return cudaGetLastError();
 }
 
-__global__ void cls_from_cell_kernel(const int *cell, unsigned char *cls, size_t count, int ngrains) {
+__global__ void cls_from_cell_kernel(const int *cell, unsigned char *cls, unsigned short *own16, size_t count, int ngrains) {
   const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < count) cls[k] = cell_class(cell[k], ngrains);
+  if (k < count) {
+    cls[k] = cell_class(cell[k], ngrains);
+    own16[k] = cell_own16(cell[k]);
+  }
 }
-cudaError_t launch_cls_from_cell(const int *cell, unsigned char *cls, int nxl, int pitch, int ngrains, cudaStream_t s) {
+cudaError_t launch_cls_from_cell(const int *cell, unsigned char *cls, unsigned short *own16, int nxl, int pitch, int ngrains,
+                                 cudaStream_t s) {
   const size_t count = (size_t)nxl * pitch;
-  cls_from_cell_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(cell, cls, count, ngrains);
+  cls_from_cell_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(cell, cls, own16, count, ngrains);
   return cudaGetLastError();
 }
 
@@ -1504,7 +1514,8 @@ cudaError_t launch_fill_rest(real *f, size_t plane, const Lattice<real> &Lw, cud
   template cudaError_t launch_raster_tiles<real>(const RasterParams<real> &, int, const GrainArrays<real> &,              \
                                                  GrainRec<real> *, real *, GrainBox *, const GrainRec<real> *,            \
                                                  const real *, const GrainBox *, int *, const int *, unsigned char *,     \
-                                                 const unsigned char *, int, int, int,                                    \
+                                                 const unsigned char *, unsigned short *, const unsigned short *, int,    \
+                                                 int, int,                                                                \
                                                  const TileBins &, const BoundaryList &, const LinkList &, int *,         \
                                                  long long *, int, int, int, cudaStream_t);                               \
   template cudaError_t launch_act_map<real>(const Lattice<real> &, const Stored<real> &, int, int, int *, cudaStream_t);  \

@@ -29,8 +29,9 @@ namespace lbmdem {
  * x; each TMA transaction brings ONE lattice row of the strip into a ring of NS shared-memory
  * slots: the nine population planes (TY nodes plus a halo of HY nodes per side), the matching row
  * of this step's obstacle map (halo HC) -- its class bytes only, lbm_node.cuh cell_class -- and of the
- * stored step's map (no halo; int32: the re-initialised nodes need their owner, and fetching it from
- * global memory inside the loop put two dependent loads in front of the equilibrium: measured 27 % slower).
+ * stored step's map (no halo): the owner in 16 bits (cell_own16; the re-initialised nodes need it, and
+ * fetching it from global memory inside the loop, even a row ahead, was slower) or, for samples of 65 534
+ * grains and more, the int32 map itself.
  * The TMA unit wants the byte offset of the box origin along the contiguous dimension to be a
  * multiple of 16 (measured on B200: any other inner coordinate raises "illegal instruction",
  * tools/tma_probe.cu), so the y halo is 16 / sizeof(real) nodes wide instead of one; a box is at
@@ -70,6 +71,7 @@ struct FusedArgs {
   real *out;                               /* [q][x-x0][y] */
   int xlo, xhi;                            /* owned global rows [xlo, xhi) */
   int stream_only;                         /* 1: sweep 5 alone (materialises the reference's f) */
+  int prev16;                              /* 1: the row kernel's tensor map of the stored step's map is the 16-bit owner plane */
 };
 
 /* links of the bounce-back sweep that must not be written while others are evaluated */
@@ -176,17 +178,19 @@ cudaError_t launch_raster_tiles(const lbm::RasterParams<real> &P, int ngrains, c
                                 lbm::GrainRec<real> *rec, real *R2, lbm::GrainBox *boxes,
                                 const lbm::GrainRec<real> *rec_old, const real *R2_old, const lbm::GrainBox *boxes_old,
                                 int *cell, const int *cell_other /* the previous step's map */,
-                                unsigned char *cls, const unsigned char *cls_other /* their class bytes */, int x0, int nxl,
-                                int pitch,
+                                unsigned char *cls, const unsigned char *cls_other /* their class bytes */,
+                                unsigned short *own16, const unsigned short *own16_other /* their 16-bit owners */, int x0,
+                                int nxl, int pitch,
                                 const TileBins &T, const BoundaryList &B, const LinkList &K,
                                 int *defer_count /* emptied as well */,
                                 long long *facc /* nullptr, or [3][n] force sums to be zeroed */, int step,
                                 int first_run /* no previous records */, int force_full /* rebuild every tile */,
                                 cudaStream_t s);
-cudaError_t launch_cell_frame(int *cell, unsigned char *cls, int lx, int ly, int x0, int nxl, int pitch, int ring_value,
-                              cudaStream_t s);
+cudaError_t launch_cell_frame(int *cell, unsigned char *cls, unsigned short *own16, int lx, int ly, int x0, int nxl, int pitch,
+                              int ring_value, cudaStream_t s);
 /* class bytes of a map that came from outside (lbmdem_set_obst): fluid / solid / ring only */
-cudaError_t launch_cls_from_cell(const int *cell, unsigned char *cls, int nxl, int pitch, int ngrains, cudaStream_t s);
+cudaError_t launch_cls_from_cell(const int *cell, unsigned char *cls, unsigned short *own16, int nxl, int pitch, int ngrains,
+                                 cudaStream_t s);
 /* act[x][y] as the reference would hold it (tests / diagnostics) */
 template <typename real>
 cudaError_t launch_act_map(const lbm::Lattice<real> &L, const lbm::Stored<real> &S, int xlo, int xhi, int *act_out,

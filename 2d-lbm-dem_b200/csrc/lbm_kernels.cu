@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(K1_THREADS(RowCfg<real>), sizeof(real) == 8 ? 
     tma_load_2d(base + C::A_PAD + C::CN_PAD, &tmCp, &full[slot], y0, row);
     return;
 #endif
-    mbar_expect_tx(&full[slot], (uint32_t)(C::A_BYTES + C::CN_BYTES + C::CP_BYTES));
+    mbar_expect_tx(&full[slot], (uint32_t)(C::A_BYTES + C::CN_BYTES + (a.prev16 ? C::CP_BYTES / 2 : C::CP_BYTES)));
 #if defined(LBMDEM_K1_LD_EVICT_FIRST)
     tma_load_3d_ef(base, &tmA, &full[slot], y0 - C::HY, row, 0);
 #else
@@ -217,7 +217,12 @@ __global__ void __launch_bounds__(K1_THREADS(RowCfg<real>), sizeof(real) == 8 ? 
     bool work = active;
     if (active) {
       know = Kn0[jy + C::HC];
-      cprev = reinterpret_cast<const int *>(Kn0 + C::CN_PAD)[jy];
+      if (a.prev16) {
+        const unsigned short o = reinterpret_cast<const unsigned short *>(Kn0 + C::CN_PAD)[jy];
+        cprev = o == OWN16_FLUID ? -1 : (int)o;
+      } else {
+        cprev = reinterpret_cast<const int *>(Kn0 + C::CN_PAD)[jy];
+      }
     }
     {
       /* deep inside a grain under both maps: nothing reads what the re-init sweep would leave here (lbm_node.cuh,

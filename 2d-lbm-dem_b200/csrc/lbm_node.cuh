@@ -72,6 +72,15 @@ LBM_HD unsigned char cell_class(int c, int ngrains) {
                          ((c & CELL_IDX) >= ngrains ? CLS_RING : 0));
 }
 
+/* ... and the owner in 16 bits, for samples of fewer than 65 534 grains: what the fused kernel streams of the STORED
+ * step's map (it needs nothing else of it: fluid or not, and whose equilibrium a re-initialised node takes) */
+constexpr unsigned short OWN16_FLUID = 0xFFFF, OWN16_NONE = 0xFFFE; /* NONE: wall ring / index out of range */
+LBM_HD unsigned short cell_own16(int c) {
+  if (c < 0) return OWN16_FLUID;
+  const int i = c & CELL_IDX;
+  return i < (int)OWN16_NONE ? (unsigned short)i : OWN16_NONE;
+}
+
 /* what the LBM kernels need to know about one grain (filled by the rasteriser, K2) */
 template <typename real>
 struct GrainRec {

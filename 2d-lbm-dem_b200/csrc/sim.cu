@@ -227,6 +227,8 @@ struct Sim : SimBase {
   real *f[2] = {nullptr, nullptr};
   int *cell[2] = {nullptr, nullptr};
   unsigned char *cls[2] = {nullptr, nullptr}; /* class byte per node of cell[k] (lbm_node.cuh cell_class): what the row kernel streams */
+  unsigned short *own16[2] = {nullptr, nullptr}; /* 16-bit owner per node of cell[k] (cell_own16): the stored step's map as streamed */
+  CUtensorMap tmC16[2];
   int cur = 0, cur_cell = 0;
   bool holds_A = false;      /* f[cur] holds A of the last step (stream pending) instead of f */
   bool scratch_valid = false; /* f[1 - cur] holds the materialised f of the pending stream */
@@ -276,7 +278,7 @@ struct Sim : SimBase {
   ~Sim() override {
     if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
     for (auto &e : ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
-    for (int k = 0; k < 2; ++k) { cudaFree(f[k]); cudaFree(cell[k]); cudaFree(cls[k]); }
+    for (int k = 0; k < 2; ++k) { cudaFree(f[k]); cudaFree(cell[k]); cudaFree(cls[k]); cudaFree(own16[k]); }
     for (real *p : grain_bufs) cudaFree(p);
     for (int k = 0; k < 2; ++k) { cudaFree(rec[k]); cudaFree(R2[k]); cudaFree(boxes[k]); }
     for (int k = 0; k < 2; ++k) { cudaFree(facc_buf[k]); cudaFree(fpartial_buf[k]); }
@@ -340,6 +342,7 @@ struct Sim : SimBase {
       CK(cudaMemsetAsync(f[k], 0, sizeof(real) * plane * NQ, stream));
       CK(cudaMalloc(&cell[k], sizeof(int) * plane));
       CK(cudaMalloc(&cls[k], plane));
+      CK(cudaMalloc(&own16[k], sizeof(unsigned short) * plane));
     }
     CK(cudaMalloc(&dens_partials, sizeof(double) * DENS_BLOCKS));
     CK(cudaMalloc(&dens_out, sizeof(double)));
@@ -373,6 +376,10 @@ struct Sim : SimBase {
       const cuuint32_t cboxh[2] = {(cuuint32_t)C::BC, 1};
       if (r == CUDA_SUCCESS)
         r = encode(&tmCh[k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, cls[k], cdims, bstr, cboxh, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      const cuuint64_t sstr[1] = {(cuuint64_t)pitch * sizeof(unsigned short)};
+      if (r == CUDA_SUCCESS)
+        r = encode(&tmC16[k], CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, own16[k], cdims, sstr, cbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return fail(LBMDEM_ECUDA, "cuTensorMapEncodeTiled(map) failed with code " + std::to_string((int)r));
     }
@@ -545,7 +552,7 @@ struct Sim : SimBase {
     const Lattice<real> L = lattice();
     CK(launch_fill_rest<real>(f[0], plane, L, stream));
     CK(launch_fill_rest<real>(f[1], plane, L, stream));
-    for (int k = 0; k < 2; ++k) CK(launch_cell_frame(cell[k], cls[k], lx, ly, x0, nxl, pitch, n, stream));
+    for (int k = 0; k < 2; ++k) CK(launch_cell_frame(cell[k], cls[k], own16[k], lx, ly, x0, nxl, pitch, n, stream));
     cur = 0;
     cur_cell = 0;
     holds_A = false;
@@ -627,8 +634,8 @@ struct Sim : SimBase {
     /* params.kernel bit 1: every tile rebuilt every step (the cross-check of the incremental rasteriser) */
     const int full = (raster_step <= raster_full_until || (P.kernel & 2)) ? 1 : 0;
     CK(launch_raster_tiles<real>(raster_params(), n, g, rec[cslot], R2[cslot], boxes[cslot], rec[1 - cslot], R2[1 - cslot],
-                                 boxes[1 - cslot], cell[cslot], cell[1 - cslot], cls[cslot], cls[1 - cslot], x0, nxl, pitch, tbins,
-                                 blist, llist,
+                                 boxes[1 - cslot], cell[cslot], cell[1 - cslot], cls[cslot], cls[1 - cslot], own16[cslot],
+                                 own16[1 - cslot], x0, nxl, pitch, tbins, blist, llist,
                                  defer.count, fa, raster_step, raster_step == 1 ? 1 : 0, full, stream));
     ++raster_step;
     all_launches += 2; /* grain_bin, raster_tile */
@@ -772,6 +779,7 @@ struct Sim : SimBase {
     a.out = f[out_buf];
     a.xlo = xlo; a.xhi = xhi;
     a.stream_only = stream_only;
+    a.prev16 = n < (int)OWN16_NONE ? 1 : 0;
     return a;
   }
   /* sweep 5 of the stored array (+ sweeps 1-2 of the new step unless stream_only) into f[1 - cur] */
@@ -785,8 +793,9 @@ struct Sim : SimBase {
     std::pair<cudaEvent_t, cudaEvent_t> *ev = nullptr;
     int rc;
     if (timed && (rc = record_k1_begin(&ev))) return rc;
-    CK(P.strict_fp ? k1_strict::launch_lbm_rows<real>(tmA[cur], tmC[1 - cur_cell], tmCh[cur_cell], a, stream)
-                   : k1_fast::launch_lbm_rows<real>(tmA[cur], tmC[1 - cur_cell], tmCh[cur_cell], a, stream));
+    const CUtensorMap &tmPrev = a.prev16 ? tmC16[1 - cur_cell] : tmC[1 - cur_cell];
+    CK(P.strict_fp ? k1_strict::launch_lbm_rows<real>(tmA[cur], tmPrev, tmCh[cur_cell], a, stream)
+                   : k1_fast::launch_lbm_rows<real>(tmA[cur], tmPrev, tmCh[cur_cell], a, stream));
     if (ev) CK(cudaEventRecord(ev->second, stream));
     if (timed) ++k1_launches;
     CK(P.strict_fp ? k1_strict::launch_lbm_plain<real>(a, 1, stream) : k1_fast::launch_lbm_plain<real>(a, 1, stream));
@@ -1133,7 +1142,7 @@ struct Sim : SimBase {
     raster_invalidate(); /* this map is not what the grain records would give */
     CK(cudaMemcpy2DAsync(cell[cur_cell] + (size_t)(xlo - x0) * pitch, sizeof(int) * pitch, in, sizeof(int) * ly,
                          sizeof(int) * ly, xhi - xlo, cudaMemcpyHostToDevice, stream));
-    CK(launch_cls_from_cell(cell[cur_cell], cls[cur_cell], nxl, pitch, n, stream));
+    CK(launch_cls_from_cell(cell[cur_cell], cls[cur_cell], own16[cur_cell], nxl, pitch, n, stream));
     CK(cudaStreamSynchronize(stream));
     return 0;
   }

@@ -1,4 +1,4 @@
-OUT=gpurun_out; RUN=r02j; mkdir -p $OUT
+OUT=gpurun_out; RUN=r02k; mkdir -p $OUT
 timeout 900 python -m pytest tests -m gpu -q -x > $OUT/${RUN}_pytest.log 2>&1; tail -4 $OUT/${RUN}_pytest.log
 timeout 300 python bench.py --steps 300 --no-cpu-baseline > $OUT/${RUN}_bench.json 2> $OUT/${RUN}_bench.err
 for w in cfg2 cfg3; do timeout 300 python bench.py --workload $w --steps 300 --no-cpu-baseline > $OUT/${RUN}_$w.json 2> $OUT/${RUN}_$w.err; done
