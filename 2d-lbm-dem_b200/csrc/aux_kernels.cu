@@ -420,7 +420,15 @@ __global__ void __launch_bounds__(RT_THREADS) raster_tile_kernel(int n, int *cel
       const int bit = __ffs(links) - 1;
       links &= links - 1;
       const bool isw = !((fluid >> bit) & 1u);
-      if (kl < K.cap) Kseg[kl] = make_uint2(knode, i | ((unsigned)(bit + 1) << 24) | (isw ? LL_W : 0u));
+      /* the node two steps along the link, where the painted region (tile + one halo node) reaches it: fluid or wall
+       * ring there means the link is not one across a one-node gap, and the sweep need not read the map to find out */
+      const int r2 = r + 2 * ex_of(bit + 1), c2 = c + 2 * ey_of(bit + 1);
+      bool clear = false;
+      if (r2 >= -1 && r2 <= RTX && c2 >= -1 && c2 <= RTY) {
+        const int o2 = own[r2 + 1][c2 + RTC0];
+        clear = o2 < 0 || o2 >= n;
+      }
+      if (kl < K.cap) Kseg[kl] = make_uint2(knode, i | ((unsigned)(bit + 1) << 24) | (isw ? LL_W : 0u) | (clear ? LL_CLEAR : 0u));
       else *(volatile int *)K.overflow = 1;
       ++kl;
     }
@@ -651,7 +659,7 @@ __device__ __forceinline__ void bounce_tile_links(const Lattice<real> &L, const 
           bool gap;
           /* listed bounce links have a fluid neighbour; a link across a one-node gap is evaluated from the
            * pre-sweep state and filed in the deferred list (lbm_node.cuh, sweep_link) */
-          const int r = sweep_link_core(L, S, g, x, y, q, true, &v, true, &gap, &Fn_oq);
+          const int r = sweep_link_core(L, S, g, x, y, q, true, &v, true, &gap, &Fn_oq, (en.y & LL_CLEAR) != 0);
           if (r == SWEEP_WRITE) {
             if (!gap) {
               A[e] = v;

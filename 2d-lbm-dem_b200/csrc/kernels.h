@@ -52,7 +52,17 @@ struct RowCfg {
   static constexpr int A_PAD = (A_BYTES + 127) / 128 * 128;
   static constexpr int CN_PAD = (CN_BYTES + 127) / 128 * 128;
   static constexpr int CP_PAD = (CP_BYTES + 127) / 128 * 128;
-  static constexpr int SLOT = A_PAD + CN_PAD + CP_PAD;
+  /* A CTA owns NB adjacent blocks of TY columns with TY consumer threads each; every block has its own boxes (halo
+   * included: as if NB CTAs shared one ring, one producer and one set of barriers).  fp32 rows are half the bytes of fp64
+   * rows, and what a row costs besides its bytes -- barrier round trips, TMA issue, one row of prefetch to hide a DRAM
+   * latency behind -- is per row: two blocks per row bring fp32 to the bytes-per-row of fp64 (which runs at 0.95+ of the
+   * HBM peak). */
+#ifndef LBMDEM_K1_NB
+#define LBMDEM_K1_NB 1 /* 2 (fp32): 0.2335 ms with 256 + 32 threads, 0.2558 ms with 128 + 32 looping over both blocks, against 0.2301 ms (r02l, r02m) */
+#endif
+  static constexpr int NB = LBMDEM_K1_NB;
+  static constexpr int BLOCK = A_PAD + CN_PAD + CP_PAD;
+  static constexpr int SLOT = NB * BLOCK;
   static constexpr int SMEM = NS * SLOT;
 };
 
@@ -143,6 +153,7 @@ struct LinkList {
   int *overflow;       /* flag in mapped host memory */
 };
 constexpr unsigned LL_W = 1u << 28;
+constexpr unsigned LL_CLEAR = 1u << 29; /* the node two steps along the link is known to be fluid or wall ring: no gap */
 
 /* Grains binned by the lattice tiles (RTX rows x RTY columns, plus one halo node all round) that their bounding
  * box touches: filled by the first kernel of the rasteriser, consumed and emptied by the tile kernel. */

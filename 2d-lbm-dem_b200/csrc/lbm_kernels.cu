@@ -102,9 +102,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
  * (the same moment the producer could: when every warp has released row t-2), and the 1920 registers of the idle
  * producer lanes buy two more resident CTAs per SM */
 #if defined(LBMDEM_K1_NOPROD)
-#define K1_THREADS(C) (C::TY)
+#define K1_THREADS(C) (C::TY * C::NB)
 #else
-#define K1_THREADS(C) (C::TY + 32)
+#define K1_THREADS(C) (C::TY * C::NB + 32)
 #endif
 #ifndef LBMDEM_K1_MINB_F32
 #define LBMDEM_K1_MINB_F32 7   /* 56 registers: 7 CTAs per SM (r02W: 0.2294 ms against 0.2351 ms with 64 registers) */
@@ -113,18 +113,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 #define LBMDEM_K1_MINB_F64 4   /* caps the fp64 build at 102 registers: 4 CTAs per SM (profiles/r01_k1_tuning.txt) */
 #endif
 template <typename real>
-__global__ void __launch_bounds__(K1_THREADS(RowCfg<real>), sizeof(real) == 8 ? LBMDEM_K1_MINB_F64 : LBMDEM_K1_MINB_F32)
+__global__ void __launch_bounds__(K1_THREADS(RowCfg<real>), (sizeof(real) == 8 ? LBMDEM_K1_MINB_F64 : LBMDEM_K1_MINB_F32 + RowCfg<real>::NB - 1) / RowCfg<real>::NB)
     lbm_rows_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                          const __grid_constant__ CUtensorMap tmCp,
                                                                          const __grid_constant__ CUtensorMap tmCn,
                                                                          const __grid_constant__ FusedArgs<real> a) {
   using C = RowCfg<real>;
-  constexpr int NCW = C::TY / 32; /* consumer warps */
+  constexpr int NCW = C::TY * C::NB / 32; /* consumer warps */
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t full[C::NS], empty[C::NS];
 
   const Lattice<real> &L = a.L;
-  const int y0 = blockIdx.x * C::TY;
+  const int y0 = blockIdx.x * (C::TY * C::NB);
   /* rows of this CTA: a balanced share of the interior rows [R0, R1) of the strip */
   const int R0 = max(a.xlo, 1), R1 = min(a.xhi, L.lx - 1);
   const int r0 = R0 + (int)((long long)(R1 - R0) * blockIdx.y / gridDim.y);
@@ -144,30 +144,35 @@ __global__ void __launch_bounds__(K1_THREADS(RowCfg<real>), sizeof(real) == 8 ? 
   __syncthreads();
 
   auto issue_row = [&](int t, int slot) { /* loaded row t is global row r0 - 1 + t */
-    unsigned char *base = smem + (size_t)slot * C::SLOT;
     const int row = r0 - 1 + t - L.x0; /* local row */
+    const uint32_t cp_bytes = a.prev16 ? C::CP_BYTES / 2 : C::CP_BYTES;
 #if defined(LBMDEM_K1_PROBE) && LBMDEM_K1_PROBE == 3 /* 3 = writes alone: only the two map rows are loaded */
-    mbar_expect_tx(&full[slot], (uint32_t)(C::CN_BYTES + C::CP_BYTES));
-    tma_load_2d(base + C::A_PAD, &tmCn, &full[slot], y0 - C::HC, row);
-    tma_load_2d(base + C::A_PAD + C::CN_PAD, &tmCp, &full[slot], y0, row);
-    return;
-#endif
-    mbar_expect_tx(&full[slot], (uint32_t)(C::A_BYTES + C::CN_BYTES + (a.prev16 ? C::CP_BYTES / 2 : C::CP_BYTES)));
-#if defined(LBMDEM_K1_LD_EVICT_FIRST)
-    tma_load_3d_ef(base, &tmA, &full[slot], y0 - C::HY, row, 0);
+    mbar_expect_tx(&full[slot], (uint32_t)C::NB * (C::CN_BYTES + cp_bytes));
 #else
-    tma_load_3d(base, &tmA, &full[slot], y0 - C::HY, row, 0);
+    mbar_expect_tx(&full[slot], (uint32_t)C::NB * (C::A_BYTES + C::CN_BYTES + cp_bytes));
 #endif
-    tma_load_2d(base + C::A_PAD, &tmCn, &full[slot], y0 - C::HC, row);
-    tma_load_2d(base + C::A_PAD + C::CN_PAD, &tmCp, &full[slot], y0, row);
+#pragma unroll
+    for (int b = 0; b < C::NB; ++b) {
+      unsigned char *base = smem + (size_t)slot * C::SLOT + (size_t)b * C::BLOCK;
+      const int yb = y0 + b * C::TY;
+#if !(defined(LBMDEM_K1_PROBE) && LBMDEM_K1_PROBE == 3)
+#if defined(LBMDEM_K1_LD_EVICT_FIRST)
+      tma_load_3d_ef(base, &tmA, &full[slot], yb - C::HY, row, 0);
+#else
+      tma_load_3d(base, &tmA, &full[slot], yb - C::HY, row, 0);
+#endif
+#endif
+      tma_load_2d(base + C::A_PAD, &tmCn, &full[slot], yb - C::HC, row);
+      tma_load_2d(base + C::A_PAD + C::CN_PAD, &tmCp, &full[slot], yb, row);
+    }
   };
 #if defined(LBMDEM_K1_NOPROD)
   if (threadIdx.x == 0) /* fill the ring */
     for (int t = 0; t < min(nload, C::NS); ++t) issue_row(t, t);
 #else
-  if (threadIdx.x >= C::TY) {
+  if (threadIdx.x >= C::TY * C::NB) {
     /* ---- producer warp: one lane keeps the ring full ---- */
-    if (threadIdx.x == C::TY) {
+    if (threadIdx.x == C::TY * C::NB) {
       int slot = 0;
       uint32_t round = 0; /* how many times the ring has wrapped */
       for (int t = 0; t < nload; ++t) {
@@ -181,13 +186,12 @@ __global__ void __launch_bounds__(K1_THREADS(RowCfg<real>), sizeof(real) == 8 ? 
 #endif
 
   /* ---- consumer warps ---- */
-  const int jy = threadIdx.x;
-  const int gy = y0 + jy;
-  const bool active = gy >= 1 && gy <= L.ly - 2;
+  const int b = threadIdx.x / C::TY;     /* the block of TY columns this warp works in (warp-uniform) */
+  const int jy = threadIdx.x - b * C::TY;
   const int by = jy + C::HY;
-  /* one 64-bit pointer + q * plane: 64 registers, 6 CTAs per SM.  (A 32-bit offset from uniform plane bases needs
-   * 48 registers and gives 8 CTAs per SM -- measured 4 % SLOWER, profiles/r01_k1_tuning.txt.) */
-  real *out = a.out + node_index(L, r0, gy);
+  /* one 64-bit pointer + q * plane.  (A 32-bit offset from uniform plane bases needs fewer registers and gives more
+   * CTAs per SM -- measured 4 % SLOWER, profiles/r01_k1_tuning.txt.) */
+  real *out_row = a.out + node_index(L, r0, y0 + b * C::TY + jy);
   mbar_wait(&full[0], 0);
   mbar_wait(&full[1], 0);
 
@@ -209,9 +213,14 @@ __global__ void __launch_bounds__(K1_THREADS(RowCfg<real>), sizeof(real) == 8 ? 
     }
 #endif
     mbar_wait(&full[slot_p], round_p & 1);
-    /* class bytes (lbm_node.cuh cell_class) of this step's map, row t with its y halo; behind them the stored step's map */
-    const unsigned char *Kn0 = smem + (size_t)slot_0 * C::SLOT + C::A_PAD;
     const int gx = r0 - 1 + t;
+    { /* this thread's node */
+    const int gy = y0 + b * C::TY + jy;
+    const bool active = gy >= 1 && gy <= L.ly - 2;
+    real *out = out_row;
+    const size_t boff = (size_t)b * C::BLOCK;
+    /* class bytes (lbm_node.cuh cell_class) of this step's map, row t with its y halo; behind them the stored step's map */
+    const unsigned char *Kn0 = smem + (size_t)slot_0 * C::SLOT + boff + C::A_PAD;
     unsigned know = 0;
     int cprev = 0;
     bool work = active;
@@ -243,9 +252,9 @@ __global__ void __launch_bounds__(K1_THREADS(RowCfg<real>), sizeof(real) == 8 ? 
       if (skip) work = false;
     }
     if (work) {
-      const real *Am = reinterpret_cast<const real *>(smem + (size_t)slot_m * C::SLOT);
-      const real *A0 = reinterpret_cast<const real *>(smem + (size_t)slot_0 * C::SLOT);
-      const real *Ap = reinterpret_cast<const real *>(smem + (size_t)slot_p * C::SLOT);
+      const real *Am = reinterpret_cast<const real *>(smem + (size_t)slot_m * C::SLOT + boff);
+      const real *A0 = reinterpret_cast<const real *>(smem + (size_t)slot_0 * C::SLOT + boff);
+      const real *Ap = reinterpret_cast<const real *>(smem + (size_t)slot_p * C::SLOT + boff);
       real f[NQ];
       /* a node that is solid under the stored step's map is overwritten by the re-init sweep,
        * whatever streams into it: skip the pull */
@@ -270,8 +279,8 @@ __global__ void __launch_bounds__(K1_THREADS(RowCfg<real>), sizeof(real) == 8 ? 
         if (know == 0) mrt_collide(L, f);
         if ((know & CLS_ACT) && w_links_with_collide(L, gx, gy)) {
           /* active solid node: links into non-fluid neighbours take the rest value (:1161-1162) */
-          const unsigned char *Knm = smem + (size_t)slot_m * C::SLOT + C::A_PAD;
-          const unsigned char *Knp = smem + (size_t)slot_p * C::SLOT + C::A_PAD;
+          const unsigned char *Knm = smem + (size_t)slot_m * C::SLOT + boff + C::A_PAD;
+          const unsigned char *Knp = smem + (size_t)slot_p * C::SLOT + boff + C::A_PAD;
 #pragma unroll
           for (int q = 1; q < NQ; ++q) {
             const int ex = ex_of(q), ey = ey_of(q);
@@ -296,7 +305,8 @@ __global__ void __launch_bounds__(K1_THREADS(RowCfg<real>), sizeof(real) == 8 ? 
       for (int q = 0; q < NQ; ++q) out[q * L.plane] = f[q];
 #endif
     }
-    out += L.pitch;
+    }
+    out_row += L.pitch;
     /* this warp is done with row t-1 */
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[slot_m]);
@@ -420,7 +430,7 @@ cudaError_t launch_lbm_rows(const CUtensorMap &tmA, const CUtensorMap &tmCp, con
   }
   const int R0 = a.xlo > 1 ? a.xlo : 1, R1 = a.xhi < a.L.lx - 1 ? a.xhi : a.L.lx - 1;
   if (R1 <= R0) return cudaSuccess;
-  const int strips = (a.L.ly + C::TY - 1) / C::TY;
+  const int strips = (a.L.ly + C::TY * C::NB - 1) / (C::TY * C::NB);
   /* all CTAs co-resident (one wave), rows split evenly between the CTAs of a strip */
   int chunks = resident / strips;
   if (chunks < 1) chunks = 1;
