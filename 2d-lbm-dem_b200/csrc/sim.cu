@@ -1399,7 +1399,15 @@ struct Sim : SimBase {
     char *gs = reinterpret_cast<char *>(gstage), *hs = reinterpret_cast<char *>(hstage); /* hstage: 16 n doubles, pinned */
     const bool pin_in = state_in && host_is_pinned(state_in);
     const bool pin_out = (!state_out || host_is_pinned(state_out)) && (!fhf_out || host_is_pinned(fhf_out));
-    if (state_in) {
+    /* Page-locked buffers that the device can address (lbmdem_host_alloc) are read and written IN PLACE by the
+     * unpack / pack kernels -- the rows cross PCIe inside those kernels, coalesced, and the two copy operations with
+     * their staging slab drop out of the step (0.5 MB per step: the copies were latency, not bandwidth). */
+    const void *in_dev = (state_in && pin_in && !(share && P.nranks > 1)) ? host_device_ptr(state_in) : nullptr;
+    const bool one_block = state_out && fhf_out && static_cast<char *>(fhf_out) == static_cast<char *>(state_out) + eb * 9 * N;
+    void *out_dev = (pin_out && !share && one_block) ? host_device_ptr(state_out) : nullptr;
+    if (state_in && in_dev) {
+      CK(launch_grain_unpack<real>(in_dev, rows_f32, n, 9, g.x1, stream));
+    } else if (state_in) {
       const void *src = state_in;
       if (!pin_in) { memcpy(hs, state_in, eb * 9 * M); src = hs; }
       CK(cudaMemcpyAsync(gs + eb * 9 * (size_t)i0, src, eb * 9 * M, cudaMemcpyHostToDevice, stream));
@@ -1423,10 +1431,12 @@ struct Sim : SimBase {
     if (rc) return done(rc);
     (void)built;
     if ((rc = materialise_fhf())) return rc;
-    if (state_out || fhf_out) {
+    if (out_dev) {
+      CK(launch_grain_pack2<real>(g.x1, 9, g.fhf1, 3, n, out_dev, rows_f32, stream)); /* [n][9] state, then [n][3] fhf, on the host */
+    } else if (state_out || fhf_out) {
       CK(launch_grain_pack2<real>(g.x1, 9, g.fhf1, 3, n, gs, rows_f32, stream)); /* [n][9] state, then [n][3] fhf */
       const char *st = gs + eb * 9 * (size_t)i0, *fh = gs + eb * 9 * N + eb * 3 * (size_t)i0;
-      if (pin_out && !share && state_out && fhf_out && static_cast<char *>(fhf_out) == static_cast<char *>(state_out) + eb * 9 * N) {
+      if (pin_out && !share && one_block) {
         CK(cudaMemcpyAsync(state_out, gs, eb * 12 * N, cudaMemcpyDeviceToHost, stream)); /* one block on the host too */
       } else if (pin_out) {
         if (state_out) CK(cudaMemcpyAsync(state_out, st, eb * 9 * M, cudaMemcpyDeviceToHost, stream));
@@ -1448,6 +1458,12 @@ struct Sim : SimBase {
       if (fhf_out) memcpy(fhf_out, hs + eb * 9 * M, eb * 3 * M);
     }
     return 0;
+  }
+  /* the device's address of page-locked host memory, nullptr if the device cannot address it */
+  static void *host_device_ptr(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
   }
   static bool host_is_pinned(const void *p) {
     cudaPointerAttributes a;
@@ -1713,7 +1729,8 @@ API int lbmdem_get_list_counts(lbmdem_ctx *ctx, long counts[4]) {
 API int lbmdem_host_alloc(size_t bytes, void **ptr) {
   if (!ptr || !bytes) return LBMDEM_EINVAL;
   *ptr = nullptr;
-  return cudaHostAlloc(ptr, bytes, cudaHostAllocDefault) == cudaSuccess ? 0 : LBMDEM_ECUDA;
+  /* mapped and portable: lbmdem_step_host's pack / unpack kernels read and write these buffers in place */
+  return cudaHostAlloc(ptr, bytes, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess ? 0 : LBMDEM_ECUDA;
 }
 API int lbmdem_host_free(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? 0 : LBMDEM_ECUDA; }
 API void *lbmdem_stream(lbmdem_ctx *ctx) { return (ctx && ctx->sim) ? ctx->sim->stream_ptr() : nullptr; }

@@ -1,12 +1,8 @@
-OUT=gpurun_out; RUN=r02s; mkdir -p $OUT
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/${RUN}_strips8.csv python tools/strip_launches.py 8 4 > $OUT/${RUN}_strips8.log 2>&1
-tail -3 $OUT/${RUN}_strips8.log
+OUT=gpurun_out; RUN=r02t; mkdir -p $OUT
+timeout 900 python -m pytest tests -m gpu -q -x > $OUT/${RUN}_pytest.log 2>&1; tail -3 $OUT/${RUN}_pytest.log
+timeout 300 python bench.py --steps 1000 --no-cpu-baseline --no-cfg5 > $OUT/${RUN}_bench.json 2> $OUT/${RUN}_bench.err
 python - <<PY
-import csv, collections, re
-rows=[l for l in open("$OUT/${RUN}_strips8.csv") if l.startswith('"')]
-agg=collections.defaultdict(list)
-for x in csv.DictReader(rows):
-    try: agg[re.sub(r"\\(.*","",x["Kernel Name"])[:50]].append(float(x["Metric Value"].replace(",","")))
-    except Exception: pass
-for k,v in sorted(agg.items(), key=lambda kv:-sum(kv[1]))[:24]: print("  %-50s n=%4d avg %9.1f total %10.1f"%(k,len(v),sum(v)/len(v),sum(v)))
+import json
+d=json.loads(open("$OUT/${RUN}_bench.json").read().strip().splitlines()[-1])
+print("MLUPS %.0f ms/step %.4f K1 %.4f frac %.3f e2e %.0f (%.4f ms) launches %d" % (d["value"], d["ms_per_step"], d["roofline"]["avg_launch_ms"], d["roofline"]["frac"], d["e2e"]["value"], d["e2e"]["ms_per_step"], d["gpu_launches"]))
 PY
