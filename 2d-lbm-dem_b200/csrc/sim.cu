@@ -63,6 +63,7 @@ struct NcclApi {
   typedef int (*Group_t)(void);
   typedef int (*AllReduce_t)(const void *, void *, size_t, int, int, void *, cudaStream_t);
   typedef int (*Broadcast_t)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+  typedef int (*AllGather_t)(const void *, void *, size_t, int, void *, cudaStream_t);
   typedef const char *(*ErrStr_t)(int);
   void *handle = nullptr;
   GetUniqueId_t GetUniqueId = nullptr;
@@ -73,6 +74,7 @@ struct NcclApi {
   Group_t GroupStart = nullptr, GroupEnd = nullptr;
   AllReduce_t AllReduce = nullptr;
   Broadcast_t Broadcast = nullptr;
+  AllGather_t AllGather = nullptr;
   ErrStr_t GetErrorString = nullptr;
   enum { Int64 = 4, Float32 = 7, Float64 = 8, Sum = 0 };
   bool load(std::string *why) {
@@ -88,7 +90,7 @@ struct NcclApi {
   if (!field) { *why = std::string("dlsym ") + name; return false; }
     SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
     SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd")
-    SYM(AllReduce, "ncclAllReduce") SYM(Broadcast, "ncclBroadcast") SYM(GetErrorString, "ncclGetErrorString")
+    SYM(AllReduce, "ncclAllReduce") SYM(Broadcast, "ncclBroadcast") SYM(AllGather, "ncclAllGather") SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
     return true;
   }
@@ -1412,7 +1414,12 @@ struct Sim : SimBase {
       if (!pin_in) { memcpy(hs, state_in, eb * 9 * M); src = hs; }
       CK(cudaMemcpyAsync(gs + eb * 9 * (size_t)i0, src, eb * 9 * M, cudaMemcpyHostToDevice, stream));
       if (share && P.nranks > 1) {
-        /* every rank's rows to every rank, over NVLink instead of PCIe: one broadcast per rank, in place, one group */
+        /* every rank's rows to every rank, over NVLink instead of PCIe, in place: ONE all-gather when the shares are
+         * equal, else one broadcast per rank in one group */
+        if (n % P.nranks == 0) {
+          const int r = g_nccl.AllGather(gs + eb * 9 * (size_t)i0, gs, (size_t)9 * M, rows_f32 ? NcclApi::Float32 : NcclApi::Float64, comm, stream);
+          if (r) return nccl_fail(r, "ncclAllGather");
+        } else {
         int r = g_nccl.GroupStart();
         for (int k = 0; k < P.nranks && !r; ++k) {
           int a, b;
@@ -1423,6 +1430,7 @@ struct Sim : SimBase {
         const int r2 = g_nccl.GroupEnd();
         if (r) return nccl_fail(r, "ncclBroadcast");
         if (r2) return nccl_fail(r2, "ncclGroupEnd");
+        }
       }
       CK(launch_grain_unpack<real>(gs, rows_f32, n, 9, g.x1, stream)); /* x1 .. a3 are contiguous in the slab */
     }
