@@ -82,6 +82,7 @@ struct FusedArgs {
   int xlo, xhi;                            /* owned global rows [xlo, xhi) */
   int stream_only;                         /* 1: sweep 5 alone (materialises the reference's f) */
   int prev16;                              /* 1: the row kernel's tensor map of the stored step's map is the 16-bit owner plane */
+  const unsigned char *cls_prev;           /* class bytes of the stored step's map: which populations nobody pulls (LDGSTS rows) */
 };
 
 /* links of the bounce-back sweep that must not be written while others are evaluated */

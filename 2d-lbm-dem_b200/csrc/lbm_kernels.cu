@@ -93,6 +93,15 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
       : "memory");
 }
 
+/* 16 bytes global -> shared without a register round trip (LDGSTS, L2 only), and the arrival on an mbarrier that
+ * fires when all of the calling thread's earlier copies have landed (the barrier's count already includes it) */
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(uint64_t *bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -101,6 +110,12 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
  * LBMDEM_K1_NOPROD, no producer warp: the first consumer lane issues the loads of row t+2 at the top of iteration t
  * (the same moment the producer could: when every warp has released row t-2), and the 1920 registers of the idle
  * producer lanes buy two more resident CTAs per SM */
+#ifndef LBMDEM_K1_LDGSTS_ALL
+#define LBMDEM_K1_LDGSTS_ALL 0 /* measurement: 1 = load every piece (the copy mechanism alone, no skipping) */
+#endif
+#if defined(LBMDEM_K1_LDGSTS) && !defined(LBMDEM_K1_NOPROD)
+#define LBMDEM_K1_NOPROD 1 /* the consumer threads load the rows themselves */
+#endif
 #if defined(LBMDEM_K1_NOPROD)
 #define K1_THREADS(C) (C::TY * C::NB)
 #else
@@ -135,7 +150,11 @@ __global__ void __launch_bounds__(K1_THREADS(RowCfg<real>), (sizeof(real) == 8 ?
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < C::NS; ++s) {
+#if defined(LBMDEM_K1_LDGSTS)
+      mbar_init(&full[s], 1 + C::TY); /* thread 0's expect_tx (the two map boxes) + one copy-completion arrival per thread */
+#else
       mbar_init(&full[s], 1);
+#endif
       mbar_init(&empty[s], NCW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -166,7 +185,58 @@ __global__ void __launch_bounds__(K1_THREADS(RowCfg<real>), (sizeof(real) == 8 ?
       tma_load_2d(base + C::A_PAD + C::CN_PAD, &tmCp, &full[slot], yb, row);
     }
   };
-#if defined(LBMDEM_K1_NOPROD)
+#if defined(LBMDEM_K1_LDGSTS)
+  /* The population rows come in 16-byte pieces copied by the consumer threads themselves (LDGSTS) instead of one TMA
+   * box: a piece whose nodes are all solid, not active and not wall ring under the STORED step's map is not loaded --
+   * no fluid node neighbours it, so nothing pulls from it (solid nodes do not pull: the re-init sweep overwrites
+   * them).  In a dense packing that is a quarter of the population reads, and the read stream is what bounds this
+   * kernel (profiles/r02_k1_probes.txt).  The class bytes of a row's pieces are fetched one row ahead (kw). */
+  static_assert(C::NB == 1, "LDGSTS rows: one block per CTA");
+  constexpr int NPG = 16 / (int)sizeof(real);          /* nodes per piece */
+  constexpr int GPR = C::BY / NPG;                     /* pieces per plane row */
+  constexpr int NGR = NQ * GPR;                        /* pieces per row */
+  constexpr int G = (NGR + C::TY - 1) / C::TY;         /* pieces per thread */
+  static_assert(C::BY % NPG == 0, "row box is a whole number of 16-byte pieces");
+  uint32_t kw[G];
+  auto load_kw = [&](int t) { /* class bytes of this thread's pieces of loaded row t */
+    const unsigned char *crow = a.cls_prev + (size_t)(r0 - 1 + t - L.x0) * L.pitch;
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+      const int g = (int)threadIdx.x + k * C::TY, q = g / GPR, c = g - q * GPR;
+      const int y = y0 - C::HY + c * NPG;
+      kw[k] = 0;
+      if (g < NGR && y >= 0 && y < L.pitch)
+        kw[k] = sizeof(real) == 4 ? *reinterpret_cast<const uint32_t *>(crow + y) : *reinterpret_cast<const unsigned short *>(crow + y);
+    }
+  };
+  auto issue_pieces = [&](int t, int slot) {
+    if (threadIdx.x == 0) { /* the two map rows still travel as TMA boxes */
+      const int row = r0 - 1 + t - L.x0;
+      const uint32_t cp_bytes = a.prev16 ? C::CP_BYTES / 2 : C::CP_BYTES;
+      unsigned char *base = smem + (size_t)slot * C::SLOT;
+      mbar_expect_tx(&full[slot], (uint32_t)(C::CN_BYTES + cp_bytes));
+      tma_load_2d(base + C::A_PAD, &tmCn, &full[slot], y0 - C::HC, row);
+      tma_load_2d(base + C::A_PAD + C::CN_PAD, &tmCp, &full[slot], y0, row);
+    }
+    const real *rowp = a.A + (size_t)(r0 - 1 + t - L.x0) * L.pitch;
+    real *dst = reinterpret_cast<real *>(smem + (size_t)slot * C::SLOT);
+    constexpr uint32_t KEEP = sizeof(real) == 4 ? 0x0B0B0B0Bu : 0x0B0Bu; /* CLS_SOLID | CLS_ACT | CLS_RING per node */
+    constexpr uint32_t DEAD = sizeof(real) == 4 ? 0x01010101u : 0x0101u; /* ... == CLS_SOLID for every node of the piece */
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+      const int g = (int)threadIdx.x + k * C::TY, q = g / GPR, c = g - q * GPR;
+      const int y = y0 - C::HY + c * NPG;
+      if (g < NGR && y >= 0 && y < L.pitch && (a.stream_only || LBMDEM_K1_LDGSTS_ALL || (kw[k] & KEEP) != DEAD))
+        cp_async16(dst + q * C::BY + c * NPG, rowp + q * L.plane + y);
+    }
+    cp_async_arrive(&full[slot]);
+  };
+  for (int t = 0; t < min(nload, C::NS); ++t) { /* fill the ring */
+    load_kw(t);
+    issue_pieces(t, t);
+  }
+  if (C::NS < nload) load_kw(C::NS);
+#elif defined(LBMDEM_K1_NOPROD)
   if (threadIdx.x == 0) /* fill the ring */
     for (int t = 0; t < min(nload, C::NS); ++t) issue_row(t, t);
 #else
@@ -203,7 +273,15 @@ __global__ void __launch_bounds__(K1_THREADS(RowCfg<real>), (sizeof(real) == 8 ?
   for (int t = 1; t <= nload - 2; ++t) {
     int slot_p = slot_0 + 1;
     if (slot_p == C::NS) { slot_p = 0; ++round_p; }
-#if defined(LBMDEM_K1_NOPROD)
+#if defined(LBMDEM_K1_LDGSTS)
+    /* row t-2 was released by every warp at the end of iteration t-1 (or is about to be): its slot takes row t-2+NS */
+    if (t >= 2 && t - 2 + C::NS < nload) {
+      const int tl = t - 2 + C::NS, sl = (t - 2) % C::NS;
+      mbar_wait(&empty[sl], ((t - 2) / C::NS) & 1);
+      issue_pieces(tl, sl);
+      if (tl + 1 < nload) load_kw(tl + 1);
+    }
+#elif defined(LBMDEM_K1_NOPROD)
     /* row t-2 was released by every warp at the end of iteration t-1 (or is about to be): its slot takes row
      * t-2+NS.  Loaded rows 0 .. NS-1 went in before the loop. */
     if (threadIdx.x == 0 && t >= 2 && t - 2 + C::NS < nload) {

@@ -782,6 +782,7 @@ struct Sim : SimBase {
     a.xlo = xlo; a.xhi = xhi;
     a.stream_only = stream_only;
     a.prev16 = n < (int)OWN16_NONE ? 1 : 0;
+    a.cls_prev = cls[1 - cur_cell];
     return a;
   }
   /* sweep 5 of the stored array (+ sweeps 1-2 of the new step unless stream_only) into f[1 - cur] */
