@@ -139,8 +139,10 @@ int lbmdem_get_fields(lbmdem_ctx *ctx, const double *grain_p_in, float *grain_pr
 
 /* End-to-end form of one coupled step with HOST buffers: upload the grain kinematic state,
  * run n_dem_steps renderScene() calls, download the new state, fhf and the density checksum.
- * Any of the output pointers may be NULL.  Buffers in page-locked memory (lbmdem_host_alloc, or
- * anything cudaHostRegister'ed) are the source / target of the PCIe copies themselves; pageable
+ * Any of the output pointers may be NULL.  Buffers in page-locked memory the device can address
+ * (lbmdem_host_alloc, or anything cudaHostRegister'ed as mapped) cross PCIe without a copy operation:
+ * the kernels that convert between grain rows and the device's columns read state_in and -- when fhf_out
+ * directly follows state_out, i.e. fhf_out == state_out + 9 n -- write the outputs in place; pageable
  * buffers go through one staging copy each way. */
 int lbmdem_step_host(lbmdem_ctx *ctx, const double *state_in /* [n][9] or NULL */, long n_dem_steps,
                      double *state_out /* [n][9] */, double *fhf_out /* [n][3] */, double *density_out);
@@ -152,7 +154,7 @@ int lbmdem_step_host_f32(lbmdem_ctx *ctx, const float *state_in /* [n][9] or NUL
 /* Strip-decomposed runs replicate the grains on every GPU, but only one copy has to cross the host boundary: in the
  * `share` form every rank uploads and downloads the rows of ITS share of the grains -- the contiguous index range
  * [i0, i1) of lbmdem_get_share, a balanced split over the ranks -- and the ranks pass the uploaded rows on to each other
- * over NVLink (one ncclBroadcast per rank) before the step.  state_in / state_out: [i1-i0][9], fhf_out: [i1-i0][3].
+ * over NVLink (one ncclAllGather when the shares are equal, else one ncclBroadcast per rank) before the step.  state_in / state_out: [i1-i0][9], fhf_out: [i1-i0][3].
  * With one rank it is lbmdem_step_host. */
 int lbmdem_get_share(lbmdem_ctx *ctx, int *i0, int *i1);
 int lbmdem_step_host_share(lbmdem_ctx *ctx, const double *state_in, long n_dem_steps, double *state_out, double *fhf_out,
