@@ -1292,6 +1292,59 @@ cudaError_t launch_peer_sum(const PeerPtrs &pp, int len, T *out, cudaStream_t s)
   peer_sum_kernel<T><<<(len + 255) / 256, 256, 0, s>>>(pp, len, out);
   return cudaGetLastError();
 }
+/* ---- the same across PROCESSES (one rank per GPU): peers' sums through CUDA IPC mappings ----
+ * publish: runs behind this rank's last force kernel; tells every peer (a word in the PEER's memory) that this rank's
+ * partial sums of step `step` are complete.  sum: waits until every peer has said so, then adds, per grain, the sums of
+ * the ranks whose rows the grain's bounding box touches (+- one row) -- every force contribution comes from a solid node
+ * of the grain in an owned row, so the other ranks hold zeros there -- which keeps the NVLink traffic at about one copy
+ * of the sums instead of nranks - 1.  Integer adds: the result does not depend on who adds in which order. */
+__global__ void ipc_publish_kernel(IpcPeers pp, unsigned step) {
+  const int p = threadIdx.x;
+  if (p < pp.nranks && p != pp.rank) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pp.flags[p] + pp.rank), "r"(step) : "memory");
+  }
+}
+__global__ void __launch_bounds__(256) ipc_sum_kernel(IpcPeers pp, unsigned step, int n, const GrainBox *boxes, long long *out,
+                                                      int *timeout_flag) {
+  if ((int)threadIdx.x < pp.nranks && (int)threadIdx.x != pp.rank) {
+    const unsigned *fl = pp.flags[pp.rank] + threadIdx.x;
+    const long long t0 = clock64();
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(fl) : "memory");
+    } while ((int)(v - step) < 0 && clock64() - t0 < 40000000000ll); /* ~20 s: a peer is gone, not late */
+    if ((int)(v - step) < 0) *(volatile int *)timeout_flag = 1;
+  }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const GrainBox b = boxes[i];
+  long long s1 = 0, s2 = 0, s3 = 0;
+  const int base = pp.lx / pp.nranks, rem = pp.lx % pp.nranks;
+  for (int k = 0; k < pp.nranks; ++k) {
+    const int klo = k * base + min(k, rem), khi = klo + base + (k < rem ? 1 : 0); /* rank k owns rows [klo, khi) */
+    if (k == pp.rank || (b.xf + 1 >= klo && b.xi - 1 < khi && b.xf >= b.xi)) {
+      const long long *f = pp.facc[k];
+      s1 += __ldcv(f + i);
+      s2 += __ldcv(f + n + i);
+      s3 += __ldcv(f + 2 * (size_t)n + i);
+    }
+  }
+  out[i] = s1;
+  out[n + i] = s2;
+  out[2 * (size_t)n + i] = s3;
+}
+cudaError_t launch_ipc_publish(const IpcPeers &pp, unsigned step, cudaStream_t s) {
+  ipc_publish_kernel<<<1, 32, 0, s>>>(pp, step);
+  return cudaGetLastError();
+}
+cudaError_t launch_ipc_sum(const IpcPeers &pp, unsigned step, int n, const GrainBox *boxes, long long *out, int *timeout_flag,
+                           cudaStream_t s) {
+  ipc_sum_kernel<<<(n + 255) / 256, 256, 0, s>>>(pp, step, n, boxes, out, timeout_flag);
+  return cudaGetLastError();
+}
+
 template cudaError_t launch_peer_sum<long long>(const PeerPtrs &, int, long long *, cudaStream_t);
 template cudaError_t launch_peer_sum<double>(const PeerPtrs &, int, double *, cudaStream_t);
 

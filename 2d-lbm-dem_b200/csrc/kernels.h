@@ -258,6 +258,20 @@ struct PeerPtrs {
 template <typename T>
 cudaError_t launch_peer_sum(const PeerPtrs &pp, int len, T *out, cudaStream_t s);
 
+/* One process per GPU (the NCCL transport): the fixed-point force sums of the ranks added by a kernel that reads the
+ * peers' partial sums through CUDA IPC mappings over NVLink instead of ncclAllReduce (which costs ~30 us on 8 GPUs
+ * whatever the size, profiles/r02_k1_probes.txt).  facc[k]: rank k's partial sums of this step (3 n int64, rank k's
+ * memory); flags[k]: rank k's arrival words (flags[k][j] = the last step whose sums rank j has completed, written by
+ * rank j into rank k's memory). */
+struct IpcPeers {
+  const long long *facc[MAX_LOCAL_RANKS];
+  unsigned *flags[MAX_LOCAL_RANKS];
+  int nranks, rank, lx;
+};
+cudaError_t launch_ipc_publish(const IpcPeers &pp, unsigned step, cudaStream_t s);
+cudaError_t launch_ipc_sum(const IpcPeers &pp, unsigned step, int n, const lbm::GrainBox *boxes, long long *out, int *timeout_flag,
+                           cudaStream_t s);
+
 struct VerletBuffers {
   int nbuckets;        /* power of two */
   int *bucket_count;   /* [nbuckets + 1] -> exclusive offsets after the scan */

@@ -16,7 +16,10 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def test_strips_are_bit_identical_to_one_gpu():
+@pytest.mark.parametrize("peer_sums", ["1", "0"])
+def test_strips_are_bit_identical_to_one_gpu(peer_sums):
+    """peer_sums: the force sums of the ranks added through CUDA IPC mappings of the peers' buffers (the default) or
+    with ncclAllReduce (LBMDEM_PEER_SUMS=0); both must reproduce the one-GPU run bit for bit."""
     import torch
     ngpu = torch.cuda.device_count()
     if ngpu < 2:
@@ -24,10 +27,14 @@ def test_strips_are_bit_identical_to_one_gpu():
     world = min(ngpu, 4)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), os.path.join(HERE, "multigpu_worker.py")]
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    env = dict(os.environ, LBMDEM_PEER_SUMS=peer_sums, LBMDEM_VERBOSE="1")
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert p.returncode == 0, (p.stdout + p.stderr)[-4000:]
     for rank in range(world):
         assert f"rank {rank}: ok" in p.stdout
+    assert ("peer-memory force sums" in p.stderr) == (peer_sums == "1"), p.stderr[-2000:]
+    if peer_sums == "1":
+        assert "peer-memory force sums on" in p.stderr, "CUDA IPC between the ranks' GPUs is expected to work on one box"
 
 
 def test_executable_on_two_gpus_writes_the_same_files_as_on_one(tmp_path):

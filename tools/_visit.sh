@@ -1,16 +1,13 @@
-OUT=gpurun_out; RUN=r02w; mkdir -p $OUT
-timeout 900 python -m pytest tests -m gpu -q -x > $OUT/${RUN}_pytest.log 2>&1; tail -3 $OUT/${RUN}_pytest.log
-for v in "" _old; do
-LBMDEM_LIB=$PWD/2d-lbm-dem_b200/liblbmdem_gpu$v.so timeout 300 python bench.py --steps 300 --no-cpu-baseline --no-cfg5 > $OUT/${RUN}_bench$v.json 2> $OUT/${RUN}_bench$v.err
-LBMDEM_LIB=$PWD/2d-lbm-dem_b200/liblbmdem_gpu$v.so timeout 300 python tools/_prof_default.py 2>&1 | grep -v Warn | head -4
-done
+OUT=gpurun_out; RUN=r02z; mkdir -p $OUT
+export LBMDEM_PEER_SUMS=1 LBMDEM_VERBOSE=1
+N=$(nvidia-smi -L | wc -l)
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 300 --warmup 20 --no-cfg5 > $OUT/${RUN}_bench_ipc_${N}gpu.json 2> $OUT/${RUN}_bench_ipc_${N}gpu.err
+grep -m1 "peer-memory" $OUT/${RUN}_bench_ipc_${N}gpu.err
 python - <<PY
 import json
-for nm in ("bench","bench_old"):
+for nm in ("bench_ipc_${N}gpu",):
     try:
-        d=json.loads(open("$OUT/${RUN}_%s.json"%nm).read().strip().splitlines()[-1])
-        print(nm, "MLUPS %.0f ms/step %.4f K1 %.4f frac %.3f e2e %.0f launches %d" % (d["value"], d["ms_per_step"], d["roofline"]["avg_launch_ms"], d["roofline"]["frac"], d["e2e"]["value"], d["gpu_launches"]))
-    except Exception as e: print(nm, e); print(open("$OUT/${RUN}_%s.err"%nm).read()[-800:])
+        d = json.loads(open("$OUT/${RUN}_%s.json"%nm).read().strip().splitlines()[-1])
+        print(nm, "N=%d MLUPS %.0f ms/step %.4f e2e %.0f launches %d strip_check %s" % (d["n_gpus"], d["value"], d["ms_per_step"], d["e2e"]["value"], d["gpu_launches"], d.get("strip_check", {}).get("ok")))
+    except Exception as e: print(nm, e); print(open("$OUT/${RUN}_%s.err"%nm).read()[-1500:])
 PY
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:dem_coop -c 12 --csv --log-file $OUT/${RUN}_dem.csv python bench.py --steps 3 --warmup 8 --no-cpu-baseline --no-cfg5 > /dev/null 2>&1
-grep dem_coop $OUT/${RUN}_dem.csv | tail -3 | cut -d, -f5,15- 
