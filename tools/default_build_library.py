@@ -1,5 +1,8 @@
+"""tools/default_build_library.py -- the reference's DEFAULT build (7826 x 2325 fp64) on bin/50000-test.data through the
+library alone (lbmdem_step, state resident): ms per coupled step, batched and one renderScene() call at a time
+(profiles/r02_default_build_application.txt)."""
 import sys, time, os
-ROOT="/root/repo"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, ROOT+"/2d-lbm-dem_b200"): sys.path.insert(0,p)
 import lbmdem_gpu as G, torch
 s = G.Solver(7826, 2325, 1.0, "f64")
