@@ -53,6 +53,25 @@ def local_map(obst, x0, nxl, ring):
     return out
 
 
+def peer_rule_sum(parts, gtab, scal, lx, n, world):
+    """ipc_sum_kernel's rule on the CPU: grain i takes the partial sums of rank k iff its clamped bounding box
+    (src/main.c:1009-1023, csrc/raster_node.cuh grain_geometry), widened by one row, meets rank k's rows."""
+    dx, mgx = scal[0], scal[2]
+    xc, rbl0 = (gtab[:, 0] - mgx) / dx, gtab[:, 5] / dx
+    xi = np.maximum(np.trunc(xc - rbl0).astype(np.int64), 1)
+    xf = np.minimum(np.trunc(xc + rbl0).astype(np.int64), lx - 2)
+    out = np.zeros(3 * n, dtype=np.int64)
+    used = 0
+    for k in range(world):
+        klo, khi = D.strip_bounds(lx, k, world)
+        take = (xf + 1 >= klo) & (xi - 1 < khi) & (xf >= xi)
+        used += int(take.sum())
+        for c in range(3):
+            out[c * n:(c + 1) * n] += np.where(take, parts[k][c * n:(c + 1) * n], 0)
+    assert used < world * n, "the rule selects every rank for every grain: nothing is tested"
+    return out
+
+
 def run_strips(hc, lx, ly, n, scal, gtab, f_in, obst_old, rank, world):
     xlo, xhi = D.strip_bounds(lx, rank, world)
     multi = world > 1
@@ -82,7 +101,14 @@ def run_strips(hc, lx, ly, n, scal, gtab, f_in, obst_old, rank, world):
     assert hc.hc_strip_stage2_f64(lx, ly, n, x0, nxl, xlo, xhi, world, scal, gtab, f, facc) == 0
     if multi:
         t = torch.from_numpy(facc)
+        # the default transport of a multi-process GPU run does not all-reduce: a rank reads, per grain, the partial sums of
+        # the ranks whose rows the grain's bounding box touches (ipc_sum_kernel, csrc/aux_kernels.cu).  Same rule here,
+        # from all-gathered partial sums; it must give the all-reduce's integers.
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t.clone())
+        by_rule = peer_rule_sum([p.numpy() for p in parts], gtab, scal, lx, n, world)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)   # integer sum: exact
+        assert np.array_equal(by_rule, facc), f"rank {rank}: the peer-memory selection rule drops a contribution"
     f_out = np.empty((xhi - xlo, ly, 9))
     assert hc.hc_strip_stage3_f64(lx, ly, x0, nxl, xlo, xhi, scal, f, f_out) == 0
     return xlo, xhi, f_out, facc, cell_new[(xlo - x0):(xhi - x0)]
