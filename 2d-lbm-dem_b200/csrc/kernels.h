@@ -145,7 +145,10 @@ constexpr unsigned BL_ACT = 1u << 23;
 constexpr unsigned BL_GRAIN = BL_ACT - 1;
 /* Links of the bounce-back sweep that the fused kernel cannot do on its own: entry.x = local node
  * index of the active solid node, entry.y = grain index | q << 24 | LL_W if the link just takes
- * the rest value (a w-link next to the wall ring, lbm_node.cuh w_links_with_collide). */
+ * the rest value (a w-link next to the wall ring, lbm_node.cuh w_links_with_collide) | LL_CLEAR if
+ * the rasteriser saw that the node two steps along the link is fluid or wall ring (it lies inside the
+ * painted tile + halo for 95 % of the links): such a link cannot be one across a one-node gap, and
+ * the sweep skips the map read that would tell. */
 struct LinkList {
   uint2 *entry;
   int *tcount;
